@@ -1,0 +1,131 @@
+"""Lower a pair of :class:`~gwinferno_b200.models.LazyWeight` products (PE samples, found
+injections) to the static :class:`~gwinferno_b200.spec.ModelSpec` + column arrays that the C-ABI
+consumes, and the per-call flat hyper-parameter vector ``Lambda``.
+
+The static part depends only on WHICH model objects / sample arrays appear and on how parameter
+objects are shared between terms (IID models pass one coefficient vector to two columns,
+gwinferno/models/bsplines/separable.py:77-79), so it is cached by that structure; every later
+call with new hyper-parameter values only rebuilds ``Lambda``.
+"""
+
+import numpy as np
+
+from . import spec as S
+
+
+def host_spline_on_grid(grid_xi, xi_range, n_splines, coefs):
+    """Cubic B-spline ``sum_k B_k(xi) c_k`` on the <= 1500-point normalisation grid (host-side
+    scalar glue for ``normalization()``; NaN grid entries are outside the basis range => 0)."""
+    lo, hi = xi_range
+    n_int = n_splines - 2
+    dx = (hi - lo) / (n_int - 1)
+    ok = np.isfinite(grid_xi)
+    t = (np.where(ok, grid_xi, lo) - lo) / dx
+    j = np.clip(np.floor(t), 0, n_int - 2).astype(np.int64)
+    u = t - j
+    w = np.stack([(1 - u) ** 3, 3 * u**3 - 6 * u**2 + 4, -3 * u**3 + 3 * u**2 + 3 * u + 1, u**3], axis=-1) / 6.0
+    s = np.einsum("gk,gk->g", w, coefs[j[:, None] + np.arange(4)])
+    return np.where(ok, s, 0.0)
+
+
+class Lowered:
+    """Static lowering result: spec, column arrays, and the recipe to flatten parameters."""
+
+    def __init__(self, spec, pe_cols, inj_cols, param_layout, slot_of):
+        self.spec = spec
+        self.pe_cols = pe_cols  # name -> (E, S) float64
+        self.inj_cols = inj_cols  # name -> (I,) float64
+        self.param_layout = param_layout  # list of (slot, size) in order of first appearance
+        self.slot_of = slot_of  # id(parameter object of the lowering call) -> first Lambda slot
+
+    def slots_for(self, obj):
+        """Lambda index range of a parameter object that was passed to the model calls."""
+        off = self.slot_of[id(obj)]
+        return slice(off, off + int(np.size(obj)))
+
+
+def _structure(pe_w, inj_w):
+    """Hashable description of the static structure + the parameter-sharing pattern."""
+    if len(pe_w.terms) != len(inj_w.terms):
+        raise ValueError("PE and injection weights must be built from the same sequence of model terms")
+    seen = {}
+    pattern = []
+    for t in pe_w.terms:
+        for p, k in zip(t.params, t.param_keys):
+            if k not in seen:
+                seen[k] = len(seen)
+            pattern.append((seen[k], p.size))
+    keys = tuple(t.key for t in pe_w.terms) + tuple(t.key for t in inj_w.terms)
+    return keys, tuple(pattern)
+
+
+def flatten_params(pe_w, n_params, param_layout=None):
+    """Flat ``Lambda`` from the parameter values carried by the PE-side lazy terms."""
+    Lam = np.zeros(n_params)
+    seen = {}
+    off = 0
+    for t in pe_w.terms:
+        for p, k in zip(t.params, t.param_keys):
+            if k in seen:
+                continue
+            seen[k] = off
+            Lam[off : off + p.size] = p
+            off += p.size
+    if off != n_params:
+        raise ValueError("parameter structure changed between calls")
+    return Lam
+
+
+def lower(pe_w, inj_w):
+    if pe_w.pe_samples is False or inj_w.pe_samples is True:
+        raise ValueError("first argument must be the PE-sample weights, second the injection weights")
+    # ---- parameter slots (shared objects share slots) -----------------------------------------
+    slot_of = {}
+    layout = []
+    off = 0
+    for t in pe_w.terms:
+        for p, k in zip(t.params, t.param_keys):
+            if k not in slot_of:
+                slot_of[k] = off
+                layout.append((off, p.size))
+                off += p.size
+    n_params = off
+    # ---- columns ---------------------------------------------------------------------------------
+    col_names = {}
+    pe_cols, inj_cols = {}, {}
+
+    def col_name(cpe, cinj):
+        pe_arr = cpe.pe if cpe.pe is not None else cinj.pe
+        inj_arr = cinj.inj if cinj.inj is not None else cpe.inj
+        if pe_arr is None or inj_arr is None:
+            raise ValueError("a term is missing its PE or injection sample array")
+        key = (id(pe_arr), id(inj_arr))
+        if key not in col_names:
+            name = f"c{len(col_names)}"
+            col_names[key] = name
+            if pe_arr.ndim != 2 or inj_arr.ndim != 1:
+                raise ValueError("PE columns must be (E, S) arrays and injection columns (I,) arrays")
+            pe_cols[name] = pe_arr
+            inj_cols[name] = inj_arr
+        return col_names[key]
+
+    terms, groups, cuts = [], [], []
+    for tp, ti in zip(pe_w.terms, inj_w.terms):
+        if len(tp.columns) != len(ti.columns):
+            raise ValueError("PE / injection term mismatch")
+        names = [col_name(a, b) for a, b in zip(tp.columns, ti.columns)]
+        slots = [slot_of[k] for k in tp.param_keys]
+        tt, gg, cc = tp.build(slots, len(groups), names)
+        terms += tt
+        groups += gg
+        for c in cc:
+            if not any(c.kind == o.kind and c.cols == o.cols and c.lo == o.lo and c.hi == o.hi for o in cuts):
+                cuts.append(c)
+    spec = S.ModelSpec(terms, groups, cuts, n_params)
+    shapes = {v.shape for v in pe_cols.values()}
+    if len(shapes) != 1:
+        raise ValueError(f"PE columns have inconsistent shapes: {shapes}")
+    shapes = {v.shape for v in inj_cols.values()}
+    if len(shapes) != 1:
+        raise ValueError(f"injection columns have inconsistent shapes: {shapes}")
+    return Lowered(spec, pe_cols, inj_cols, layout, slot_of)

@@ -1,0 +1,538 @@
+"""Host-side mirror of the reference's population-model classes (drop-in call surface).
+
+Same class names, constructor signatures and ``__call__`` arguments as
+``gwinferno/models/bsplines/{single,separable}.py``, ``gwinferno/models/spline_perturbation.py``
+and ``gwinferno/models/parametric/parametric.py`` -- but instead of building dense design
+matrices (single.py:56-57) and returning a dense pdf array, ``__call__`` returns a
+:class:`LazyWeight`: a symbolic product of per-dimension terms that
+:func:`gwinferno_b200.likelihood.hierarchical_likelihood` lowers to ONE fused CUDA evaluation
+through the C-ABI (include/gwi.h).  ``LazyWeight`` supports ``*`` and ``/`` exactly as the
+reference's weight assembly uses them (examples/simple_bspline_example.py:58-68).
+
+Nothing here evaluates a density on the CPU: there is no CPU fallback.
+"""
+
+import numpy as np
+
+from . import spec as S
+from .cosmology import Planck15
+
+__all__ = [
+    "BSpline",
+    "LogXBSpline",
+    "LogYBSpline",
+    "LogXLogYBSpline",
+    "LazyWeight",
+    "Base1DBSplineModel",
+    "BSplineSpinMagnitude",
+    "BSplineSpinTilt",
+    "BSplineRatio",
+    "BSplineMass",
+    "BSplineIIDSpinMagnitudes",
+    "BSplineIndependentSpinMagnitudes",
+    "BSplineIIDSpinTilts",
+    "BSplineIndependentSpinTilts",
+    "BSplinePrimaryBSplineRatio",
+    "BSplinePrimaryPowerlawRatio",
+    "PLPeakPrimaryBSplineRatio",
+    "BSplineIIDComponentMasses",
+    "BSplineIndependentComponentMasses",
+    "PowerlawRedshiftModel",
+    "PowerlawSplineRedshiftModel",
+    "powerlaw_primary_ratio_pdf",
+    "plpeak_primary_ratio_pdf",
+    "plpeak_primary_pdf",
+    "beta_spin_magnitude",
+    "iid_spin_magnitude",
+    "independent_spin_magnitude_beta_dist",
+    "mixture_isoalign_spin_tilt",
+    "iid_spin_tilt",
+    "independent_spin_tilt",
+    "weight_from_prior",
+]
+
+
+# ---- basis "classes": only used as tags selecting the projection, like the reference's
+#      ``basis=`` keyword (single.py:42; interpolation.py:240,320,360,410) -------------------
+class BSpline:
+    logx, logy, default_normalize, n_grid = False, False, False, 1000
+
+
+class LogXBSpline(BSpline):
+    logx, logy, default_normalize, n_grid = True, False, True, 1000
+
+
+class LogYBSpline(BSpline):
+    logx, logy, default_normalize, n_grid = False, True, True, 1000
+
+
+class LogXLogYBSpline(LogYBSpline):
+    logx, logy, default_normalize, n_grid = True, True, True, 1500
+
+
+class _Column:
+    """A (PE array, injection array) pair of one physical sample coordinate."""
+
+    def __init__(self, pe, inj):
+        self.pe = None if pe is None else np.asarray(pe, dtype=np.float64)
+        self.inj = None if inj is None else np.asarray(inj, dtype=np.float64)
+
+
+class _LazyTerm:
+    """One additive log-density term; ``params`` are the hyper-parameter VALUES of this call,
+    ``build(slots, group_base)`` produces the static spec entries (terms, groups, cuts)."""
+
+    def __init__(self, key, columns, params, build):
+        self.key = key  # hashable identity of the STATIC part (model object id, dimension)
+        self.columns = columns  # list[_Column]
+        # parameter OBJECTS passed by the caller: the same object given to two terms (IID models,
+        # separable.py:77-79) shares its Lambda slots, so gradients come back per object
+        self._orig = list(params)
+        self.param_keys = [id(p) for p in self._orig]
+        self.params = [np.atleast_1d(np.asarray(p, dtype=np.float64)) for p in params]
+        self.build = build
+
+
+class LazyWeight:
+    """Symbolic per-sample weight  prod_d p_d(theta_d; Lambda) / prior  for one sample set
+    (``pe_samples=True`` or ``False``)."""
+
+    def __init__(self, terms, pe_samples):
+        self.terms = list(terms)
+        self.pe_samples = pe_samples
+
+    def _merge(self, other):
+        if self.pe_samples is None:
+            return other.pe_samples
+        if other.pe_samples is None or other.pe_samples == self.pe_samples:
+            return self.pe_samples
+        raise ValueError("cannot mix PE-sample and injection weights in one product")
+
+    def __mul__(self, other):
+        if isinstance(other, LazyWeight):
+            return LazyWeight(self.terms + other.terms, self._merge(other))
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        if isinstance(other, LazyWeight):
+            raise TypeError("division by a population term is not supported")
+        # division by the sampling-prior array (examples/simple_bspline_example.py:66)
+        arr = np.asarray(other, dtype=np.float64)
+        return self * weight_from_prior(arr, pe_samples=self.pe_samples)
+
+
+def weight_from_prior(prior, pe_samples=None):
+    """``1/prior`` as a lazy static term.  ``pe_samples`` is inferred from the dimensionality when
+    omitted (2-D = PE samples, 1-D = injections; same convention as parametric.py:130)."""
+    prior = np.asarray(prior, dtype=np.float64)
+    if pe_samples is None:
+        pe_samples = prior.ndim == 2
+    col = _Column(prior if pe_samples else None, None if pe_samples else prior)
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_STATIC, [cols[0]], feature=S.FEAT_NEG_LOG, name="1/prior")], [], []
+
+    return LazyWeight([_LazyTerm(("prior",), [col], [], build)], pe_samples)
+
+
+def _is_pe(arr):
+    return np.ndim(arr) == 2
+
+
+# ================================================================================================
+# 1-D B-spline models (gwinferno/models/bsplines/single.py)
+# ================================================================================================
+class Base1DBSplineModel:
+    """Mirror of ``Base1DBSplineModel`` (single.py:16-128): holds the static samples and the
+    basis description; ``__call__(coefs, pe_samples)`` returns a :class:`LazyWeight`."""
+
+    def __init__(self, n_splines, xx, xx_inj, xrange=(0.0, 1.0), degree=3, basis=BSpline, **kwargs):
+        if degree != 3:
+            raise NotImplementedError("only cubic B-splines (degree=3) are implemented on the CUDA path")
+        if kwargs.get("knots") is not None or kwargs.get("interior_knots") is not None:
+            raise NotImplementedError("non-uniform knot vectors are not implemented on the CUDA path")
+        if not getattr(basis, "logy", False):
+            raise NotImplementedError(
+                "linear-in-y bases (BSpline/LogXBSpline as a density) are not implemented on the CUDA path; "
+                "use LogYBSpline / LogXLogYBSpline"
+            )
+        self.n_splines = int(n_splines)
+        self.xmin, self.xmax = float(xrange[0]), float(xrange[1])
+        self.degree = degree
+        self.basis = basis
+        self.normalize = bool(kwargs.get("normalize", basis.default_normalize))
+        self.column = _Column(xx, xx_inj)
+        # spline-coordinate range and the normalisation grid, exactly as the reference builds them
+        if basis.logx:
+            self.xi_range = (float(np.log(self.xmin)), float(np.log(self.xmax)))  # interpolation.py:428
+            grid = np.linspace(*np.exp(np.array(self.xi_range)), basis.n_grid)  # :433
+            grid_xi = np.log(grid)  # :447
+        else:
+            self.xi_range = (self.xmin, self.xmax)
+            grid = np.linspace(self.xmin, self.xmax, basis.n_grid)  # interpolation.py:378
+            grid_xi = grid
+        self.grid = grid
+        inside = (grid_xi >= self.xi_range[0]) & (grid_xi <= self.xi_range[1])
+        with np.errstate(divide="ignore"):
+            log_w = np.log(S.trapezoid_weights(grid))
+        # LogY bases are -inf outside the range => integrand exp(-inf) = 0 (interpolation.py:393-394,449)
+        self.grid_log_w = np.where(inside, log_w, -np.inf)
+        self.grid_xi = np.clip(grid_xi, *self.xi_range)
+
+    def _lazy(self, coefs, pe_samples, tag=""):
+        model = self
+
+        def build(slots, group_base, cols):
+            groups = []
+            g = -1
+            if model.normalize:
+                groups = [S.NormGroup(model.grid_log_w, name=f"Z[{cols[0]}]")]
+                g = group_base
+            term = S.Term(
+                S.TERM_SPLINE,
+                [cols[0]],
+                slots=[slots[0]],
+                n_splines=model.n_splines,
+                logx=model.basis.logx,
+                outside=S.OUTSIDE_DROP,
+                xrange=(model.xmin, model.xmax),
+                norm_group=g,
+                grid_xi=model.grid_xi if model.normalize else None,
+                name=f"spline[{cols[0]}]",
+            )
+            term.xi_range = model.xi_range
+            return [term], groups, []
+
+        if np.shape(coefs) != (self.n_splines,):
+            raise ValueError(f"expected {self.n_splines} coefficients, got shape {np.shape(coefs)}")
+        return LazyWeight([_LazyTerm((id(self), tag), [self.column], [coefs], build)], pe_samples)
+
+    def __call__(self, coefs, pe_samples=True):
+        return self._lazy(coefs, pe_samples)
+
+
+class BSplineSpinMagnitude(Base1DBSplineModel):
+    def __init__(self, n_splines, a, a_inj, basis=LogYBSpline, **kwargs):
+        xrange = kwargs.pop("xrange", (0.0, 1.0))
+        super().__init__(n_splines, a, a_inj, basis=basis, xrange=xrange, **kwargs)
+
+
+class BSplineSpinTilt(Base1DBSplineModel):
+    def __init__(self, n_splines, ct, ct_inj, basis=LogYBSpline, **kwargs):
+        xrange = kwargs.pop("xrange", (-1.0, 1.0))
+        super().__init__(n_splines, ct, ct_inj, basis=basis, xrange=xrange, **kwargs)
+
+
+class BSplineRatio(Base1DBSplineModel):
+    def __init__(self, n_splines, q, q_inj, qmin=0, basis=LogYBSpline, **kwargs):
+        xrange = kwargs.pop("xrange", (qmin, 1))
+        super().__init__(n_splines, q, q_inj, basis=basis, xrange=xrange, **kwargs)
+
+
+class BSplineMass(Base1DBSplineModel):
+    def __init__(self, n_splines, m, m_inj, mmin=2, mmax=100, basis=LogXLogYBSpline, **kwargs):
+        xrange = kwargs.pop("xrange", (mmin, mmax))
+        super().__init__(n_splines, m, m_inj, basis=basis, xrange=xrange, **kwargs)
+
+
+# ================================================================================================
+# separable products (gwinferno/models/bsplines/separable.py)
+# ================================================================================================
+class _IIDPair:
+    _cls = None
+
+    def __init__(self, n_splines, x1, x2, x1_inj, x2_inj, **kwargs):
+        self.primary_model = self._cls(n_splines, x1, x1_inj, **kwargs)
+        self.secondary_model = self._cls(n_splines, x2, x2_inj, **kwargs)
+
+    def __call__(self, coefs, pe_samples=True):
+        # same coefficient vector on both columns (separable.py:77-79, 216-218)
+        return self.primary_model(coefs, pe_samples=pe_samples) * self.secondary_model(coefs, pe_samples=pe_samples)
+
+
+class _IndependentPair:
+    _cls = None
+
+    def __init__(self, n_splines1, n_splines2, x1, x2, x1_inj, x2_inj, kwargs1={}, kwargs2={}, **kwargs):
+        self.primary_model = self._cls(n_splines1, x1, x1_inj, **kwargs1, **kwargs)
+        self.secondary_model = self._cls(n_splines2, x2, x2_inj, **kwargs2, **kwargs)
+
+    def __call__(self, pcoefs, scoefs, pe_samples=True):
+        return self.primary_model(pcoefs, pe_samples=pe_samples) * self.secondary_model(scoefs, pe_samples=pe_samples)
+
+
+class BSplineIIDSpinMagnitudes(_IIDPair):
+    _cls = BSplineSpinMagnitude
+
+
+class BSplineIndependentSpinMagnitudes(_IndependentPair):
+    _cls = BSplineSpinMagnitude
+
+
+class BSplineIIDSpinTilts(_IIDPair):
+    _cls = BSplineSpinTilt
+
+
+class BSplineIndependentSpinTilts(_IndependentPair):
+    _cls = BSplineSpinTilt
+
+
+class BSplinePrimaryBSplineRatio:
+    """separable.py:446-530."""
+
+    def __init__(self, n_splines_m, n_splines_q, m1, m1_inj, q, q_inj, mmax=100.0, m1min=3.0, m2min=3.0, kwargs_m={}, kwargs_q={}, **kwargs):
+        self.primary_model = BSplineMass(n_splines_m, m1, m1_inj, mmin=m1min, mmax=mmax, **kwargs_m, **kwargs)
+        self.ratio_model = BSplineRatio(n_splines_q, q, q_inj, qmin=m2min / mmax, **kwargs_q, **kwargs)
+
+    def __call__(self, mcoefs, qcoefs, pe_samples=True):
+        return self.ratio_model(qcoefs, pe_samples=pe_samples) * self.primary_model(mcoefs, pe_samples=pe_samples)
+
+
+def _pairing_term(m1col, m2col, beta, pe_samples, cut01):
+    """``(m2/m1)^beta`` (separable.py:608-613, 703); the IID form zeroes q outside [0, 1]."""
+
+    def build(slots, group_base, cols):
+        t = S.Term(S.TERM_LINEAR, [cols[0], cols[1]], slots=[slots[0]], cst=[0.0], feature=S.FEAT_LOG_RATIO, name="q^beta")
+        cuts = [S.Cut(S.CUT_RATIO_RANGE, [cols[0], cols[1]], 0.0, 1.0)] if cut01 else []
+        return [t], [], cuts
+
+    return LazyWeight([_LazyTerm(("pairing", id(m1col), id(m2col), cut01), [m2col, m1col], [beta], build)], pe_samples)
+
+
+class BSplineIIDComponentMasses:
+    """separable.py:533-613."""
+
+    def __init__(self, n_splines, m1, m2, m1_inj, m2_inj, mmin=2, mmax=100, **kwargs):
+        self.primary_model = BSplineMass(n_splines, m1, m1_inj, mmin=mmin, mmax=mmax, **kwargs)
+        self.secondary_model = BSplineMass(n_splines, m2, m2_inj, mmin=mmin, mmax=mmax, **kwargs)
+
+    def __call__(self, coefs, beta=0, pe_samples=True):
+        w = self.primary_model(coefs, pe_samples=pe_samples) * self.secondary_model(coefs, pe_samples=pe_samples)
+        return w * _pairing_term(self.primary_model.column, self.secondary_model.column, beta, pe_samples, cut01=True)
+
+
+class BSplineIndependentComponentMasses:
+    """separable.py:616-703."""
+
+    def __init__(self, n_splines1, n_splines2, m1, m2, m1_inj, m2_inj, mmin1=2, mmax1=100, mmin2=2, mmax2=100, kwargs1={}, kwargs2={}, **kwargs):
+        self.primary_model = BSplineMass(n_splines1, m1, m1_inj, mmin=mmin1, mmax=mmax1, **kwargs1, **kwargs)
+        self.secondary_model = BSplineMass(n_splines2, m2, m2_inj, mmin=mmin2, mmax=mmax2, **kwargs2, **kwargs)
+
+    def __call__(self, pcoefs, scoefs, beta=0, pe_samples=True):
+        w = self.primary_model(pcoefs, pe_samples=pe_samples) * self.secondary_model(scoefs, pe_samples=pe_samples)
+        return w * _pairing_term(self.primary_model.column, self.secondary_model.column, beta, pe_samples, cut01=False)
+
+
+# ================================================================================================
+# parametric densities (gwinferno/models/parametric/parametric.py, gwinferno/distributions.py)
+# Free functions of sample arrays, as in the reference; the sample set is inferred from the
+# dimensionality of the arrays (2-D = PE samples, 1-D = injections).
+# ================================================================================================
+_COLUMN_CACHE = {}
+
+
+def _col_of(arr):
+    """One _Column per distinct sample array (identity-keyed so the static plan can be cached)."""
+    key = id(arr)
+    hit = _COLUMN_CACHE.get(key)
+    if hit is not None and hit[0] is arr:
+        return hit[1]
+    a = np.asarray(arr, dtype=np.float64)
+    col = _Column(a if _is_pe(a) else None, None if _is_pe(a) else a)
+    _COLUMN_CACHE[key] = (arr, col)
+    return col
+
+
+def _powerlaw_term(x, alpha, lo, hi, tag):
+    col = _col_of(x)
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_POWERLAW, [cols[0]], slots=[slots[0]], cst=[float(lo), float(hi)], name=f"powerlaw[{cols[0]}]")], [], []
+
+    return LazyWeight([_LazyTerm(("pl", id(x), float(lo), float(hi), tag), [col], [alpha], build)], _is_pe(x))
+
+
+def _powerlaw_ratio_term(q, m1, beta, mmin):
+    cq, cm = _col_of(q), _col_of(m1)
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_POWERLAW_RATIO, [cols[0], cols[1]], slots=[slots[0]], cst=[float(mmin)], name="powerlaw[q|m1]")], [], []
+
+    return LazyWeight([_LazyTerm(("plq", id(q), id(m1), float(mmin)), [cq, cm], [beta], build)], _is_pe(q))
+
+
+def powerlaw_primary_ratio_pdf(m1, q, alpha, beta, mmin, mmax):
+    """parametric.py:27-30."""
+    return _powerlaw_ratio_term(q, m1, beta, mmin) * _powerlaw_term(m1, alpha, mmin, mmax, "m1")
+
+
+def plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=None):
+    """parametric.py:49-53 (``delta`` smoothing is not implemented on the CUDA path)."""
+    if delta is not None:
+        raise NotImplementedError("low-mass smoothing (delta) is not implemented on the CUDA path")
+    col = _col_of(m1)
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_PLPEAK, [cols[0]], slots=list(slots[:4]), cst=[float(mmin), float(mmax)], name="plpeak[m1]")], [], []
+
+    return LazyWeight([_LazyTerm(("plpeak", id(m1), float(mmin), float(mmax)), [col], [alpha, mpp, sigpp, lam], build)], _is_pe(m1))
+
+
+def plpeak_primary_ratio_pdf(m1, q, alpha, beta, mmin, mmax, mpp, sigpp, lam, delta=None):
+    """parametric.py:39-46."""
+    return _powerlaw_ratio_term(q, m1, beta, mmin) * plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=delta)
+
+
+def beta_spin_magnitude(a, alpha, beta, amax=1):
+    """parametric.py:63-64 -> distributions.py:146-162."""
+    col = _col_of(a)
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_BETA, [cols[0]], slots=list(slots[:2]), cst=[float(amax)], name=f"beta[{cols[0]}]")], [], []
+
+    return LazyWeight([_LazyTerm(("beta", id(a), float(amax)), [col], [alpha, beta], build)], _is_pe(a))
+
+
+def iid_spin_magnitude(a1, a2, alpha_mag, beta_mag, amax=1):
+    return beta_spin_magnitude(a1, alpha_mag, beta_mag, amax) * beta_spin_magnitude(a2, alpha_mag, beta_mag, amax)
+
+
+def independent_spin_magnitude_beta_dist(a1, a2, alpha_mag1, beta_mag1, alpha_mag2, beta_mag2, amax1=1, amax2=1):
+    return beta_spin_magnitude(a1, alpha_mag1, beta_mag1, amax1) * beta_spin_magnitude(a2, alpha_mag2, beta_mag2, amax2)
+
+
+def mixture_isoalign_spin_tilt(ct, xi_tilt, sigma_tilt):
+    """parametric.py:84-86."""
+    col = _col_of(ct)
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_ISOALIGN, [cols[0]], slots=list(slots[:2]), name=f"isoalign[{cols[0]}]")], [], []
+
+    return LazyWeight([_LazyTerm(("isoalign", id(ct)), [col], [xi_tilt, sigma_tilt], build)], _is_pe(ct))
+
+
+def iid_spin_tilt(ct1, ct2, xi_tilt, sigma_tilt):
+    return mixture_isoalign_spin_tilt(ct1, xi_tilt, sigma_tilt) * mixture_isoalign_spin_tilt(ct2, xi_tilt, sigma_tilt)
+
+
+def independent_spin_tilt(ct1, ct2, xi_tilt_1, xi_tilt_2, sigma_tilt1, sigma_tilt2):
+    return mixture_isoalign_spin_tilt(ct1, xi_tilt_1, sigma_tilt1) * mixture_isoalign_spin_tilt(ct2, xi_tilt_2, sigma_tilt2)
+
+
+class BSplinePrimaryPowerlawRatio:
+    """separable.py:295-365."""
+
+    def __init__(self, n_splines, m1, m1_inj, mmin=2, mmax=100, **kwargs):
+        self.primary_model = BSplineMass(n_splines, m1, m1_inj, mmin=mmin, mmax=mmax, **kwargs)
+
+    def __call__(self, m1, q, beta, mmin, coefs, pe_samples=True):
+        return self.primary_model(coefs, pe_samples=pe_samples) * _powerlaw_ratio_term(q, m1, beta, mmin)
+
+
+class PLPeakPrimaryBSplineRatio:
+    """separable.py:368-443."""
+
+    def __init__(self, n_splines, q, q_inj, **kwargs):
+        self.ratio_model = BSplineRatio(n_splines, q, q_inj, **kwargs)
+
+    def __call__(self, m1, alpha, mmin, mmax, peak_mean, peak_sd, peak_frac, coefs, pe_samples=True):
+        return plpeak_primary_pdf(m1, alpha, mmin, mmax, peak_mean, peak_sd, peak_frac) * self.ratio_model(coefs, pe_samples=pe_samples)
+
+
+# ================================================================================================
+# redshift models (parametric.py:112-145, spline_perturbation.py:304-372)
+# ================================================================================================
+class PowerlawRedshiftModel:
+    def __init__(self, z_pe, z_inj):
+        self.column = _Column(z_pe, z_inj)
+        z_pe = self.column.pe
+        z_inj = self.column.inj
+        self.zmin = float(max(np.min(z_pe), np.min(z_inj)))  # parametric.py:114
+        self.zmax = float(min(np.max(z_pe), np.max(z_inj)))  # parametric.py:115
+        self.zs = np.linspace(self.zmin, self.zmax, 1000)  # :116
+        self.dVdz_ = Planck15.dVcdz(self.zs)  # :117
+        with np.errstate(divide="ignore"):
+            self._grid_log_w = np.log(S.trapezoid_weights(self.zs) * self.dVdz_)
+        self._grid_log1pz = np.log(1.0 + self.zs)
+        self._norm_cache = None
+
+    def _which(self, z):
+        if z is self.column.pe or (_is_pe(z) and np.shape(z) == np.shape(self.column.pe)):
+            return True
+        return False
+
+    def _terms(self, slots, group_base, cols, spline=None):
+        zc = cols[0]
+        terms = [
+            S.Term(S.TERM_STATIC, [zc], feature=S.FEAT_LOG_DVDZ, name="dVc/dz"),
+            S.Term(
+                S.TERM_LINEAR, [zc], slots=[slots[0]], cst=[-1.0], feature=S.FEAT_LOG1P, norm_group=group_base, grid_feat=self._grid_log1pz, name="(1+z)^(lamb-1)"
+            ),
+        ]
+        groups = [S.NormGroup(self._grid_log_w, name="Z[redshift]")]
+        # where(z <= zmax, ., 0)   (parametric.py:141-145, spline_perturbation.py:368-372)
+        cuts = [S.Cut(S.CUT_RANGE, [zc], -np.inf, self.zmax)]
+        return terms, groups, cuts
+
+    def __call__(self, z, lamb):
+        pe_samples = self._which(z)
+        model = self
+
+        def build(slots, group_base, cols):
+            return model._terms(slots, group_base, cols)
+
+        return LazyWeight([_LazyTerm((id(self), "plz"), [self.column], [lamb], build)], pe_samples)
+
+    # host-side value of the normaliser (a 1000-point sum; used for ``surveyed_hypervolume``)
+    def normalization(self, lamb):
+        lamb = float(np.asarray(lamb))
+        return float(np.sum(np.exp(self._grid_log_w + (lamb - 1.0) * self._grid_log1pz)))
+
+
+class PowerlawSplineRedshiftModel(PowerlawRedshiftModel):
+    def __init__(self, n_splines, z_pe, z_inj, basis=LogXBSpline):
+        super().__init__(z_pe=z_pe, z_inj=z_inj)
+        if basis is not LogXBSpline:
+            raise NotImplementedError("only the LogXBSpline perturbation basis is implemented")
+        self.n_splines = int(n_splines)
+        self.xi_range = (float(np.log(self.zmin)), float(np.log(self.zmax)))
+        gxi = np.log(self.zs)
+        inside = (gxi >= self.xi_range[0]) & (gxi <= self.xi_range[1])
+        # LogX bases are ZERO outside the range (interpolation.py:175): mark with NaN
+        self._grid_xi = np.where(inside, np.clip(gxi, *self.xi_range), np.nan)
+
+    def __call__(self, z, lamb, cs):
+        pe_samples = self._which(z)
+        model = self
+
+        def build(slots, group_base, cols):
+            terms, groups, cuts = model._terms(slots, group_base, cols)
+            t = S.Term(
+                S.TERM_SPLINE,
+                [cols[0]],
+                slots=[slots[1]],
+                n_splines=model.n_splines,
+                logx=True,
+                outside=S.OUTSIDE_ZERO,
+                xrange=(model.zmin, model.zmax),
+                norm_group=group_base,
+                grid_xi=model._grid_xi,
+                name="spline[log z]",
+            )
+            t.xi_range = model.xi_range
+            return terms + [t], groups, cuts
+
+        if np.shape(cs) != (self.n_splines,):
+            raise ValueError(f"expected {self.n_splines} redshift coefficients, got shape {np.shape(cs)}")
+        return LazyWeight([_LazyTerm((id(self), "plsz"), [self.column], [lamb, cs], build)], pe_samples)
+
+    def normalization(self, lamb, cs):
+        """Host-side ``Z(lamb, cs)`` (spline_perturbation.py:323-336): a 1000-point sum used for
+        the ``surveyed_hypervolume`` argument; the likelihood path itself gets log Z on the GPU."""
+        from .lowering import host_spline_on_grid  # tiny, grid-only helper
+
+        lamb = float(np.asarray(lamb))
+        s = host_spline_on_grid(self._grid_xi, self.xi_range, self.n_splines, np.asarray(cs, dtype=np.float64))
+        return float(np.sum(np.exp(self._grid_log_w + (lamb - 1.0) * self._grid_log1pz + s)))

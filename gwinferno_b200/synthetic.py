@@ -1,0 +1,134 @@
+"""Deterministic synthetic catalogs of the BASELINE.json shapes.
+
+There is no network for GWTC data, so benchmarks and parity tests run on seeded synthetic
+catalogs with the reference's column schema (gwinferno/pipeline/utils.py:51-96):
+PE columns ``(E, S)`` and found-injection columns ``(I,)`` named
+``mass_1, mass_ratio, mass_2, a_1, a_2, cos_tilt_1, cos_tilt_2, redshift, prior``.
+
+  * events: centres from a fiducial population, samples = centre + Gaussian scatter reflected
+    into the support (so N_eff,i >> E);
+  * injections: uniform over the support with ``prior`` = the analytic draw density (so
+    N_eff,inj >> 4E); ``total_inj = 4 I``.
+Seeds: ``1000*cfg + {0: PE, 1: injections, 2: Lambda}``.
+"""
+
+import numpy as np
+
+from .cosmology import Planck15
+
+MMIN, MMAX = 3.0, 100.0
+ZLO, ZHI = 1e-3, 1.9
+
+CONFIGS = {
+    # cfg: (E, S, I)  -- BASELINE.json "configs"
+    1: (69, 3000, 100_000),
+    2: (70, 4000, 500_000),
+    3: (300, 10_000, 100_000_000),
+    5: (200, 8000, 20_000_000),
+}
+
+
+def _reflect(x, lo, hi):
+    """Reflect values into [lo, hi] (keeps the scatter smooth at the boundaries)."""
+    w = hi - lo
+    y = np.mod(x - lo, 2.0 * w)
+    y = np.where(y > w, 2.0 * w - y, y)
+    return lo + y
+
+
+def make_injections(I, seed, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    m1 = rng.uniform(MMIN, MMAX, I)
+    qlo = MMIN / m1
+    q = rng.uniform(qlo, 1.0, I)
+    a1 = rng.uniform(0.0, 1.0, I)
+    a2 = rng.uniform(0.0, 1.0, I)
+    ct1 = rng.uniform(-1.0, 1.0, I)
+    ct2 = rng.uniform(-1.0, 1.0, I)
+    z = rng.uniform(ZLO, ZHI, I)
+    # density of the draw in (m1, q, a1, a2, ct1, ct2, z)
+    prior = 1.0 / (MMAX - MMIN) / (1.0 - qlo) / 4.0 / (ZHI - ZLO)
+    return {
+        "mass_1": m1,
+        "mass_ratio": q,
+        "mass_2": m1 * q,
+        "a_1": a1,
+        "a_2": a2,
+        "cos_tilt_1": ct1,
+        "cos_tilt_2": ct2,
+        "redshift": z,
+        "prior": prior,
+    }
+
+
+def make_events(E, S, seed):
+    rng = np.random.default_rng(seed)
+    # fiducial population for the event centres
+    u = rng.uniform(size=E)
+    a = -2.5 + 1.0
+    m1c = (u * (90.0**a - 5.0**a) + 5.0**a) ** (1.0 / a)  # p(m1) ~ m1^-2.5 on [5, 90]
+    qc = rng.uniform(0.4, 1.0, E)
+    a1c = rng.beta(2.0, 5.0, E)
+    a2c = rng.beta(2.0, 5.0, E)
+    ct1c = rng.uniform(-1.0, 1.0, E)
+    ct2c = rng.uniform(-1.0, 1.0, E)
+    zg = np.linspace(0.01, 1.5, 4000)
+    pz = Planck15.dVcdz(zg) * (1.0 + zg) ** 1.7
+    cdf = np.cumsum(pz)
+    cdf /= cdf[-1]
+    zc = np.interp(rng.uniform(size=E), cdf, zg)
+
+    def scat(c, sig, lo, hi):
+        return _reflect(c[:, None] + sig * rng.standard_normal((E, S)), lo, hi)
+
+    m1 = scat(m1c, 0.1 * m1c[:, None], MMIN + 1e-3, MMAX - 1e-3)
+    q = scat(qc, 0.15, 0.0, 1.0)
+    q = np.maximum(q, (MMIN + 1e-3) / m1)  # keep m2 >= mmin
+    q = np.minimum(q, 1.0)
+    a1 = scat(a1c, 0.15, 0.0, 1.0)
+    a2 = scat(a2c, 0.15, 0.0, 1.0)
+    ct1 = scat(ct1c, 0.4, -1.0, 1.0)
+    ct2 = scat(ct2c, 0.4, -1.0, 1.0)
+    z = scat(zc, 0.2 * zc[:, None], ZLO + 1e-3, ZHI - 1e-3)
+    # sampling prior ~ the usual LVK PE prior shape: p(m1,q) ~ m1 (flat in component masses),
+    # flat spins/tilts, p(z) ~ dVc/dz / (1+z); un-normalised constants do not matter for parity
+    prior = m1 * Planck15.dVcdz(z) / (1.0 + z) * 1e-12
+    return {
+        "mass_1": m1,
+        "mass_ratio": q,
+        "mass_2": m1 * q,
+        "a_1": a1,
+        "a_2": a2,
+        "cos_tilt_1": ct1,
+        "cos_tilt_2": ct2,
+        "redshift": z,
+        "prior": prior,
+    }
+
+
+def make_catalog(E, S, I, cfg=0):
+    """Return ``(pedict, injdict, constants)`` in the reference's schema."""
+    pedict = make_events(E, S, 1000 * cfg + 0)
+    injdict = make_injections(I, 1000 * cfg + 1)
+    constants = {"total_inj": float(4 * I), "obs_time": 1.0, "nObs": E}
+    return pedict, injdict, constants
+
+
+def make_config(cfg, scale=1.0):
+    """Catalog of BASELINE.json config ``cfg``; ``scale`` < 1 shrinks S and I for parity tests."""
+    E, S, I = CONFIGS[cfg]
+    S = max(8, int(round(S * scale)))
+    I = max(64, int(round(I * scale)))
+    return make_catalog(E, S, I, cfg=cfg)
+
+
+def bspline_lambda(nsplines, seed, scale=1.0):
+    """Test point for the B-spline model: coefficients ~ N(0, scale), c_z[0] = 0, lamb = 2.7."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for k, n in nsplines.items():
+        out[k] = scale * rng.standard_normal(n)
+    if "redshift" in out:
+        out["redshift"][0] = 0.0
+    out["lamb"] = 2.7
+    return out

@@ -1,0 +1,141 @@
+"""Shared test helpers: rebuild the golden cases (tests/golden/*.npz) with THIS repo's mirror of
+the reference model classes, giving the lazy weights, the lowered spec and the flat Lambda."""
+
+import os
+
+import numpy as np
+
+from gwinferno_b200 import lowering
+from gwinferno_b200 import models as M
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COLS = ["mass_1", "mass_ratio", "mass_2", "a_1", "a_2", "cos_tilt_1", "cos_tilt_2", "redshift", "prior"]
+GOLDEN_CASES = [
+    "bspline_full",
+    "bspline_full_margsel",
+    "bspline_full_cutfail",
+    "bspline_iid",
+    "bspline_indep_masses",
+    "inference_test_bspline",
+    "inference_test_parametric",
+    "plpeak",
+]
+LIKE_KW = {
+    "bspline_full": dict(marginalize_selection=False, min_neff_cut=True),
+    "bspline_full_margsel": dict(marginalize_selection=True, min_neff_cut=True),
+    "bspline_full_cutfail": dict(marginalize_selection=False, min_neff_cut=True),
+    "bspline_iid": dict(min_neff_cut=True),
+    "bspline_indep_masses": dict(min_neff_cut=False),
+    "inference_test_bspline": dict(marginalize_selection=False, min_neff_cut=False),
+    "inference_test_parametric": dict(marginalize_selection=False, min_neff_cut=False),
+    "plpeak": dict(min_neff_cut=True),
+}
+
+
+class Case:
+    pass
+
+
+def build_weight_fn(model, pe, inj, meta):
+    """Return ``weights(datadict, pe_samples, params) -> LazyWeight`` written like the reference's
+    example models (examples/simple_bspline_example.py:58-68 etc.)."""
+    mmin, mmax = float(meta["mmin"]), float(meta["mmax"])
+    if model == "bspline_full":
+        mm = M.BSplinePrimaryBSplineRatio(
+            int(meta["n_m1"]), int(meta["n_q"]), pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax,
+            kwargs_m={"basis": M.LogXLogYBSpline}, kwargs_q={"basis": M.LogYBSpline},
+        )
+        ma = M.BSplineIndependentSpinMagnitudes(int(meta["n_a"]), int(meta["n_a"]), pe["a_1"], pe["a_2"], inj["a_1"], inj["a_2"], normalize=True)
+        mt = M.BSplineIndependentSpinTilts(int(meta["n_t"]), int(meta["n_t"]), pe["cos_tilt_1"], pe["cos_tilt_2"], inj["cos_tilt_1"], inj["cos_tilt_2"], normalize=True)
+        mz = M.PowerlawSplineRedshiftModel(int(meta["n_z"]), pe["redshift"], inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            w = mm(p["mass_cs"], p["q_cs"], pe_samples=pe_samples) * ma(p["a1_cs"], p["a2_cs"], pe_samples=pe_samples)
+            w = w * mt(p["tilt1_cs"], p["tilt2_cs"], pe_samples=pe_samples) * mz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+            return w
+
+        return weights, (lambda p: mz.normalization(p["lamb"], p["z_cs"]))
+    if model == "bspline_iid":
+        mm = M.BSplineIIDComponentMasses(int(meta["n_m"]), pe["mass_1"], pe["mass_2"], inj["mass_1"], inj["mass_2"], mmin=mmin, mmax=mmax)
+        ma = M.BSplineIIDSpinMagnitudes(int(meta["n_a"]), pe["a_1"], pe["a_2"], inj["a_1"], inj["a_2"], normalize=True)
+        mt = M.BSplineIIDSpinTilts(int(meta["n_t"]), pe["cos_tilt_1"], pe["cos_tilt_2"], inj["cos_tilt_1"], inj["cos_tilt_2"], normalize=True)
+        mz = M.PowerlawSplineRedshiftModel(int(meta["n_z"]), pe["redshift"], inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            w = mm(p["mass_cs"], beta=p["beta"], pe_samples=pe_samples) * ma(p["a_cs"], pe_samples=pe_samples) * mt(p["tilt_cs"], pe_samples=pe_samples)
+            return w * mz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(p["lamb"], p["z_cs"]))
+    if model == "bspline_indep_masses":
+        mm = M.BSplineIndependentComponentMasses(int(meta["n_m1"]), int(meta["n_m2"]), pe["mass_1"], pe["mass_2"], inj["mass_1"], inj["mass_2"], mmin1=mmin, mmax1=mmax, mmin2=mmin, mmax2=mmax)
+        mz = M.PowerlawSplineRedshiftModel(int(meta["n_z"]), pe["redshift"], inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            return mm(p["m1_cs"], p["m2_cs"], beta=p["beta"], pe_samples=pe_samples) * mz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(p["lamb"], p["z_cs"]))
+    if model == "inference_test_bspline":
+        mm = M.BSplinePrimaryBSplineRatio(10, 5, pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax)
+        mz = M.PowerlawSplineRedshiftModel(5, pe["redshift"], inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            return mm(p["m1_coefs"], p["q_coefs"], pe_samples=pe_samples) * mz(d["redshift"], p["lamb"], p["z_coefs"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(lamb=p["lamb"], cs=p["z_coefs"]))
+    if model == "inference_test_parametric":
+        mz = M.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            return M.powerlaw_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], alpha=p["alpha"], beta=p["beta"], mmin=mmin, mmax=mmax) * mz(d["redshift"], p["lamb"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
+    if model == "plpeak":
+        mz = M.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            p_m1q = M.plpeak_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], p["alpha"], p["beta"], mmin, mmax, p["mu_peak"], p["sig_peak"], p["lambda_m"])
+            p_a = M.independent_spin_magnitude_beta_dist(d["a_1"], d["a_2"], p["alpha_a1"], p["beta_a1"], p["alpha_a2"], p["beta_a2"])
+            p_ct = M.independent_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["lambda_ct1"], p["lambda_ct2"], p["sig_ct1"], p["sig_ct2"])
+            return p_m1q * p_a * p_ct * mz(d["redshift"], p["lamb"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
+    raise KeyError(model)
+
+
+def load_case(name):
+    """Load a golden case and lower it with the mirror classes."""
+    d = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    c = Case()
+    c.name = name
+    c.pe = {k: d[f"pe_{k}"] for k in COLS}
+    c.inj = {k: d[f"inj_{k}"] for k in COLS}
+    c.total_inj = float(d["const_total_inj"])
+    c.Nobs = int(d["const_nObs"])
+    c.Tobs = float(d["const_obs_time"])
+    c.names = [str(n) for n in d["param_order"]]
+    c.params = {n: (np.array(d[f"param_{n}"]) if d[f"param_{n}"].ndim else np.float64(d[f"param_{n}"])) for n in c.names}
+    c.meta = {k[5:]: d[k] for k in d.files if k.startswith("meta_")}
+    c.out = {k[4:]: d[k] for k in d.files if k.startswith("out_")}
+    c.jac = {k[4:]: d[k] for k in d.files if k.startswith("jac_")}
+    c.like_kw = LIKE_KW[name]
+    model = str(c.meta["model"])
+    c.weights, c.vt = build_weight_fn(model, c.pe, c.inj, c.meta)
+    c.pe_w = c.weights(c.pe, True, c.params)
+    c.inj_w = c.weights(c.inj, False, c.params)
+    c.low = lowering.lower(c.pe_w, c.inj_w)
+    c.Lam = lowering.flatten_params(c.pe_w, c.low.spec.n_params)
+    # golden Jacobian columns follow ``names`` flattened; map them to Lambda slots
+    perm = []
+    for n in c.names:
+        sl = c.low.slots_for(c.params[n])
+        perm += list(range(sl.start, sl.stop))
+    c.golden_to_lambda = np.array(perm)
+    return c
+
+
+def golden_jac_in_lambda_order(c, key):
+    """Golden Jacobian ``key`` re-ordered to this repo's Lambda layout (shape (..., P))."""
+    J = c.jac[key]
+    out = np.zeros(J.shape[:-1] + (c.low.spec.n_params,))
+    out[..., c.golden_to_lambda] = J
+    return out
