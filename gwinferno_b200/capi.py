@@ -1,0 +1,475 @@
+"""ctypes binding of libgwi.so (include/gwi.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present, the
+calls raise :class:`GwiError` -- they never route to NumPy.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgwi.so")
+
+GWI_LIKE_HEADER = 8
+LIKE_FIELDS = ("log_l", "passed", "log_mu", "logNeff_inj", "min_logNeff", "sum_logBF", "variance", "status")
+PARTIAL_HEADER = 8
+
+
+class GwiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libgwi error {code}: {msg}")
+        self.code = code
+
+
+class gwi_term(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("feature", C.c_int32),
+        ("outside", C.c_int32),
+        ("logx", C.c_int32),
+        ("col", C.c_int32 * 2),
+        ("slot", C.c_int32 * 4),
+        ("cst", C.c_double * 4),
+        ("n_splines", C.c_int32),
+        ("norm_group", C.c_int32),
+        ("x_lo", C.c_double),
+        ("x_hi", C.c_double),
+        ("xi_lo", C.c_double),
+        ("xi_hi", C.c_double),
+        ("grid", C.POINTER(C.c_double)),
+    ]
+
+
+class gwi_norm_group(C.Structure):
+    _fields_ = [("n_grid", C.c_int32), ("log_w", C.POINTER(C.c_double))]
+
+
+class gwi_cut(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("col", C.c_int32 * 2), ("lo", C.c_double), ("hi", C.c_double)]
+
+
+class gwi_model_desc(C.Structure):
+    _fields_ = [
+        ("n_terms", C.c_int32),
+        ("terms", C.POINTER(gwi_term)),
+        ("n_groups", C.c_int32),
+        ("groups", C.POINTER(gwi_norm_group)),
+        ("n_cuts", C.c_int32),
+        ("cuts", C.POINTER(gwi_cut)),
+        ("n_params", C.c_int32),
+        ("need_neff_grad", C.c_int32),
+        ("chunk_steps", C.c_int32),
+        ("n_deep", C.c_int32),
+    ]
+
+
+class gwi_catalog_desc(C.Structure):
+    _fields_ = [
+        ("n_columns", C.c_int32),
+        ("n_events", C.c_int32),
+        ("pe_offsets", C.POINTER(C.c_int64)),
+        ("pe_columns", C.POINTER(C.POINTER(C.c_double))),
+        ("n_inj", C.c_int64),
+        ("inj_columns", C.POINTER(C.POINTER(C.c_double))),
+        ("total_inj", C.c_double),
+        ("device", C.c_int32),
+    ]
+
+
+class gwi_outputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("logBF", "logNeff", "log_mu", "logNeff_inj", "J_logBF", "J_logNeff", "J_log_mu", "J_logNeff_inj", "logZ")]
+
+
+class gwi_like_opts(C.Structure):
+    _fields_ = [("Nobs", C.c_int32), ("marginalize_selection", C.c_int32), ("min_neff_cut", C.c_int32), ("max_variance_cut", C.c_int32)]
+
+
+class gwi_model_info(C.Structure):
+    _fields_ = [
+        ("n_samples_pe", C.c_int64),
+        ("n_samples_inj", C.c_int64),
+        ("n_valid_pe", C.c_int64),
+        ("n_valid_inj", C.c_int64),
+        ("n_padded", C.c_int64),
+        ("bytes_per_eval", C.c_int64),
+        ("n_chunks", C.c_int32),
+        ("n_stream_columns", C.c_int32),
+        ("n_spline_dims", C.c_int32),
+        ("n_deep", C.c_int32),
+        ("n_linear", C.c_int32),
+        ("n_param_terms", C.c_int32),
+        ("grid_blocks", C.c_int32),
+        ("block_threads", C.c_int32),
+        ("kernel_launches_per_eval", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+# every symbol include/gwi.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "gwi_catalog_create",
+    "gwi_catalog_destroy",
+    "gwi_model_create",
+    "gwi_model_destroy",
+    "gwi_eval",
+    "gwi_loglike",
+    "gwi_loglike_host",
+    "gwi_partial_size",
+    "gwi_partial",
+    "gwi_combine",
+    "gwi_model_get_info",
+    "gwi_last_error",
+    "gwi_version",
+    "gwi_debug_plan_build",
+    "gwi_debug_plan_destroy",
+    "gwi_debug_plan_read",
+]
+
+_lib = None
+_cudart = None
+
+
+def load_library():
+    """Load libgwi.so (built in-tree by ``__graft_entry__.build()`` / ``make -C gwinferno_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GwiError(-2, f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` " "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.gwi_last_error.restype = C.c_char_p
+    lib.gwi_partial_size.restype = C.c_int64
+    lib.gwi_partial_size.argtypes = [C.c_void_p]
+    lib.gwi_debug_plan_read.restype = C.c_int64
+    lib.gwi_debug_plan_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    lib.gwi_catalog_create.argtypes = [C.POINTER(gwi_catalog_desc), C.POINTER(C.c_void_p)]
+    lib.gwi_catalog_destroy.argtypes = [C.c_void_p]
+    lib.gwi_catalog_destroy.restype = None
+    lib.gwi_model_create.argtypes = [C.c_void_p, C.POINTER(gwi_model_desc), C.POINTER(C.c_void_p)]
+    lib.gwi_model_destroy.argtypes = [C.c_void_p]
+    lib.gwi_model_destroy.restype = None
+    lib.gwi_eval.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(gwi_outputs), C.c_void_p]
+    lib.gwi_loglike.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
+    lib.gwi_loglike_host.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(gwi_like_opts), C.POINTER(C.c_double)]
+    lib.gwi_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gwi_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
+    lib.gwi_model_get_info.argtypes = [C.c_void_p, C.POINTER(gwi_model_info)]
+    lib.gwi_debug_plan_build.argtypes = [C.c_void_p, C.POINTER(gwi_model_desc), C.c_int32, C.POINTER(C.c_void_p)]
+    lib.gwi_debug_plan_destroy.argtypes = [C.c_void_p]
+    lib.gwi_debug_plan_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise GwiError(rc, load_library().gwi_last_error().decode())
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ---- minimal CUDA runtime access for device buffers (same libcudart libgwi.so links) -----------
+def cudart():
+    global _cudart
+    if _cudart is None:
+        load_library()
+        for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so.12"):
+            try:
+                _cudart = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _cudart is None:
+            raise GwiError(-2, "libcudart not found")
+        _cudart.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        _cudart.cudaFree.argtypes = [C.c_void_p]
+        _cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        _cudart.cudaGetErrorString.restype = C.c_char_p
+        _cudart.cudaGetErrorString.argtypes = [C.c_int]
+    return _cudart
+
+
+def _cuda_check(rc, what):
+    if rc != 0:
+        raise GwiError(-2, f"{what}: {cudart().cudaGetErrorString(rc).decode()}")
+
+
+class DeviceBuffer:
+    """fp64 device array (cudaMalloc) with host <-> device copies."""
+
+    def __init__(self, n, device=0):
+        rt = cudart()
+        _cuda_check(rt.cudaSetDevice(int(device)), "cudaSetDevice")
+        self.n = int(n)
+        self.device = device
+        p = C.c_void_p()
+        _cuda_check(rt.cudaMalloc(C.byref(p), max(1, self.n) * 8), "cudaMalloc")
+        self.ptr = p.value
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.size == self.n
+        _cuda_check(cudart().cudaMemcpy(self.ptr, a.ctypes.data, a.size * 8, 1), "cudaMemcpy H2D")
+
+    def download(self):
+        out = np.empty(self.n, dtype=np.float64)
+        _cuda_check(cudart().cudaMemcpy(out.ctypes.data, self.ptr, self.n * 8, 2), "cudaMemcpy D2H")
+        return out
+
+    def free(self):
+        if self.ptr:
+            cudart().cudaFree(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def synchronize():
+    _cuda_check(cudart().cudaDeviceSynchronize(), "cudaDeviceSynchronize")
+
+
+# ---- description marshalling -----------------------------------------------------------------
+class _Desc:
+    """Keeps the ctypes structures and every NumPy array they point to alive."""
+
+    def __init__(self, spec, col_index, need_neff_grad=False, chunk_steps=0, n_deep=-1):
+        self.keep = []
+        nt = len(spec.terms)
+        self.terms = (gwi_term * max(1, nt))()
+        for i, t in enumerate(spec.terms):
+            ct = self.terms[i]
+            ct.kind = t.kind
+            ct.feature = t.feature
+            ct.outside = t.outside
+            ct.logx = int(bool(t.logx))
+            cols = [col_index[c] for c in t.cols] + [-1, -1]
+            ct.col[0], ct.col[1] = cols[0], cols[1]
+            slots = list(t.slots) + [-1] * 4
+            for k in range(4):
+                ct.slot[k] = int(slots[k])
+            cst = list(t.cst) + [0.0] * 4
+            for k in range(4):
+                ct.cst[k] = float(cst[k])
+            ct.n_splines = int(t.n_splines)
+            ct.norm_group = int(t.norm_group)
+            ct.x_lo, ct.x_hi = float(t.xrange[0]), float(t.xrange[1])
+            if t.xi_range is not None:
+                ct.xi_lo, ct.xi_hi = float(t.xi_range[0]), float(t.xi_range[1])
+            else:
+                ct.xi_lo, ct.xi_hi = ct.x_lo, ct.x_hi
+            grid = t.grid_xi if t.grid_xi is not None else t.grid_feat
+            if grid is not None and t.norm_group >= 0:
+                g = np.ascontiguousarray(grid, dtype=np.float64)
+                if g.size != np.size(spec.groups[t.norm_group].log_w):
+                    raise ValueError(f"term {t.name}: grid length does not match its norm group")
+                self.keep.append(g)
+                ct.grid = _dptr(g)
+        ng = len(spec.groups)
+        self.groups = (gwi_norm_group * max(1, ng))()
+        for i, g in enumerate(spec.groups):
+            lw = np.ascontiguousarray(g.log_w, dtype=np.float64)
+            self.keep.append(lw)
+            self.groups[i].n_grid = lw.size
+            self.groups[i].log_w = _dptr(lw)
+        nc = len(spec.cuts)
+        self.cuts = (gwi_cut * max(1, nc))()
+        for i, c in enumerate(spec.cuts):
+            cols = [col_index[x] for x in c.cols] + [-1, -1]
+            self.cuts[i].kind = c.kind
+            self.cuts[i].col[0], self.cuts[i].col[1] = cols[0], cols[1]
+            self.cuts[i].lo, self.cuts[i].hi = float(c.lo), float(c.hi)
+        d = gwi_model_desc()
+        d.n_terms, d.terms = nt, self.terms
+        d.n_groups, d.groups = ng, self.groups
+        d.n_cuts, d.cuts = nc, self.cuts
+        d.n_params = int(spec.n_params)
+        d.need_neff_grad = int(bool(need_neff_grad))
+        d.chunk_steps = int(chunk_steps)
+        d.n_deep = int(n_deep)
+        self.desc = d
+
+
+class Catalog:
+    """gwi_catalog over NumPy columns.  PE columns: dict name -> (E, S) array (or a ragged list of
+    per-event 1-D arrays); injection columns: dict name -> (I,) array."""
+
+    def __init__(self, pe_cols, inj_cols, total_inj, device=0):
+        lib = load_library()
+        self.names = list(pe_cols.keys())
+        if list(inj_cols.keys()) != self.names:
+            raise ValueError("PE and injection column names must match")
+        self.col_index = {n: i for i, n in enumerate(self.names)}
+        first = pe_cols[self.names[0]]
+        if isinstance(first, np.ndarray) and first.ndim == 2:
+            E, S_ = first.shape
+            self.offsets = np.arange(E + 1, dtype=np.int64) * S_
+            self.pe = [np.ascontiguousarray(pe_cols[n], dtype=np.float64).reshape(-1) for n in self.names]
+        else:  # ragged: list of 1-D arrays per event
+            E = len(first)
+            sizes = [len(x) for x in first]
+            self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            self.pe = [np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64) for x in pe_cols[n]]) if E else np.zeros(0)) for n in self.names]
+        self.inj = [np.ascontiguousarray(inj_cols[n], dtype=np.float64).reshape(-1) for n in self.names]
+        self.n_events = int(E)
+        self.n_inj = int(self.inj[0].size)
+        self.total_inj = float(total_inj)
+        ncol = len(self.names)
+        self._pe_ptrs = (C.POINTER(C.c_double) * ncol)(*[_dptr(a) for a in self.pe])
+        self._inj_ptrs = (C.POINTER(C.c_double) * ncol)(*[_dptr(a) for a in self.inj])
+        d = gwi_catalog_desc()
+        d.n_columns = ncol
+        d.n_events = self.n_events
+        d.pe_offsets = self.offsets.ctypes.data_as(C.POINTER(C.c_int64))
+        d.pe_columns = self._pe_ptrs
+        d.n_inj = self.n_inj
+        d.inj_columns = self._inj_ptrs
+        d.total_inj = self.total_inj
+        d.device = int(device)
+        self.device = int(device)
+        self._desc = d
+        h = C.c_void_p()
+        _check(lib.gwi_catalog_create(C.byref(d), C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            load_library().gwi_catalog_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostPlan:
+    """Test hook: the static plan built on the host (no CUDA needed)."""
+
+    def __init__(self, catalog, spec, need_neff_grad=False, chunk_steps=0, n_deep=-1, n_workers=0):
+        lib = load_library()
+        self._d = _Desc(spec, catalog.col_index, need_neff_grad, chunk_steps, n_deep)
+        h = C.c_void_p()
+        _check(lib.gwi_debug_plan_build(catalog.handle, C.byref(self._d.desc), int(n_workers), C.byref(h)))
+        self.handle = h
+
+    def read(self, what, dtype=np.int64):
+        lib = load_library()
+        n = lib.gwi_debug_plan_read(self.handle, what, None, 0)
+        if n < 0:
+            raise GwiError(n, "gwi_debug_plan_read")
+        out = np.empty(n, dtype=dtype)
+        lib.gwi_debug_plan_read(self.handle, what, out.ctypes.data, n)
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            load_library().gwi_debug_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Model:
+    """gwi_model: the device-resident evaluation plan of one (catalog, model description)."""
+
+    def __init__(self, catalog, spec, need_neff_grad=False, chunk_steps=0, n_deep=-1):
+        lib = load_library()
+        self.catalog = catalog
+        self.n_params = int(spec.n_params)
+        self.n_events = catalog.n_events
+        self.n_groups = len(spec.groups)
+        self.need_neff_grad = bool(need_neff_grad)
+        self._d = _Desc(spec, catalog.col_index, need_neff_grad, chunk_steps, n_deep)
+        h = C.c_void_p()
+        _check(lib.gwi_model_create(catalog.handle, C.byref(self._d.desc), C.byref(h)))
+        self.handle = h
+        self._bufs = None
+
+    # -- introspection ---------------------------------------------------------------------
+    def info(self):
+        i = gwi_model_info()
+        _check(load_library().gwi_model_get_info(self.handle, C.byref(i)))
+        return {n: getattr(i, n) for n, _ in gwi_model_info._fields_ if n != "reserved"}
+
+    def partial_size(self):
+        return int(load_library().gwi_partial_size(self.handle))
+
+    # -- host-buffer calls -----------------------------------------------------------------
+    def loglike_host(self, lam, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False):
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        if lam.size != self.n_params:
+            raise ValueError(f"expected {self.n_params} hyper-parameters, got {lam.size}")
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        out = np.empty(GWI_LIKE_HEADER + self.n_params, dtype=np.float64)
+        rc = load_library().gwi_loglike_host(self.handle, _dptr(lam), C.byref(o), _dptr(out))
+        if rc not in (0, -5):
+            _check(rc)
+        head = dict(zip(LIKE_FIELDS, out[:GWI_LIKE_HEADER]))
+        return head, out[GWI_LIKE_HEADER:].copy()
+
+    def evaluate(self, lam, jacobians=True):
+        """gwi_eval with temporary device buffers; returns NumPy arrays."""
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        if lam.size != self.n_params:
+            raise ValueError(f"expected {self.n_params} hyper-parameters, got {lam.size}")
+        E, P, G = self.n_events, self.n_params, self.n_groups
+        dev = self.catalog.device
+        sizes = dict(logBF=E, logNeff=E, log_mu=1, logNeff_inj=1, logZ=G)
+        if jacobians:
+            sizes.update(J_logBF=E * P, J_log_mu=P)
+            if self.need_neff_grad:
+                sizes.update(J_logNeff=E * P, J_logNeff_inj=P)
+        bufs = {k: DeviceBuffer(n, dev) for k, n in sizes.items()}
+        lam_d = DeviceBuffer(P, dev)
+        lam_d.upload(lam)
+        outs = gwi_outputs()
+        for k, b in bufs.items():
+            setattr(outs, k, b.ptr)
+        _check(load_library().gwi_eval(self.handle, lam_d.ptr, C.byref(outs), None))
+        synchronize()
+        res = {k: b.download() for k, b in bufs.items()}
+        for k in ("J_logBF", "J_logNeff"):
+            if k in res:
+                res[k] = res[k].reshape(E, P)
+        res["log_mu"] = float(res["log_mu"][0])
+        res["logNeff_inj"] = float(res["logNeff_inj"][0])
+        for b in bufs.values():
+            b.free()
+        lam_d.free()
+        return res
+
+    # -- device-pointer calls (multi-GPU plumbing) --------------------------------------------
+    def partial(self, lam_ptr, record_ptr, stream=None):
+        _check(load_library().gwi_partial(self.handle, lam_ptr, record_ptr, stream))
+
+    def combine(self, records_ptr, n_ranks, out_ptr, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False, stream=None):
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        _check(load_library().gwi_combine(self.handle, records_ptr, int(n_ranks), C.byref(o), out_ptr, stream))
+
+    def loglike(self, lam_ptr, out_ptr, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False, stream=None):
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        _check(load_library().gwi_loglike(self.handle, lam_ptr, C.byref(o), out_ptr, stream))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            load_library().gwi_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

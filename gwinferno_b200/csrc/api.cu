@@ -1,0 +1,583 @@
+// C-ABI entry points of libgwi.so (include/gwi.h): handle management, plan upload, and the
+// per-evaluation launch sequence.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dev_structs.h"
+
+namespace gwi {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+typedef void (*stream_fn)(const ModelDev*);
+stream_fn pick_stream_kernel(int ns, int ndeep, bool g2, bool maxonly);
+void launch_prologue(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t st);
+void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st);
+void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st);
+void launch_finish(const ModelDev* Md, int n_seg, cudaStream_t st);
+void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
+void launch_partial(const ModelDev* Md, double* rec, cudaStream_t st);
+void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, cudaStream_t st);
+
+}  // namespace gwi
+
+using namespace gwi;
+
+struct gwi_catalog {
+  CatalogView view;
+};
+
+struct gwi_plan {
+  Plan plan;
+};
+
+struct gwi_model {
+  int device = 0;
+  Plan plan;  // columns are released after the upload
+  ModelDev host{};      // host copy of the device descriptor
+  ModelDev* dev = nullptr;
+  std::vector<void*> allocs;
+  std::vector<std::pair<ReduceTask*, int>> level_tasks;  // device task arrays
+  std::vector<double*> level_out;                        // output buffer of every level
+  stream_fn k_full = nullptr, k_max = nullptr;
+  size_t smem_full = 0, smem_max = 0;
+  int max_grid = 0;
+  int launches_per_eval = 0;
+  // scratch for the host-buffer call and single-rank likelihood
+  double* lam_dev = nullptr;
+  double* out_dev = nullptr;
+  double* partial_dev = nullptr;
+  double* lam_pinned = nullptr;
+  double* out_pinned = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int64_t bytes_per_eval = 0;
+};
+
+#define CUDA_TRY(expr)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                            \
+      return GWI_ERR_CUDA;                                                                             \
+    }                                                                                                  \
+  } while (0)
+
+extern "C" {
+
+const char* gwi_last_error(void) { return g_error.c_str(); }
+int gwi_version(void) { return GWI_VERSION; }
+
+int gwi_catalog_create(const gwi_catalog_desc* d, gwi_catalog** out) {
+  if (!d || !out) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  if (d->n_columns <= 0 || d->n_events < 0 || d->n_inj < 0 || (d->n_events > 0 && (!d->pe_offsets || !d->pe_columns)) || (d->n_inj > 0 && !d->inj_columns)) {
+    set_error("catalog description is incomplete");
+    return GWI_ERR_INVALID;
+  }
+  if (!(d->total_inj > 0.0) || d->total_inj < (double)d->n_inj) {
+    set_error("total_inj must be positive and at least the number of found injections");
+    return GWI_ERR_INVALID;
+  }
+  gwi_catalog* c = new (std::nothrow) gwi_catalog();
+  if (!c) return GWI_ERR_ALLOC;
+  c->view.n_columns = d->n_columns;
+  c->view.n_events = d->n_events;
+  c->view.n_inj = d->n_inj;
+  c->view.total_inj = d->total_inj;
+  c->view.device = d->device;
+  c->view.pe_offsets.assign(1, 0);
+  if (d->n_events > 0) {
+    c->view.pe_offsets.assign(d->pe_offsets, d->pe_offsets + d->n_events + 1);
+    for (int e = 0; e < d->n_events; ++e)
+      if (c->view.pe_offsets[e + 1] < c->view.pe_offsets[e] || c->view.pe_offsets[0] != 0) {
+        delete c;
+        set_error("pe_offsets must start at 0 and be non-decreasing");
+        return GWI_ERR_INVALID;
+      }
+  }
+  for (int k = 0; k < d->n_columns; ++k) {
+    const double* p = d->n_events > 0 ? d->pe_columns[k] : nullptr;
+    const double* q = d->n_inj > 0 ? d->inj_columns[k] : nullptr;
+    if ((d->n_events > 0 && c->view.pe_offsets.back() > 0 && !p) || (d->n_inj > 0 && !q)) {
+      delete c;
+      set_error("null column pointer");
+      return GWI_ERR_INVALID;
+    }
+    c->view.pe_columns.push_back(p);
+    c->view.inj_columns.push_back(q);
+  }
+  *out = c;
+  return GWI_OK;
+}
+
+void gwi_catalog_destroy(gwi_catalog* c) { delete c; }
+
+int gwi_debug_plan_build(const gwi_catalog* cat, const gwi_model_desc* desc, int32_t n_workers, gwi_plan** out) {
+  if (!cat || !desc || !out) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  gwi_plan* p = new (std::nothrow) gwi_plan();
+  if (!p) return GWI_ERR_ALLOC;
+  const int rc = build_plan(cat->view, *desc, 148, n_workers, p->plan);
+  if (rc != GWI_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return GWI_OK;
+}
+void gwi_debug_plan_destroy(gwi_plan* p) { delete p; }
+
+int64_t gwi_debug_plan_read(const gwi_plan* pp, int32_t what, void* dst, int64_t cap) {
+  if (!pp) return GWI_ERR_INVALID;
+  const Plan& p = pp->plan;
+  std::vector<int64_t> v;
+  const void* src = nullptr;
+  int64_t n = 0;
+  switch (what) {
+    case 0:
+      v = {p.n_columns, p.n_padded, (int64_t)p.chunks.size(), (int64_t)p.segments.size(), (int64_t)p.dims.size(), (int64_t)p.kops.size(),
+           p.rows_total, p.n_deep, (int64_t)p.n_gslots, p.rec_doubles};
+      break;
+    case 1:
+      src = p.columns.data();
+      n = (int64_t)p.n_columns * p.n_padded;
+      break;
+    case 2:
+      for (auto& c : p.chunks) {
+        v.push_back(c.segment);
+        v.push_back(c.first);
+        v.push_back(c.steps);
+        v.push_back(c.record_slot);
+      }
+      break;
+    case 3:
+      for (auto& s : p.segments) {
+        v.push_back(s.n_total);
+        v.push_back(s.n_valid);
+        v.push_back(s.first_chunk);
+        v.push_back(s.n_chunks);
+      }
+      break;
+    case 4:
+      for (auto& d : p.dims) {
+        v.push_back(d.term);
+        v.push_back(d.rows);
+        v.push_back(d.row_off);
+        v.push_back(d.deep);
+      }
+      break;
+    case 5:
+      for (auto& k : p.kops) {
+        int64_t bits;
+        std::memcpy(&bits, &k.cst[0], 8);
+        v.push_back(k.kind);
+        v.push_back(k.col[0]);
+        v.push_back(k.col[1]);
+        v.push_back(k.slot[0]);
+        v.push_back(k.slot[1]);
+        v.push_back(k.slot[2]);
+        v.push_back(k.slot[3]);
+        v.push_back(bits);
+      }
+      break;
+    default:
+      return GWI_ERR_INVALID;
+  }
+  if (!src) {
+    src = v.data();
+    n = (int64_t)v.size();
+  }
+  if (dst) {
+    if (cap < n) return GWI_ERR_INVALID;
+    std::memcpy(dst, src, (size_t)n * 8);
+  }
+  return n;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+template <class T>
+static int upload(gwi_model* m, const T* src, size_t count, T** dst) {
+  *dst = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    return GWI_ERR_ALLOC;
+  }
+  m->allocs.push_back(p);
+  if (src && count) {
+    e = cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_error(std::string("cudaMemcpy H2D failed: ") + cudaGetErrorString(e));
+      return GWI_ERR_CUDA;
+    }
+  } else {
+    cudaMemset(p, 0, bytes);
+  }
+  *dst = (T*)p;
+  return GWI_OK;
+}
+
+extern "C" {
+
+void gwi_model_destroy(gwi_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  for (void* p : m->allocs) cudaFree(p);
+  if (m->lam_pinned) cudaFreeHost(m->lam_pinned);
+  if (m->out_pinned) cudaFreeHost(m->out_pinned);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+
+int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** out) {
+  if (!cat || !desc || !out) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    set_error("no CUDA device available: libgwi has no CPU fallback");
+    return GWI_ERR_CUDA;
+  }
+  if (cat->view.device < 0 || cat->view.device >= ndev) {
+    set_error("bad device ordinal");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(cat->view.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cat->view.device));
+  for (int g = 0; g < desc->n_groups; ++g)
+    if (desc->groups[g].n_grid > 5000) {
+      set_error("norm grids are limited to 5000 points");
+      return GWI_ERR_UNSUPPORTED;
+    }
+  gwi_model* m = new (std::nothrow) gwi_model();
+  if (!m) return GWI_ERR_ALLOC;
+  m->device = cat->view.device;
+  int rc = build_plan(cat->view, *desc, prop.multiProcessorCount, 0, m->plan);
+  if (rc != GWI_OK) {
+    delete m;
+    return rc;
+  }
+  Plan& p = m->plan;
+  ModelDev& H = m->host;
+  const int P = p.n_params, NS = (int)p.dims.size(), nseg = (int)p.segments.size();
+  H.n_params = P;
+  H.n_dims = NS;
+  H.n_deep = p.n_deep;
+  H.n_kops = (int)p.kops.size();
+  H.n_gslots = p.n_gslots;
+  H.n_sops = (int)p.sops.size();
+  H.n_groups = (int)p.groups.size();
+  H.n_segments = nseg;
+  H.rows_total = p.rows_total;
+  H.rec_doubles = p.rec_doubles;
+  H.n_columns = p.n_columns;
+  H.col_static = p.col_static;
+  H.g2 = p.g2 ? 1 : 0;
+  H.n_chunks = (int)p.chunks.size();
+  H.n_padded = p.n_padded;
+  H.total_inj = p.total_inj;
+  H.two_pass = 0;
+  const int mom = p.g2 ? 2 : 1;
+  int deep_entries = 0;
+  for (int d = 0; d < NS; ++d) {
+    const SplineDim& D = p.dims[d];
+    const gwi_term& t = desc->terms[D.term];
+    DimDev& X = H.dims[d];
+    X.rows = D.rows;
+    X.row_off = D.row_off;
+    X.slot = D.slot;
+    X.n_splines = D.n_splines;
+    X.deep = D.deep;
+    X.deep_off = D.deep ? deep_entries : 0;
+    if (D.deep) deep_entries += D.rows * 4 * mom;
+    X.norm_group = D.norm_group;
+    X.grid_off = D.grid_off;
+    X.xi_lo = t.xi_lo;
+    X.inv_dxi = (double)(D.rows - 1) / (t.xi_hi - t.xi_lo);
+  }
+  H.deep_entries = deep_entries;
+  for (int q = 0; q < H.n_kops; ++q) {
+    const Kop& K = p.kops[q];
+    KopDev& X = H.kops[q];
+    X.kind = K.kind;
+    X.col0 = K.col[0];
+    X.col1 = K.col[1];
+    X.gslot = K.gslot;
+    X.n_gslots = K.n_gslots;
+    X.norm_group = K.norm_group;
+    X.grid_off = K.grid_off;
+    for (int i = 0; i < 4; ++i) {
+      X.slot[i] = K.slot[i];
+      X.cst[i] = K.cst[i];
+    }
+    for (int i = 0; i < K.n_gslots; ++i) H.gslot_slot[K.gslot + i] = K.slot[i];
+    if (K.kind != KOP_LIN) H.two_pass = 1;  // no a-priori bound for the non-linear terms: exact max first
+  }
+  for (int q = 0; q < H.n_sops; ++q) {
+    const Sop& S = p.sops[q];
+    H.sops[q] = SopDev{S.kind, S.slot[0], S.slot[1], 0, S.cst[0], S.cst[1]};
+  }
+  m->max_grid = 1;
+  std::vector<GroupDev> groups;
+  for (auto& g : p.groups) {
+    groups.push_back(GroupDev{g.n_grid, g.logw_off});
+    m->max_grid = std::max(m->max_grid, g.n_grid);
+  }
+  std::vector<SegDev> segs(nseg);
+  for (int s = 0; s < nseg; ++s) {
+    const Segment& S = p.segments[s];
+    SegDev& X = segs[s];
+    X.n_total = (double)S.n_total;
+    X.max_static = S.max_static;
+    for (int d = 0; d < MAX_SPLINE_DIMS; ++d) X.occ[d] = S.occ[d];
+    for (int q = 0; q < MAX_KOPS; ++q) {
+      X.fmin[q] = S.fmin[q];
+      X.fmax[q] = S.fmax[q];
+    }
+    X.first_chunk = S.first_chunk;
+    X.n_chunks = S.n_chunks;
+  }
+
+#define UP(expr)            \
+  do {                      \
+    rc = (expr);            \
+    if (rc != GWI_OK) {     \
+      gwi_model_destroy(m); \
+      return rc;            \
+    }                       \
+  } while (0)
+
+  uint64_t* d_cols;
+  UP(upload(m, p.columns.data(), p.columns.size(), &d_cols));
+  m->bytes_per_eval = (int64_t)p.n_columns * p.n_padded * 8;
+  std::vector<uint64_t>().swap(p.columns);  // host copy no longer needed
+  H.columns = d_cols;
+  Chunk* d_chunks;
+  UP(upload(m, p.chunks.data(), p.chunks.size(), &d_chunks));
+  H.chunks = d_chunks;
+  SegDev* d_segs;
+  UP(upload(m, segs.data(), segs.size(), &d_segs));
+  H.segs = d_segs;
+  GroupDev* d_groups;
+  UP(upload(m, groups.data(), groups.size(), &d_groups));
+  H.groups = d_groups;
+  double* d_pool;
+  UP(upload(m, p.grid_pool.data(), p.grid_pool.size(), &d_pool));
+  H.grid_pool = d_pool;
+  UP(upload<double>(m, nullptr, (size_t)p.rows_total * 4, &H.tables));
+  UP(upload<double>(m, nullptr, (size_t)p.rows_total, &H.piece_ub));
+  UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_kops) * KC_STRIDE, &H.kc));
+  UP(upload<double>(m, nullptr, (size_t)nseg, &H.shift));
+  UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_groups), &H.logZ));
+  UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_groups) * P, &H.dlogZ));
+  UP(upload<double>(m, nullptr, (size_t)P + 1, &H.Ksum));
+  UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_chunks), &H.chunk_max));
+  UP(upload<double>(m, nullptr, (size_t)std::max(1, p.n_records0) * p.rec_doubles, &H.records0));
+  UP(upload<double>(m, nullptr, (size_t)nseg * p.rec_doubles, &H.seg_rec));
+  UP(upload<double>(m, nullptr, (size_t)nseg * 4, &H.seg_out));
+  UP(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_J1));
+  UP(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_Jn));
+  UP(upload<double>(m, nullptr, (size_t)3 + 2 * P, &H.inj_raw));
+  for (size_t l = 0; l < p.levels.size(); ++l) {
+    ReduceTask* d_t;
+    UP(upload(m, p.levels[l].data(), p.levels[l].size(), &d_t));
+    m->level_tasks.push_back({d_t, (int)p.levels[l].size()});
+    if (l + 1 == p.levels.size()) {
+      m->level_out.push_back(H.seg_rec);
+    } else {
+      double* buf;
+      UP(upload<double>(m, nullptr, p.levels[l].size() * (size_t)p.rec_doubles, &buf));
+      m->level_out.push_back(buf);
+    }
+  }
+  UP(upload(m, &H, 1, &m->dev));
+  UP(upload<double>(m, nullptr, (size_t)P, &m->lam_dev));
+  UP(upload<double>(m, nullptr, (size_t)GWI_LIKE_HEADER + P, &m->out_dev));
+  UP(upload<double>(m, nullptr, (size_t)PR_HEADER + 3 * P, &m->partial_dev));
+#undef UP
+  if (cudaMallocHost((void**)&m->lam_pinned, sizeof(double) * P) != cudaSuccess ||
+      cudaMallocHost((void**)&m->out_pinned, sizeof(double) * (GWI_LIKE_HEADER + P)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("pinned host allocation / stream creation failed");
+    gwi_model_destroy(m);
+    return GWI_ERR_ALLOC;
+  }
+
+  // ---- kernels + shared memory ----
+  m->k_full = pick_stream_kernel(NS, p.n_deep, p.g2, false);
+  m->k_max = pick_stream_kernel(NS, p.n_deep, p.g2, true);
+  if (!m->k_full || !m->k_max) {
+    set_error("no stream kernel instantiated for this (spline dims, deep dims) combination");
+    gwi_model_destroy(m);
+    return GWI_ERR_UNSUPPORTED;
+  }
+  const size_t per_warp = (size_t)p.rows_total * 4 * mom + (size_t)deep_entries * 32 + (size_t)p.n_gslots * 32 * (1 + mom);
+  const size_t fixed = (size_t)p.rows_total * 4 + (size_t)H.n_kops * KC_STRIDE;
+  int wpb = p.warps_per_block;
+  while (wpb > 1 && (fixed + per_warp * wpb) * 8 > (size_t)prop.sharedMemPerBlockOptin) --wpb;
+  if (wpb != p.warps_per_block) {
+    set_error("internal: plan geometry does not fit the device's shared memory");
+    gwi_model_destroy(m);
+    return GWI_ERR_UNSUPPORTED;
+  }
+  m->smem_full = (fixed + per_warp * wpb) * 8;
+  m->smem_max = m->smem_full;
+  if (cudaFuncSetAttribute((const void*)m->k_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_full) != cudaSuccess ||
+      cudaFuncSetAttribute((const void*)m->k_max, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_max) != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(shared memory) failed: ") + cudaGetErrorString(cudaGetLastError()));
+    gwi_model_destroy(m);
+    return GWI_ERR_CUDA;
+  }
+  m->launches_per_eval = 1 + (H.two_pass ? 2 : 0) + 1 + (int)p.levels.size() + 1 + 2;
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = m;
+  return GWI_OK;
+}
+
+// launches prologue .. finish on `st`
+static int run_eval(gwi_model* m, const double* lam_dev, cudaStream_t st) {
+  const Plan& p = m->plan;
+  const ModelDev& H = m->host;
+  launch_prologue(m->dev, lam_dev, H.n_groups, m->max_grid, st);
+  const dim3 grid(p.grid_blocks), block(p.warps_per_block * 32);
+  if (H.n_chunks > 0) {
+    if (H.two_pass) {
+      m->k_max<<<grid, block, m->smem_max, st>>>(m->dev);
+      launch_segmax(m->dev, H.n_segments, st);
+    }
+    m->k_full<<<grid, block, m->smem_full, st>>>(m->dev);
+  }
+  const double* in = H.records0;
+  for (size_t l = 0; l < m->level_tasks.size(); ++l) {
+    launch_reduce(in, m->level_out[l], m->level_tasks[l].first, m->level_tasks[l].second, H.rec_doubles, st);
+    in = m->level_out[l];
+  }
+  launch_finish(m->dev, H.n_segments, st);
+  CUDA_TRY(cudaGetLastError());
+  return GWI_OK;
+}
+
+int gwi_eval(gwi_model* m, const double* lambda_dev, const gwi_outputs* out, void* stream) {
+  if (!m || !lambda_dev || !out) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  if ((out->J_logNeff || out->J_logNeff_inj) && !m->plan.g2) {
+    set_error("N_eff Jacobians requested but the model was created without need_neff_grad");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rc = run_eval(m, lambda_dev, st);
+  if (rc != GWI_OK) return rc;
+  launch_export(m->dev, *out, st);
+  CUDA_TRY(cudaGetLastError());
+  return GWI_OK;
+}
+
+int64_t gwi_partial_size(const gwi_model* m) { return m ? (int64_t)PR_HEADER + 3 * (int64_t)m->plan.n_params : (int64_t)GWI_ERR_INVALID; }
+
+int gwi_partial(gwi_model* m, const double* lambda_dev, double* record_dev, void* stream) {
+  if (!m || !lambda_dev || !record_dev) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rc = run_eval(m, lambda_dev, st);
+  if (rc != GWI_OK) return rc;
+  launch_partial(m->dev, record_dev, st);
+  CUDA_TRY(cudaGetLastError());
+  return GWI_OK;
+}
+
+int gwi_combine(gwi_model* m, const double* records_dev, int32_t n_ranks, const gwi_like_opts* opts, double* out_dev, void* stream) {
+  if (!m || !records_dev || !opts || !out_dev || n_ranks < 1) {
+    set_error("bad argument");
+    return GWI_ERR_INVALID;
+  }
+  if (opts->marginalize_selection && !m->plan.g2) {
+    set_error("marginalize_selection needs a model created with need_neff_grad");
+    return GWI_ERR_INVALID;
+  }
+  if (opts->max_variance_cut && (opts->marginalize_selection || opts->min_neff_cut)) {
+    set_error("max_variance_cut requires marginalize_selection and min_neff_cut to be off (analysis.py:237-244)");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  launch_combine(m->dev, records_dev, n_ranks, *opts, out_dev, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return GWI_OK;
+}
+
+int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opts, double* out_dev, void* stream) {
+  if (!m) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  int rc = gwi_partial(m, lambda_dev, m->partial_dev, stream);
+  if (rc != GWI_OK) return rc;
+  return gwi_combine(m, m->partial_dev, 1, opts, out_dev, stream);
+}
+
+int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opts* opts, double* out_host) {
+  if (!m || !lambda_host || !out_host) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  const int P = m->plan.n_params;
+  std::memcpy(m->lam_pinned, lambda_host, sizeof(double) * P);
+  CUDA_TRY(cudaMemcpyAsync(m->lam_dev, m->lam_pinned, sizeof(double) * P, cudaMemcpyHostToDevice, m->own_stream));
+  const int rc = gwi_loglike(m, m->lam_dev, opts, m->out_dev, m->own_stream);
+  if (rc != GWI_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(m->out_pinned, m->out_dev, sizeof(double) * (GWI_LIKE_HEADER + P), cudaMemcpyDeviceToHost, m->own_stream));
+  CUDA_TRY(cudaStreamSynchronize(m->own_stream));
+  std::memcpy(out_host, m->out_pinned, sizeof(double) * (GWI_LIKE_HEADER + P));
+  if (out_host[GWI_LIKE_STATUS] != 0.0) {
+    set_error("a segment's weights all under/overflowed the fp64 range");
+    return GWI_ERR_RANGE;
+  }
+  return GWI_OK;
+}
+
+int gwi_model_get_info(const gwi_model* m, gwi_model_info* info) {
+  if (!m || !info) return GWI_ERR_INVALID;
+  const Plan& p = m->plan;
+  std::memset(info, 0, sizeof(*info));
+  info->n_samples_pe = p.n_samples_pe;
+  info->n_samples_inj = p.n_samples_inj;
+  info->n_valid_pe = p.n_valid_pe;
+  info->n_valid_inj = p.n_valid_inj;
+  info->n_padded = p.n_padded;
+  info->bytes_per_eval = m->bytes_per_eval * (m->host.two_pass ? 2 : 1);
+  info->n_chunks = (int)p.chunks.size();
+  info->n_stream_columns = p.n_columns;
+  info->n_spline_dims = (int)p.dims.size();
+  info->n_deep = p.n_deep;
+  info->n_linear = 0;
+  for (auto& k : p.kops) (k.kind == KOP_LIN ? info->n_linear : info->n_param_terms)++;
+  info->grid_blocks = p.grid_blocks;
+  info->block_threads = p.warps_per_block * 32;
+  info->kernel_launches_per_eval = m->launches_per_eval;
+  return GWI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// Device-visible, trivially copyable mirrors of the plan (passed to kernels by value / pointer).
+#pragma once
+#include <cstdint>
+
+#include "gwi_internal.h"
+
+namespace gwi {
+
+struct DimDev {
+  int32_t rows, row_off, slot, n_splines;
+  int32_t deep, deep_off;  // deep_off: first entry of this dim in the lane-private deep block
+  int32_t norm_group, grid_off;
+  double xi_lo, inv_dxi;
+};
+
+struct KopDev {
+  int32_t kind, col0, col1, gslot;
+  int32_t n_gslots, norm_group, grid_off, pad;
+  int32_t slot[4];
+  double cst[4];
+};
+
+struct SopDev {
+  int32_t kind, slot0, slot1, pad;
+  double cst0, cst1;
+};
+
+struct SegDev {
+  double n_total;     // Monte-Carlo denominator (events); injections use total_inj
+  double max_static;
+  uint64_t occ[MAX_SPLINE_DIMS];
+  double fmin[MAX_KOPS], fmax[MAX_KOPS];
+  int32_t first_chunk, n_chunks;
+};
+
+struct GroupDev {
+  int32_t n_grid, logw_off;
+};
+
+// everything the kernels need, resident in device global memory (one copy per model)
+struct ModelDev {
+  int32_t n_params, n_dims, n_deep, n_kops, n_gslots, n_sops, n_groups, n_segments;
+  int32_t rows_total, rec_doubles, n_columns, col_static, g2, two_pass, n_chunks, deep_entries;
+  int64_t n_padded;
+  double total_inj;
+  DimDev dims[MAX_SPLINE_DIMS];
+  KopDev kops[MAX_KOPS];
+  SopDev sops[MAX_SOPS];
+  int32_t gslot_slot[MAX_GSLOTS];  // generic gradient slot -> Lambda slot
+  // static arrays
+  const uint64_t* columns;  // [n_columns][n_padded]
+  const Chunk* chunks;
+  const SegDev* segs;
+  const GroupDev* groups;
+  const double* grid_pool;
+  // per-evaluation scratch
+  double* tables;     // [rows_total*4] polynomial pieces in w = u - 1/2
+  double* piece_ub;   // [rows_total]   max of the 4 coefficients of each piece
+  double* kc;         // [n_kops*KC_STRIDE]
+  double* shift;      // [n_segments]
+  double* logZ;       // [n_groups]
+  double* dlogZ;      // [n_groups*P]
+  double* Ksum;       // [1 + P] : K = sum(sops) - sum(logZ), then dK
+  double* chunk_max;  // [n_chunks] (two-pass mode)
+  double* records0;   // [n_records0 * rec]
+  double* seg_rec;    // [n_segments * rec]
+  double* seg_out;    // [n_segments * 4] {logmean, logneff, var, status}
+  double* seg_J1;     // [n_segments * P]
+  double* seg_Jn;     // [n_segments * P]
+  double* inj_raw;    // [3 + 2P] {shift, S1, S2, G1raw[P], G2raw[P]}
+};
+
+// partial (per-rank) likelihood record: 8 header doubles + 3P
+enum { PR_SHIFT = 0, PR_S1 = 1, PR_S2 = 2, PR_SUM_LOGBF = 3, PR_MIN_LOGNEFF = 4, PR_SUM_VAR = 5, PR_N_EVENTS = 6, PR_STATUS = 7, PR_HEADER = 8 };
+
+}  // namespace gwi

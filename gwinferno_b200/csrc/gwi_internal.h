@@ -1,0 +1,153 @@
+// Internal structures shared by the host plan builder (plan.cpp), the kernels (kernels.cu) and
+// the C-ABI glue (api.cu).  Not part of the public interface (include/gwi.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "gwi.h"
+
+namespace gwi {
+
+constexpr int MAX_SPLINE_DIMS = 8;  // spline dimensions per model
+constexpr int MAX_ROWS = 62;        // polynomial pieces per dimension incl. the dummy row (12-bit field, 64-bit occupancy mask)
+constexpr int MAX_KOPS = 16;        // non-spline per-sample operations
+constexpr int MAX_GSLOTS = 32;      // gradient slots of the non-spline operations
+constexpr int MAX_SOPS = 16;        // scalar (sample-independent) normaliser operations
+constexpr int KC_STRIDE = 12;       // doubles of per-eval constants per kop
+constexpr int LANES = 32;
+constexpr int UNROLL = 2;           // samples per lane per load (16-byte vector loads)
+
+// ---- packed spline word: bits 63..52 = piece index J, bits 51..0 = mantissa of (1 + u) --------
+constexpr uint64_t MANT_MASK = 0x000FFFFFFFFFFFFFull;
+constexpr uint64_t ONE_BITS = 0x3FF0000000000000ull;
+
+// per-sample operation executed by the stream kernel besides the spline dimensions
+enum KopKind : int32_t {
+  KOP_LIN = 1,       // x += theta * F                       gslots: theta
+  KOP_PLRATIO = 2,   // powerlaw in q with per-sample lower bound: cols (log q, log lo)   gslots: beta
+  KOP_PLPEAK = 3,    // cols (log m1, m1)                     gslots: alpha, mu, sigma, lam
+  KOP_ISOALIGN = 4,  // col (cos tilt)                        gslots: xi, sigma
+  KOP_QUAD = 5       // truncated normal body: col (x)        gslots: mu, sigma
+};
+
+struct Kop {
+  int32_t kind;
+  int32_t col[2];     // stream-column indices of its features
+  int32_t gslot;      // first generic gradient slot
+  int32_t n_gslots;
+  int32_t slot[4];    // Lambda slots
+  double cst[4];      // LIN: cst[0] = offset added to Lambda[slot]; PLPEAK/QUAD: lo, hi
+  int32_t norm_group; // LIN only
+  int32_t grid_off;   // offset of its grid feature in the grid pool (doubles), -1 none
+};
+
+// scalar normaliser operation (prologue): K += value, dK[slot] += derivative
+enum SopKind : int32_t {
+  SOP_POWERLAW_NORM = 1,  // log[(1+a)/(hi^(1+a) - lo^(1+a))]
+  SOP_BETA_NORM = 2,      // -betaln(a,b) - (a+b-1) log s
+  SOP_TRUNCNORM_NORM = 3  // -log(sigma) - log sqrt(2 pi) - log(Phi(b) - Phi(a))
+};
+struct Sop {
+  int32_t kind;
+  int32_t slot[2];
+  double cst[2];
+};
+
+struct SplineDim {
+  int32_t term;      // index in the model description
+  int32_t n_splines;
+  int32_t rows;      // n_splines - 2 : pieces 0..rows-2 are real, piece rows-1 is the all-zero dummy
+  int32_t row_off;   // first row in the concatenated tables
+  int32_t slot;      // first coefficient in Lambda
+  int32_t column;    // stream column
+  int32_t deep;      // accumulated in lane-private shared memory
+  int32_t norm_group;
+  int32_t grid_off;  // offset of its grid xi array in the grid pool, -1 none
+  int32_t outside;
+};
+
+struct NormGroup {
+  int32_t n_grid;
+  int32_t logw_off;  // offset in the grid pool
+};
+
+struct Chunk {
+  int32_t segment;
+  int32_t steps;        // samples per lane (multiple of UNROLL)
+  int64_t first;        // first padded sample index (multiple of 32*UNROLL)
+  int32_t record_slot;  // level-0 record receiving this chunk's sums
+  int32_t flush;        // 1 = the warp must write + clear its record after this chunk
+};
+
+struct Segment {
+  int64_t n_total;      // samples given (denominator of the Monte-Carlo mean)
+  int64_t n_valid;
+  int32_t first_chunk, n_chunks;
+  double max_static;    // max_j of the static log-weight
+  uint64_t occ[MAX_SPLINE_DIMS];  // occupied pieces per spline dim
+  double fmin[MAX_KOPS], fmax[MAX_KOPS];  // LIN feature range (for the shift bound)
+};
+
+struct ReduceTask {
+  int32_t out_slot;  // slot in the output buffer of this level
+  int32_t in_first;  // first slot in the input buffer
+  int32_t in_count;
+  int32_t pad;
+};
+
+// Host-side evaluation plan ("what the stream kernel reads")
+struct Plan {
+  // model structure
+  int n_params = 0, n_terms = 0;
+  bool g2 = false;
+  std::vector<SplineDim> dims;   // in SORT-KEY order; the last n_deep are "deep"
+  int n_deep = 0;
+  int rows_total = 0;
+  std::vector<Kop> kops;
+  int n_gslots = 0;
+  std::vector<Sop> sops;
+  std::vector<NormGroup> groups;
+  std::vector<double> grid_pool;  // all grid arrays back to back
+  // sample streams
+  int n_columns = 0;              // spline columns, then kop feature columns, then the static log-weight
+  int col_static = 0;
+  int64_t n_padded = 0;
+  std::vector<uint64_t> columns;  // column-major [n_columns][n_padded]
+  std::vector<Chunk> chunks;
+  std::vector<Segment> segments;  // segment 0 = injections, 1..E = events
+  // level-0 records and the reduction tree
+  int rec_doubles = 0;
+  int n_records0 = 0;
+  std::vector<std::vector<ReduceTask>> levels;  // levels.back() writes one record per segment (slot = segment)
+  // launch geometry (fixed at plan time: the chunk -> warp assignment depends on it)
+  int grid_blocks = 0, warps_per_block = 0;
+  int chunk_steps = 0;
+  double total_inj = 0.0;
+  int64_t n_samples_pe = 0, n_samples_inj = 0, n_valid_pe = 0, n_valid_inj = 0;
+};
+
+struct CatalogView {
+  int n_columns = 0;
+  int n_events = 0;
+  std::vector<int64_t> pe_offsets;
+  std::vector<const double*> pe_columns, inj_columns;
+  int64_t n_inj = 0;
+  double total_inj = 0.0;
+  int device = 0;
+};
+
+// record layout helpers --------------------------------------------------------------------------
+// [0]=S1 [1]=S2 | g1[n_gslots] | g2[n_gslots] (g2 only) | M1[rows_total*4] | M2[rows_total*4] (g2 only)
+inline int rec_off_g1() { return 2; }
+inline int rec_off_g2(int ngs) { return 2 + ngs; }
+inline int rec_off_m1(int ngs, bool g2) { return 2 + ngs * (g2 ? 2 : 1); }
+inline int rec_off_m2(int ngs, bool g2, int rows_total) { return rec_off_m1(ngs, g2) + rows_total * 4; }
+inline int rec_size(int ngs, bool g2, int rows_total) { return 2 + (ngs + rows_total * 4) * (g2 ? 2 : 1); }
+
+void set_error(const std::string& msg);
+int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count, int n_workers, Plan& plan);
+// flat LCDM Planck15-LVK dVc/dz (cosmology.py:48-120)
+double log_dvcdz(double z);
+
+}  // namespace gwi

@@ -1,0 +1,855 @@
+// sm_100a kernels of the population-likelihood path.
+//
+//   prologue_kernel   per evaluation, from Lambda: polynomial pieces of every spline dimension,
+//                     grid normalisers log Z_g and their gradients (interpolation.py:290;
+//                     spline_perturbation.py:323-336), scalar normalisers, per-segment shift.
+//   stream_kernel     THE hot kernel: one pass over the plan columns.  Per sample: unpack the
+//                     (piece, offset) words, Horner-evaluate every spline dimension, add the
+//                     non-spline terms and the static log-weight, p = exp(x - shift), and
+//                     accumulate (sum p, sum p^2) plus the gradient moments sum p w^n per piece.
+//                     Moments of the leading ("shallow") dimensions live in registers and are
+//                     spilled only when the piece index changes (samples are piece-sorted); the
+//                     trailing ("deep") dimensions use lane-private shared-memory accumulators.
+//   reduce_kernel     fixed-order tree sum of the per-warp records.
+//   finish_kernel     per segment: log-mean, log N_eff, Jacobian rows (moments -> coefficients).
+//   partial/combine   likelihood glue (analysis.py:257-319) split around the multi-GPU exchange.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+
+#include "dev_structs.h"
+
+namespace gwi {
+
+// cubic B-spline piece basis in w = u - 1/2 :  b_k(u) = sum_n BETA[k][n] w^n
+__constant__ double BETA[4][4] = {{1.0 / 48.0, -1.0 / 8.0, 1.0 / 4.0, -1.0 / 6.0},
+                                  {23.0 / 48.0, -5.0 / 8.0, -1.0 / 4.0, 1.0 / 2.0},
+                                  {23.0 / 48.0, 5.0 / 8.0, -1.0 / 4.0, -1.0 / 2.0},
+                                  {1.0 / 48.0, 1.0 / 8.0, 1.0 / 4.0, 1.0 / 6.0}};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// deterministic block reductions (blockDim.x multiple of 32, <= 1024); scratch: 32 doubles
+__device__ double block_sum(double v, double* scratch) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; ++i) r += scratch[i];
+  return r;
+}
+__device__ double block_max(double v, double* scratch) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  double r = -INFINITY;
+  for (int i = 0; i < nw; ++i) r = fmax(r, scratch[i]);
+  return r;
+}
+
+__device__ __forceinline__ void tap_weights(double u, double w[4]) {
+  const double omu = 1.0 - u;
+  w[0] = omu * omu * omu * (1.0 / 6.0);
+  w[1] = (3.0 * u * u * u - 6.0 * u * u + 4.0) * (1.0 / 6.0);
+  w[2] = (-3.0 * u * u * u + 3.0 * u * u + 3.0 * u + 1.0) * (1.0 / 6.0);
+  w[3] = u * u * u * (1.0 / 6.0);
+}
+
+__device__ double digamma_dev(double x) {
+  double r = 0.0;
+  while (x < 10.0) {
+    r -= 1.0 / x;
+    x += 1.0;
+  }
+  const double f = 1.0 / (x * x);
+  // asymptotic series: ln x - 1/2x - sum B_2n / (2n x^2n)
+  const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
+}
+
+__device__ __forceinline__ double norm_pdf(double x) { return exp(-0.5 * x * x) * 0.3989422804014327; }
+
+// log-normalisation of the truncated normal and the two ratios its gradient needs
+// (distributions.py:122-143): D = Phi(b) - Phi(a)
+__device__ void truncnorm_consts(double mu, double sig, double lo, double hi, double& lognorm, double& dDmu_D, double& dDsig_D) {
+  const double a = (lo - mu) / sig, b = (hi - mu) / sig;
+  const double D = 0.5 * (1.0 + erf(b * 0.7071067811865476)) - 0.5 * (1.0 + erf(a * 0.7071067811865476));
+  lognorm = -log(sig) - 0.9189385332046727 - log(D);
+  dDmu_D = (-norm_pdf(b) + norm_pdf(a)) / sig / D;
+  dDsig_D = (-b * norm_pdf(b) + a * norm_pdf(a)) / sig / D;
+}
+
+// log[(1+a)/(hi^(1+a) - lo^(1+a))] and d/da (distributions.py:111-116)
+__device__ void powerlaw_lognorm(double alpha, double lo, double hi, double& lognorm, double& dnorm) {
+  const double a1 = 1.0 + alpha;
+  if (fabs(a1) < 1e-9) {
+    const double L = log(hi / lo);
+    lognorm = -log(L);
+    dnorm = -0.5 * (log(hi) + log(lo));  // limit of the derivative at alpha = -1
+    return;
+  }
+  const double ha = pow(hi, a1), la = pow(lo, a1);
+  const double den = ha - la;
+  lognorm = log(a1 / den);
+  dnorm = 1.0 / a1 - (ha * log(hi) - la * log(lo)) / den;
+}
+
+// =================================================================================================
+// prologue
+// =================================================================================================
+__global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam) {
+  const ModelDev& M = *Mp;
+  extern __shared__ double sm[];
+  __shared__ double scratch[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int P = M.n_params;
+  if ((int)blockIdx.x < M.n_groups) {
+    // ---------------- one norm group ----------------
+    const int g = blockIdx.x;
+    const int G = M.groups[g].n_grid;
+    const double* logw = M.grid_pool + M.groups[g].logw_off;
+    double* li = sm;  // [G]
+    for (int i = tid; i < G; i += nt) {
+      double v = logw[i];
+      for (int d = 0; d < M.n_dims; ++d) {
+        const DimDev& D = M.dims[d];
+        if (D.norm_group != g) continue;
+        const double xi = M.grid_pool[D.grid_off + i];
+        if (xi == xi) {
+          const double t = (xi - D.xi_lo) * D.inv_dxi;
+          int J = (int)floor(t);
+          J = max(0, min(J, D.rows - 2));
+          double w[4];
+          tap_weights(t - (double)J, w);
+          const double* c = Lam + D.slot + J;
+          v += w[0] * c[0] + w[1] * c[1] + w[2] * c[2] + w[3] * c[3];
+        }
+      }
+      for (int q = 0; q < M.n_kops; ++q) {
+        const KopDev& K = M.kops[q];
+        if (K.kind == KOP_LIN && K.norm_group == g) v += (Lam[K.slot[0]] + K.cst[0]) * M.grid_pool[K.grid_off + i];
+      }
+      li[i] = v;
+    }
+    __syncthreads();
+    double mx = -INFINITY;
+    for (int i = tid; i < G; i += nt) mx = fmax(mx, li[i]);
+    mx = block_max(mx, scratch);
+    double s = 0.0;
+    for (int i = tid; i < G; i += nt) {
+      const double e = exp(li[i] - mx);
+      li[i] = e;
+      s += e;
+    }
+    s = block_sum(s, scratch);
+    if (tid == 0) M.logZ[g] = mx + log(s);
+    const double inv = 1.0 / s;
+    for (int i = tid; i < P; i += nt) M.dlogZ[(size_t)g * P + i] = 0.0;
+    __syncthreads();
+    for (int d = 0; d < M.n_dims; ++d) {
+      const DimDev& D = M.dims[d];
+      if (D.norm_group != g) continue;
+      for (int k = tid; k < D.n_splines; k += nt) {
+        double acc = 0.0;
+        for (int i = 0; i < G; ++i) {
+          const double xi = M.grid_pool[D.grid_off + i];
+          if (!(xi == xi)) continue;
+          const double t = (xi - D.xi_lo) * D.inv_dxi;
+          int J = (int)floor(t);
+          J = max(0, min(J, D.rows - 2));
+          const int kk = k - J;
+          if (kk < 0 || kk > 3) continue;
+          double w[4];
+          tap_weights(t - (double)J, w);
+          acc += li[i] * w[kk];
+        }
+        M.dlogZ[(size_t)g * P + D.slot + k] += acc * inv;
+      }
+      __syncthreads();
+    }
+    for (int q = 0; q < M.n_kops; ++q) {
+      const KopDev& K = M.kops[q];
+      if (K.kind != KOP_LIN || K.norm_group != g) continue;
+      double acc = 0.0;
+      for (int i = tid; i < G; i += nt) acc += li[i] * M.grid_pool[K.grid_off + i];
+      acc = block_sum(acc, scratch);
+      if (tid == 0) M.dlogZ[(size_t)g * P + K.slot[0]] += acc * inv;
+      __syncthreads();
+    }
+    return;
+  }
+  // ---------------- tables, kop constants, scalar normalisers, shifts ----------------
+  for (int r = tid; r < M.rows_total; r += nt) {
+    int d = 0;
+    while (d + 1 < M.n_dims && r >= M.dims[d + 1].row_off) ++d;
+    const DimDev& D = M.dims[d];
+    const int J = r - D.row_off;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    double ub = 0.0;
+    if (J < D.rows - 1) {
+      const double* c = Lam + D.slot + J;
+      ub = fmax(fmax(c[0], c[1]), fmax(c[2], c[3]));
+#pragma unroll
+      for (int n = 0; n < 4; ++n) a[n] = c[0] * BETA[0][n] + c[1] * BETA[1][n] + c[2] * BETA[2][n] + c[3] * BETA[3][n];
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) M.tables[r * 4 + n] = a[n];
+    M.piece_ub[r] = ub;
+  }
+  for (int q = tid; q < M.n_kops; q += nt) {
+    const KopDev& K = M.kops[q];
+    double* kc = M.kc + q * KC_STRIDE;
+    for (int i = 0; i < KC_STRIDE; ++i) kc[i] = 0.0;
+    if (K.kind == KOP_LIN) {
+      kc[0] = Lam[K.slot[0]] + K.cst[0];
+    } else if (K.kind == KOP_PLRATIO) {
+      kc[0] = Lam[K.slot[0]];
+      kc[1] = 1.0 + kc[0];
+    } else if (K.kind == KOP_PLPEAK) {
+      const double alpha = Lam[K.slot[0]], mu = Lam[K.slot[1]], sig = Lam[K.slot[2]], lam = Lam[K.slot[3]];
+      double ln, dn, lt, dmu, dsg;
+      powerlaw_lognorm(alpha, K.cst[0], K.cst[1], ln, dn);
+      truncnorm_consts(mu, sig, K.cst[0], K.cst[1], lt, dmu, dsg);
+      kc[0] = alpha; kc[1] = ln; kc[2] = mu; kc[3] = 0.5 / (sig * sig); kc[4] = lt; kc[5] = lam;
+      kc[6] = dn; kc[7] = sig; kc[8] = dmu; kc[9] = dsg;
+    } else if (K.kind == KOP_ISOALIGN) {
+      const double xi = Lam[K.slot[0]], sig = Lam[K.slot[1]];
+      double lt, dmu, dsg;
+      truncnorm_consts(1.0, sig, -1.0, 1.0, lt, dmu, dsg);
+      kc[0] = xi; kc[1] = sig; kc[2] = lt; kc[3] = 0.5 / (sig * sig); kc[4] = dsg;
+    } else if (K.kind == KOP_QUAD) {
+      const double mu = Lam[K.slot[0]], sig = Lam[K.slot[1]];
+      kc[0] = mu; kc[1] = sig; kc[2] = 0.5 / (sig * sig);
+    }
+  }
+  for (int i = tid; i < P + 1; i += nt) M.Ksum[i] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    double K = 0.0;
+    for (int q = 0; q < M.n_sops; ++q) {
+      const SopDev& S = M.sops[q];
+      if (S.kind == SOP_POWERLAW_NORM) {
+        double ln, dn;
+        powerlaw_lognorm(Lam[S.slot0], S.cst0, S.cst1, ln, dn);
+        K += ln;
+        M.Ksum[1 + S.slot0] += dn;
+      } else if (S.kind == SOP_BETA_NORM) {
+        const double a = Lam[S.slot0], b = Lam[S.slot1], ls = log(S.cst0);
+        K += -(lgamma(a) + lgamma(b) - lgamma(a + b)) - (a + b - 1.0) * ls;
+        const double pab = digamma_dev(a + b);
+        M.Ksum[1 + S.slot0] += -(digamma_dev(a) - pab) - ls;
+        M.Ksum[1 + S.slot1] += -(digamma_dev(b) - pab) - ls;
+      } else if (S.kind == SOP_TRUNCNORM_NORM) {
+        double lt, dmu, dsg;
+        const double sig = Lam[S.slot1];
+        truncnorm_consts(Lam[S.slot0], sig, S.cst0, S.cst1, lt, dmu, dsg);
+        K += lt;
+        M.Ksum[1 + S.slot0] += -dmu;
+        M.Ksum[1 + S.slot1] += -1.0 / sig - dsg;
+      }
+    }
+    M.Ksum[0] = K;
+  }
+  if (!M.two_pass) {
+    __syncthreads();  // tables / piece_ub / kc written by this block are visible below
+    __threadfence_block();
+    for (int s = tid; s < M.n_segments; s += nt) {
+      const SegDev& S = M.segs[s];
+      double sh = S.max_static;
+      for (int d = 0; d < M.n_dims; ++d) {
+        const DimDev& D = M.dims[d];
+        double mx = -INFINITY;
+        for (int J = 0; J < D.rows; ++J)
+          if ((S.occ[d] >> J) & 1ull) mx = fmax(mx, M.piece_ub[D.row_off + J]);
+        if (mx > -INFINITY) sh += mx;
+      }
+      for (int q = 0; q < M.n_kops; ++q) {
+        if (M.kops[q].kind != KOP_LIN) continue;
+        const double th = M.kc[q * KC_STRIDE];
+        if (S.fmax[q] >= S.fmin[q]) sh += fmax(th * S.fmin[q], th * S.fmax[q]);
+      }
+      M.shift[s] = (sh == sh && sh > -INFINITY && sh < INFINITY) ? sh : 0.0;
+    }
+  }
+}
+
+// =================================================================================================
+// stream kernel
+// =================================================================================================
+template <int NS, int NDEEP, bool G2>
+struct LaneAcc {
+  static constexpr int NSH = NS - NDEEP;
+  double m1[NSH > 0 ? NSH : 1][4];
+  double m2[(G2 && NSH > 0) ? NSH : 1][4];
+  int cur[NSH > 0 ? NSH : 1];
+  double S1, S2;
+};
+
+// spill the register moments of shallow dim d (piece `J`) into the warp's shared accumulator
+template <bool G2>
+__device__ __forceinline__ void spill(double* msh, int idx, int m2_off, double (&a1)[4], double (&a2)[4]) {
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    atomicAdd(&msh[idx + n], a1[n]);
+    a1[n] = 0.0;
+    if (G2) {
+      atomicAdd(&msh[m2_off + idx + n], a2[n]);
+      a2[n] = 0.0;
+    }
+  }
+}
+
+template <int NS, int NDEEP, bool G2, bool MAXONLY>
+__global__ void __launch_bounds__(256) stream_kernel(const ModelDev* __restrict__ Mp) {
+  const ModelDev& M = *Mp;
+  constexpr int NSH = NS - NDEEP;
+  constexpr int MOM = G2 ? 2 : 1;
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int rows_total = M.rows_total;
+  const int n_kops = M.n_kops, n_gs = M.n_gslots;
+  // shared layout: tables | kc | per warp { msh[rows_total*4*MOM] | deep[deep_entries*32] | gscr[n_gs*32] | gacc[n_gs*MOM*32] }
+  double* tables = sm;
+  double* kcs = tables + rows_total * 4;
+  const int per_warp = rows_total * 4 * MOM + M.deep_entries * 32 + n_gs * 32 * (1 + MOM);
+  double* msh = kcs + n_kops * KC_STRIDE + (size_t)warp * per_warp;
+  double* deep = msh + rows_total * 4 * MOM;
+  double* gscr = deep + M.deep_entries * 32;
+  double* gacc = gscr + n_gs * 32;
+  for (int i = threadIdx.x; i < rows_total * 4; i += blockDim.x) tables[i] = M.tables[i];
+  for (int i = threadIdx.x; i < n_kops * KC_STRIDE; i += blockDim.x) kcs[i] = M.kc[i];
+  if (!MAXONLY)
+    for (int i = lane; i < per_warp; i += 32) msh[i] = 0.0;
+  __syncthreads();
+
+  // per-dim constants in registers (compile-time indexed)
+  int row_off[NS > 0 ? NS : 1], deep_off[NS > 0 ? NS : 1], rows_d[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int d = 0; d < NS; ++d) {
+    row_off[d] = M.dims[d].row_off;
+    deep_off[d] = M.dims[d].deep_off;
+    rows_d[d] = M.dims[d].rows;
+  }
+  const int m2_off = rows_total * 4;
+
+  LaneAcc<NS, NDEEP, G2> A;
+  A.S1 = 0.0;
+  A.S2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < NSH; ++d) {
+    A.cur[d] = -1;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      A.m1[d][n] = 0.0;
+      if (G2) A.m2[d][n] = 0.0;
+    }
+  }
+
+  const int W = gridDim.x * wpb;
+  const int gw = blockIdx.x * wpb + warp;
+  const int64_t np = M.n_padded;
+  const uint64_t* __restrict__ cols = M.columns;
+
+  for (int c = gw; c < M.n_chunks; c += W) {
+    const Chunk C = M.chunks[c];
+    const double shift = MAXONLY ? 0.0 : M.shift[C.segment];
+    double xmax = -INFINITY;
+    const int64_t base = C.first + lane * UNROLL;
+    const int iters = C.steps / UNROLL;
+    for (int it = 0; it < iters; ++it) {
+      const int64_t p0 = base + (int64_t)it * (LANES * UNROLL);
+      // ---- loads (16 B per column) ----
+      ulonglong2 wd[NS > 0 ? NS : 1];
+#pragma unroll
+      for (int d = 0; d < NS; ++d) wd[d] = *reinterpret_cast<const ulonglong2*>(cols + (size_t)d * np + p0);
+      const double2 st = *reinterpret_cast<const double2*>(cols + (size_t)M.col_static * np + p0);
+#pragma unroll
+      for (int s = 0; s < UNROLL; ++s) {
+        double x = s == 0 ? st.x : st.y;
+        double wv[NS > 0 ? NS : 1];
+        int Jv[NS > 0 ? NS : 1];
+#pragma unroll
+        for (int d = 0; d < NS; ++d) {
+          const unsigned long long word = s == 0 ? wd[d].x : wd[d].y;
+          const int J = (int)(word >> 52);
+          const double w = __longlong_as_double((long long)((word & MANT_MASK) | ONE_BITS)) - 1.5;
+          Jv[d] = J;
+          wv[d] = w;
+          const double2 a01 = *reinterpret_cast<const double2*>(tables + (row_off[d] + J) * 4);
+          const double2 a23 = *reinterpret_cast<const double2*>(tables + (row_off[d] + J) * 4 + 2);
+          x += fma(fma(fma(a23.y, w, a23.x), w, a01.y), w, a01.x);
+        }
+        // ---- non-spline terms ----
+        for (int q = 0; q < n_kops; ++q) {
+          const KopDev& K = M.kops[q];
+          const double* kc = kcs + q * KC_STRIDE;
+          const double f0 = __longlong_as_double((long long)cols[(size_t)K.col0 * np + p0 + s]);
+          double* scr = gscr + K.gslot * 32 + lane;
+          if (K.kind == KOP_LIN) {
+            x = fma(kc[0], f0, x);
+            if (!MAXONLY) scr[0] = f0;
+          } else if (K.kind == KOP_PLRATIO) {
+            const double ll = __longlong_as_double((long long)cols[(size_t)K.col1 * np + p0 + s]);
+            const double beta = kc[0], a1 = kc[1];
+            double lognorm, dn;
+            if (fabs(a1) < 1e-9) {
+              lognorm = -log(-ll) - 0.5 * a1 * ll;
+              dn = -0.5 * ll;
+            } else {
+              const double e = exp(a1 * ll);
+              lognorm = log(a1 / (1.0 - e));
+              dn = 1.0 / a1 + e * ll / (1.0 - e);
+            }
+            x += beta * f0 + lognorm;
+            if (!MAXONLY) scr[0] = f0 + dn;
+          } else if (K.kind == KOP_PLPEAK) {
+            const double m = __longlong_as_double((long long)cols[(size_t)K.col1 * np + p0 + s]);
+            const double PL = exp(kc[0] * f0 + kc[1]);
+            const double z = m - kc[2];
+            const double TN = exp(-z * z * kc[3] + kc[4]);
+            const double Aa = (1.0 - kc[5]) * PL, Bb = kc[5] * TN;
+            const double tot = Aa + Bb;
+            x += tot > 0.0 ? log(tot) : -INFINITY;
+            if (!MAXONLY) {
+              const double it_ = tot > 0.0 ? 1.0 / tot : 0.0, sig = kc[7];
+              scr[0] = Aa * (f0 + kc[6]) * it_;
+              scr[32] = Bb * (z / (sig * sig) - kc[8]) * it_;
+              scr[64] = Bb * (z * z / (sig * sig * sig) - 1.0 / sig - kc[9]) * it_;
+              scr[96] = (TN - PL) * it_;
+            }
+          } else if (K.kind == KOP_ISOALIGN) {
+            const double z = f0 - 1.0, sig = kc[1];
+            const double TN = exp(-z * z * kc[3] + kc[2]);
+            const double Aa = 0.5 * (1.0 - kc[0]), Bb = kc[0] * TN;
+            const double tot = Aa + Bb;
+            x += tot > 0.0 ? log(tot) : -INFINITY;
+            if (!MAXONLY) {
+              const double it_ = tot > 0.0 ? 1.0 / tot : 0.0;
+              scr[0] = (TN - 0.5) * it_;
+              scr[32] = Bb * (z * z / (sig * sig * sig) - 1.0 / sig - kc[4]) * it_;
+            }
+          } else if (K.kind == KOP_QUAD) {
+            const double z = f0 - kc[0], sig = kc[1];
+            x -= z * z * kc[2];
+            if (!MAXONLY) {
+              scr[0] = z / (sig * sig);
+              scr[32] = z * z / (sig * sig * sig);
+            }
+          }
+        }
+        if (MAXONLY) {
+          xmax = fmax(xmax, x);
+          continue;
+        }
+        const double p = exp(x - shift);
+        const double p2 = p * p;
+        A.S1 += p;
+        A.S2 += p2;
+        for (int g = 0; g < n_gs; ++g) {
+          const double dv = gscr[g * 32 + lane];
+          gacc[g * 32 + lane] = fma(p, dv, gacc[g * 32 + lane]);
+          if (G2) gacc[(n_gs + g) * 32 + lane] = fma(p2, dv, gacc[(n_gs + g) * 32 + lane]);
+        }
+#pragma unroll
+        for (int d = 0; d < NS; ++d) {
+          const double w = wv[d];
+          const double pw = p * w, pw2 = pw * w, pw3 = pw2 * w;
+          if (d < NSH) {
+            if (Jv[d] != A.cur[d]) {
+              if (A.cur[d] >= 0) spill<G2>(msh, (row_off[d] + A.cur[d]) * 4, m2_off, A.m1[d], A.m2[G2 ? d : 0]);
+              A.cur[d] = Jv[d];
+            }
+            A.m1[d][0] += p;
+            A.m1[d][1] += pw;
+            A.m1[d][2] += pw2;
+            A.m1[d][3] += pw3;
+            if (G2) {
+              const double qw = p2 * w, qw2 = qw * w, qw3 = qw2 * w;
+              A.m2[d][0] += p2;
+              A.m2[d][1] += qw;
+              A.m2[d][2] += qw2;
+              A.m2[d][3] += qw3;
+            }
+          } else {
+            // lane-private shared accumulators, layout [entry][lane]: conflict-free for any J
+            double* e = deep + (size_t)(deep_off[d] + Jv[d] * 4) * 32 + lane;
+            e[0] += p;
+            e[32] += pw;
+            e[64] += pw2;
+            e[96] += pw3;
+            if (G2) {
+              double* e2 = e + (size_t)rows_d[d] * 4 * 32;
+              const double qw = p2 * w, qw2 = qw * w, qw3 = qw2 * w;
+              e2[0] += p2;
+              e2[32] += qw;
+              e2[64] += qw2;
+              e2[96] += qw3;
+            }
+          }
+        }
+      }
+    }
+    if (MAXONLY) {
+      xmax = warp_max(xmax);
+      if (lane == 0) M.chunk_max[c] = xmax;
+      continue;
+    }
+    if (C.flush) {
+      // ---- write this warp's record and clear its accumulators ----
+#pragma unroll
+      for (int d = 0; d < NSH; ++d) {
+        if (A.cur[d] >= 0) spill<G2>(msh, (row_off[d] + A.cur[d]) * 4, m2_off, A.m1[d], A.m2[G2 ? d : 0]);
+        A.cur[d] = -1;
+      }
+      __syncwarp();
+      double* rec = M.records0 + (size_t)C.record_slot * M.rec_doubles;
+      const double s1 = warp_sum(A.S1), s2 = warp_sum(A.S2);
+      A.S1 = 0.0;
+      A.S2 = 0.0;
+      if (lane == 0) {
+        rec[0] = s1;
+        rec[1] = s2;
+      }
+      for (int g = 0; g < n_gs * MOM; ++g) {
+        const double v = warp_sum(gacc[g * 32 + lane]);
+        gacc[g * 32 + lane] = 0.0;
+        if (lane == 0) rec[2 + g] = v;
+      }
+      // deep dims: sum the 32 lane-private copies (rotated start: bank-conflict-free, fixed order)
+#pragma unroll
+      for (int d = NSH; d < NS; ++d) {
+        const int ne = rows_d[d] * 4 * MOM;
+        for (int e = lane; e < ne; e += 32) {
+          double* row = deep + (size_t)(deep_off[d] + e) * 32;
+          double acc = 0.0;
+          for (int i = 0; i < 32; ++i) {
+            const int l = (i + lane) & 31;
+            acc += row[l];
+            row[l] = 0.0;
+          }
+          const int mm = e / (rows_d[d] * 4), r = e - mm * rows_d[d] * 4;
+          msh[mm * m2_off + row_off[d] * 4 + r] = acc;
+        }
+      }
+      __syncwarp();
+      double* recM = rec + 2 + n_gs * MOM;
+      for (int i = lane; i < rows_total * 4 * MOM; i += 32) {
+        recM[i] = msh[i];
+        msh[i] = 0.0;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// =================================================================================================
+// reductions
+// =================================================================================================
+__global__ void reduce_kernel(const double* __restrict__ in, double* __restrict__ out, const ReduceTask* __restrict__ tasks, int rec) {
+  const ReduceTask T = tasks[blockIdx.x];
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= rec) return;
+  double acc = 0.0;
+  for (int r = 0; r < T.in_count; ++r) acc += in[(size_t)(T.in_first + r) * rec + i];
+  out[(size_t)T.out_slot * rec + i] = acc;
+}
+
+__global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict__ Mp) {
+  const ModelDev& M = *Mp;
+  __shared__ double scratch[32];
+  const int s = blockIdx.x;
+  const SegDev& S = M.segs[s];
+  double mx = -INFINITY;
+  for (int c = threadIdx.x; c < S.n_chunks; c += blockDim.x) mx = fmax(mx, M.chunk_max[S.first_chunk + c]);
+  mx = block_max(mx, scratch);
+  if (threadIdx.x == 0) M.shift[s] = (mx > -INFINITY && mx < INFINITY) ? mx : 0.0;
+}
+
+// =================================================================================================
+// finish: per segment
+// =================================================================================================
+__global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp) {
+  const ModelDev& M = *Mp;
+  const int s = blockIdx.x;
+  const int P = M.n_params;
+  const double* rec = M.seg_rec + (size_t)s * M.rec_doubles;
+  const double S1 = rec[0], S2 = rec[1];
+  const double shift = M.shift[s];
+  const int ngs = M.n_gslots;
+  const bool g2 = M.g2 != 0;
+  const double* g1 = rec + 2;
+  const double* g2v = rec + 2 + ngs;
+  const double* M1 = rec + 2 + ngs * (g2 ? 2 : 1);
+  const double* M2 = M1 + M.rows_total * 4;
+  double K = M.Ksum[0];
+  for (int g = 0; g < M.n_groups; ++g) K -= M.logZ[g];
+  const bool ok = (S1 > 0.0) && (S1 < INFINITY) && (S2 > 0.0) && (S2 < INFINITY);
+  const double N = M.total_inj;
+  const double den_inj = S2 - S1 * S1 / N;
+  if (threadIdx.x == 0) {
+    double* o = M.seg_out + (size_t)s * 4;
+    const SegDev& S = M.segs[s];
+    if (s == 0) {
+      o[0] = shift + log(S1) - log(N) + K;
+      o[1] = 2.0 * log(S1) - log(den_inj);
+      o[2] = 1.0 / exp(o[1]) - 1.0 / N;
+      M.inj_raw[0] = shift;
+      M.inj_raw[1] = S1;
+      M.inj_raw[2] = S2;
+    } else {
+      o[0] = shift + log(S1) - log(S.n_total) + K;
+      o[1] = 2.0 * log(S1) - log(S2);
+      o[2] = 1.0 / exp(o[1]) - 1.0 / S.n_total;
+    }
+    o[3] = ok ? 0.0 : 1.0;
+  }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    double G1 = 0.0, G2s = 0.0;
+    for (int d = 0; d < M.n_dims; ++d) {
+      const DimDev& D = M.dims[d];
+      const int k = i - D.slot;
+      if (k < 0 || k >= D.n_splines) continue;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int J = k - kk;
+        if (J < 0 || J > D.rows - 2) continue;
+        const double* m1 = M1 + (D.row_off + J) * 4;
+        G1 += BETA[kk][0] * m1[0] + BETA[kk][1] * m1[1] + BETA[kk][2] * m1[2] + BETA[kk][3] * m1[3];
+        if (g2) {
+          const double* m2 = M2 + (D.row_off + J) * 4;
+          G2s += BETA[kk][0] * m2[0] + BETA[kk][1] * m2[1] + BETA[kk][2] * m2[2] + BETA[kk][3] * m2[3];
+        }
+      }
+    }
+    for (int g = 0; g < ngs; ++g)
+      if (M.gslot_slot[g] == i) {
+        G1 += g1[g];
+        if (g2) G2s += g2v[g];
+      }
+    double dK = M.Ksum[1 + i];
+    for (int g = 0; g < M.n_groups; ++g) dK -= M.dlogZ[(size_t)g * P + i];
+    const double n1 = ok ? G1 / S1 : 0.0;
+    M.seg_J1[(size_t)s * P + i] = n1 + dK;
+    if (s == 0) {
+      M.inj_raw[3 + i] = G1;
+      M.inj_raw[3 + P + i] = G2s;
+      M.seg_Jn[(size_t)s * P + i] = (ok && g2) ? 2.0 * n1 - (2.0 * G2s - 2.0 * S1 * S1 / N * n1) / den_inj : 0.0;
+    } else {
+      M.seg_Jn[(size_t)s * P + i] = (ok && g2) ? 2.0 * n1 - 2.0 * G2s / S2 : 0.0;
+    }
+  }
+}
+
+// gather the per-segment results into the caller's gwi_outputs buffers
+__global__ void export_kernel(const ModelDev* __restrict__ Mp, gwi_outputs out) {
+  const ModelDev& M = *Mp;
+  const int P = M.n_params, E = M.n_segments - 1;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int e = tid; e < E; e += nt) {
+    if (out.logBF) out.logBF[e] = M.seg_out[(size_t)(e + 1) * 4 + 0];
+    if (out.logNeff) out.logNeff[e] = M.seg_out[(size_t)(e + 1) * 4 + 1];
+  }
+  if (tid == 0) {
+    if (out.log_mu) out.log_mu[0] = M.seg_out[0];
+    if (out.logNeff_inj) out.logNeff_inj[0] = M.seg_out[1];
+  }
+  for (int g = tid; g < M.n_groups; g += nt)
+    if (out.logZ) out.logZ[g] = M.logZ[g];
+  for (size_t i = tid; i < (size_t)E * P; i += nt) {
+    if (out.J_logBF) out.J_logBF[i] = M.seg_J1[(size_t)P + i];
+    if (out.J_logNeff) out.J_logNeff[i] = M.seg_Jn[(size_t)P + i];
+  }
+  for (int i = tid; i < P; i += nt) {
+    if (out.J_log_mu) out.J_log_mu[i] = M.seg_J1[i];
+    if (out.J_logNeff_inj) out.J_logNeff_inj[i] = M.seg_Jn[i];
+  }
+}
+
+// =================================================================================================
+// likelihood: per-rank partial record, then the rank-ordered combine (analysis.py:257-319)
+// =================================================================================================
+__global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict__ Mp, double* __restrict__ recd) {
+  const ModelDev& M = *Mp;
+  const int P = M.n_params, E = M.n_segments - 1;
+  if (threadIdx.x == 0) {
+    double sum_logBF = 0.0, min_ln = INFINITY, sum_var = 0.0, status = M.seg_out[3];
+    for (int e = 1; e <= E; ++e) {
+      const double* o = M.seg_out + (size_t)e * 4;
+      sum_logBF += o[0];
+      // analysis.py:296: min over nan_to_num(logn_effs)
+      double ln = o[1];
+      if (ln != ln) ln = 0.0;
+      ln = fmin(fmax(ln, -DBL_MAX), DBL_MAX);
+      min_ln = fmin(min_ln, ln);
+      sum_var += o[2];
+      status = fmax(status, o[3]);
+    }
+    recd[PR_SHIFT] = M.inj_raw[0];
+    recd[PR_S1] = M.inj_raw[1];
+    recd[PR_S2] = M.inj_raw[2];
+    recd[PR_SUM_LOGBF] = sum_logBF;
+    recd[PR_MIN_LOGNEFF] = min_ln;
+    recd[PR_SUM_VAR] = sum_var;
+    recd[PR_N_EVENTS] = (double)E;
+    recd[PR_STATUS] = status;
+  }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    recd[PR_HEADER + i] = M.inj_raw[3 + i];
+    recd[PR_HEADER + P + i] = M.inj_raw[3 + P + i];
+    double acc = 0.0;
+    for (int e = 1; e <= E; ++e) acc += M.seg_J1[(size_t)e * P + i];
+    recd[PR_HEADER + 2 * P + i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ recs, int R, gwi_like_opts opts, double* __restrict__ out) {
+  const ModelDev& M = *Mp;
+  const int P = M.n_params;
+  const int stride = PR_HEADER + 3 * P;
+  const double N = M.total_inj;
+  const double SENT = -DBL_MAX;  // nan_to_num(-inf)
+  // injection sums of all ranks on a common shift
+  double m = -INFINITY;
+  for (int r = 0; r < R; ++r)
+    if (recs[(size_t)r * stride + PR_S1] > 0.0) m = fmax(m, recs[(size_t)r * stride + PR_SHIFT]);
+  double S1 = 0.0, S2 = 0.0, sum_logBF = 0.0, min_ln = INFINITY, sum_var = 0.0, status = 0.0;
+  for (int r = 0; r < R; ++r) {
+    const double* q = recs + (size_t)r * stride;
+    if (q[PR_S1] > 0.0) {
+      const double f = exp(q[PR_SHIFT] - m);
+      S1 += q[PR_S1] * f;
+      S2 += q[PR_S2] * f * f;
+    }
+    sum_logBF += q[PR_SUM_LOGBF];
+    min_ln = fmin(min_ln, q[PR_MIN_LOGNEFF]);
+    sum_var += q[PR_SUM_VAR];
+    status = fmax(status, q[PR_STATUS]);
+  }
+  double K = M.Ksum[0];
+  for (int g = 0; g < M.n_groups; ++g) K -= M.logZ[g];
+  const double den = S2 - S1 * S1 / N;
+  const double log_mu = m + log(S1) - log(N) + K;
+  const double logneff_inj = 2.0 * log(S1) - log(den);
+  const double neff_inj = exp(logneff_inj);
+  const double var_inj = 1.0 / neff_inj - 1.0 / N;
+  const double Nobs = (double)opts.Nobs;
+  double log_det = log_mu;
+  if (opts.marginalize_selection) log_det -= (3.0 + Nobs) / (2.0 * neff_inj);
+  bool passed = true;
+  if (opts.min_neff_cut && !(logneff_inj >= log(4.0 * Nobs))) {
+    log_det = INFINITY;
+    passed = false;
+  }
+  const double sel = isinf(log_det) ? SENT : -Nobs * log_det;
+  double log_l = sel + sum_logBF;
+  if (log_l != log_l) log_l = SENT;
+  log_l = fmin(fmax(log_l, -DBL_MAX), DBL_MAX);
+  if (opts.min_neff_cut && exp(min_ln) <= Nobs) {
+    log_l = SENT;
+    passed = false;
+  }
+  const double variance = Nobs * Nobs * var_inj + sum_var;
+  if (opts.max_variance_cut && !(variance <= 1.0)) {
+    log_l = SENT;
+    passed = false;
+  }
+  if (status != 0.0) passed = false;
+  if (threadIdx.x == 0) {
+    out[GWI_LIKE_LOG_L] = log_l;
+    out[GWI_LIKE_PASSED] = passed ? 1.0 : 0.0;
+    out[GWI_LIKE_LOG_MU] = log_mu;
+    out[GWI_LIKE_LOGNEFF_INJ] = logneff_inj;
+    out[GWI_LIKE_MIN_LOGNEFF] = min_ln;
+    out[GWI_LIKE_SUM_LOGBF] = sum_logBF;
+    out[GWI_LIKE_VARIANCE] = variance;
+    out[GWI_LIKE_STATUS] = status;
+  }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    double G1 = 0.0, G2s = 0.0, sumJ = 0.0;
+    for (int r = 0; r < R; ++r) {
+      const double* q = recs + (size_t)r * stride;
+      if (q[PR_S1] > 0.0) {
+        const double f = exp(q[PR_SHIFT] - m);
+        G1 += q[PR_HEADER + i] * f;
+        G2s += q[PR_HEADER + P + i] * f * f;
+      }
+      sumJ += q[PR_HEADER + 2 * P + i];
+    }
+    double dK = M.Ksum[1 + i];
+    for (int g = 0; g < M.n_groups; ++g) dK -= M.dlogZ[(size_t)g * P + i];
+    const double n1 = G1 / S1;
+    double g_det = n1 + dK;
+    if (opts.marginalize_selection) {
+      const double Jn = 2.0 * n1 - (2.0 * G2s - 2.0 * S1 * S1 / N * n1) / den;
+      g_det += (3.0 + Nobs) / (2.0 * neff_inj) * Jn;
+    }
+    out[GWI_LIKE_HEADER + i] = passed ? (-Nobs * g_det + sumJ) : 0.0;
+  }
+}
+
+// =================================================================================================
+// host-side launch helpers (called from api.cu)
+// =================================================================================================
+typedef void (*stream_fn)(const ModelDev*);
+
+template <int NS, int NDEEP>
+static stream_fn pick_g2(bool g2, bool maxonly) {
+  if (maxonly) return stream_kernel<NS, 0, false, true>;
+  return g2 ? (stream_fn)stream_kernel<NS, NDEEP, true, false> : (stream_fn)stream_kernel<NS, NDEEP, false, false>;
+}
+template <int NS>
+static stream_fn pick_deep(int nd, bool g2, bool maxonly) {
+  if (maxonly) return stream_kernel<NS, 0, false, true>;
+  switch (nd) {
+    case 0: return pick_g2<NS, 0>(g2, maxonly);
+    case 1: if (NS >= 1) return pick_g2<NS, (NS >= 1 ? 1 : 0)>(g2, maxonly); break;
+    case 2: if (NS >= 2) return pick_g2<NS, (NS >= 2 ? 2 : 0)>(g2, maxonly); break;
+    case 3: if (NS >= 3) return pick_g2<NS, (NS >= 3 ? 3 : 0)>(g2, maxonly); break;
+  }
+  return nullptr;
+}
+
+stream_fn pick_stream_kernel(int ns, int ndeep, bool g2, bool maxonly) {
+  switch (ns) {
+    case 0: return pick_deep<0>(ndeep, g2, maxonly);
+    case 1: return pick_deep<1>(ndeep, g2, maxonly);
+    case 2: return pick_deep<2>(ndeep, g2, maxonly);
+    case 3: return pick_deep<3>(ndeep, g2, maxonly);
+    case 4: return pick_deep<4>(ndeep, g2, maxonly);
+    case 5: return pick_deep<5>(ndeep, g2, maxonly);
+    case 6: return pick_deep<6>(ndeep, g2, maxonly);
+    case 7: return pick_deep<7>(ndeep, g2, maxonly);
+    case 8: return pick_deep<8>(ndeep, g2, maxonly);
+  }
+  return nullptr;
+}
+
+void launch_prologue(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t st) {
+  prologue_kernel<<<n_groups + 1, 256, (size_t)max_grid * sizeof(double), st>>>(Md, lam);
+}
+void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st) {
+  dim3 grid(n_tasks, (rec + 255) / 256);
+  reduce_kernel<<<grid, 256, 0, st>>>(in, out, tasks, rec);
+}
+void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st) { segmax_kernel<<<n_seg, 256, 0, st>>>(Md); }
+void launch_finish(const ModelDev* Md, int n_seg, cudaStream_t st) { finish_kernel<<<n_seg, 256, 0, st>>>(Md); }
+void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { export_kernel<<<64, 256, 0, st>>>(Md, out); }
+void launch_partial(const ModelDev* Md, double* rec, cudaStream_t st) { partial_kernel<<<1, 256, 0, st>>>(Md, rec); }
+void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, cudaStream_t st) {
+  combine_kernel<<<1, 256, 0, st>>>(Md, recs, R, o, out);
+}
+
+}  // namespace gwi

@@ -1,0 +1,820 @@
+// Host-side plan builder: turns the borrowed catalog columns + model description into the static
+// device-resident evaluation plan.  This replaces the reference's model construction
+// (gwinferno/models/bsplines/single.py:35-58 -- masks + dense Cox-de Boor design matrices,
+// gwinferno/interpolation.py:128-149) with, per sample and spline dimension, ONE 8-byte word
+// (piece index J | mantissa of 1+u) so that the kernel re-creates the 4 non-zero basis weights on
+// the fly.  Samples whose population density is identically zero (outside the model masks,
+// single.py:54-55,90-92; z > zmax, spline_perturbation.py:368-372; non-finite static weight) are
+// dropped here; the Monte-Carlo denominators keep the full sample counts.
+//
+// Samples of every segment (injection set, each event) are sorted lexicographically by their
+// piece indices so that consecutive samples of one GPU lane share polynomial pieces: the kernel
+// keeps the per-piece gradient moments in registers and only spills when a piece index changes.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <thread>
+
+#include "gwi_internal.h"
+
+namespace gwi {
+
+// ---------------------------------------------------------------------------------------------
+// cosmology: flat LCDM, Planck15-LVK constants (gwinferno/cosmology.py:19-22), comoving-distance
+// table by sequential trapezoid on z = arange(0, 10, 1e-3) (cosmology.py:48-77), dVc/dz with Dc
+// linearly interpolated (cosmology.py:95-120).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Cosmo {
+  static constexpr double C_SI = 299792458.0;
+  static constexpr double Ho = 67.90 / 1e-3;
+  static constexpr double Om = 0.3065;
+  static constexpr double Ol = 1.0 - 0.3065;
+  static constexpr double DZ = 1e-3;
+  double c_over_Ho;
+  std::vector<double> z, Dc;
+  double dDcdz(double zz) const {
+    const double opz = 1.0 + zz;
+    return c_over_Ho / std::sqrt(Ol + Om * opz * opz * opz);
+  }
+  Cosmo() {
+    c_over_Ho = C_SI / Ho;
+    const int n = (int)std::ceil(10.0 / DZ);
+    z.resize(n);
+    Dc.resize(n);
+    for (int i = 0; i < n; ++i) z[i] = i * DZ;  // numpy arange(0, 10, 1e-3): start + i*step
+    Dc[0] = 0.0;
+    for (int i = 0; i + 1 < n; ++i) Dc[i + 1] = Dc[i] + 0.5 * (dDcdz(z[i]) + dDcdz(z[i] + DZ)) * DZ;
+  }
+  double interp_Dc(double zz) const {
+    if (!(zz >= 0.0)) return std::numeric_limits<double>::quiet_NaN();
+    const int n = (int)z.size();
+    if (zz >= z[n - 1]) return std::numeric_limits<double>::quiet_NaN();  // beyond the table (z < 10)
+    int i = (int)(zz / DZ);
+    if (i > n - 2) i = n - 2;
+    while (i > 0 && z[i] > zz) --i;
+    while (i < n - 2 && z[i + 1] <= zz) ++i;
+    const double f = (zz - z[i]) / (z[i + 1] - z[i]);
+    return Dc[i] + f * (Dc[i + 1] - Dc[i]);
+  }
+};
+const Cosmo& cosmo() {
+  static Cosmo c;
+  return c;
+}
+}  // namespace
+
+double log_dvcdz(double z) {
+  const Cosmo& c = cosmo();
+  const double Dc = c.interp_Dc(z);
+  return std::log(4.0 * M_PI * Dc * Dc * c.dDcdz(z));
+}
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+enum FeatKind : int { F_LOG1P = 1, F_LOG = 2, F_LOG_RATIO = 3, F_LOG_DVDZ = 4, F_NEG_LOG = 5, F_RAW = 6, F_LOG_C_OVER = 7, F_LOG_S_MINUS = 8 };
+struct Feat {
+  int kind;
+  int col[2];
+  double cst;
+};
+
+inline double eval_feat(const Feat& f, const double* const* cols, int64_t j) {
+  const double a = cols[f.col[0]][j];
+  switch (f.kind) {
+    case F_LOG1P: return std::log(1.0 + a);
+    case F_LOG: return std::log(a);
+    case F_LOG_RATIO: return std::log(a / cols[f.col[1]][j]);
+    case F_LOG_DVDZ: return log_dvcdz(a);
+    case F_NEG_LOG: return -std::log(a);
+    case F_RAW: return a;
+    case F_LOG_C_OVER: return std::log(f.cst / a);
+    case F_LOG_S_MINUS: return std::log(f.cst - a);
+  }
+  return std::numeric_limits<double>::quiet_NaN();
+}
+
+struct RangeCut {
+  int kind;  // 1 range, 2 ratio range, 3 open range (lo < x < hi), 4 q >= c/m1 && q <= 1 && c/m1 < 1
+  int col[2];
+  double lo, hi;
+};
+
+inline bool pass_cut(const RangeCut& c, const double* const* cols, int64_t j) {
+  const double a = cols[c.col[0]][j];
+  switch (c.kind) {
+    case 1: return a >= c.lo && a <= c.hi;
+    case 2: {
+      const double r = a / cols[c.col[1]][j];
+      return r >= c.lo && r <= c.hi;
+    }
+    case 3: return a > c.lo && a < c.hi;
+    case 4: {
+      const double lo = c.lo / cols[c.col[1]][j];
+      return a >= lo && a <= 1.0 && lo < 1.0;
+    }
+  }
+  return false;
+}
+
+struct SplineGeom {
+  int col;
+  bool logx;
+  int outside;
+  double x_lo, x_hi, xi_lo, xi_hi, inv_dxi;
+  int rows;
+};
+
+// piece index and local coordinate u in [0,1) of one sample; returns false if the sample must be
+// dropped (GWI_OUTSIDE_DROP and outside the mask)
+inline bool spline_locate(const SplineGeom& g, double x, int& J, double& u) {
+  const bool inside = (x >= g.x_lo) && (x <= g.x_hi);
+  if (!inside) {
+    if (g.outside == GWI_OUTSIDE_DROP) return false;
+    J = g.rows - 1;  // dummy all-zero piece: bases are 0 outside the range (interpolation.py:175)
+    u = 0.0;
+    return x == x;  // NaN coordinate => drop
+  }
+  double xi = g.logx ? std::log(x) : x;
+  if (xi < g.xi_lo) xi = g.xi_lo;
+  if (xi > g.xi_hi) xi = g.xi_hi;
+  const double t = (xi - g.xi_lo) * g.inv_dxi;
+  int j = (int)std::floor(t);
+  if (j < 0) j = 0;
+  if (j > g.rows - 2) j = g.rows - 2;
+  double uu = t - (double)j;
+  if (uu < 0.0) uu = 0.0;
+  const double top = 1.0 - 0x1p-52;  // 1 + top = 2 - 2^-52 is the largest double below 2
+  if (uu > top) uu = top;
+  J = j;
+  u = uu;
+  return true;
+}
+
+inline uint64_t pack_word(int J, double u) {
+  const double v = 1.0 + u;  // [1, 2): exponent bits are constant, the mantissa carries u exactly to 2^-52
+  uint64_t b;
+  std::memcpy(&b, &v, 8);
+  return ((uint64_t)J << 52) | (b & MANT_MASK);
+}
+
+template <class F>
+void parallel_for(int64_t n, int n_workers, F&& fn) {
+  if (n_workers <= 1 || n < 4096) {
+    fn(0, n, 0);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t per = (n + n_workers - 1) / n_workers;
+  for (int w = 0; w < n_workers; ++w) {
+    const int64_t a = w * per, b = std::min<int64_t>(n, a + per);
+    if (a >= b) break;
+    th.emplace_back([=, &fn] { fn(a, b, w); });
+  }
+  for (auto& t : th) t.join();
+}
+
+// LSD radix sort of (key, index) pairs by the low `bits` bits of the key, 11-bit digits
+void radix_sort_pairs(std::vector<uint64_t>& keys, std::vector<uint32_t>& idx, int bits) {
+  const size_t n = keys.size();
+  if (n < 2) return;
+  if (n < 4096) {
+    std::vector<uint32_t> perm(n);
+    std::iota(perm.begin(), perm.end(), 0u);
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint64_t> k2(n);
+    std::vector<uint32_t> i2(n);
+    for (size_t i = 0; i < n; ++i) {
+      k2[i] = keys[perm[i]];
+      i2[i] = idx[perm[i]];
+    }
+    keys.swap(k2);
+    idx.swap(i2);
+    return;
+  }
+  constexpr int RB = 11;
+  std::vector<uint64_t> k2(n);
+  std::vector<uint32_t> i2(n);
+  for (int shift = 0; shift < bits; shift += RB) {
+    size_t cnt[1 << RB] = {0};
+    for (size_t i = 0; i < n; ++i) ++cnt[(keys[i] >> shift) & ((1 << RB) - 1)];
+    size_t acc = 0;
+    for (int b = 0; b < (1 << RB); ++b) {
+      const size_t c = cnt[b];
+      cnt[b] = acc;
+      acc += c;
+    }
+    for (size_t i = 0; i < n; ++i) {
+      const size_t p = cnt[(keys[i] >> shift) & ((1 << RB) - 1)]++;
+      k2[p] = keys[i];
+      i2[p] = idx[i];
+    }
+    keys.swap(k2);
+    idx.swap(i2);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count, int n_workers, Plan& plan) {
+  if (desc.n_terms <= 0 || !desc.terms || desc.n_params <= 0) {
+    set_error("model description needs at least one term and one parameter");
+    return GWI_ERR_INVALID;
+  }
+  if (n_workers <= 0) n_workers = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_workers = std::min(n_workers, 64);
+  plan = Plan();
+  plan.n_params = desc.n_params;
+  plan.n_terms = desc.n_terms;
+  plan.g2 = desc.need_neff_grad != 0;
+  plan.total_inj = cat.total_inj;
+
+  auto col_ok = [&](int c) { return c >= 0 && c < cat.n_columns; };
+  auto slot_ok = [&](int s, int n) { return s >= 0 && s + n <= desc.n_params; };
+
+  // ---- norm groups --------------------------------------------------------------------------
+  for (int g = 0; g < desc.n_groups; ++g) {
+    const gwi_norm_group& G = desc.groups[g];
+    if (G.n_grid < 2 || !G.log_w) {
+      set_error("norm group needs >= 2 grid points and a log_w array");
+      return GWI_ERR_INVALID;
+    }
+    NormGroup ng;
+    ng.n_grid = G.n_grid;
+    ng.logw_off = (int)plan.grid_pool.size();
+    plan.grid_pool.insert(plan.grid_pool.end(), G.log_w, G.log_w + G.n_grid);
+    plan.groups.push_back(ng);
+  }
+  auto add_grid = [&](const gwi_term& t, int& off) -> bool {
+    off = -1;
+    if (t.norm_group < 0) return true;
+    if (t.norm_group >= desc.n_groups || !t.grid) return false;
+    off = (int)plan.grid_pool.size();
+    const int n = desc.groups[t.norm_group].n_grid;
+    plan.grid_pool.insert(plan.grid_pool.end(), t.grid, t.grid + n);
+    return true;
+  };
+
+  // ---- classify terms -----------------------------------------------------------------------
+  std::vector<SplineGeom> geom;  // parallel to plan.dims (before ordering)
+  std::vector<Feat> kop_feats;   // feature columns of the kops, in stream-column order
+  std::vector<Feat> static_feats;
+  std::vector<RangeCut> cuts;
+  std::vector<int> used_cols;
+  auto use_col = [&](int c) {
+    if (std::find(used_cols.begin(), used_cols.end(), c) == used_cols.end()) used_cols.push_back(c);
+  };
+  auto add_feat = [&](int kind, int c0, int c1, double cst) {
+    kop_feats.push_back(Feat{kind, {c0, c1}, cst});
+    return (int)kop_feats.size() - 1;  // index among kop features (stream column assigned later)
+  };
+  auto add_kop = [&](int kind, int f0, int f1, int n_gs, const int* slots, const double* cst, int group, int grid_off) -> bool {
+    if ((int)plan.kops.size() >= MAX_KOPS || plan.n_gslots + n_gs > MAX_GSLOTS) return false;
+    Kop k{};
+    k.kind = kind;
+    k.col[0] = f0;
+    k.col[1] = f1;
+    k.gslot = plan.n_gslots;
+    k.n_gslots = n_gs;
+    for (int i = 0; i < 4; ++i) {
+      k.slot[i] = i < n_gs ? slots[i] : -1;
+      k.cst[i] = cst ? cst[i] : 0.0;
+    }
+    k.norm_group = group;
+    k.grid_off = grid_off;
+    plan.n_gslots += n_gs;
+    plan.kops.push_back(k);
+    return true;
+  };
+
+  for (int ti = 0; ti < desc.n_terms; ++ti) {
+    const gwi_term& t = desc.terms[ti];
+    if (!col_ok(t.col[0])) {
+      set_error("term " + std::to_string(ti) + ": bad column index");
+      return GWI_ERR_INVALID;
+    }
+    use_col(t.col[0]);
+    bool ok = true;
+    switch (t.kind) {
+      case GWI_TERM_SPLINE: {
+        if (t.n_splines < 4 || t.n_splines - 2 > MAX_ROWS || !slot_ok(t.slot[0], t.n_splines) || !(t.xi_hi > t.xi_lo)) {
+          set_error("term " + std::to_string(ti) + ": bad spline description");
+          return GWI_ERR_INVALID;
+        }
+        if ((int)plan.dims.size() >= MAX_SPLINE_DIMS) {
+          set_error("too many spline dimensions");
+          return GWI_ERR_UNSUPPORTED;
+        }
+        SplineDim d{};
+        d.term = ti;
+        d.n_splines = t.n_splines;
+        d.rows = t.n_splines - 2;
+        d.slot = t.slot[0];
+        d.norm_group = t.norm_group;
+        d.outside = t.outside;
+        if (!add_grid(t, d.grid_off)) ok = false;
+        plan.dims.push_back(d);
+        SplineGeom g{};
+        g.col = t.col[0];
+        g.logx = t.logx != 0;
+        g.outside = t.outside;
+        g.x_lo = t.x_lo;
+        g.x_hi = t.x_hi;
+        g.xi_lo = t.xi_lo;
+        g.xi_hi = t.xi_hi;
+        g.rows = d.rows;
+        g.inv_dxi = (double)(d.rows - 1) / (t.xi_hi - t.xi_lo);
+        geom.push_back(g);
+        break;
+      }
+      case GWI_TERM_LINEAR: {
+        if (!slot_ok(t.slot[0], 1)) ok = false;
+        int fk = 0;
+        switch (t.feature) {
+          case GWI_FEAT_LOG1P: fk = F_LOG1P; break;
+          case GWI_FEAT_LOG: fk = F_LOG; break;
+          case GWI_FEAT_LOG_RATIO: fk = F_LOG_RATIO; break;
+          case GWI_FEAT_LOG_DVDZ: fk = F_LOG_DVDZ; break;
+          case GWI_FEAT_NEG_LOG: fk = F_NEG_LOG; break;
+          default: ok = false;
+        }
+        if (fk == F_LOG_RATIO) {
+          if (!col_ok(t.col[1])) ok = false; else use_col(t.col[1]);
+        }
+        int goff;
+        if (!add_grid(t, goff)) ok = false;
+        if (ok) {
+          const int f = add_feat(fk, t.col[0], t.col[1], 0.0);
+          const double cst[4] = {t.cst[0], 0, 0, 0};
+          ok = add_kop(KOP_LIN, f, -1, 1, t.slot, cst, t.norm_group, goff);
+        }
+        break;
+      }
+      case GWI_TERM_STATIC: {
+        int fk = 0;
+        switch (t.feature) {
+          case GWI_FEAT_LOG1P: fk = F_LOG1P; break;
+          case GWI_FEAT_LOG: fk = F_LOG; break;
+          case GWI_FEAT_LOG_RATIO: fk = F_LOG_RATIO; break;
+          case GWI_FEAT_LOG_DVDZ: fk = F_LOG_DVDZ; break;
+          case GWI_FEAT_NEG_LOG: fk = F_NEG_LOG; break;
+          default: ok = false;
+        }
+        if (fk == F_LOG_RATIO) {
+          if (!col_ok(t.col[1])) ok = false; else use_col(t.col[1]);
+        }
+        if (ok) static_feats.push_back(Feat{fk, {t.col[0], t.col[1]}, 0.0});
+        break;
+      }
+      case GWI_TERM_POWERLAW: {
+        if (!slot_ok(t.slot[0], 1) || !(t.cst[0] > 0.0) || !(t.cst[1] > t.cst[0])) ok = false;
+        if (ok) {
+          const int f = add_feat(F_LOG, t.col[0], -1, 0.0);
+          const double cst[4] = {0, 0, 0, 0};
+          ok = add_kop(KOP_LIN, f, -1, 1, t.slot, cst, -1, -1);
+          if ((int)plan.sops.size() >= MAX_SOPS) ok = false;
+          plan.sops.push_back(Sop{SOP_POWERLAW_NORM, {t.slot[0], -1}, {t.cst[0], t.cst[1]}});
+          cuts.push_back(RangeCut{1, {t.col[0], -1}, t.cst[0], t.cst[1]});
+        }
+        break;
+      }
+      case GWI_TERM_POWERLAW_RATIO: {
+        if (!slot_ok(t.slot[0], 1) || !col_ok(t.col[1]) || !(t.cst[0] > 0.0)) ok = false;
+        if (ok) {
+          use_col(t.col[1]);
+          const int f0 = add_feat(F_LOG, t.col[0], -1, 0.0);
+          const int f1 = add_feat(F_LOG_C_OVER, t.col[1], -1, t.cst[0]);
+          ok = add_kop(KOP_PLRATIO, f0, f1, 1, t.slot, nullptr, -1, -1);
+          cuts.push_back(RangeCut{4, {t.col[0], t.col[1]}, t.cst[0], 1.0});
+        }
+        break;
+      }
+      case GWI_TERM_PLPEAK: {
+        for (int i = 0; i < 4; ++i)
+          if (!slot_ok(t.slot[i], 1)) ok = false;
+        if (!(t.cst[0] > 0.0) || !(t.cst[1] > t.cst[0])) ok = false;
+        if (ok) {
+          const int f0 = add_feat(F_LOG, t.col[0], -1, 0.0);
+          const int f1 = add_feat(F_RAW, t.col[0], -1, 0.0);
+          const double cst[4] = {t.cst[0], t.cst[1], 0, 0};
+          ok = add_kop(KOP_PLPEAK, f0, f1, 4, t.slot, cst, -1, -1);
+          cuts.push_back(RangeCut{1, {t.col[0], -1}, t.cst[0], t.cst[1]});
+        }
+        break;
+      }
+      case GWI_TERM_BETA: {
+        if (!slot_ok(t.slot[0], 1) || !slot_ok(t.slot[1], 1) || !(t.cst[0] > 0.0)) ok = false;
+        if (ok) {
+          const int f0 = add_feat(F_LOG, t.col[0], -1, 0.0);
+          const int f1 = add_feat(F_LOG_S_MINUS, t.col[0], -1, t.cst[0]);
+          const double cst[4] = {-1.0, 0, 0, 0};
+          ok = add_kop(KOP_LIN, f0, -1, 1, &t.slot[0], cst, -1, -1) && add_kop(KOP_LIN, f1, -1, 1, &t.slot[1], cst, -1, -1);
+          if ((int)plan.sops.size() >= MAX_SOPS) ok = false;
+          plan.sops.push_back(Sop{SOP_BETA_NORM, {t.slot[0], t.slot[1]}, {t.cst[0], 0.0}});
+          cuts.push_back(RangeCut{3, {t.col[0], -1}, 0.0, t.cst[0]});
+        }
+        break;
+      }
+      case GWI_TERM_ISOALIGN: {
+        if (!slot_ok(t.slot[0], 1) || !slot_ok(t.slot[1], 1)) ok = false;
+        if (ok) {
+          const int f0 = add_feat(F_RAW, t.col[0], -1, 0.0);
+          ok = add_kop(KOP_ISOALIGN, f0, -1, 2, t.slot, nullptr, -1, -1);
+          cuts.push_back(RangeCut{1, {t.col[0], -1}, -1.0, 1.0});
+        }
+        break;
+      }
+      case GWI_TERM_TRUNCNORM: {
+        if (!slot_ok(t.slot[0], 1) || !slot_ok(t.slot[1], 1) || !(t.cst[1] > t.cst[0])) ok = false;
+        if (ok) {
+          const int f0 = add_feat(F_RAW, t.col[0], -1, 0.0);
+          const double cst[4] = {t.cst[0], t.cst[1], 0, 0};
+          ok = add_kop(KOP_QUAD, f0, -1, 2, t.slot, cst, -1, -1);
+          if ((int)plan.sops.size() >= MAX_SOPS) ok = false;
+          plan.sops.push_back(Sop{SOP_TRUNCNORM_NORM, {t.slot[0], t.slot[1]}, {t.cst[0], t.cst[1]}});
+          cuts.push_back(RangeCut{1, {t.col[0], -1}, t.cst[0], t.cst[1]});
+        }
+        break;
+      }
+      default:
+        ok = false;
+    }
+    if (!ok) {
+      set_error("term " + std::to_string(ti) + ": invalid or unsupported description (kind " + std::to_string(t.kind) + ")");
+      return GWI_ERR_INVALID;
+    }
+  }
+  for (int c = 0; c < desc.n_cuts; ++c) {
+    const gwi_cut& k = desc.cuts[c];
+    if (!col_ok(k.col[0]) || (k.kind == GWI_CUT_RATIO_RANGE && !col_ok(k.col[1])) || (k.kind != GWI_CUT_RANGE && k.kind != GWI_CUT_RATIO_RANGE)) {
+      set_error("bad cut description");
+      return GWI_ERR_INVALID;
+    }
+    use_col(k.col[0]);
+    if (k.kind == GWI_CUT_RATIO_RANGE) use_col(k.col[1]);
+    cuts.push_back(RangeCut{k.kind == GWI_CUT_RANGE ? 1 : 2, {k.col[0], k.col[1]}, k.lo, k.hi});
+  }
+
+  // ---- order the spline dims: most pieces first (sort key most significant), deep dims last ----
+  const int NS = (int)plan.dims.size();
+  {
+    std::vector<int> order(NS);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return plan.dims[a].rows > plan.dims[b].rows; });
+    std::vector<SplineDim> d2;
+    std::vector<SplineGeom> g2;
+    for (int i : order) {
+      d2.push_back(plan.dims[i]);
+      g2.push_back(geom[i]);
+    }
+    plan.dims.swap(d2);
+    geom.swap(g2);
+  }
+  int row_off = 0;
+  for (int d = 0; d < NS; ++d) {
+    plan.dims[d].row_off = row_off;
+    plan.dims[d].column = d;
+    row_off += plan.dims[d].rows;
+  }
+  plan.rows_total = row_off;
+  // deep dims: lane-private shared-memory accumulators, rows*4*(g2?2:1)*32 lanes*8 B per warp each
+  {
+    int want = desc.n_deep;
+    const int budget = 36 * 1024;  // bytes per warp
+    int nd = 0, bytes = 0;
+    const int cap = want < 0 ? std::min(NS, 2) : std::min(NS, want);
+    for (int d = NS - 1; d >= 0 && nd < cap; --d) {
+      const int b = plan.dims[d].rows * 4 * (plan.g2 ? 2 : 1) * LANES * 8;
+      if (bytes + b > budget) break;
+      bytes += b;
+      ++nd;
+    }
+    plan.n_deep = nd;
+    for (int d = 0; d < NS; ++d) plan.dims[d].deep = d >= NS - nd;
+  }
+  const int NK = (int)kop_feats.size();
+  plan.n_columns = NS + NK + 1;
+  plan.col_static = NS + NK;
+  for (auto& k : plan.kops) {
+    k.col[0] = NS + k.col[0];
+    if (k.col[1] >= 0) k.col[1] = NS + k.col[1];
+  }
+  plan.rec_doubles = rec_size(plan.n_gslots, plan.g2, plan.rows_total);
+
+  // ---- pass 1: validity + sort key per sample -----------------------------------------------
+  const int E = cat.n_events;
+  const int64_t n_pe = E > 0 ? cat.pe_offsets[E] : 0;
+  const int64_t n_inj = cat.n_inj;
+  plan.n_samples_pe = n_pe;
+  plan.n_samples_inj = n_inj;
+  if (n_pe + n_inj >= (int64_t)0xFFFFFFF0u) {
+    set_error("more than 2^32 samples per process are not supported");
+    return GWI_ERR_UNSUPPORTED;
+  }
+  int key_bits = 0;
+  std::vector<int> key_shift(NS);
+  {
+    int sh = 0;
+    for (int d = NS - 1; d >= 0; --d) {
+      key_shift[d] = sh;
+      sh += 6;
+    }
+    key_bits = sh;
+  }
+  constexpr uint64_t INVALID = ~0ull;
+  auto sample_key = [&](const double* const* cols, int64_t j) -> uint64_t {
+    for (int c : used_cols) {
+      const double v = cols[c][j];
+      if (!(v == v)) return INVALID;
+    }
+    for (const RangeCut& c : cuts)
+      if (!pass_cut(c, cols, j)) return INVALID;
+    uint64_t key = 0;
+    for (int d = 0; d < NS; ++d) {
+      int J;
+      double u;
+      if (!spline_locate(geom[d], cols[geom[d].col][j], J, u)) return INVALID;
+      key |= (uint64_t)J << key_shift[d];
+    }
+    double st = 0.0;
+    for (const Feat& f : static_feats) st += eval_feat(f, cols, j);
+    if (!std::isfinite(st)) return INVALID;
+    for (const Feat& f : kop_feats)
+      if (!std::isfinite(eval_feat(f, cols, j))) return INVALID;
+    return key;
+  };
+
+  // segments: 0 = injections, 1..E = events
+  const int n_seg = E + 1;
+  plan.segments.assign(n_seg, Segment{});
+  std::vector<std::vector<uint32_t>> order(n_seg);  // sorted valid sample indices per segment
+  {
+    // injections
+    std::vector<uint64_t> keys(n_inj);
+    parallel_for(n_inj, n_workers, [&](int64_t a, int64_t b, int) {
+      for (int64_t j = a; j < b; ++j) keys[j] = sample_key(cat.inj_columns.data(), j);
+    });
+    std::vector<uint64_t> vk;
+    std::vector<uint32_t>& vi = order[0];
+    vk.reserve(n_inj);
+    vi.reserve(n_inj);
+    for (int64_t j = 0; j < n_inj; ++j)
+      if (keys[j] != INVALID) {
+        vk.push_back(keys[j]);
+        vi.push_back((uint32_t)j);
+      }
+    keys.clear();
+    keys.shrink_to_fit();
+    radix_sort_pairs(vk, vi, key_bits);
+    plan.segments[0].n_total = n_inj;
+    plan.segments[0].n_valid = (int64_t)vi.size();
+  }
+  {
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (;;) {
+        const int e = next.fetch_add(1);
+        if (e >= E) break;
+        const int64_t a = cat.pe_offsets[e], b = cat.pe_offsets[e + 1];
+        std::vector<uint64_t> vk;
+        std::vector<uint32_t>& vi = order[e + 1];
+        for (int64_t j = a; j < b; ++j) {
+          const uint64_t k = sample_key(cat.pe_columns.data(), j);
+          if (k != INVALID) {
+            vk.push_back(k);
+            vi.push_back((uint32_t)j);
+          }
+        }
+        radix_sort_pairs(vk, vi, key_bits);
+        plan.segments[e + 1].n_total = b - a;
+        plan.segments[e + 1].n_valid = (int64_t)vi.size();
+      }
+    };
+    std::vector<std::thread> th;
+    for (int w = 0; w < std::min(n_workers, std::max(1, E)); ++w) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  for (int s = 1; s < n_seg; ++s) plan.n_valid_pe += plan.segments[s].n_valid;
+  plan.n_valid_inj = plan.segments[0].n_valid;
+
+  // ---- launch geometry + chunking -----------------------------------------------------------
+  // shared memory per warp: shallow accumulators + deep lane-private arrays + generic slots
+  const int mom = plan.g2 ? 2 : 1;
+  int rows_shallow = 0, rows_deep = 0;
+  for (int d = 0; d < NS; ++d) (plan.dims[d].deep ? rows_deep : rows_shallow) += plan.dims[d].rows;
+  (void)rows_shallow;
+  const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * LANES * 8 +
+                             (int64_t)plan.n_gslots * (1 + mom) * LANES * 8;
+  const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)plan.kops.size() * KC_STRIDE * 8 + 1024;
+  int wpb = (int)((220 * 1024 - cta_fixed) / std::max<int64_t>(1, warp_bytes));
+  wpb = std::max(1, std::min(wpb, 8));
+  plan.warps_per_block = wpb;
+  plan.grid_blocks = std::max(1, sm_count);
+  const int W = plan.grid_blocks * plan.warps_per_block;
+  const int64_t n_valid = plan.n_valid_pe + plan.n_valid_inj;
+  int K = desc.chunk_steps;
+  if (K <= 0) {
+    K = (int)(n_valid / ((int64_t)W * LANES * 4));
+    K = std::max(32, std::min(K, 512));
+  }
+  K = (K + UNROLL - 1) / UNROLL * UNROLL;
+  plan.chunk_steps = K;
+  int64_t pos = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    Segment& S = plan.segments[s];
+    S.first_chunk = (int)plan.chunks.size();
+    int64_t left = S.n_valid;
+    while (left > 0) {
+      const int64_t n_c = std::min<int64_t>(left, (int64_t)LANES * K);
+      int steps = (int)((n_c + LANES - 1) / LANES);
+      steps = (steps + UNROLL - 1) / UNROLL * UNROLL;
+      Chunk c{};
+      c.segment = s;
+      c.steps = steps;
+      c.first = pos;
+      plan.chunks.push_back(c);
+      pos += (int64_t)steps * LANES;
+      left -= n_c;
+    }
+    S.n_chunks = (int)plan.chunks.size() - S.first_chunk;
+    S.max_static = -std::numeric_limits<double>::infinity();
+    for (int k = 0; k < MAX_KOPS; ++k) {
+      S.fmin[k] = std::numeric_limits<double>::infinity();
+      S.fmax[k] = -std::numeric_limits<double>::infinity();
+    }
+  }
+  plan.n_padded = pos;
+  const int n_chunks = (int)plan.chunks.size();
+
+  // ---- pass 2: fill the stream columns ------------------------------------------------------
+  try {
+    plan.columns.assign((size_t)plan.n_columns * (size_t)std::max<int64_t>(1, plan.n_padded), 0ull);
+  } catch (const std::bad_alloc&) {
+    set_error("out of host memory building the plan");
+    return GWI_ERR_ALLOC;
+  }
+  const double NEG_INF = -std::numeric_limits<double>::infinity();
+  struct SegStat {
+    double max_static;
+    uint64_t occ[MAX_SPLINE_DIMS];
+    double fmin[MAX_KOPS], fmax[MAX_KOPS];
+  };
+  std::vector<SegStat> cstat(n_chunks);
+  {
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (;;) {
+        const int c = next.fetch_add(1);
+        if (c >= n_chunks) break;
+        const Chunk& C = plan.chunks[c];
+        const int s = C.segment;
+        const Segment& S = plan.segments[s];
+        const double* const* cols = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
+        const std::vector<uint32_t>& ord = order[s];
+        const int64_t r0 = (int64_t)(c - S.first_chunk) * LANES * K;  // first sorted rank of this chunk
+        const int64_t n_c = std::min<int64_t>(S.n_valid - r0, (int64_t)LANES * K);
+        SegStat st;
+        st.max_static = NEG_INF;
+        for (int d = 0; d < MAX_SPLINE_DIMS; ++d) st.occ[d] = 0;
+        for (int k = 0; k < MAX_KOPS; ++k) {
+          st.fmin[k] = std::numeric_limits<double>::infinity();
+          st.fmax[k] = -std::numeric_limits<double>::infinity();
+        }
+        for (int lane = 0; lane < LANES; ++lane) {
+          for (int k = 0; k < C.steps; ++k) {
+            const int64_t r = (int64_t)lane * C.steps + k;
+            const int64_t p = C.first + (int64_t)(k / UNROLL) * (LANES * UNROLL) + lane * UNROLL + (k % UNROLL);
+            if (r < n_c) {
+              const int64_t j = ord[r0 + r];
+              for (int d = 0; d < NS; ++d) {
+                int J;
+                double u;
+                spline_locate(geom[d], cols[geom[d].col][j], J, u);
+                plan.columns[(size_t)d * plan.n_padded + p] = pack_word(J, u);
+                st.occ[d] |= 1ull << J;
+              }
+              for (int f = 0; f < NK; ++f) {
+                const double v = eval_feat(kop_feats[f], cols, j);
+                std::memcpy(&plan.columns[(size_t)(NS + f) * plan.n_padded + p], &v, 8);
+              }
+              double sw = 0.0;
+              for (const Feat& f : static_feats) sw += eval_feat(f, cols, j);
+              std::memcpy(&plan.columns[(size_t)plan.col_static * plan.n_padded + p], &sw, 8);
+              st.max_static = std::max(st.max_static, sw);
+              for (size_t q = 0; q < plan.kops.size(); ++q)
+                if (plan.kops[q].kind == KOP_LIN) {
+                  double v;
+                  std::memcpy(&v, &plan.columns[(size_t)plan.kops[q].col[0] * plan.n_padded + p], 8);
+                  st.fmin[q] = std::min(st.fmin[q], v);
+                  st.fmax[q] = std::max(st.fmax[q], v);
+                }
+            } else {
+              // lane padding: a copy of the chunk's last valid sample (so every term evaluates to
+              // finite values and no piece index changes) with static log-weight -inf => weight 0
+              const int64_t j = ord[r0 + n_c - 1];
+              for (int d = 0; d < NS; ++d) {
+                int J;
+                double u;
+                spline_locate(geom[d], cols[geom[d].col][j], J, u);
+                plan.columns[(size_t)d * plan.n_padded + p] = pack_word(J, u);
+              }
+              for (int f = 0; f < NK; ++f) {
+                const double v = eval_feat(kop_feats[f], cols, j);
+                std::memcpy(&plan.columns[(size_t)(NS + f) * plan.n_padded + p], &v, 8);
+              }
+              std::memcpy(&plan.columns[(size_t)plan.col_static * plan.n_padded + p], &NEG_INF, 8);
+            }
+          }
+        }
+        cstat[c] = st;
+      }
+    };
+    std::vector<std::thread> th;
+    for (int w = 0; w < std::min(n_workers, std::max(1, n_chunks)); ++w) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    Segment& S = plan.segments[plan.chunks[c].segment];
+    S.max_static = std::max(S.max_static, cstat[c].max_static);
+    for (int d = 0; d < NS; ++d) S.occ[d] |= cstat[c].occ[d];
+    for (size_t q = 0; q < plan.kops.size(); ++q) {
+      S.fmin[q] = std::min(S.fmin[q], cstat[c].fmin[q]);
+      S.fmax[q] = std::max(S.fmax[q], cstat[c].fmax[q]);
+    }
+  }
+
+  // ---- level-0 record slots: warp w walks chunks w, w+W, ...; one record per (warp, segment run)
+  {
+    struct Run {
+      int segment, warp, seq;
+    };
+    std::vector<Run> runs;
+    std::vector<int> run_of_chunk(n_chunks, -1);
+    for (int w = 0; w < W; ++w) {
+      int prev_seg = -1;
+      for (int c = w; c < n_chunks; c += W) {
+        const int s = plan.chunks[c].segment;
+        if (s != prev_seg) {
+          runs.push_back(Run{s, w, (int)runs.size()});
+          prev_seg = s;
+        }
+        run_of_chunk[c] = (int)runs.size() - 1;
+      }
+    }
+    std::vector<int> idx(runs.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return runs[a].segment < runs[b].segment; });
+    std::vector<int> slot_of_run(runs.size());
+    for (size_t i = 0; i < idx.size(); ++i) slot_of_run[idx[i]] = (int)i;
+    plan.n_records0 = (int)runs.size();
+    for (int c = 0; c < n_chunks; ++c) {
+      plan.chunks[c].record_slot = slot_of_run[run_of_chunk[c]];
+      const int nxt = c + W;
+      plan.chunks[c].flush = (nxt >= n_chunks || run_of_chunk[nxt] != run_of_chunk[c]) ? 1 : 0;
+    }
+    // reduction tree, fan-in 32; the last level writes slot == segment
+    std::vector<int> cnt(n_seg, 0), first(n_seg, 0);
+    for (auto& r : runs) cnt[r.segment]++;
+    {
+      int acc = 0;
+      for (int s = 0; s < n_seg; ++s) {
+        first[s] = acc;
+        acc += cnt[s];
+      }
+    }
+    constexpr int FAN = 32;
+    for (;;) {
+      bool last = true;
+      for (int s = 0; s < n_seg; ++s)
+        if (cnt[s] > FAN) last = false;
+      std::vector<ReduceTask> tasks;
+      std::vector<int> ncnt(n_seg), nfirst(n_seg);
+      int acc = 0;
+      for (int s = 0; s < n_seg; ++s) {
+        const int nt = last ? 1 : std::max(1, (cnt[s] + FAN - 1) / FAN);
+        nfirst[s] = last ? s : acc;
+        ncnt[s] = nt;
+        for (int t = 0; t < nt; ++t) {
+          ReduceTask T{};
+          T.out_slot = nfirst[s] + t;
+          T.in_first = first[s] + t * FAN;
+          T.in_count = std::max(0, std::min(FAN, cnt[s] - t * FAN));
+          tasks.push_back(T);
+        }
+        acc += nt;
+      }
+      plan.levels.push_back(tasks);
+      cnt.swap(ncnt);
+      first.swap(nfirst);
+      if (last) break;
+    }
+  }
+  return GWI_OK;
+}
+
+}  // namespace gwi

@@ -1,0 +1,238 @@
+/*
+ * gwi.h -- C-ABI of libgwi.so: the B200-native hierarchical population likelihood
+ *          (forward + VJP) that replaces GWInferno's JAX hot path.
+ *
+ * The reference (FarrOutLab/GWInferno) has no FFI of its own; this boundary is cut where its
+ * static data ends and the hyper-parameters Lambda begin:
+ *
+ *   gwi_catalog_create   <- the (pedict, injdict, constants) triple produced by
+ *                           gwinferno/pipeline/utils.py:51-96 (load_pe_and_injections_as_dict)
+ *   gwi_model_create     <- model construction, gwinferno/models/bsplines/single.py:35-58
+ *                           (Base1DBSplineModel.__init__ : masks + design matrices),
+ *                           gwinferno/models/spline_perturbation.py:305-321,
+ *                           gwinferno/models/parametric/parametric.py:113-121
+ *   gwi_eval             <- per-step model __call__'s (single.py:111-128, separable.py __call__
+ *                           bodies, spline_perturbation.py:354-372) + per_event_log_bayes_factors
+ *                           and detection_efficiency (gwinferno/pipeline/analysis.py:50-136),
+ *                           plus their reverse-mode derivative (jax.value_and_grad of the above)
+ *   gwi_loglike[_host]   <- hierarchical_likelihood's scalar glue and cuts
+ *                           (gwinferno/pipeline/analysis.py:257-319) and its gradient
+ *   gwi_partial / gwi_combine  <- the same, split around the one multi-GPU exchange step
+ *
+ * Conventions: every entry point returns 0 on success or a negative gwi_status; the message of
+ * the last failure on the calling thread is available from gwi_last_error().  Nothing throws,
+ * exits or synchronises the device unless documented.  All floating point is IEEE fp64.
+ * A gwi_model is NOT re-entrant (one evaluation in flight per handle); distinct handles are
+ * independent.  There is no CPU fallback: without a CUDA device every compute call fails with
+ * GWI_ERR_CUDA.
+ */
+#ifndef GWI_H
+#define GWI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWI_VERSION 1
+
+typedef enum {
+  GWI_OK = 0,
+  GWI_ERR_INVALID = -1,     /* bad argument / unsupported model description */
+  GWI_ERR_CUDA = -2,        /* CUDA runtime failure (no device, launch error, ...) */
+  GWI_ERR_ALLOC = -3,       /* host or device allocation failed */
+  GWI_ERR_UNSUPPORTED = -4, /* valid request that this build cannot serve */
+  GWI_ERR_RANGE = -5        /* every weight of a segment under/overflowed the fp64 range */
+} gwi_status;
+
+/* ---- model description (numeric values mirrored in gwinferno_b200/spec.py) --------------- */
+typedef enum {
+  GWI_TERM_SPLINE = 1,         /* sum_k B_k(xi) c_k, uniform cubic knots (interpolation.py:98-106,268-317) */
+  GWI_TERM_LINEAR = 2,         /* (Lambda[slot0] + cst0) * F(col)   e.g. (lamb-1) log(1+z), beta log q   */
+  GWI_TERM_STATIC = 3,         /* F(col), no parameter             e.g. log dVc/dz, -log prior            */
+  GWI_TERM_POWERLAW = 4,       /* log powerlaw_pdf(col0; alpha=L[slot0], lo=cst0, hi=cst1)  distributions.py:100-119 */
+  GWI_TERM_POWERLAW_RATIO = 5, /* log powerlaw_pdf(q=col0; beta=L[slot0], lo=cst0/col1, hi=1) parametric.py:28,40    */
+  GWI_TERM_PLPEAK = 6,         /* log[(1-lam) PL + lam TN](col0); slots alpha,mu,sigma,lam; cst mmin,mmax  parametric.py:49-53 */
+  GWI_TERM_BETA = 7,           /* log betadist(col0; alpha, beta, scale=cst0)               distributions.py:146-162 */
+  GWI_TERM_ISOALIGN = 8,       /* log[(1-xi)/2 + xi TN(col0; 1, sigma, -1, 1)]              parametric.py:84-86      */
+  GWI_TERM_TRUNCNORM = 9       /* log truncnorm_pdf(col0; mu, sigma, lo=cst0, hi=cst1)      distributions.py:122-143 */
+} gwi_term_kind;
+
+typedef enum {
+  GWI_FEAT_LOG1P = 1,     /* log(1 + col0)      */
+  GWI_FEAT_LOG = 2,       /* log(col0)          */
+  GWI_FEAT_LOG_RATIO = 3, /* log(col0 / col1)   */
+  GWI_FEAT_LOG_DVDZ = 4,  /* log dVc/dz(col0), flat LCDM Planck15-LVK table (cosmology.py:48-120) */
+  GWI_FEAT_NEG_LOG = 5    /* -log(col0)         */
+} gwi_feature;
+
+typedef enum {
+  GWI_OUTSIDE_DROP = 0, /* sample has zero density outside [x_lo, x_hi]   (single.py:54-55; interpolation.py:407,449) */
+  GWI_OUTSIDE_ZERO = 1  /* spline term contributes 0 outside the range    (interpolation.py:175)                      */
+} gwi_outside;
+
+typedef enum {
+  GWI_CUT_RANGE = 1,      /* keep lo <= col0 <= hi        (e.g. z <= zmax, spline_perturbation.py:368-372) */
+  GWI_CUT_RATIO_RANGE = 2 /* keep lo <= col0/col1 <= hi   (separable.py:608-613)                           */
+} gwi_cut_kind;
+
+typedef struct {
+  int32_t kind;       /* gwi_term_kind */
+  int32_t feature;    /* gwi_feature (LINEAR, STATIC) */
+  int32_t outside;    /* gwi_outside (SPLINE) */
+  int32_t logx;       /* SPLINE: spline coordinate xi = log(col0) instead of col0 */
+  int32_t col[2];     /* catalog column indices, -1 if unused */
+  int32_t slot[4];    /* offsets into Lambda, -1 if unused; SPLINE: slot[0] = first coefficient */
+  double cst[4];      /* constants, see gwi_term_kind */
+  int32_t n_splines;  /* SPLINE: number of basis functions (>= 4, <= 256) */
+  int32_t norm_group; /* index into groups[], -1 = term has no grid normaliser */
+  double x_lo, x_hi;   /* SPLINE: support in col0 units (the model mask) */
+  double xi_lo, xi_hi; /* SPLINE: support in spline-coordinate units (= log of the above if logx) */
+  const double* grid;  /* member of a norm group: per grid point, SPLINE: xi (NaN = outside the
+                          basis range => contributes 0), LINEAR: feature value.  Host pointer,
+                          n_grid doubles, copied during gwi_model_create. */
+} gwi_term;
+
+typedef struct {
+  int32_t n_grid;
+  const double* log_w; /* host pointer: log(trapezoid weight x static integrand) per grid point, -inf allowed */
+} gwi_norm_group;
+
+typedef struct {
+  int32_t kind; /* gwi_cut_kind */
+  int32_t col[2];
+  double lo, hi;
+} gwi_cut;
+
+typedef struct {
+  int32_t n_terms;
+  const gwi_term* terms;
+  int32_t n_groups;
+  const gwi_norm_group* groups;
+  int32_t n_cuts;
+  const gwi_cut* cuts;
+  int32_t n_params;       /* length of Lambda */
+  int32_t need_neff_grad; /* also accumulate d logN_eff/dLambda (marginalize_selection, analysis.py:270-271) */
+  int32_t chunk_steps;    /* tuning: samples per lane per work chunk; 0 = default */
+  int32_t n_deep;         /* tuning: spline dims accumulated in lane-private shared memory; -1 = auto */
+} gwi_model_desc;
+
+/* ---- catalog ------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_columns;
+  int32_t n_events;
+  const int64_t* pe_offsets;       /* n_events+1 : event i owns samples [off[i], off[i+1]) of each PE column */
+  const double* const* pe_columns; /* n_columns host pointers */
+  int64_t n_inj;                   /* found injections held by THIS process (its shard) */
+  const double* const* inj_columns;
+  double total_inj;                /* total generated injections of the WHOLE injection set (analysis.py:91) */
+  int32_t device;                  /* CUDA device ordinal */
+} gwi_catalog_desc;
+
+typedef struct gwi_catalog gwi_catalog;
+typedef struct gwi_model gwi_model;
+
+/* The catalog BORROWS the host column pointers: they must stay valid until the last
+ * gwi_model_create() on it has returned.  Nothing is uploaded here. */
+int gwi_catalog_create(const gwi_catalog_desc* desc, gwi_catalog** out);
+void gwi_catalog_destroy(gwi_catalog* cat);
+
+/* Builds the static evaluation plan (masks, spline interval/offset words, static log-weights,
+ * interval-sorted work chunks) on the host and uploads it to the catalog's device. */
+int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** out);
+void gwi_model_destroy(gwi_model* m);
+
+/* ---- evaluation --------------------------------------------------------------------------- */
+typedef struct {
+  /* DEVICE pointers, any may be NULL.  E = n_events, P = n_params, G = n_groups. */
+  double* logBF;         /* [E]   log( sum_j w_ij / S_i )                      analysis.py:50-88  */
+  double* logNeff;       /* [E]   log( (sum w)^2 / sum w^2 )                                       */
+  double* log_mu;        /* [1]   log( sum w / total_inj )                     analysis.py:91-136 */
+  double* logNeff_inj;   /* [1]   log( mu^2 / (sum w^2/N^2 - mu^2/N) )                             */
+  double* J_logBF;       /* [E*P] d logBF_i / d Lambda                                             */
+  double* J_logNeff;     /* [E*P] (needs need_neff_grad)                                           */
+  double* J_log_mu;      /* [P]                                                                    */
+  double* J_logNeff_inj; /* [P]   (needs need_neff_grad)                                           */
+  double* logZ;          /* [G]   log normaliser of every norm group                               */
+} gwi_outputs;
+
+/* Asynchronous on `stream` (a cudaStream_t, NULL = default stream).  lambda_dev: P doubles in
+ * device memory.  Only valid when this process holds the whole catalog (single GPU). */
+int gwi_eval(gwi_model* m, const double* lambda_dev, const gwi_outputs* out, void* stream);
+
+typedef struct {
+  int32_t Nobs;                  /* number of events in the WHOLE catalog (all ranks) */
+  int32_t marginalize_selection; /* analysis.py:270-271 */
+  int32_t min_neff_cut;          /* analysis.py:272-277, 294-303 */
+  int32_t max_variance_cut;      /* analysis.py:309-317 */
+} gwi_like_opts;
+
+/* Result vector of the likelihood calls: GWI_LIKE_HEADER scalars followed by the gradient [P]. */
+enum {
+  GWI_LIKE_LOG_L = 0,       /* log-likelihood (the reference's nan_to_num(-inf) sentinel when a cut fails) */
+  GWI_LIKE_PASSED = 1,      /* 1.0 if every enabled cut passed, else 0.0 (gradient is then 0) */
+  GWI_LIKE_LOG_MU = 2,      /* log detection efficiency */
+  GWI_LIKE_LOGNEFF_INJ = 3, /* log N_eff of the injection sum */
+  GWI_LIKE_MIN_LOGNEFF = 4, /* min_i log N_eff,i */
+  GWI_LIKE_SUM_LOGBF = 5,   /* sum_i logBF_i */
+  GWI_LIKE_VARIANCE = 6,    /* Nobs^2 var(log mu) + sum_i var_i  (analysis.py:305-308) */
+  GWI_LIKE_STATUS = 7,      /* 0 ok; 1 = a segment's weights all under/overflowed (GWI_ERR_RANGE) */
+  GWI_LIKE_HEADER = 8
+};
+
+/* Fused evaluation + likelihood glue + gradient; out_dev: GWI_LIKE_HEADER + P doubles (device).
+ * Asynchronous on `stream`. */
+int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opts, double* out_dev, void* stream);
+
+/* Same with HOST buffers: copies Lambda host->device, evaluates, copies the result back and
+ * synchronises (this is the end-to-end call timed as `e2e` by bench.py). */
+int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opts* opts, double* out_host);
+
+/* ---- multi-GPU: injections sharded by index range, whole events sharded across ranks ------
+ * Each rank evaluates its shard into a packed partial record (gwi_partial_size doubles, device
+ * memory, asynchronous); the caller all-gathers the records of all ranks (NCCL over NVLink) into
+ * one contiguous device buffer; gwi_combine then merges them in rank order -- identically on
+ * every rank -- into the same result vector as gwi_loglike. */
+int64_t gwi_partial_size(const gwi_model* m);
+int gwi_partial(gwi_model* m, const double* lambda_dev, double* record_dev, void* stream);
+int gwi_combine(gwi_model* m, const double* records_dev, int32_t n_ranks, const gwi_like_opts* opts, double* out_dev, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+typedef struct {
+  int64_t n_samples_pe;     /* PE samples given (sum of event sizes) */
+  int64_t n_samples_inj;    /* injections given */
+  int64_t n_valid_pe;       /* samples with non-zero density support (kept in the plan) */
+  int64_t n_valid_inj;
+  int64_t n_padded;         /* samples streamed per evaluation (valid + lane padding) */
+  int64_t bytes_per_eval;   /* actual bytes of plan columns the stream kernel reads per evaluation */
+  int32_t n_chunks;         /* work chunks */
+  int32_t n_stream_columns; /* 8-byte columns streamed per sample */
+  int32_t n_spline_dims, n_deep, n_linear, n_param_terms;
+  int32_t grid_blocks, block_threads;
+  int32_t kernel_launches_per_eval; /* kernels launched by one gwi_loglike call */
+  int32_t reserved;
+} gwi_model_info;
+int gwi_model_get_info(const gwi_model* m, gwi_model_info* info);
+
+const char* gwi_last_error(void);
+int gwi_version(void);
+
+/* ---- test hooks (host-only, no CUDA needed): build the plan and read it back -------------- */
+typedef struct gwi_plan gwi_plan;
+int gwi_debug_plan_build(const gwi_catalog* cat, const gwi_model_desc* desc, int32_t n_workers, gwi_plan** out);
+void gwi_debug_plan_destroy(gwi_plan* p);
+/* what: 0 = dims {n_columns, n_padded, n_chunks, n_segments, n_spline, n_linear, rows_total, n_deep,
+ *                 n_param_cols, rec_doubles}  (int64[10])
+ *       1 = stream columns [n_columns * n_padded] (uint64 bit patterns, column-major)
+ *       2 = chunk table   [n_chunks * 4] int64 {segment, first_sample, steps, record_slot}
+ *       3 = segment table [n_segments * 4] int64 {n_total, n_valid, first_chunk, n_chunks}
+ *       4 = spline dim table [n_spline * 4] int64 {term index, rows (= n_splines-2), row offset, deep?}
+ *       5 = non-spline op table [n_ops * 8] int64 {kind, column0, column1, slot0..slot3, bits of cst0}
+ * Returns the number of 8-byte items written (or needed when dst == NULL). */
+int64_t gwi_debug_plan_read(const gwi_plan* p, int32_t what, void* dst, int64_t cap_items);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWI_H */

@@ -1,0 +1,161 @@
+"""CPU (no GPU): the host plan builder of libgwi.so.
+
+The plan is read back through the gwi_debug_plan_* hooks and DECODED here in NumPy (test code
+only): per sample, unpack the (piece, offset) words, rebuild the 4 tap weights, add the linear
+terms and the static log-weight, and reduce per segment.  The result must equal the oracle on
+the golden cases -- this pins masks/cuts, packing, sorting, lane layout, padding and the Monte
+Carlo denominators without touching a GPU.  It is a checker of the static data, not a compute
+path: the product has no CPU evaluation."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from gwinferno_b200 import capi
+from oracle import popmodel
+from tests import cases
+
+MANT = np.uint64(0x000FFFFFFFFFFFFF)
+ONE = np.uint64(0x3FF0000000000000)
+SPLINE_CASES = ["bspline_full", "bspline_iid", "bspline_indep_masses", "inference_test_bspline"]
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    for name in capi.SYMBOLS:
+        assert hasattr(lib, name), name
+    assert lib.gwi_version() == 1
+    # header and binding agree on the symbol list
+    import os, re
+
+    hdr = open(os.path.join(os.path.dirname(capi._HERE), "include", "gwi.h")).read()
+    declared = set(re.findall(r"^(?:int|void|int64_t|const char\*)\s+(gwi_[a-z_]+)\s*\(", hdr, flags=re.M))
+    assert declared == set(capi.SYMBOLS)
+
+
+def test_struct_layouts_match_header_sizes():
+    # sizes implied by include/gwi.h on LP64
+    assert C.sizeof(capi.gwi_term) == 4 * 4 + 2 * 4 + 4 * 4 + 4 * 8 + 2 * 4 + 4 * 8 + 8
+    assert C.sizeof(capi.gwi_cut) == 4 + 8 + 4 + 16 or C.sizeof(capi.gwi_cut) == 32
+    assert C.sizeof(capi.gwi_like_opts) == 16
+    assert C.sizeof(capi.gwi_model_info) == 6 * 8 + 10 * 4
+
+
+def _decode(case, plan):
+    dims = plan.read(0)
+    n_cols, n_pad, n_chunks, n_seg, ns, n_kops = (int(x) for x in dims[:6])
+    cols = plan.read(1, dtype=np.uint64).reshape(n_cols, n_pad)
+    chunks = plan.read(2).reshape(n_chunks, 4)
+    segs = plan.read(3).reshape(n_seg, 4)
+    dimt = plan.read(4).reshape(ns, 4)
+    kops = plan.read(5).reshape(n_kops, 8)
+    spec, Lam = case.low.spec, case.Lam
+    x = np.zeros(n_pad)
+    x += cols[n_cols - 1].view(np.float64)  # static log-weight (-inf on lane padding)
+    for d in range(ns):
+        term = spec.terms[int(dimt[d, 0])]
+        rows = int(dimt[d, 1])
+        J = (cols[d] >> np.uint64(52)).astype(np.int64)
+        u = ((cols[d] & MANT) | ONE).view(np.float64) - 1.0
+        assert J.max() <= rows - 1
+        real = J < rows - 1
+        Jc = np.where(real, J, 0)
+        w = np.stack([(1 - u) ** 3, 3 * u**3 - 6 * u**2 + 4, -3 * u**3 + 3 * u**2 + 3 * u + 1, u**3], -1) / 6.0
+        c = Lam[term.slots[0] : term.slots[0] + term.n_splines]
+        f = np.einsum("nk,nk->n", w, c[Jc[:, None] + np.arange(4)])
+        x += np.where(real, f, 0.0)
+    for k in range(n_kops):
+        kind, c0, _, s0 = (int(v) for v in kops[k, :4])
+        assert kind == 1, "only linear ops in the spline-family cases"
+        off = np.array([kops[k, 7]], dtype=np.int64).view(np.float64)[0]
+        x += (Lam[s0] + off) * cols[c0].view(np.float64)
+    seg_of = np.full(n_pad, -1)
+    for seg, first, steps, _ in chunks:
+        seg_of[first : first + steps * 32] = seg
+    assert (seg_of >= 0).all()
+    return x, seg_of, segs, chunks, cols, dimt
+
+
+@pytest.mark.parametrize("name", SPLINE_CASES)
+def test_plan_reproduces_oracle(name):
+    case = cases.load_case(name)
+    cat = capi.Catalog(case.low.pe_cols, case.low.inj_cols, case.total_inj)
+    plan = capi.HostPlan(cat, case.low.spec, chunk_steps=8)
+    x, seg_of, segs, chunks, cols, dimt = _decode(case, plan)
+    ev = popmodel.evaluate(case.low.spec, case.low.pe_cols, case.low.inj_cols, case.total_inj, case.Lam, want_jac=False)
+    sumZ = np.sum(ev["logZ"])
+    E = case.Nobs
+    assert segs.shape[0] == E + 1
+    for s in range(E + 1):
+        xs = x[seg_of == s]
+        n_total, n_valid = int(segs[s, 0]), int(segs[s, 1])
+        assert np.isfinite(xs).sum() == n_valid
+        m = xs.max()
+        S1 = np.exp(xs - m).sum()
+        S2 = np.exp(2 * (xs - m)).sum()
+        if s == 0:
+            logmean = m + np.log(S1) - np.log(case.total_inj) - sumZ
+            logneff = 2 * np.log(S1) - np.log(S2 - S1**2 / case.total_inj)
+            assert abs(logmean - ev["log_mu"]) < 1e-11
+            assert abs(logneff - ev["logNeff_inj"]) < 1e-11
+            assert n_total == case.low.inj_cols["c0"].size
+        else:
+            logmean = m + np.log(S1) - np.log(n_total) - sumZ
+            logneff = 2 * np.log(S1) - np.log(S2)
+            assert abs(logmean - ev["logBF"][s - 1]) < 1e-11
+            assert abs(logneff - ev["logNeff"][s - 1]) < 1e-11
+    # lane runs are sorted by the composite piece key (most pieces = most significant)
+    ns = dimt.shape[0]
+    key = np.zeros(cols.shape[1], dtype=np.int64)
+    for d in range(ns):
+        key = key * 64 + (cols[d] >> np.uint64(52)).astype(np.int64)
+    valid = np.isfinite(cols[-1].view(np.float64))
+    for seg, first, steps, _ in chunks[:50]:
+        blk = np.arange(first, first + steps * 32).reshape(steps // 2, 32, 2)  # [iter][lane][unroll]
+        lane_major = blk.transpose(1, 0, 2).reshape(32, steps)  # each lane's run in order
+        kk = key[lane_major].reshape(-1)
+        vv = valid[lane_major].reshape(-1)
+        assert np.all(np.diff(kk[vv]) >= 0)
+        assert not vv[np.argmin(vv) :].any() if not vv.all() else True  # padding only at the tail
+
+
+@pytest.mark.parametrize("name", ["plpeak", "inference_test_parametric"])
+def test_plan_parametric_counts(name):
+    case = cases.load_case(name)
+    cat = capi.Catalog(case.low.pe_cols, case.low.inj_cols, case.total_inj)
+    plan = capi.HostPlan(cat, case.low.spec)
+    segs = plan.read(3).reshape(-1, 4)
+    _, valid_pe, _ = popmodel.log_weights(case.low.spec, case.low.pe_cols, case.Lam)
+    _, valid_inj, _ = popmodel.log_weights(case.low.spec, case.low.inj_cols, case.Lam)
+    assert segs[0, 1] == valid_inj.sum()
+    assert np.array_equal(segs[1:, 1], valid_pe.sum(axis=1))
+
+
+def test_bad_descriptions_are_rejected():
+    case = cases.load_case("inference_test_bspline")
+    cat = capi.Catalog(case.low.pe_cols, case.low.inj_cols, case.total_inj)
+    import copy
+
+    spec = copy.deepcopy(case.low.spec)
+    spec.terms[0].n_splines = 3
+    with pytest.raises(capi.GwiError):
+        capi.HostPlan(cat, spec)
+    spec = copy.deepcopy(case.low.spec)
+    spec.n_params = 2  # coefficient slots out of range
+    with pytest.raises(capi.GwiError):
+        capi.HostPlan(cat, spec)
+    with pytest.raises(capi.GwiError):
+        capi.Catalog(case.low.pe_cols, case.low.inj_cols, total_inj=1.0)  # fewer than found
+
+
+def test_model_create_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    case = cases.load_case("inference_test_bspline")
+    cat = capi.Catalog(case.low.pe_cols, case.low.inj_cols, case.total_inj)
+    with pytest.raises(capi.GwiError) as e:
+        capi.Model(cat, case.low.spec)
+    assert "no CPU fallback" in str(e.value)
