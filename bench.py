@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- likelihood+gradient evaluations/s of the fused population likelihood.
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg3] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one fused evaluation of log L and d log L / d Lambda over the whole synthetic catalog
+(all events x samples + all found injections).  Default workload: BASELINE.json configs[2]
+("B-spline full model, 300 events x 10k samples, 1e8 injections") -- the configuration the
+north-star's ">= 70 % of HBM roofline on 1 B200 / >= 85 % scaling at 8 GPUs" is quoted on; its
+plan (7.4 GB) is far larger than L2, so consecutive timed steps cannot be served from cache.
+Multi-GPU: injections sharded by index range, whole events dealt round-robin, one NCCL
+all-gather of ~4 KB partial records per step; total work is fixed => "scaling": "strong".
+
+PyTorch is used only as plumbing (NCCL all-gather, CUDA events, device scratch tensors); every
+kernel in the timed region is from libgwi.so.  ``--impl reference`` times the CPU arm: the oracle
+port of the reference algorithm (NumPy) on all host cores, on a bounded sample (the reference
+itself needs JAX, which this image does not have).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "likelihood+grad evals/sec"
+UNIT = "evals/s"
+ALG_BYTES_PER_SAMPLE = 64  # 8 fp64 columns read once per evaluation
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(name, n_events=8, n_inj=400_000):
+    """Oracle port on ONE host core, bounded sample of the same workload; extrapolated linearly in
+    the number of samples to the full workload."""
+    from gwinferno_b200 import workloads
+    from oracle import popmodel
+
+    _, family, E, S, I = workloads.WORKLOADS[name]
+    scale = min(1.0, n_inj / I)
+    pe, inj, const, z_range = workloads.shard_catalog(name, 0, 1, scale=scale)
+    S_full = S
+    # keep full-length events but only a few of them
+    from gwinferno_b200 import synthetic
+
+    pe_full = synthetic.make_events(E, S_full, 1000 * int(name[3:]) + 0)
+    pe = {k: np.ascontiguousarray(v[:n_events]) for k, v in pe_full.items()}
+    weights, params_fn = workloads.build_model(family, pe, inj, z_range=z_range)
+    low, lam, _ = workloads.lower_workload(weights, params_fn, pe, inj)
+    n_sample = pe["redshift"].size + inj["redshift"].size
+    popmodel.partial_record(low.spec, low.pe_cols, low.inj_cols, lam)  # warm-up (cosmology table, caches)
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        rec = popmodel.partial_record(low.spec, low.pe_cols, low.inj_cols, lam)
+        popmodel.combine_records(low.spec, [rec], const["total_inj"], lam, n_events)
+        reps += 1
+        if time.perf_counter() - t0 > 8.0 or reps >= 5:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    n_full = E * S_full + I
+    return {
+        "value": (1.0 / dt) * n_sample / n_full,
+        "unit": UNIT,
+        "cores": 1,
+        "kind": "port",
+        "sample": f"{n_events} events x {S_full} samples + {inj['redshift'].size} injections ({n_sample} of {n_full} samples), {dt:.3f} s per eval, "
+        "extrapolated linearly in samples; NumPy oracle port of the reference algorithm (JAX unavailable)",
+        "samples_per_s": n_sample / dt,
+    }
+
+
+def _ref_worker(args):
+    name, family, widx, nworkers, n_events, n_inj_each, seed_steps = args
+    from gwinferno_b200 import synthetic, workloads
+    from oracle import popmodel
+
+    _, _, E, S, I = workloads.WORKLOADS[name]
+    cfg = int(name[3:])
+    pe_full = synthetic.make_events(E, S, 1000 * cfg + 0)
+    ev_idx = [e for e in range(n_events * nworkers) if e % nworkers == widx and e < E]
+    pe = {k: np.ascontiguousarray(v[ev_idx]) for k, v in pe_full.items()}
+    zpe = (float(pe_full["redshift"].min()), float(pe_full["redshift"].max()))
+    inj = synthetic.make_injections(I, 1000 * cfg + 1, widx * n_inj_each, (widx + 1) * n_inj_each)
+    z_range = (max(zpe[0], synthetic.ZLO), min(zpe[1], synthetic.ZHI))
+    weights, params_fn = workloads.build_model(family, pe, inj, z_range=z_range)
+    low, lam, _ = workloads.lower_workload(weights, params_fn, pe, inj)
+    times = []
+    for s in seed_steps:
+        p = params_fn(s)
+        from gwinferno_b200 import lowering
+
+        lam = lowering.flatten_params(weights(pe, True, p), low.spec.n_params)
+        t0 = time.perf_counter()
+        rec = popmodel.partial_record(low.spec, low.pe_cols, low.inj_cols, lam)
+        times.append(time.perf_counter() - t0)
+    return times, pe["redshift"].size + inj["redshift"].size
+
+
+def run_reference(args):
+    """CPU arm: the oracle port on all host cores (one worker process per core, each evaluating its
+    shard of a bounded sample; the records combine exactly like the multi-GPU path)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    from gwinferno_b200 import workloads
+
+    name = args.workload
+    _, family, E, S, I = workloads.WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    n_inj_each = max(1000, min(I // cores, 250_000))
+    n_events = max(1, min(E // cores, 4))
+    steps = list(range(args.warmup + args.steps))
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(name, family, w, cores, n_events, n_inj_each, steps) for w in range(cores)])
+    n_sample = sum(r[1] for r in res)
+    # per step: all workers run concurrently; the step takes as long as the slowest worker
+    per_step = np.max(np.array([r[0] for r in res]), axis=0)[args.warmup :]
+    t = float(np.sum(per_step))
+    n_full = E * S + I
+    value = (args.steps / t) * n_sample / n_full
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps * n_full / n_sample, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "E": E, "S": S, "I": I},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} of {n_full} samples ({cores} worker processes x ({n_events} events x {S} + {n_inj_each} injections)), "
+                                   f"{1e3 * t / args.steps:.1f} ms per sampled step, extrapolated linearly in samples; NumPy oracle port (JAX unavailable)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "setup_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    from gwinferno_b200 import capi, lowering, workloads
+    from gwinferno_b200.likelihood import PopulationLikelihood
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def allreduce_minmax(lo, hi):
+        t = torch.tensor([lo, -hi], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t[0]), float(-t[1])
+
+    name = args.workload
+    t_setup = time.perf_counter()
+    pe, inj, const, z_range = workloads.shard_catalog(name, rank, world, scale=args.scale, all_reduce_minmax=allreduce_minmax)
+    weights, params_fn = workloads.build_model(const["family"], pe, inj, z_range=z_range)
+    low, lam0, _ = workloads.lower_workload(weights, params_fn, pe, inj)
+    P = low.spec.n_params
+    t_gen = time.perf_counter() - t_setup
+    eng = PopulationLikelihood(low, const["total_inj"], device=local, need_neff_grad=False)
+    t_plan = time.perf_counter() - t_setup - t_gen
+    info = eng.info()
+    mdl = eng.model
+    Nobs = const["E"]
+    n_steps = args.warmup + args.steps
+    lams = np.stack([lowering.flatten_params(weights(pe, True, params_fn(s)), P) for s in range(n_steps)])
+    lam_dev = torch.from_numpy(lams).cuda()
+    lam_pin = torch.from_numpy(lams).pin_memory()
+    nrec = mdl.partial_size()
+    rec = torch.zeros(nrec, dtype=torch.float64, device="cuda")
+    allrec = torch.zeros(world * nrec, dtype=torch.float64, device="cuda")
+    out = torch.zeros(capi.GWI_LIKE_HEADER + P, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i, lam_ptr=None):
+        ptr = lam_dev[i].data_ptr() if lam_ptr is None else lam_ptr
+        if world == 1:
+            mdl.loglike(ptr, out.data_ptr(), Nobs, stream=stream)
+        else:
+            mdl.partial(ptr, rec.data_ptr(), stream=stream)
+            dist.all_gather_into_tensor(allrec, rec)
+            mdl.combine(allrec.data_ptr(), world, out.data_ptr(), Nobs, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    mdl.set_timing(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.warmup, n_steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    kt = mdl.stream_times_ms(min(64, args.steps))
+    mdl.set_timing(False)
+    res = out.cpu().numpy()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    # ---- end-to-end: host Lambda in, host (log L, gradient) out, every step ------------------
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.warmup, n_steps):
+        if world == 1:
+            head, grad = mdl.loglike_host(lams[i], Nobs)
+        else:
+            d = lam_pin[i].to("cuda", non_blocking=True)
+            step(i, d.data_ptr())
+            host = out.cpu()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_local = info["n_samples_pe"] + info["n_samples_inj"]
+    n_total = const["E"] * const["S"] + const["I"]
+    peak, peak_src = _peaks()
+    k_ms = float(np.mean(kt)) if len(kt) else float("nan")
+    achieved = n_local * ALG_BYTES_PER_SAMPLE / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"{name}_n{world}")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "model": const["family"], "E": const["E"], "S": const["S"], "I": const["I"],
+            "n_params": P, "samples_per_eval": n_total, "parallelism": f"shard{world}" if world > 1 else "single",
+            "l2_policy": "inputs larger than L2 (plan %.2f GB per GPU)" % (info["bytes_per_eval"] / 1e9) if info["bytes_per_eval"] > 2.6e8 else "inputs fit in L2; new Lambda every step, no flush",
+            "neff_grad": False, "likelihood": "marginalize_selection=False, min_neff_cut=True (reference defaults)",
+        },
+        "samples_per_s": n_total * args.steps / (ms * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "kernel": "stream_kernel", "kernel_ms": k_ms, "alg_bytes_per_launch": n_local * ALG_BYTES_PER_SAMPLE,
+                     "actual_bytes_per_launch": info["bytes_per_eval"], "kernel_share_of_step": k_ms / (ms / args.steps)},
+        "e2e": {"value": args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * (capi.GWI_LIKE_HEADER + P)},
+        "gpu_launches": info["kernel_launches_per_eval"] * args.steps,
+        "clocks": clocks,
+        "result": {"log_l": float(res[0]), "passed": float(res[1]), "status": float(res[7])},
+        "setup_s": {"generate": t_gen, "plan_build_and_upload": t_plan},
+        "plan": {k: info[k] for k in ("n_valid_pe", "n_valid_inj", "n_padded", "n_chunks", "n_stream_columns", "n_spline_dims", "n_deep", "grid_blocks", "block_threads")},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(name)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink S and I (testing only; the reported config then differs from BASELINE's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

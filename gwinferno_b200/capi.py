@@ -120,6 +120,8 @@ SYMBOLS = [
     "gwi_partial",
     "gwi_combine",
     "gwi_model_get_info",
+    "gwi_model_set_timing",
+    "gwi_model_stream_times",
     "gwi_last_error",
     "gwi_version",
     "gwi_debug_plan_build",
@@ -156,6 +158,8 @@ def load_library():
     lib.gwi_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gwi_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
     lib.gwi_model_get_info.argtypes = [C.c_void_p, C.POINTER(gwi_model_info)]
+    lib.gwi_model_set_timing.argtypes = [C.c_void_p, C.c_int32]
+    lib.gwi_model_stream_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     lib.gwi_debug_plan_build.argtypes = [C.c_void_p, C.POINTER(gwi_model_desc), C.c_int32, C.POINTER(C.c_void_p)]
     lib.gwi_debug_plan_destroy.argtypes = [C.c_void_p]
     lib.gwi_debug_plan_destroy.restype = None
@@ -403,6 +407,16 @@ class Model:
         i = gwi_model_info()
         _check(load_library().gwi_model_get_info(self.handle, C.byref(i)))
         return {n: getattr(i, n) for n, _ in gwi_model_info._fields_ if n != "reserved"}
+
+    def set_timing(self, on=True):
+        _check(load_library().gwi_model_set_timing(self.handle, int(on)))
+
+    def stream_times_ms(self, cap=64):
+        buf = (C.c_float * cap)()
+        n = load_library().gwi_model_stream_times(self.handle, buf, cap)
+        if n < 0:
+            _check(n)
+        return np.array(buf[:n], dtype=np.float64)
 
     def partial_size(self):
         return int(load_library().gwi_partial_size(self.handle))

@@ -58,6 +58,10 @@ struct gwi_model {
   double* out_pinned = nullptr;
   cudaStream_t own_stream = nullptr;
   int64_t bytes_per_eval = 0;
+  // optional timing of the stream kernel (ring of event pairs)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev0, ev1;
+  int64_t n_timed = 0;
 };
 
 #define CUDA_TRY(expr)                                                                                 \
@@ -241,6 +245,8 @@ void gwi_model_destroy(gwi_model* m) {
   if (m->lam_pinned) cudaFreeHost(m->lam_pinned);
   if (m->out_pinned) cudaFreeHost(m->out_pinned);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  for (auto e : m->ev0) cudaEventDestroy(e);
+  for (auto e : m->ev1) cudaEventDestroy(e);
   delete m;
 }
 
@@ -462,7 +468,9 @@ static int run_eval(gwi_model* m, const double* lam_dev, cudaStream_t st) {
       m->k_max<<<grid, block, m->smem_max, st>>>(m->dev);
       launch_segmax(m->dev, H.n_segments, st);
     }
+    if (m->timing) cudaEventRecord(m->ev0[m->n_timed % 64], st);
     m->k_full<<<grid, block, m->smem_full, st>>>(m->dev);
+    if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
   }
   const double* in = H.records0;
   for (size_t l = 0; l < m->level_tasks.size(); ++l) {
@@ -556,6 +564,34 @@ int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opt
     return GWI_ERR_RANGE;
   }
   return GWI_OK;
+}
+
+int gwi_model_set_timing(gwi_model* m, int32_t on) {
+  if (!m) return GWI_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(m->device));
+  if (on && m->ev0.empty()) {
+    m->ev0.resize(64);
+    m->ev1.resize(64);
+    for (int i = 0; i < 64; ++i) {
+      CUDA_TRY(cudaEventCreate(&m->ev0[i]));
+      CUDA_TRY(cudaEventCreate(&m->ev1[i]));
+    }
+  }
+  m->timing = on != 0;
+  m->n_timed = 0;
+  return GWI_OK;
+}
+
+int gwi_model_stream_times(gwi_model* m, float* ms_out, int32_t cap) {
+  if (!m || !ms_out || cap <= 0) return GWI_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(m->device));
+  const int64_t n = std::min<int64_t>(std::min<int64_t>(m->n_timed, 64), cap);
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t k = (m->n_timed - n + i) % 64;
+    CUDA_TRY(cudaEventSynchronize(m->ev1[k]));
+    CUDA_TRY(cudaEventElapsedTime(&ms_out[i], m->ev0[k], m->ev1[k]));
+  }
+  return (int)n;
 }
 
 int gwi_model_get_info(const gwi_model* m, gwi_model_info* info) {

@@ -445,12 +445,17 @@ class PLPeakPrimaryBSplineRatio:
 # redshift models (parametric.py:112-145, spline_perturbation.py:304-372)
 # ================================================================================================
 class PowerlawRedshiftModel:
-    def __init__(self, z_pe, z_inj):
+    def __init__(self, z_pe, z_inj, z_range=None):
+        """``z_range=(zmin, zmax)`` (extension) overrides the data-derived range: a process that holds
+        only a SHARD of the catalog must be given the range of the whole catalog."""
         self.column = _Column(z_pe, z_inj)
         z_pe = self.column.pe
         z_inj = self.column.inj
-        self.zmin = float(max(np.min(z_pe), np.min(z_inj)))  # parametric.py:114
-        self.zmax = float(min(np.max(z_pe), np.max(z_inj)))  # parametric.py:115
+        if z_range is None:
+            self.zmin = float(max(np.min(z_pe), np.min(z_inj)))  # parametric.py:114
+            self.zmax = float(min(np.max(z_pe), np.max(z_inj)))  # parametric.py:115
+        else:
+            self.zmin, self.zmax = float(z_range[0]), float(z_range[1])
         self.zs = np.linspace(self.zmin, self.zmax, 1000)  # :116
         self.dVdz_ = Planck15.dVcdz(self.zs)  # :117
         with np.errstate(divide="ignore"):
@@ -492,8 +497,8 @@ class PowerlawRedshiftModel:
 
 
 class PowerlawSplineRedshiftModel(PowerlawRedshiftModel):
-    def __init__(self, n_splines, z_pe, z_inj, basis=LogXBSpline):
-        super().__init__(z_pe=z_pe, z_inj=z_inj)
+    def __init__(self, n_splines, z_pe, z_inj, basis=LogXBSpline, z_range=None):
+        super().__init__(z_pe=z_pe, z_inj=z_inj, z_range=z_range)
         if basis is not LogXBSpline:
             raise NotImplementedError("only the LogXBSpline perturbation basis is implemented")
         self.n_splines = int(n_splines)

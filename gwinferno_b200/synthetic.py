@@ -36,29 +36,45 @@ def _reflect(x, lo, hi):
     return lo + y
 
 
-def make_injections(I, seed, dtype=np.float64):
-    rng = np.random.default_rng(seed)
-    m1 = rng.uniform(MMIN, MMAX, I)
+INJ_BLOCK = 1 << 20
+
+
+def _injection_block(seed, block, n):
+    """Injections ``[block*INJ_BLOCK, block*INJ_BLOCK + n)``: every block has its own counter-based
+    stream, so any index range can be generated independently (sharded runs never materialise the
+    whole 1e8-injection set on one host)."""
+    rng = np.random.default_rng([int(seed), int(block)])
+    m1 = rng.uniform(MMIN, MMAX, n)
     qlo = MMIN / m1
-    q = rng.uniform(qlo, 1.0, I)
-    a1 = rng.uniform(0.0, 1.0, I)
-    a2 = rng.uniform(0.0, 1.0, I)
-    ct1 = rng.uniform(-1.0, 1.0, I)
-    ct2 = rng.uniform(-1.0, 1.0, I)
-    z = rng.uniform(ZLO, ZHI, I)
+    q = rng.uniform(qlo, 1.0, n)
+    a1 = rng.uniform(0.0, 1.0, n)
+    a2 = rng.uniform(0.0, 1.0, n)
+    ct1 = rng.uniform(-1.0, 1.0, n)
+    ct2 = rng.uniform(-1.0, 1.0, n)
+    z = rng.uniform(ZLO, ZHI, n)
     # density of the draw in (m1, q, a1, a2, ct1, ct2, z)
     prior = 1.0 / (MMAX - MMIN) / (1.0 - qlo) / 4.0 / (ZHI - ZLO)
-    return {
-        "mass_1": m1,
-        "mass_ratio": q,
-        "mass_2": m1 * q,
-        "a_1": a1,
-        "a_2": a2,
-        "cos_tilt_1": ct1,
-        "cos_tilt_2": ct2,
-        "redshift": z,
-        "prior": prior,
-    }
+    return [m1, q, m1 * q, a1, a2, ct1, ct2, z, prior]
+
+
+INJ_COLS = ["mass_1", "mass_ratio", "mass_2", "a_1", "a_2", "cos_tilt_1", "cos_tilt_2", "redshift", "prior"]
+
+
+def make_injections(I, seed, start=0, stop=None):
+    """Found injections ``[start, stop)`` of a set of ``I`` (uniform over the support, ``prior`` =
+    the analytic draw density)."""
+    stop = I if stop is None else stop
+    out = [np.empty(stop - start) for _ in INJ_COLS]
+    b0, b1 = start // INJ_BLOCK, (max(stop, start + 1) - 1) // INJ_BLOCK
+    for b in range(b0, b1 + 1):
+        lo, hi = b * INJ_BLOCK, min(I, (b + 1) * INJ_BLOCK)
+        cols = _injection_block(seed, b, hi - lo)
+        a, e = max(lo, start), min(hi, stop)
+        if e <= a:
+            continue
+        for o, c in zip(out, cols):
+            o[a - start : e - start] = c[a - lo : e - lo]
+    return dict(zip(INJ_COLS, out))
 
 
 def make_events(E, S, seed):

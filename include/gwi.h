@@ -215,6 +215,14 @@ typedef struct {
 } gwi_model_info;
 int gwi_model_get_info(const gwi_model* m, gwi_model_info* info);
 
+/* Per-launch device time of the dominant (stream) kernel, for the roofline line of bench.py:
+ * after gwi_model_set_timing(m, 1) every evaluation brackets its stream-kernel launch with CUDA
+ * events on the launching stream (a ring of 64 pairs).  gwi_model_stream_times synchronises those
+ * events and writes the durations (milliseconds, oldest first) of the last min(n, cap, 64)
+ * launches; returns how many were written. */
+int gwi_model_set_timing(gwi_model* m, int32_t on);
+int gwi_model_stream_times(gwi_model* m, float* ms_out, int32_t cap);
+
 const char* gwi_last_error(void);
 int gwi_version(void);
 
