@@ -17,7 +17,7 @@ static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
 typedef void (*stream_fn)(const ModelDev*);
-stream_fn pick_stream_kernel(int ns, int ndeep, bool g2, bool maxonly);
+stream_fn pick_stream_kernel(int ns, int ndeep, bool g2, bool param, bool maxonly);
 void launch_prologue(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t st);
 void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st);
 void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st);
@@ -312,7 +312,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     X.n_splines = D.n_splines;
     X.deep = D.deep;
     X.deep_off = D.deep ? deep_entries : 0;
-    if (D.deep) deep_entries += D.rows * 4 * mom;
+    if (D.deep) deep_entries += D.rows * 2 * mom;  // double2 entries
     X.norm_group = D.norm_group;
     X.grid_off = D.grid_off;
     X.xi_lo = t.xi_lo;
@@ -336,6 +336,8 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     for (int i = 0; i < K.n_gslots; ++i) H.gslot_slot[K.gslot + i] = K.slot[i];
     if (K.kind != KOP_LIN) H.two_pass = 1;  // no a-priori bound for the non-linear terms: exact max first
   }
+  H.n_lin_fast = std::min(p.n_lin, 2);
+  const bool param = H.n_kops > H.n_lin_fast;
   for (int q = 0; q < H.n_sops; ++q) {
     const Sop& S = p.sops[q];
     H.sops[q] = SopDev{S.kind, S.slot[0], S.slot[1], 0, S.cst[0], S.cst[1]};
@@ -427,15 +429,16 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   }
 
   // ---- kernels + shared memory ----
-  m->k_full = pick_stream_kernel(NS, p.n_deep, p.g2, false);
-  m->k_max = pick_stream_kernel(NS, p.n_deep, p.g2, true);
+  m->k_full = pick_stream_kernel(NS, p.n_deep, p.g2, param, false);
+  m->k_max = pick_stream_kernel(NS, p.n_deep, p.g2, true, true);
   if (!m->k_full || !m->k_max) {
     set_error("no stream kernel instantiated for this (spline dims, deep dims) combination");
     gwi_model_destroy(m);
     return GWI_ERR_UNSUPPORTED;
   }
-  const size_t per_warp = (size_t)p.rows_total * 4 * mom + (size_t)deep_entries * 32 + (size_t)p.n_gslots * 32 * (1 + mom);
-  const size_t fixed = (size_t)p.rows_total * 4 + (size_t)H.n_kops * KC_STRIDE;
+  const size_t per_warp = (size_t)p.rows_total * 4 * mom + (size_t)deep_entries * 64 + (size_t)p.n_gslots * 32 * (1 + mom);
+  const size_t fixed = (size_t)p.rows_total * 4 + (size_t)H.n_kops * KC_STRIDE + (size_t)H.n_kops * (sizeof(KopDev) / 8);
+  static_assert(sizeof(KopDev) % 16 == 0, "KopDev copies must keep the shared layout 16-byte aligned");
   int wpb = p.warps_per_block;
   while (wpb > 1 && (fixed + per_warp * wpb) * 8 > (size_t)prop.sharedMemPerBlockOptin) --wpb;
   if (wpb != p.warps_per_block) {

@@ -8,7 +8,7 @@ namespace gwi {
 
 struct DimDev {
   int32_t rows, row_off, slot, n_splines;
-  int32_t deep, deep_off;  // deep_off: first entry of this dim in the lane-private deep block
+  int32_t deep, deep_off;  // deep_off: first double2 entry of this dim in the lane-private deep block
   int32_t norm_group, grid_off;
   double xi_lo, inv_dxi;
 };
@@ -41,6 +41,7 @@ struct GroupDev {
 struct ModelDev {
   int32_t n_params, n_dims, n_deep, n_kops, n_gslots, n_sops, n_groups, n_segments;
   int32_t rows_total, rec_doubles, n_columns, col_static, g2, two_pass, n_chunks, deep_entries;
+  int32_t n_lin_fast, pad0;  // leading LIN kops handled in registers by the stream kernel
   int64_t n_padded;
   double total_inj;
   DimDev dims[MAX_SPLINE_DIMS];

@@ -104,7 +104,8 @@ struct Plan {
   std::vector<SplineDim> dims;   // in SORT-KEY order; the last n_deep are "deep"
   int n_deep = 0;
   int rows_total = 0;
-  std::vector<Kop> kops;
+  std::vector<Kop> kops;         // LIN kops first
+  int n_lin = 0;                 // number of leading LIN kops
   int n_gslots = 0;
   std::vector<Sop> sops;
   std::vector<NormGroup> groups;

@@ -287,275 +287,6 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
 }
 
 // =================================================================================================
-// stream kernel
-// =================================================================================================
-template <int NS, int NDEEP, bool G2>
-struct LaneAcc {
-  static constexpr int NSH = NS - NDEEP;
-  double m1[NSH > 0 ? NSH : 1][4];
-  double m2[(G2 && NSH > 0) ? NSH : 1][4];
-  int cur[NSH > 0 ? NSH : 1];
-  double S1, S2;
-};
-
-// spill the register moments of shallow dim d (piece `J`) into the warp's shared accumulator
-template <bool G2>
-__device__ __forceinline__ void spill(double* msh, int idx, int m2_off, double (&a1)[4], double (&a2)[4]) {
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    atomicAdd(&msh[idx + n], a1[n]);
-    a1[n] = 0.0;
-    if (G2) {
-      atomicAdd(&msh[m2_off + idx + n], a2[n]);
-      a2[n] = 0.0;
-    }
-  }
-}
-
-template <int NS, int NDEEP, bool G2, bool MAXONLY>
-__global__ void __launch_bounds__(256) stream_kernel(const ModelDev* __restrict__ Mp) {
-  const ModelDev& M = *Mp;
-  constexpr int NSH = NS - NDEEP;
-  constexpr int MOM = G2 ? 2 : 1;
-  extern __shared__ double sm[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int rows_total = M.rows_total;
-  const int n_kops = M.n_kops, n_gs = M.n_gslots;
-  // shared layout: tables | kc | per warp { msh[rows_total*4*MOM] | deep[deep_entries*32] | gscr[n_gs*32] | gacc[n_gs*MOM*32] }
-  double* tables = sm;
-  double* kcs = tables + rows_total * 4;
-  const int per_warp = rows_total * 4 * MOM + M.deep_entries * 32 + n_gs * 32 * (1 + MOM);
-  double* msh = kcs + n_kops * KC_STRIDE + (size_t)warp * per_warp;
-  double* deep = msh + rows_total * 4 * MOM;
-  double* gscr = deep + M.deep_entries * 32;
-  double* gacc = gscr + n_gs * 32;
-  for (int i = threadIdx.x; i < rows_total * 4; i += blockDim.x) tables[i] = M.tables[i];
-  for (int i = threadIdx.x; i < n_kops * KC_STRIDE; i += blockDim.x) kcs[i] = M.kc[i];
-  if (!MAXONLY)
-    for (int i = lane; i < per_warp; i += 32) msh[i] = 0.0;
-  __syncthreads();
-
-  // per-dim constants in registers (compile-time indexed)
-  int row_off[NS > 0 ? NS : 1], deep_off[NS > 0 ? NS : 1], rows_d[NS > 0 ? NS : 1];
-#pragma unroll
-  for (int d = 0; d < NS; ++d) {
-    row_off[d] = M.dims[d].row_off;
-    deep_off[d] = M.dims[d].deep_off;
-    rows_d[d] = M.dims[d].rows;
-  }
-  const int m2_off = rows_total * 4;
-
-  LaneAcc<NS, NDEEP, G2> A;
-  A.S1 = 0.0;
-  A.S2 = 0.0;
-#pragma unroll
-  for (int d = 0; d < NSH; ++d) {
-    A.cur[d] = -1;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      A.m1[d][n] = 0.0;
-      if (G2) A.m2[d][n] = 0.0;
-    }
-  }
-
-  const int W = gridDim.x * wpb;
-  const int gw = blockIdx.x * wpb + warp;
-  const int64_t np = M.n_padded;
-  const uint64_t* __restrict__ cols = M.columns;
-
-  for (int c = gw; c < M.n_chunks; c += W) {
-    const Chunk C = M.chunks[c];
-    const double shift = MAXONLY ? 0.0 : M.shift[C.segment];
-    double xmax = -INFINITY;
-    const int64_t base = C.first + lane * UNROLL;
-    const int iters = C.steps / UNROLL;
-    for (int it = 0; it < iters; ++it) {
-      const int64_t p0 = base + (int64_t)it * (LANES * UNROLL);
-      // ---- loads (16 B per column) ----
-      ulonglong2 wd[NS > 0 ? NS : 1];
-#pragma unroll
-      for (int d = 0; d < NS; ++d) wd[d] = *reinterpret_cast<const ulonglong2*>(cols + (size_t)d * np + p0);
-      const double2 st = *reinterpret_cast<const double2*>(cols + (size_t)M.col_static * np + p0);
-#pragma unroll
-      for (int s = 0; s < UNROLL; ++s) {
-        double x = s == 0 ? st.x : st.y;
-        double wv[NS > 0 ? NS : 1];
-        int Jv[NS > 0 ? NS : 1];
-#pragma unroll
-        for (int d = 0; d < NS; ++d) {
-          const unsigned long long word = s == 0 ? wd[d].x : wd[d].y;
-          const int J = (int)(word >> 52);
-          const double w = __longlong_as_double((long long)((word & MANT_MASK) | ONE_BITS)) - 1.5;
-          Jv[d] = J;
-          wv[d] = w;
-          const double2 a01 = *reinterpret_cast<const double2*>(tables + (row_off[d] + J) * 4);
-          const double2 a23 = *reinterpret_cast<const double2*>(tables + (row_off[d] + J) * 4 + 2);
-          x += fma(fma(fma(a23.y, w, a23.x), w, a01.y), w, a01.x);
-        }
-        // ---- non-spline terms ----
-        for (int q = 0; q < n_kops; ++q) {
-          const KopDev& K = M.kops[q];
-          const double* kc = kcs + q * KC_STRIDE;
-          const double f0 = __longlong_as_double((long long)cols[(size_t)K.col0 * np + p0 + s]);
-          double* scr = gscr + K.gslot * 32 + lane;
-          if (K.kind == KOP_LIN) {
-            x = fma(kc[0], f0, x);
-            if (!MAXONLY) scr[0] = f0;
-          } else if (K.kind == KOP_PLRATIO) {
-            const double ll = __longlong_as_double((long long)cols[(size_t)K.col1 * np + p0 + s]);
-            const double beta = kc[0], a1 = kc[1];
-            double lognorm, dn;
-            if (fabs(a1) < 1e-9) {
-              lognorm = -log(-ll) - 0.5 * a1 * ll;
-              dn = -0.5 * ll;
-            } else {
-              const double e = exp(a1 * ll);
-              lognorm = log(a1 / (1.0 - e));
-              dn = 1.0 / a1 + e * ll / (1.0 - e);
-            }
-            x += beta * f0 + lognorm;
-            if (!MAXONLY) scr[0] = f0 + dn;
-          } else if (K.kind == KOP_PLPEAK) {
-            const double m = __longlong_as_double((long long)cols[(size_t)K.col1 * np + p0 + s]);
-            const double PL = exp(kc[0] * f0 + kc[1]);
-            const double z = m - kc[2];
-            const double TN = exp(-z * z * kc[3] + kc[4]);
-            const double Aa = (1.0 - kc[5]) * PL, Bb = kc[5] * TN;
-            const double tot = Aa + Bb;
-            x += tot > 0.0 ? log(tot) : -INFINITY;
-            if (!MAXONLY) {
-              const double it_ = tot > 0.0 ? 1.0 / tot : 0.0, sig = kc[7];
-              scr[0] = Aa * (f0 + kc[6]) * it_;
-              scr[32] = Bb * (z / (sig * sig) - kc[8]) * it_;
-              scr[64] = Bb * (z * z / (sig * sig * sig) - 1.0 / sig - kc[9]) * it_;
-              scr[96] = (TN - PL) * it_;
-            }
-          } else if (K.kind == KOP_ISOALIGN) {
-            const double z = f0 - 1.0, sig = kc[1];
-            const double TN = exp(-z * z * kc[3] + kc[2]);
-            const double Aa = 0.5 * (1.0 - kc[0]), Bb = kc[0] * TN;
-            const double tot = Aa + Bb;
-            x += tot > 0.0 ? log(tot) : -INFINITY;
-            if (!MAXONLY) {
-              const double it_ = tot > 0.0 ? 1.0 / tot : 0.0;
-              scr[0] = (TN - 0.5) * it_;
-              scr[32] = Bb * (z * z / (sig * sig * sig) - 1.0 / sig - kc[4]) * it_;
-            }
-          } else if (K.kind == KOP_QUAD) {
-            const double z = f0 - kc[0], sig = kc[1];
-            x -= z * z * kc[2];
-            if (!MAXONLY) {
-              scr[0] = z / (sig * sig);
-              scr[32] = z * z / (sig * sig * sig);
-            }
-          }
-        }
-        if (MAXONLY) {
-          xmax = fmax(xmax, x);
-          continue;
-        }
-        const double p = exp(x - shift);
-        const double p2 = p * p;
-        A.S1 += p;
-        A.S2 += p2;
-        for (int g = 0; g < n_gs; ++g) {
-          const double dv = gscr[g * 32 + lane];
-          gacc[g * 32 + lane] = fma(p, dv, gacc[g * 32 + lane]);
-          if (G2) gacc[(n_gs + g) * 32 + lane] = fma(p2, dv, gacc[(n_gs + g) * 32 + lane]);
-        }
-#pragma unroll
-        for (int d = 0; d < NS; ++d) {
-          const double w = wv[d];
-          const double pw = p * w, pw2 = pw * w, pw3 = pw2 * w;
-          if (d < NSH) {
-            if (Jv[d] != A.cur[d]) {
-              if (A.cur[d] >= 0) spill<G2>(msh, (row_off[d] + A.cur[d]) * 4, m2_off, A.m1[d], A.m2[G2 ? d : 0]);
-              A.cur[d] = Jv[d];
-            }
-            A.m1[d][0] += p;
-            A.m1[d][1] += pw;
-            A.m1[d][2] += pw2;
-            A.m1[d][3] += pw3;
-            if (G2) {
-              const double qw = p2 * w, qw2 = qw * w, qw3 = qw2 * w;
-              A.m2[d][0] += p2;
-              A.m2[d][1] += qw;
-              A.m2[d][2] += qw2;
-              A.m2[d][3] += qw3;
-            }
-          } else {
-            // lane-private shared accumulators, layout [entry][lane]: conflict-free for any J
-            double* e = deep + (size_t)(deep_off[d] + Jv[d] * 4) * 32 + lane;
-            e[0] += p;
-            e[32] += pw;
-            e[64] += pw2;
-            e[96] += pw3;
-            if (G2) {
-              double* e2 = e + (size_t)rows_d[d] * 4 * 32;
-              const double qw = p2 * w, qw2 = qw * w, qw3 = qw2 * w;
-              e2[0] += p2;
-              e2[32] += qw;
-              e2[64] += qw2;
-              e2[96] += qw3;
-            }
-          }
-        }
-      }
-    }
-    if (MAXONLY) {
-      xmax = warp_max(xmax);
-      if (lane == 0) M.chunk_max[c] = xmax;
-      continue;
-    }
-    if (C.flush) {
-      // ---- write this warp's record and clear its accumulators ----
-#pragma unroll
-      for (int d = 0; d < NSH; ++d) {
-        if (A.cur[d] >= 0) spill<G2>(msh, (row_off[d] + A.cur[d]) * 4, m2_off, A.m1[d], A.m2[G2 ? d : 0]);
-        A.cur[d] = -1;
-      }
-      __syncwarp();
-      double* rec = M.records0 + (size_t)C.record_slot * M.rec_doubles;
-      const double s1 = warp_sum(A.S1), s2 = warp_sum(A.S2);
-      A.S1 = 0.0;
-      A.S2 = 0.0;
-      if (lane == 0) {
-        rec[0] = s1;
-        rec[1] = s2;
-      }
-      for (int g = 0; g < n_gs * MOM; ++g) {
-        const double v = warp_sum(gacc[g * 32 + lane]);
-        gacc[g * 32 + lane] = 0.0;
-        if (lane == 0) rec[2 + g] = v;
-      }
-      // deep dims: sum the 32 lane-private copies (rotated start: bank-conflict-free, fixed order)
-#pragma unroll
-      for (int d = NSH; d < NS; ++d) {
-        const int ne = rows_d[d] * 4 * MOM;
-        for (int e = lane; e < ne; e += 32) {
-          double* row = deep + (size_t)(deep_off[d] + e) * 32;
-          double acc = 0.0;
-          for (int i = 0; i < 32; ++i) {
-            const int l = (i + lane) & 31;
-            acc += row[l];
-            row[l] = 0.0;
-          }
-          const int mm = e / (rows_d[d] * 4), r = e - mm * rows_d[d] * 4;
-          msh[mm * m2_off + row_off[d] * 4 + r] = acc;
-        }
-      }
-      __syncwarp();
-      double* recM = rec + 2 + n_gs * MOM;
-      for (int i = lane; i < rows_total * 4 * MOM; i += 32) {
-        recM[i] = msh[i];
-        msh[i] = 0.0;
-      }
-      __syncwarp();
-    }
-  }
-}
-
-// =================================================================================================
 // reductions
 // =================================================================================================
 __global__ void reduce_kernel(const double* __restrict__ in, double* __restrict__ out, const ReduceTask* __restrict__ tasks, int rec) {
@@ -803,40 +534,6 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
 // =================================================================================================
 // host-side launch helpers (called from api.cu)
 // =================================================================================================
-typedef void (*stream_fn)(const ModelDev*);
-
-template <int NS, int NDEEP>
-static stream_fn pick_g2(bool g2, bool maxonly) {
-  if (maxonly) return stream_kernel<NS, 0, false, true>;
-  return g2 ? (stream_fn)stream_kernel<NS, NDEEP, true, false> : (stream_fn)stream_kernel<NS, NDEEP, false, false>;
-}
-template <int NS>
-static stream_fn pick_deep(int nd, bool g2, bool maxonly) {
-  if (maxonly) return stream_kernel<NS, 0, false, true>;
-  switch (nd) {
-    case 0: return pick_g2<NS, 0>(g2, maxonly);
-    case 1: if (NS >= 1) return pick_g2<NS, (NS >= 1 ? 1 : 0)>(g2, maxonly); break;
-    case 2: if (NS >= 2) return pick_g2<NS, (NS >= 2 ? 2 : 0)>(g2, maxonly); break;
-    case 3: if (NS >= 3) return pick_g2<NS, (NS >= 3 ? 3 : 0)>(g2, maxonly); break;
-  }
-  return nullptr;
-}
-
-stream_fn pick_stream_kernel(int ns, int ndeep, bool g2, bool maxonly) {
-  switch (ns) {
-    case 0: return pick_deep<0>(ndeep, g2, maxonly);
-    case 1: return pick_deep<1>(ndeep, g2, maxonly);
-    case 2: return pick_deep<2>(ndeep, g2, maxonly);
-    case 3: return pick_deep<3>(ndeep, g2, maxonly);
-    case 4: return pick_deep<4>(ndeep, g2, maxonly);
-    case 5: return pick_deep<5>(ndeep, g2, maxonly);
-    case 6: return pick_deep<6>(ndeep, g2, maxonly);
-    case 7: return pick_deep<7>(ndeep, g2, maxonly);
-    case 8: return pick_deep<8>(ndeep, g2, maxonly);
-  }
-  return nullptr;
-}
-
 void launch_prologue(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t st) {
   prologue_kernel<<<n_groups + 1, 256, (size_t)max_grid * sizeof(double), st>>>(Md, lam);
 }

@@ -460,6 +460,18 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     cuts.push_back(RangeCut{k.kind == GWI_CUT_RANGE ? 1 : 2, {k.col[0], k.col[1]}, k.lo, k.hi});
   }
 
+  // ---- linear terms first (the stream kernel keeps the leading ones in registers) --------------
+  {
+    std::stable_partition(plan.kops.begin(), plan.kops.end(), [](const Kop& k) { return k.kind == KOP_LIN; });
+    int gs = 0;
+    plan.n_lin = 0;
+    for (auto& k : plan.kops) {
+      k.gslot = gs;
+      gs += k.n_gslots;
+      if (k.kind == KOP_LIN) ++plan.n_lin;
+    }
+  }
+
   // ---- order the spline dims: most pieces first (sort key most significant), deep dims last ----
   const int NS = (int)plan.dims.size();
   {
@@ -610,7 +622,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   (void)rows_shallow;
   const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * LANES * 8 +
                              (int64_t)plan.n_gslots * (1 + mom) * LANES * 8;
-  const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)plan.kops.size() * KC_STRIDE * 8 + 1024;
+  const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
   int wpb = (int)((220 * 1024 - cta_fixed) / std::max<int64_t>(1, warp_bytes));
   wpb = std::max(1, std::min(wpb, 8));
   plan.warps_per_block = wpb;

@@ -1,0 +1,6 @@
+// stream kernel instantiations for 0 spline dimension(s) (one translation unit per count so that
+// make -j compiles them in parallel)
+#include "stream.cuh"
+namespace gwi {
+stream_fn pick_stream_ns0(int nd, bool g2, bool param, bool maxonly) { return pick_stream_for_ns<0>(nd, g2, param, maxonly); }
+}  // namespace gwi

@@ -1,0 +1,6 @@
+// stream kernel instantiations for 8 spline dimension(s) (one translation unit per count so that
+// make -j compiles them in parallel)
+#include "stream.cuh"
+namespace gwi {
+stream_fn pick_stream_ns8(int nd, bool g2, bool param, bool maxonly) { return pick_stream_for_ns<8>(nd, g2, param, maxonly); }
+}  // namespace gwi
