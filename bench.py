@@ -223,7 +223,7 @@ def run_ours(args):
     low, lam0, _ = workloads.lower_workload(weights, params_fn, pe, inj)
     P = low.spec.n_params
     t_gen = time.perf_counter() - t_setup
-    eng = PopulationLikelihood(low, const["total_inj"], device=local, need_neff_grad=False)
+    eng = PopulationLikelihood(low, const["total_inj"], device=local, need_neff_grad=False, chunk_steps=args.chunk_steps, n_deep=args.n_deep)
     t_plan = time.perf_counter() - t_setup - t_gen
     info = eng.info()
     mdl = eng.model
@@ -342,6 +342,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink S and I (testing only; the reported config then differs from BASELINE's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-deep", type=int, default=-1, help="tuning experiment: spline dims with lane-private accumulators (-1 = auto)")
+    ap.add_argument("--chunk-steps", type=int, default=0, help="tuning experiment: samples per lane per chunk (0 = auto)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -74,7 +74,7 @@ struct NormGroup {
 
 struct Chunk {
   int32_t segment;
-  int32_t steps;        // samples per lane (multiple of UNROLL)
+  int32_t steps;        // samples per lane (multiple of 2*UNROLL)
   int64_t first;        // first padded sample index (multiple of 32*UNROLL)
   int32_t record_slot;  // level-0 record receiving this chunk's sums
   int32_t flush;        // 1 = the warp must write + clear its record after this chunk

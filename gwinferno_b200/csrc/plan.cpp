@@ -494,21 +494,6 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     row_off += plan.dims[d].rows;
   }
   plan.rows_total = row_off;
-  // deep dims: lane-private shared-memory accumulators, rows*4*(g2?2:1)*32 lanes*8 B per warp each
-  {
-    int want = desc.n_deep;
-    const int budget = 36 * 1024;  // bytes per warp
-    int nd = 0, bytes = 0;
-    const int cap = want < 0 ? std::min(NS, 2) : std::min(NS, want);
-    for (int d = NS - 1; d >= 0 && nd < cap; --d) {
-      const int b = plan.dims[d].rows * 4 * (plan.g2 ? 2 : 1) * LANES * 8;
-      if (bytes + b > budget) break;
-      bytes += b;
-      ++nd;
-    }
-    plan.n_deep = nd;
-    for (int d = 0; d < NS; ++d) plan.dims[d].deep = d >= NS - nd;
-  }
   const int NK = (int)kop_feats.size();
   plan.n_columns = NS + NK + 1;
   plan.col_static = NS + NK;
@@ -614,13 +599,63 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   for (int s = 1; s < n_seg; ++s) plan.n_valid_pe += plan.segments[s].n_valid;
   plan.n_valid_inj = plan.segments[0].n_valid;
 
+  // ---- deep dims: how often does each dim's piece index change along the sorted order? -------
+  // Leading sort keys change rarely (register-resident moments, spilled on change); a dim whose
+  // piece changes more than about once per 100 consecutive samples would make some lane of every
+  // warp take the spill path on nearly every sample, so it (and every later key) gets
+  // lane-pair-private shared-memory accumulators instead ("deep").
+  {
+    std::vector<double> changes(NS, 0.0);
+    double total = 0.0;
+    for (int s = 0; s < n_seg; ++s) {
+      const double* const* cols = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
+      const std::vector<uint32_t>& ord = order[s];
+      const size_t n = ord.size();
+      const size_t stride = std::max<size_t>(1, n / 200000);  // sample long segments
+      for (size_t i = 0; i + 1 < n; i += stride) {
+        for (int d = 0; d < NS; ++d) {
+          int J0, J1;
+          double u;
+          spline_locate(geom[d], cols[geom[d].col][ord[i]], J0, u);
+          spline_locate(geom[d], cols[geom[d].col][ord[i + 1]], J1, u);
+          if (J0 != J1) changes[d] += (double)stride;  // weight by the samples each pair stands for
+        }
+        total += (double)stride;
+      }
+    }
+    int want = desc.n_deep;
+    int nd = 0;
+    if (want < 0) {
+      for (int d = NS - 1; d >= 0; --d) {
+        bool any = false;
+        for (int e = 0; e <= d; ++e)
+          if (total > 0 && changes[e] / total > 0.01) any = true;  // a frequent changer at or before d
+        if (total > 0 && changes[d] / total > 0.01) nd = NS - d;
+        (void)any;
+      }
+    } else {
+      nd = want;
+    }
+    nd = std::min(std::min(nd, NS), 4);
+    // shared-memory budget: keep at least 4 warps per CTA
+    const int mom_ = plan.g2 ? 2 : 1;
+    for (;;) {
+      int64_t bytes = (int64_t)plan.rows_total * 4 * mom_ * 8;
+      for (int d = NS - nd; d < NS; ++d) bytes += (int64_t)plan.dims[d].rows * 4 * mom_ * 16 * 8;
+      if (nd == 0 || bytes * 4 <= 200 * 1024) break;
+      --nd;
+    }
+    plan.n_deep = nd;
+    for (int d = 0; d < NS; ++d) plan.dims[d].deep = d >= NS - nd;
+  }
+
   // ---- launch geometry + chunking -----------------------------------------------------------
   // shared memory per warp: shallow accumulators + deep lane-private arrays + generic slots
   const int mom = plan.g2 ? 2 : 1;
   int rows_shallow = 0, rows_deep = 0;
   for (int d = 0; d < NS; ++d) (plan.dims[d].deep ? rows_deep : rows_shallow) += plan.dims[d].rows;
   (void)rows_shallow;
-  const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * LANES * 8 +
+  const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * 16 * 8 +
                              (int64_t)plan.n_gslots * (1 + mom) * LANES * 8;
   const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
   int wpb = (int)((220 * 1024 - cta_fixed) / std::max<int64_t>(1, warp_bytes));
@@ -634,7 +669,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     K = (int)(n_valid / ((int64_t)W * LANES * 4));
     K = std::max(32, std::min(K, 512));
   }
-  K = (K + UNROLL - 1) / UNROLL * UNROLL;
+  K = (K + 2 * UNROLL - 1) / (2 * UNROLL) * (2 * UNROLL);
   plan.chunk_steps = K;
   int64_t pos = 0;
   for (int s = 0; s < n_seg; ++s) {
@@ -644,7 +679,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     while (left > 0) {
       const int64_t n_c = std::min<int64_t>(left, (int64_t)LANES * K);
       int steps = (int)((n_c + LANES - 1) / LANES);
-      steps = (steps + UNROLL - 1) / UNROLL * UNROLL;
+      steps = (steps + 2 * UNROLL - 1) / (2 * UNROLL) * (2 * UNROLL);  // the kernel's load pipeline is 2 iterations deep
       Chunk c{};
       c.segment = s;
       c.steps = steps;
