@@ -23,7 +23,7 @@ void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n
 void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st);
 void launch_finish(const ModelDev* Md, int n_seg, cudaStream_t st);
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
-void launch_partial(const ModelDev* Md, double* rec, cudaStream_t st);
+void launch_partial(const ModelDev* Md, double* rec, int n_params, cudaStream_t st);
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, cudaStream_t st);
 
 }  // namespace gwi
@@ -315,6 +315,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     if (D.deep) deep_entries += D.rows * 2 * mom;  // double2 entries
     X.norm_group = D.norm_group;
     X.grid_off = D.grid_off;
+    X.grid_aux = D.grid_aux;
     X.xi_lo = t.xi_lo;
     X.inv_dxi = (double)(D.rows - 1) / (t.xi_hi - t.xi_lo);
   }
@@ -514,7 +515,7 @@ int gwi_partial(gwi_model* m, const double* lambda_dev, double* record_dev, void
   cudaStream_t st = (cudaStream_t)stream;
   const int rc = run_eval(m, lambda_dev, st);
   if (rc != GWI_OK) return rc;
-  launch_partial(m->dev, record_dev, st);
+  launch_partial(m->dev, record_dev, m->plan.n_params, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }

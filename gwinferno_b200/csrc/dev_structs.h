@@ -10,6 +10,7 @@ struct DimDev {
   int32_t rows, row_off, slot, n_splines;
   int32_t deep, deep_off;  // deep_off: first double2 entry of this dim in the lane-private deep block
   int32_t norm_group, grid_off;
+  int32_t grid_aux, pad1;  // derived grid taps (see SplineDim::grid_aux)
   double xi_lo, inv_dxi;
 };
 

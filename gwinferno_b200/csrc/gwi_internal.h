@@ -64,6 +64,7 @@ struct SplineDim {
   int32_t deep;      // accumulated in lane-private shared memory
   int32_t norm_group;
   int32_t grid_off;  // offset of its grid xi array in the grid pool, -1 none
+  int32_t grid_aux;  // offset of the derived per-grid-point taps: W[4G], J[G], then lo[n], hi[n] per basis
   int32_t outside;
 };
 

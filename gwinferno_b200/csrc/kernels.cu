@@ -127,13 +127,10 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
       for (int d = 0; d < M.n_dims; ++d) {
         const DimDev& D = M.dims[d];
         if (D.norm_group != g) continue;
-        const double xi = M.grid_pool[D.grid_off + i];
-        if (xi == xi) {
-          const double t = (xi - D.xi_lo) * D.inv_dxi;
-          int J = (int)floor(t);
-          J = max(0, min(J, D.rows - 2));
-          double w[4];
-          tap_weights(t - (double)J, w);
+        const double* aux = M.grid_pool + D.grid_aux;  // W[4G] | J[G] | lo[n] | hi[n]
+        const int J = (int)aux[4 * G + i];
+        if (J >= 0) {
+          const double* w = aux + 4 * i;
           const double* c = Lam + D.slot + J;
           v += w[0] * c[0] + w[1] * c[1] + w[2] * c[2] + w[3] * c[3];
         }
@@ -162,19 +159,15 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     for (int d = 0; d < M.n_dims; ++d) {
       const DimDev& D = M.dims[d];
       if (D.norm_group != g) continue;
+      const double* aux = M.grid_pool + D.grid_aux;
       for (int k = tid; k < D.n_splines; k += nt) {
         double acc = 0.0;
-        for (int i = 0; i < G; ++i) {
-          const double xi = M.grid_pool[D.grid_off + i];
-          if (!(xi == xi)) continue;
-          const double t = (xi - D.xi_lo) * D.inv_dxi;
-          int J = (int)floor(t);
-          J = max(0, min(J, D.rows - 2));
+        const int lo = (int)aux[5 * G + k], hi = (int)aux[5 * G + D.n_splines + k];
+        for (int i = lo; i < hi; ++i) {
+          const int J = (int)aux[4 * G + i];
           const int kk = k - J;
-          if (kk < 0 || kk > 3) continue;
-          double w[4];
-          tap_weights(t - (double)J, w);
-          acc += li[i] * w[kk];
+          if (J < 0 || kk < 0 || kk > 3) continue;
+          acc += li[i] * aux[4 * i + kk];
         }
         M.dlogZ[(size_t)g * P + D.slot + k] += acc * inv;
       }
@@ -415,34 +408,45 @@ __global__ void export_kernel(const ModelDev* __restrict__ Mp, gwi_outputs out) 
 __global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict__ Mp, double* __restrict__ recd) {
   const ModelDev& M = *Mp;
   const int P = M.n_params, E = M.n_segments - 1;
-  if (threadIdx.x == 0) {
-    double sum_logBF = 0.0, min_ln = INFINITY, sum_var = 0.0, status = M.seg_out[3];
-    for (int e = 1; e <= E; ++e) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  if (blockIdx.x == 0 && warp == 0) {
+    // header: fixed-order (lane-strided, then butterfly) sums over this rank's events
+    double sum_logBF = 0.0, min_ln = INFINITY, sum_var = 0.0, status = 0.0;
+    for (int e = 1 + lane; e <= E; e += 32) {
       const double* o = M.seg_out + (size_t)e * 4;
       sum_logBF += o[0];
-      // analysis.py:296: min over nan_to_num(logn_effs)
-      double ln = o[1];
+      double ln = o[1];  // analysis.py:296: min over nan_to_num(logn_effs)
       if (ln != ln) ln = 0.0;
       ln = fmin(fmax(ln, -DBL_MAX), DBL_MAX);
       min_ln = fmin(min_ln, ln);
       sum_var += o[2];
       status = fmax(status, o[3]);
     }
-    recd[PR_SHIFT] = M.inj_raw[0];
-    recd[PR_S1] = M.inj_raw[1];
-    recd[PR_S2] = M.inj_raw[2];
-    recd[PR_SUM_LOGBF] = sum_logBF;
-    recd[PR_MIN_LOGNEFF] = min_ln;
-    recd[PR_SUM_VAR] = sum_var;
-    recd[PR_N_EVENTS] = (double)E;
-    recd[PR_STATUS] = status;
+    sum_logBF = warp_sum(sum_logBF);
+    sum_var = warp_sum(sum_var);
+    min_ln = -warp_max(-min_ln);
+    status = warp_max(status);
+    if (lane == 0) {
+      recd[PR_SHIFT] = M.inj_raw[0];
+      recd[PR_S1] = M.inj_raw[1];
+      recd[PR_S2] = M.inj_raw[2];
+      recd[PR_SUM_LOGBF] = sum_logBF;
+      recd[PR_MIN_LOGNEFF] = min_ln;
+      recd[PR_SUM_VAR] = sum_var;
+      recd[PR_N_EVENTS] = (double)E;
+      recd[PR_STATUS] = fmax(status, M.seg_out[3]);
+    }
   }
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    recd[PR_HEADER + i] = M.inj_raw[3 + i];
-    recd[PR_HEADER + P + i] = M.inj_raw[3 + P + i];
+  // one warp per hyper-parameter: sum_e J_logBF[e][i]
+  for (int i = blockIdx.x * wpb + warp; i < P; i += gridDim.x * wpb) {
     double acc = 0.0;
-    for (int e = 1; e <= E; ++e) acc += M.seg_J1[(size_t)e * P + i];
-    recd[PR_HEADER + 2 * P + i] = acc;
+    for (int e = 1 + lane; e <= E; e += 32) acc += M.seg_J1[(size_t)e * P + i];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      recd[PR_HEADER + i] = M.inj_raw[3 + i];
+      recd[PR_HEADER + P + i] = M.inj_raw[3 + P + i];
+      recd[PR_HEADER + 2 * P + i] = acc;
+    }
   }
 }
 
@@ -544,7 +548,7 @@ void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n
 void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st) { segmax_kernel<<<n_seg, 256, 0, st>>>(Md); }
 void launch_finish(const ModelDev* Md, int n_seg, cudaStream_t st) { finish_kernel<<<n_seg, 256, 0, st>>>(Md); }
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { export_kernel<<<64, 256, 0, st>>>(Md, out); }
-void launch_partial(const ModelDev* Md, double* rec, cudaStream_t st) { partial_kernel<<<1, 256, 0, st>>>(Md, rec); }
+void launch_partial(const ModelDev* Md, double* rec, int n_params, cudaStream_t st) { partial_kernel<<<(n_params + 7) / 8, 256, 0, st>>>(Md, rec); }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, cudaStream_t st) {
   combine_kernel<<<1, 256, 0, st>>>(Md, recs, R, o, out);
 }

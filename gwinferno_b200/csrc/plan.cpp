@@ -494,6 +494,56 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     row_off += plan.dims[d].rows;
   }
   plan.rows_total = row_off;
+  // ---- static taps of the normalisation grids (the grid never changes between evaluations) ----
+  for (int d = 0; d < NS; ++d) {
+    SplineDim& D = plan.dims[d];
+    D.grid_aux = -1;
+    if (D.grid_off < 0) continue;
+    const int G = plan.groups[D.norm_group].n_grid;
+    const int n = D.n_splines;
+    std::vector<double> aux((size_t)G * 5 + 2 * n, 0.0);
+    std::vector<int> Jg(G, -1);
+    bool monotone = true;
+    int lastJ = -1;
+    for (int i = 0; i < G; ++i) {
+      const double xi = plan.grid_pool[D.grid_off + i];
+      if (!(xi == xi)) {
+        aux[(size_t)4 * G + i] = -1.0;
+        continue;
+      }
+      const double t = (xi - geom[d].xi_lo) * geom[d].inv_dxi;
+      int J = (int)std::floor(t);
+      J = std::max(0, std::min(J, D.rows - 2));
+      const double u = t - (double)J, omu = 1.0 - u;
+      aux[(size_t)4 * i + 0] = omu * omu * omu * (1.0 / 6.0);
+      aux[(size_t)4 * i + 1] = (3.0 * u * u * u - 6.0 * u * u + 4.0) * (1.0 / 6.0);
+      aux[(size_t)4 * i + 2] = (-3.0 * u * u * u + 3.0 * u * u + 3.0 * u + 1.0) * (1.0 / 6.0);
+      aux[(size_t)4 * i + 3] = u * u * u * (1.0 / 6.0);
+      aux[(size_t)4 * G + i] = (double)J;
+      Jg[i] = J;
+      if (J < lastJ) monotone = false;
+      lastJ = J;
+    }
+    for (int k = 0; k < n; ++k) {
+      int lo = G, hi = 0;
+      if (monotone) {
+        for (int i = 0; i < G; ++i)
+          if (Jg[i] >= 0 && k - Jg[i] >= 0 && k - Jg[i] <= 3) {
+            lo = std::min(lo, i);
+            hi = std::max(hi, i + 1);
+          }
+        if (lo > hi) lo = hi = 0;
+      } else {
+        lo = 0;
+        hi = G;
+      }
+      aux[(size_t)5 * G + k] = (double)lo;
+      aux[(size_t)5 * G + n + k] = (double)hi;
+    }
+    D.grid_aux = (int)plan.grid_pool.size();
+    plan.grid_pool.insert(plan.grid_pool.end(), aux.begin(), aux.end());
+  }
+
   const int NK = (int)kop_feats.size();
   plan.n_columns = NS + NK + 1;
   plan.col_static = NS + NK;
