@@ -253,11 +253,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None  # samples clocks through warm-up + timed region
     for i in range(args.warmup):
         step(i)
     barrier()
     mdl.set_timing(True)
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

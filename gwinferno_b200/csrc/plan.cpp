@@ -655,33 +655,44 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   // warp take the spill path on nearly every sample, so it (and every later key) gets
   // lane-pair-private shared-memory accumulators instead ("deep").
   {
-    std::vector<double> changes(NS, 0.0);
-    double total = 0.0;
+    // per segment: fraction of consecutive sorted samples whose piece index differs, per dim
+    std::vector<std::vector<double>> rate(n_seg, std::vector<double>(NS, 0.0));
     for (int s = 0; s < n_seg; ++s) {
       const double* const* cols = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
       const std::vector<uint32_t>& ord = order[s];
       const size_t n = ord.size();
       const size_t stride = std::max<size_t>(1, n / 200000);  // sample long segments
+      double pairs = 0.0;
       for (size_t i = 0; i + 1 < n; i += stride) {
         for (int d = 0; d < NS; ++d) {
           int J0, J1;
           double u;
           spline_locate(geom[d], cols[geom[d].col][ord[i]], J0, u);
           spline_locate(geom[d], cols[geom[d].col][ord[i + 1]], J1, u);
-          if (J0 != J1) changes[d] += (double)stride;  // weight by the samples each pair stands for
+          if (J0 != J1) rate[s][d] += 1.0;
         }
-        total += (double)stride;
+        pairs += 1.0;
       }
+      for (int d = 0; d < NS; ++d) rate[s][d] = pairs > 0 ? rate[s][d] / pairs : 0.0;
     }
+    // cost model (issue slots per sample): a register-resident dim pays the warp-wide spill path
+    // whenever ANY of its 32 lanes changes piece (~60 slots incl. the shared-memory atomics); a
+    // deep dim pays ~17 extra slots on every sample.  Deep dims must be a suffix of the sort order.
     int want = desc.n_deep;
     int nd = 0;
     if (want < 0) {
-      for (int d = NS - 1; d >= 0; --d) {
-        bool any = false;
-        for (int e = 0; e <= d; ++e)
-          if (total > 0 && changes[e] / total > 0.01) any = true;  // a frequent changer at or before d
-        if (total > 0 && changes[d] / total > 0.01) nd = NS - d;
-        (void)any;
+      double best = -1.0;
+      for (int cand = 0; cand <= std::min(NS, 4); ++cand) {
+        double cost = 0.0;
+        for (int s = 0; s < n_seg; ++s) {
+          const double n = (double)order[s].size();
+          for (int d = 0; d < NS - cand; ++d) cost += n * std::min(1.0, 32.0 * rate[s][d]) * 60.0;
+          cost += n * cand * 17.0;
+        }
+        if (best < 0.0 || cost < best) {
+          best = cost;
+          nd = cand;
+        }
       }
     } else {
       nd = want;
