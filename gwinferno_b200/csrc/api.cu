@@ -17,7 +17,7 @@ static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
 typedef void (*stream_fn)(const ModelDev*);
-stream_fn pick_stream_kernel(int ns, int ndeep, bool g2, bool param, bool maxonly);
+stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, bool maxonly);
 void launch_prologue(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t st);
 void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st);
 void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st);
@@ -337,8 +337,10 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     for (int i = 0; i < K.n_gslots; ++i) H.gslot_slot[K.gslot + i] = K.slot[i];
     if (K.kind != KOP_LIN) H.two_pass = 1;  // no a-priori bound for the non-linear terms: exact max first
   }
-  H.n_lin_fast = std::min(p.n_lin, 2);
-  const bool param = H.n_kops > H.n_lin_fast;
+  // up to 2 linear terms are register-resident in the stream kernel; any other non-spline term
+  // selects the generic-term variant, which then handles ALL non-spline terms
+  const bool param = H.n_kops > std::min(p.n_lin, 2);
+  H.n_lin_fast = param ? 0 : std::min(p.n_lin, 2);
   for (int q = 0; q < H.n_sops; ++q) {
     const Sop& S = p.sops[q];
     H.sops[q] = SopDev{S.kind, S.slot[0], S.slot[1], 0, S.cst[0], S.cst[1]};
@@ -430,8 +432,8 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   }
 
   // ---- kernels + shared memory ----
-  m->k_full = pick_stream_kernel(NS, p.n_deep, p.g2, param, false);
-  m->k_max = pick_stream_kernel(NS, p.n_deep, p.g2, true, true);
+  m->k_full = pick_stream_kernel(NS, p.n_deep, H.n_lin_fast, p.g2, param, false);
+  m->k_max = pick_stream_kernel(NS, p.n_deep, 0, p.g2, true, true);
   if (!m->k_full || !m->k_max) {
     set_error("no stream kernel instantiated for this (spline dims, deep dims) combination");
     gwi_model_destroy(m);

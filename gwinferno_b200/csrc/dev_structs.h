@@ -50,7 +50,7 @@ struct ModelDev {
   SopDev sops[MAX_SOPS];
   int32_t gslot_slot[MAX_GSLOTS];  // generic gradient slot -> Lambda slot
   // static arrays
-  const uint64_t* columns;  // [n_columns][n_padded]
+  const uint64_t* columns;  // [n_padded/64][n_columns][64]
   const Chunk* chunks;
   const SegDev* segs;
   const GroupDev* groups;

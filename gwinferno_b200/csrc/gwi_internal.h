@@ -115,7 +115,7 @@ struct Plan {
   int n_columns = 0;              // spline columns, then kop feature columns, then the static log-weight
   int col_static = 0;
   int64_t n_padded = 0;
-  std::vector<uint64_t> columns;  // column-major [n_columns][n_padded]
+  std::vector<uint64_t> columns;  // [n_padded/64][n_columns][64]: blocks of one warp iteration
   std::vector<Chunk> chunks;
   std::vector<Segment> segments;  // segment 0 = injections, 1..E = events
   // level-0 records and the reduction tree

@@ -767,6 +767,10 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     return GWI_ERR_ALLOC;
   }
   const double NEG_INF = -std::numeric_limits<double>::infinity();
+  // stream layout: blocks of 64 consecutive padded samples (one warp iteration: 32 lanes x UNROLL),
+  // inside a block the columns follow each other: word(col, p) = [p/64][col][p%64]
+  const size_t ncol_ = (size_t)plan.n_columns;
+  auto col_index = [ncol_](int col, int64_t p) -> size_t { return ((size_t)(p >> 6) * ncol_ + (size_t)col) * 64 + (size_t)(p & 63); };
   struct SegStat {
     double max_static;
     uint64_t occ[MAX_SPLINE_DIMS];
@@ -803,21 +807,21 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
                 int J;
                 double u;
                 spline_locate(geom[d], cols[geom[d].col][j], J, u);
-                plan.columns[(size_t)d * plan.n_padded + p] = pack_word(J, u);
+                plan.columns[col_index(d, p)] = pack_word(J, u);
                 st.occ[d] |= 1ull << J;
               }
               for (int f = 0; f < NK; ++f) {
                 const double v = eval_feat(kop_feats[f], cols, j);
-                std::memcpy(&plan.columns[(size_t)(NS + f) * plan.n_padded + p], &v, 8);
+                std::memcpy(&plan.columns[col_index(NS + f, p)], &v, 8);
               }
               double sw = 0.0;
               for (const Feat& f : static_feats) sw += eval_feat(f, cols, j);
-              std::memcpy(&plan.columns[(size_t)plan.col_static * plan.n_padded + p], &sw, 8);
+              std::memcpy(&plan.columns[col_index(plan.col_static, p)], &sw, 8);
               st.max_static = std::max(st.max_static, sw);
               for (size_t q = 0; q < plan.kops.size(); ++q)
                 if (plan.kops[q].kind == KOP_LIN) {
                   double v;
-                  std::memcpy(&v, &plan.columns[(size_t)plan.kops[q].col[0] * plan.n_padded + p], 8);
+                  std::memcpy(&v, &plan.columns[col_index(plan.kops[q].col[0], p)], 8);
                   st.fmin[q] = std::min(st.fmin[q], v);
                   st.fmax[q] = std::max(st.fmax[q], v);
                 }
@@ -829,13 +833,13 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
                 int J;
                 double u;
                 spline_locate(geom[d], cols[geom[d].col][j], J, u);
-                plan.columns[(size_t)d * plan.n_padded + p] = pack_word(J, u);
+                plan.columns[col_index(d, p)] = pack_word(J, u);
               }
               for (int f = 0; f < NK; ++f) {
                 const double v = eval_feat(kop_feats[f], cols, j);
-                std::memcpy(&plan.columns[(size_t)(NS + f) * plan.n_padded + p], &v, 8);
+                std::memcpy(&plan.columns[col_index(NS + f, p)], &v, 8);
               }
-              std::memcpy(&plan.columns[(size_t)plan.col_static * plan.n_padded + p], &NEG_INF, 8);
+              std::memcpy(&plan.columns[col_index(plan.col_static, p)], &NEG_INF, 8);
             }
           }
         }

@@ -2,5 +2,5 @@
 // make -j compiles them in parallel)
 #include "stream.cuh"
 namespace gwi {
-stream_fn pick_stream_ns7(int nd, bool g2, bool param, bool maxonly) { return pick_stream_for_ns<7>(nd, g2, param, maxonly); }
+stream_fn pick_stream_ns7(int nd, int nlin, bool g2, bool param, bool maxonly) { return pick_stream_for_ns<7>(nd, nlin, g2, param, maxonly); }
 }  // namespace gwi

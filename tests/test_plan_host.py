@@ -45,7 +45,7 @@ def test_struct_layouts_match_header_sizes():
 def _decode(case, plan):
     dims = plan.read(0)
     n_cols, n_pad, n_chunks, n_seg, ns, n_kops = (int(x) for x in dims[:6])
-    cols = plan.read(1, dtype=np.uint64).reshape(n_cols, n_pad)
+    cols = np.ascontiguousarray(plan.read(1, dtype=np.uint64).reshape(n_pad // 64, n_cols, 64).transpose(1, 0, 2).reshape(n_cols, n_pad))
     chunks = plan.read(2).reshape(n_chunks, 4)
     segs = plan.read(3).reshape(n_seg, 4)
     dimt = plan.read(4).reshape(ns, 4)
