@@ -17,6 +17,12 @@ constexpr int MAX_SOPS = 16;        // scalar (sample-independent) normaliser op
 constexpr int KC_STRIDE = 12;       // doubles of per-eval constants per kop
 constexpr int LANES = 32;
 constexpr int UNROLL = 2;           // samples per lane per load (16-byte vector loads)
+#ifndef GWI_DEEP_LANES
+#define GWI_DEEP_LANES 16
+#endif
+// copies of the deep accumulators per warp: 16 = lanes l and l+16 share a slot (two update phases,
+// half the shared memory), 32 = fully lane-private (one phase)
+constexpr int DEEP_LANES = GWI_DEEP_LANES;
 
 // ---- packed spline word: bits 63..52 = piece index J, bits 51..0 = mantissa of (1 + u) --------
 constexpr uint64_t MANT_MASK = 0x000FFFFFFFFFFFFFull;

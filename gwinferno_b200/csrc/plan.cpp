@@ -702,7 +702,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     const int mom_ = plan.g2 ? 2 : 1;
     for (;;) {
       int64_t bytes = (int64_t)plan.rows_total * 4 * mom_ * 8;
-      for (int d = NS - nd; d < NS; ++d) bytes += (int64_t)plan.dims[d].rows * 4 * mom_ * 16 * 8;
+      for (int d = NS - nd; d < NS; ++d) bytes += (int64_t)plan.dims[d].rows * 4 * mom_ * DEEP_LANES * 8;
       if (nd == 0 || bytes * 4 <= 200 * 1024) break;
       --nd;
     }
@@ -716,7 +716,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   int rows_shallow = 0, rows_deep = 0;
   for (int d = 0; d < NS; ++d) (plan.dims[d].deep ? rows_deep : rows_shallow) += plan.dims[d].rows;
   (void)rows_shallow;
-  const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * 16 * 8 +
+  const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * DEEP_LANES * 8 +
                              (int64_t)plan.n_gslots * (1 + mom) * LANES * 8;
   const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
   int wpb = (int)((220 * 1024 - cta_fixed) / std::max<int64_t>(1, warp_bytes));
@@ -728,7 +728,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   int K = desc.chunk_steps;
   if (K <= 0) {
     K = (int)(n_valid / ((int64_t)W * LANES * 4));
-    K = std::max(32, std::min(K, 512));
+    K = std::max(32, std::min(K, 256));  // measured on cfg3: 256 beats 512 and 128 by 3 %
   }
   K = (K + 2 * UNROLL - 1) / (2 * UNROLL) * (2 * UNROLL);
   plan.chunk_steps = K;
