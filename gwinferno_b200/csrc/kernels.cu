@@ -160,16 +160,18 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
       const DimDev& D = M.dims[d];
       if (D.norm_group != g) continue;
       const double* aux = M.grid_pool + D.grid_aux;
-      for (int k = tid; k < D.n_splines; k += nt) {
+      // one warp per basis function, lanes stride over the grid points in its support
+      for (int k = tid >> 5; k < D.n_splines; k += nt >> 5) {
         double acc = 0.0;
         const int lo = (int)aux[5 * G + k], hi = (int)aux[5 * G + D.n_splines + k];
-        for (int i = lo; i < hi; ++i) {
+        for (int i = lo + (tid & 31); i < hi; i += 32) {
           const int J = (int)aux[4 * G + i];
           const int kk = k - J;
           if (J < 0 || kk < 0 || kk > 3) continue;
           acc += li[i] * aux[4 * i + kk];
         }
-        M.dlogZ[(size_t)g * P + D.slot + k] += acc * inv;
+        acc = warp_sum(acc);
+        if ((tid & 31) == 0) M.dlogZ[(size_t)g * P + D.slot + k] += acc * inv;
       }
       __syncthreads();
     }

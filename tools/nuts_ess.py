@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""NUTS ESS/s of the B-spline population model through the fused GPU likelihood (the second half of
+BASELINE.json's metric).  Priors and smoothing penalties follow examples/simple_bspline_example.py
+(bspline_mass_prior m_tau=1 q_tau=1, bspline_spin_prior a_tau=25 ct_tau=25, bspline_redshift_prior
+z_tau=1, lamb ~ N(0,3)); the sampler is gwinferno_b200/nuts.py.  Prints one JSON line."""
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from gwinferno_b200 import nuts, workloads  # noqa: E402
+from gwinferno_b200.likelihood import PopulationLikelihood  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--warmup", type=int, default=150)
+    ap.add_argument("--samples", type=int, default=200)
+    ap.add_argument("--max-depth", type=int, default=8)
+    args = ap.parse_args()
+    pe, inj, const, z_range = workloads.shard_catalog(args.workload, 0, 1, scale=args.scale)
+    weights, params_fn = workloads.build_model(const["family"], pe, inj, z_range=z_range)
+    low, lam0, p0 = workloads.lower_workload(weights, params_fn, pe, inj)
+    eng = PopulationLikelihood(low, const["total_inj"])
+    Nobs = const["E"]
+
+    def loglike(lam):
+        log_l, grad, head = eng.loglike(lam, Nobs=Nobs)
+        return log_l, grad
+
+    S = low.slots_for
+    blocks = [
+        (S(p0["mass_cs"]), 15.0, 1.0, 1, False),
+        (S(p0["q_cs"]), 5.0, 1.0, 1, False),
+        (S(p0["a1_cs"]), 5.0, 25.0, 2, False),
+        (S(p0["a2_cs"]), 5.0, 25.0, 2, False),
+        (S(p0["tilt1_cs"]), 5.0, 25.0, 2, False),
+        (S(p0["tilt2_cs"]), 5.0, 25.0, 2, False),
+        (S(p0["z_cs"]), 1.0, 1.0, 2, True),
+        (S(p0["lamb"]), 3.0, None, 0, False),
+    ]
+    post = nuts.BSplinePosterior(loglike, low.spec.n_params, blocks)
+    rng = np.random.default_rng(0)
+    theta0 = 0.1 * rng.standard_normal(post.dim)
+    t0 = time.perf_counter()
+    samples, info = nuts.nuts(post, theta0, args.warmup, args.samples, rng, max_depth=args.max_depth)
+    wall = time.perf_counter() - t0
+    ess = np.array([nuts.effective_sample_size(samples[:, i]) for i in range(samples.shape[1])])
+    out = {
+        "metric": "NUTS ESS/s", "workload": args.workload, "E": const["E"], "S": const["S"], "I": const["I"], "dim": post.dim,
+        "warmup": args.warmup, "samples": args.samples, "max_tree_depth": args.max_depth,
+        "ess_min": float(ess.min()), "ess_median": float(np.median(ess)),
+        "ess_min_per_s": float(ess.min() / info["sampling_seconds"]), "ess_median_per_s": float(np.median(ess) / info["sampling_seconds"]),
+        "grad_evals_total": post.n_evals, "grad_evals_per_s_overall": post.n_evals / wall, "wall_s": wall, **info,
+        "sampler": "gwinferno_b200/nuts.py (NumPy NUTS, diagonal mass); likelihood+gradient on the GPU via gwi_loglike_host",
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
