@@ -889,7 +889,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       const int nxt = c + W;
       plan.chunks[c].flush = (nxt >= n_chunks || run_of_chunk[nxt] != run_of_chunk[c]) ? 1 : 0;
     }
-    // reduction tree, fan-in 32; the last level writes slot == segment
+    // reduction tree, fan-in 64; the last level writes slot == segment
     std::vector<int> cnt(n_seg, 0), first(n_seg, 0);
     for (auto& r : runs) cnt[r.segment]++;
     {
@@ -899,7 +899,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         acc += cnt[s];
       }
     }
-    constexpr int FAN = 32;
+    constexpr int FAN = 64;
     for (;;) {
       bool last = true;
       for (int s = 0; s < n_seg; ++s)

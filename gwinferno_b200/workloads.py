@@ -20,9 +20,10 @@ WORKLOADS = {
 }
 
 
-def shard_catalog(name, rank=0, world=1, scale=1.0, all_reduce_minmax=None):
-    """This rank's share of workload ``name``: whole events ``e % world == rank`` and the injection
-    index range ``[rank I/world, (rank+1) I/world)``.  Returns ``(pe, inj, constants, z_range)``;
+def shard_catalog(name, rank=0, world=1, scale=1.0, all_reduce_minmax=None, shard_by="m1"):
+    """This rank's share of workload ``name``: whole events ``e % world == rank`` and either an
+    equal-count primary-mass band of the found injections (``shard_by="m1"``, default) or the index
+    range ``[rank I/world, (rank+1) I/world)`` (``shard_by="index"``).  Returns ``(pe, inj, constants, z_range)``;
     ``z_range`` is the redshift range of the WHOLE catalog (parametric.py:114-115), obtained with
     ``all_reduce_minmax(lo, hi) -> (min over ranks of lo, max over ranks of hi)`` when sharded."""
     cfg_idx, family, E, S, I = WORKLOADS[name]
@@ -33,8 +34,23 @@ def shard_catalog(name, rank=0, world=1, scale=1.0, all_reduce_minmax=None):
     zpe = (float(pe_all["redshift"].min()), float(pe_all["redshift"].max()))
     pe = {k: np.ascontiguousarray(v[rank::world]) for k, v in pe_all.items()}
     del pe_all
-    a, b = rank * I // world, (rank + 1) * I // world
-    inj = synthetic.make_injections(I, 1000 * cfg + 1, a, b)
+    if world == 1 or shard_by == "index":
+        a, b = rank * I // world, (rank + 1) * I // world
+        inj = synthetic.make_injections(I, 1000 * cfg + 1, a, b)
+    else:
+        # shard by PRIMARY-MASS BAND (equal-count quantile bands): any partition of the found
+        # injections gives the same sums, and a band keeps each rank's samples concentrated in a few
+        # pieces of the leading spline dimension, so the piece-sorted runs stay as long as on one GPU
+        first = synthetic.make_injections(I, 1000 * cfg + 1, 0, min(I, synthetic.INJ_BLOCK))
+        edges = np.quantile(first["mass_1"], np.linspace(0.0, 1.0, world + 1))
+        edges[0], edges[-1] = -np.inf, np.inf
+        parts = {k: [] for k in synthetic.INJ_COLS}
+        for blk in range(0, I, synthetic.INJ_BLOCK):
+            cols = synthetic.make_injections(I, 1000 * cfg + 1, blk, min(I, blk + synthetic.INJ_BLOCK))
+            keep = (cols["mass_1"] >= edges[rank]) & (cols["mass_1"] < edges[rank + 1])
+            for k in parts:
+                parts[k].append(cols[k][keep])
+        inj = {k: np.concatenate(v) for k, v in parts.items()}
     zlo, zhi = float(inj["redshift"].min()), float(inj["redshift"].max())
     if world > 1:
         zlo, zhi = all_reduce_minmax(zlo, zhi)
