@@ -383,6 +383,10 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   Chunk* d_chunks;
   UP(upload(m, p.chunks.data(), p.chunks.size(), &d_chunks));
   H.chunks = d_chunks;
+  int32_t* d_slices;
+  UP(upload(m, p.slice_begin.data(), p.slice_begin.size(), &d_slices));
+  H.slice_begin = d_slices;
+  H.n_slices = (int)p.slice_begin.size() - 1;
   SegDev* d_segs;
   UP(upload(m, segs.data(), segs.size(), &d_segs));
   H.segs = d_segs;

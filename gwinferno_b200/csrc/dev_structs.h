@@ -42,7 +42,7 @@ struct GroupDev {
 struct ModelDev {
   int32_t n_params, n_dims, n_deep, n_kops, n_gslots, n_sops, n_groups, n_segments;
   int32_t rows_total, rec_doubles, n_columns, col_static, g2, two_pass, n_chunks, deep_entries;
-  int32_t n_lin_fast, pad0;  // leading LIN kops handled in registers by the stream kernel
+  int32_t n_lin_fast, n_slices;  // leading LIN kops handled in registers by the stream kernel
   int64_t n_padded;
   double total_inj;
   DimDev dims[MAX_SPLINE_DIMS];
@@ -52,6 +52,7 @@ struct ModelDev {
   // static arrays
   const uint64_t* columns;  // [n_padded/64][n_columns][64]
   const Chunk* chunks;
+  const int32_t* slice_begin;  // [n_slices + 1]
   const SegDev* segs;
   const GroupDev* groups;
   const double* grid_pool;

@@ -123,6 +123,7 @@ struct Plan {
   int64_t n_padded = 0;
   std::vector<uint64_t> columns;  // [n_padded/64][n_columns][64]: blocks of one warp iteration
   std::vector<Chunk> chunks;
+  std::vector<int32_t> slice_begin;  // slice i = chunks [slice_begin[i], slice_begin[i+1]); warp = i % W
   std::vector<Segment> segments;  // segment 0 = injections, 1..E = events
   // level-0 records and the reduction tree
   int rec_doubles = 0;

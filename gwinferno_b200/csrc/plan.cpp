@@ -724,30 +724,53 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   plan.warps_per_block = wpb;
   plan.grid_blocks = std::max(1, sm_count);
   const int W = plan.grid_blocks * plan.warps_per_block;
-  const int64_t n_valid = plan.n_valid_pe + plan.n_valid_inj;
-  int K = desc.chunk_steps;
-  if (K <= 0) {
-    K = (int)(n_valid / ((int64_t)W * LANES * 4));
-    K = std::max(32, std::min(K, 256));  // measured on cfg3: 256 beats 512 and 128 by 3 %
-  }
-  K = (K + 2 * UNROLL - 1) / (2 * UNROLL) * (2 * UNROLL);
-  plan.chunk_steps = K;
-  int64_t pos = 0;
+  // Balanced slicing: the piece-sorted sample stream of all segments (injections first, then the
+  // events) is cut into SLICES of L steps (32 samples per step); slice i belongs to warp i % W.
+  // By default L = ceil(total steps / W): every warp gets exactly one slice, i.e. the same amount
+  // of work.  A slice is split into CHUNKS at segment boundaries; the lanes of the warp own
+  // contiguous sorted runs inside each chunk.  (desc.chunk_steps > 0 caps L: tests use it to force
+  // many slices per warp.)
+  constexpr int Q = 2 * UNROLL;  // chunk steps are a multiple of the kernel's load pipeline depth
+  auto roundQ = [](int64_t v) { return (v + Q - 1) / Q * Q; };
+  int64_t total_steps = 0;
+  for (int s = 0; s < n_seg; ++s) total_steps += roundQ((plan.segments[s].n_valid + LANES - 1) / LANES);
+  // m slices per warp, dealt round-robin: the cost per sample varies along the sorted stream
+  // (sparse piece combinations spill more often), so every warp must sample the whole stream; m*W
+  // slices of equal length give every warp exactly m of them.  ~192 steps per slice measured best.
+  const int64_t per_warp = (total_steps + W - 1) / W;
+  const int64_t m_slices = std::max<int64_t>(4, (per_warp + 96) / 192);  // >= 4: small shards need the interleaving most
+  int64_t L = roundQ((total_steps + W * m_slices - 1) / (W * m_slices) + Q);  // + Q: per-chunk rounding
+  L = std::max<int64_t>(L, 8 * Q);
+  if (desc.chunk_steps > 0) L = std::min<int64_t>(L, roundQ(desc.chunk_steps));
+  plan.chunk_steps = (int)L;
+  std::vector<int64_t> chunk_r0, chunk_nc;  // first sorted rank / valid samples of every chunk
+  plan.slice_begin.clear();
+  plan.slice_begin.push_back(0);
+  int64_t pos = 0, fill = 0;
   for (int s = 0; s < n_seg; ++s) {
     Segment& S = plan.segments[s];
     S.first_chunk = (int)plan.chunks.size();
-    int64_t left = S.n_valid;
+    int64_t left = S.n_valid, r0 = 0;
     while (left > 0) {
-      const int64_t n_c = std::min<int64_t>(left, (int64_t)LANES * K);
-      int steps = (int)((n_c + LANES - 1) / LANES);
-      steps = (steps + 2 * UNROLL - 1) / (2 * UNROLL) * (2 * UNROLL);  // the kernel's load pipeline is 2 iterations deep
+      // slice full -- or a new segment that does not fit into the rest of this slice: start it on a
+      // fresh slice instead of fragmenting it (every chunk boundary costs a record flush)
+      if (L - fill < Q || (r0 == 0 && fill > 0 && roundQ((left + LANES - 1) / LANES) > L - fill)) {
+        plan.slice_begin.push_back((int)plan.chunks.size());
+        fill = 0;
+      }
+      const int64_t steps = std::min<int64_t>(L - fill, roundQ((left + LANES - 1) / LANES));
+      const int64_t n_c = std::min<int64_t>(left, steps * LANES);
       Chunk c{};
       c.segment = s;
-      c.steps = steps;
+      c.steps = (int)steps;
       c.first = pos;
       plan.chunks.push_back(c);
-      pos += (int64_t)steps * LANES;
+      chunk_r0.push_back(r0);
+      chunk_nc.push_back(n_c);
+      pos += steps * LANES;
+      fill += steps;
       left -= n_c;
+      r0 += n_c;
     }
     S.n_chunks = (int)plan.chunks.size() - S.first_chunk;
     S.max_static = -std::numeric_limits<double>::infinity();
@@ -756,6 +779,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       S.fmax[k] = -std::numeric_limits<double>::infinity();
     }
   }
+  plan.slice_begin.push_back((int)plan.chunks.size());
   plan.n_padded = pos;
   const int n_chunks = (int)plan.chunks.size();
 
@@ -788,8 +812,9 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         const Segment& S = plan.segments[s];
         const double* const* cols = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
         const std::vector<uint32_t>& ord = order[s];
-        const int64_t r0 = (int64_t)(c - S.first_chunk) * LANES * K;  // first sorted rank of this chunk
-        const int64_t n_c = std::min<int64_t>(S.n_valid - r0, (int64_t)LANES * K);
+        const int64_t r0 = chunk_r0[c];  // first sorted rank of this chunk
+        const int64_t n_c = chunk_nc[c];
+        (void)S;
         SegStat st;
         st.max_static = NEG_INF;
         for (int d = 0; d < MAX_SPLINE_DIMS; ++d) st.occ[d] = 0;
@@ -867,15 +892,21 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     };
     std::vector<Run> runs;
     std::vector<int> run_of_chunk(n_chunks, -1);
+    const int n_slices = (int)plan.slice_begin.size() - 1;
+    std::vector<int> next_chunk(n_chunks, -1);  // the chunk the same warp processes next
     for (int w = 0; w < W; ++w) {
-      int prev_seg = -1;
-      for (int c = w; c < n_chunks; c += W) {
-        const int s = plan.chunks[c].segment;
-        if (s != prev_seg) {
-          runs.push_back(Run{s, w, (int)runs.size()});
-          prev_seg = s;
+      int prev_seg = -1, prev_chunk = -1;
+      for (int sl = w; sl < n_slices; sl += W) {
+        for (int c = plan.slice_begin[sl]; c < plan.slice_begin[sl + 1]; ++c) {
+          const int s = plan.chunks[c].segment;
+          if (s != prev_seg) {
+            runs.push_back(Run{s, w, (int)runs.size()});
+            prev_seg = s;
+          }
+          run_of_chunk[c] = (int)runs.size() - 1;
+          if (prev_chunk >= 0) next_chunk[prev_chunk] = c;
+          prev_chunk = c;
         }
-        run_of_chunk[c] = (int)runs.size() - 1;
       }
     }
     std::vector<int> idx(runs.size());
@@ -886,8 +917,8 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     plan.n_records0 = (int)runs.size();
     for (int c = 0; c < n_chunks; ++c) {
       plan.chunks[c].record_slot = slot_of_run[run_of_chunk[c]];
-      const int nxt = c + W;
-      plan.chunks[c].flush = (nxt >= n_chunks || run_of_chunk[nxt] != run_of_chunk[c]) ? 1 : 0;
+      const int nxt = next_chunk[c];
+      plan.chunks[c].flush = (nxt < 0 || run_of_chunk[nxt] != run_of_chunk[c]) ? 1 : 0;
     }
     // reduction tree, fan-in 64; the last level writes slot == segment
     std::vector<int> cnt(n_seg, 0), first(n_seg, 0);
