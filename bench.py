@@ -9,7 +9,7 @@ One "step" = one fused evaluation of log L and d log L / d Lambda over the whole
 ("B-spline full model, 300 events x 10k samples, 1e8 injections") -- the configuration the
 north-star's ">= 70 % of HBM roofline on 1 B200 / >= 85 % scaling at 8 GPUs" is quoted on; its
 plan (7.4 GB) is far larger than L2, so consecutive timed steps cannot be served from cache.
-Multi-GPU: injections sharded by primary-mass band, whole events dealt round-robin, one NCCL
+Multi-GPU: injections sharded by (m1, q) piece bucket, whole events dealt round-robin, one NCCL
 all-gather of ~4 KB partial records per step; total work is fixed => "scaling": "strong".
 
 PyTorch is used only as plumbing (NCCL all-gather, CUDA events, device scratch tensors); every
@@ -311,7 +311,7 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "model": const["family"], "E": const["E"], "S": const["S"], "I": const["I"],
-            "n_params": P, "samples_per_eval": n_total, "parallelism": (f"shard{world}: injections by primary-mass band, whole events round-robin, one all-gather" if args.shard_by == "m1" else f"shard{world}: injections by index range") if world > 1 else "single",
+            "n_params": P, "samples_per_eval": n_total, "parallelism": (f"shard{world}: injections by (m1, q) piece bucket, whole events round-robin, one all-gather" if args.shard_by == "bucket" else f"shard{world}: injections by index range") if world > 1 else "single",
             "l2_policy": "inputs larger than L2 (plan %.2f GB per GPU)" % (info["bytes_per_eval"] / 1e9) if info["bytes_per_eval"] > 2.6e8 else "inputs fit in L2; new Lambda every step, no flush",
             "neff_grad": False, "likelihood": "marginalize_selection=False, min_neff_cut=True (reference defaults)",
         },
@@ -342,7 +342,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink S and I (testing only; the reported config then differs from BASELINE's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard-by", default="m1", choices=["m1", "index"], help="multi-GPU partition of the found injections")
+    ap.add_argument("--shard-by", default="bucket", choices=["bucket", "index"], help="multi-GPU partition of the found injections")
     ap.add_argument("--n-deep", type=int, default=-1, help="tuning experiment: spline dims with lane-private accumulators (-1 = auto)")
     ap.add_argument("--chunk-steps", type=int, default=0, help="tuning experiment: samples per lane per chunk (0 = auto)")
     args = ap.parse_args()

@@ -18,7 +18,8 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 typedef void (*stream_fn)(const ModelDev*);
 stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, bool maxonly);
-void launch_prologue(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t st);
+void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, cudaStream_t st);
+void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t aux);
 void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st);
 void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st);
 void launch_finish(const ModelDev* Md, int n_seg, cudaStream_t st);
@@ -57,6 +58,8 @@ struct gwi_model {
   double* lam_pinned = nullptr;
   double* out_pinned = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;  // grid normalisers run here, concurrently with the stream kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t bytes_per_eval = 0;
   // optional timing of the stream kernel (ring of event pairs)
   bool timing = false;
@@ -245,6 +248,9 @@ void gwi_model_destroy(gwi_model* m) {
   if (m->lam_pinned) cudaFreeHost(m->lam_pinned);
   if (m->out_pinned) cudaFreeHost(m->out_pinned);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   for (auto e : m->ev0) cudaEventDestroy(e);
   for (auto e : m->ev1) cudaEventDestroy(e);
   delete m;
@@ -429,7 +435,10 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
 #undef UP
   if (cudaMallocHost((void**)&m->lam_pinned, sizeof(double) * P) != cudaSuccess ||
       cudaMallocHost((void**)&m->out_pinned, sizeof(double) * (GWI_LIKE_HEADER + P)) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     set_error("pinned host allocation / stream creation failed");
     gwi_model_destroy(m);
     return GWI_ERR_ALLOC;
@@ -461,7 +470,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     gwi_model_destroy(m);
     return GWI_ERR_CUDA;
   }
-  m->launches_per_eval = 1 + (H.two_pass ? 2 : 0) + 1 + (int)p.levels.size() + 1 + 2;
+  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + (int)p.levels.size() + 1 + 2;
   CUDA_TRY(cudaDeviceSynchronize());
   *out = m;
   return GWI_OK;
@@ -471,7 +480,12 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
 static int run_eval(gwi_model* m, const double* lam_dev, cudaStream_t st) {
   const Plan& p = m->plan;
   const ModelDev& H = m->host;
-  launch_prologue(m->dev, lam_dev, H.n_groups, m->max_grid, st);
+  // fork: the grid normalisers (needed only by finish_kernel) overlap with the stream kernel
+  cudaEventRecord(m->ev_fork, st);
+  cudaStreamWaitEvent(m->aux_stream, m->ev_fork, 0);
+  launch_prologue_groups(m->dev, lam_dev, H.n_groups, m->max_grid, m->aux_stream);
+  cudaEventRecord(m->ev_join, m->aux_stream);
+  launch_prologue_tables(m->dev, lam_dev, H.n_groups, st);
   const dim3 grid(p.grid_blocks), block(p.warps_per_block * 32);
   if (H.n_chunks > 0) {
     if (H.two_pass) {
@@ -487,6 +501,7 @@ static int run_eval(gwi_model* m, const double* lam_dev, cudaStream_t st) {
     launch_reduce(in, m->level_out[l], m->level_tasks[l].first, m->level_tasks[l].second, H.rec_doubles, st);
     in = m->level_out[l];
   }
+  cudaStreamWaitEvent(st, m->ev_join, 0);  // join
   launch_finish(m->dev, H.n_segments, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;

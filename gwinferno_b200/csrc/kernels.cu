@@ -110,15 +110,16 @@ __device__ void powerlaw_lognorm(double alpha, double lo, double hi, double& log
 // =================================================================================================
 // prologue
 // =================================================================================================
-__global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam) {
+__global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam, int role_off) {
   const ModelDev& M = *Mp;
   extern __shared__ double sm[];
   __shared__ double scratch[32];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = M.n_params;
-  if ((int)blockIdx.x < M.n_groups) {
+  const int role = (int)blockIdx.x + role_off;  // [0, n_groups): one norm group each; n_groups: tables + shifts
+  if (role < M.n_groups) {
     // ---------------- one norm group ----------------
-    const int g = blockIdx.x;
+    const int g = role;
     const int G = M.groups[g].n_grid;
     const double* logw = M.grid_pool + M.groups[g].logw_off;
     double* li = sm;  // [G]
@@ -540,8 +541,13 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
 // =================================================================================================
 // host-side launch helpers (called from api.cu)
 // =================================================================================================
-void launch_prologue(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t st) {
-  prologue_kernel<<<n_groups + 1, 256, (size_t)max_grid * sizeof(double), st>>>(Md, lam);
+// tables + shifts (what the stream kernel needs) on `st`; the grid normalisers (only needed by
+// finish_kernel) on `aux`, concurrently with the stream kernel
+void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, cudaStream_t st) {
+  prologue_kernel<<<1, 256, 0, st>>>(Md, lam, n_groups);
+}
+void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t aux) {
+  if (n_groups > 0) prologue_kernel<<<n_groups, 256, (size_t)max_grid * sizeof(double), aux>>>(Md, lam, 0);
 }
 void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st) {
   dim3 grid(n_tasks, (rec + 255) / 256);

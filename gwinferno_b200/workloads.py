@@ -20,9 +20,9 @@ WORKLOADS = {
 }
 
 
-def shard_catalog(name, rank=0, world=1, scale=1.0, all_reduce_minmax=None, shard_by="m1"):
-    """This rank's share of workload ``name``: whole events ``e % world == rank`` and either an
-    equal-count primary-mass band of the found injections (``shard_by="m1"``, default) or the index
+def shard_catalog(name, rank=0, world=1, scale=1.0, all_reduce_minmax=None, shard_by="bucket"):
+    """This rank's share of workload ``name``: whole events ``e % world == rank`` and either whole
+    (m1-piece, q-piece) buckets of the found injections (``shard_by="bucket"``, default) or the index
     range ``[rank I/world, (rank+1) I/world)`` (``shard_by="index"``).  Returns ``(pe, inj, constants, z_range)``;
     ``z_range`` is the redshift range of the WHOLE catalog (parametric.py:114-115), obtained with
     ``all_reduce_minmax(lo, hi) -> (min over ranks of lo, max over ranks of hi)`` when sharded."""
@@ -38,19 +38,27 @@ def shard_catalog(name, rank=0, world=1, scale=1.0, all_reduce_minmax=None, shar
         a, b = rank * I // world, (rank + 1) * I // world
         inj = synthetic.make_injections(I, 1000 * cfg + 1, a, b)
     else:
-        # shard by PRIMARY-MASS BAND (equal-count quantile bands): any partition of the found
-        # injections gives the same sums, and a band keeps each rank's samples concentrated in a few
-        # pieces of the leading spline dimension, so the piece-sorted runs stay as long as on one GPU
-        first = synthetic.make_injections(I, 1000 * cfg + 1, 0, min(I, synthetic.INJ_BLOCK))
-        edges = np.quantile(first["mass_1"], np.linspace(0.0, 1.0, world + 1))
-        edges[0], edges[-1] = -np.inf, np.inf
-        parts = {k: [] for k in synthetic.INJ_COLS}
-        for blk in range(0, I, synthetic.INJ_BLOCK):
-            cols = synthetic.make_injections(I, 1000 * cfg + 1, blk, min(I, blk + synthetic.INJ_BLOCK))
-            keep = (cols["mass_1"] >= edges[rank]) & (cols["mass_1"] < edges[rank + 1])
-            for k in parts:
-                parts[k].append(cols[k][keep])
-        inj = {k: np.concatenate(v) for k, v in parts.items()}
+        # Shard by PIECE BUCKET: the found injections are grouped by the spline pieces of their two
+        # leading coordinates (log m1: 48 pieces, q: 28 pieces at the default spline counts) and whole
+        # buckets are dealt to the ranks (largest first, to the least loaded rank).  Any partition
+        # gives the same sums; this one keeps every rank's piece-sorted runs exactly as long as on
+        # one GPU and spreads sparse and dense regions of parameter space evenly over the ranks.
+        n1, n2 = NSPLINES["m1"] - 3, NSPLINES["q"] - 3
+        cols_all = synthetic.make_injections(I, 1000 * cfg + 1)
+        j1 = np.clip(np.floor((np.log(cols_all["mass_1"]) - np.log(MMIN)) / (np.log(MMAX) - np.log(MMIN)) * n1), 0, n1 - 1).astype(np.int64)
+        qmin = MMIN / MMAX
+        j2 = np.clip(np.floor((cols_all["mass_ratio"] - qmin) / (1.0 - qmin) * n2), 0, n2 - 1).astype(np.int64)
+        bucket = j1 * n2 + j2
+        counts = np.bincount(bucket, minlength=n1 * n2)
+        owner = np.zeros(n1 * n2, dtype=np.int64)
+        load = np.zeros(world, dtype=np.int64)
+        for b in np.argsort(-counts, kind="stable"):
+            r = int(np.argmin(load))
+            owner[b] = r
+            load[r] += counts[b]
+        keep = owner[bucket] == rank
+        inj = {k: np.ascontiguousarray(v[keep]) for k, v in cols_all.items()}
+        del cols_all, bucket, j1, j2, keep
     zlo, zhi = float(inj["redshift"].min()), float(inj["redshift"].max())
     if world > 1:
         zlo, zhi = all_reduce_minmax(zlo, zhi)
