@@ -410,6 +410,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_groups) * P, &H.dlogZ));
   UP(upload<double>(m, nullptr, (size_t)P + 1, &H.Ksum));
   UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_chunks), &H.chunk_max));
+  UP(upload<int32_t>(m, nullptr, (size_t)2, &H.slice_counter));
   UP(upload<double>(m, nullptr, (size_t)std::max(1, p.n_records0) * p.rec_doubles, &H.records0));
   UP(upload<double>(m, nullptr, (size_t)nseg * p.rec_doubles, &H.seg_rec));
   UP(upload<double>(m, nullptr, (size_t)nseg * 4, &H.seg_out));

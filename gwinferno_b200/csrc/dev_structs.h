@@ -65,6 +65,7 @@ struct ModelDev {
   double* dlogZ;      // [n_groups*P]
   double* Ksum;       // [1 + P] : K = sum(sops) - sum(logZ), then dK
   double* chunk_max;  // [n_chunks] (two-pass mode)
+  int32_t* slice_counter;  // [2] dynamic slice scheduling: [0] full pass, [1] max-only pass; reset by the prologue
   double* records0;   // [n_records0 * rec]
   double* seg_rec;    // [n_segments * rec]
   double* seg_out;    // [n_segments * 4] {logmean, logneff, var, status}

@@ -188,6 +188,10 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     return;
   }
   // ---------------- tables, kop constants, scalar normalisers, shifts ----------------
+  if (tid == 0) {
+    M.slice_counter[0] = 0;
+    M.slice_counter[1] = 0;
+  }
   for (int r = tid; r < M.rows_total; r += nt) {
     int d = 0;
     while (d + 1 < M.n_dims && r >= M.dims[d + 1].row_off) ++d;

@@ -734,12 +734,11 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   auto roundQ = [](int64_t v) { return (v + Q - 1) / Q * Q; };
   int64_t total_steps = 0;
   for (int s = 0; s < n_seg; ++s) total_steps += roundQ((plan.segments[s].n_valid + LANES - 1) / LANES);
-  // m slices per warp, dealt round-robin: the cost per sample varies along the sorted stream
-  // (sparse piece combinations spill more often), so every warp must sample the whole stream; m*W
-  // slices of equal length give every warp exactly m of them.  ~192 steps per slice measured best.
+  // Slices are pulled dynamically by the warps (stream.cuh), so they only need to be small enough
+  // for a good tail (>= ~8 per warp when the problem allows) and large enough to amortise the
+  // per-chunk record flush (~2 us): 32..256 steps.
   const int64_t per_warp = (total_steps + W - 1) / W;
-  const int64_t m_slices = std::max<int64_t>(4, (per_warp + 96) / 192);  // >= 4: small shards need the interleaving most
-  int64_t L = roundQ((total_steps + W * m_slices - 1) / (W * m_slices) + Q);  // + Q: per-chunk rounding
+  int64_t L = roundQ(std::max<int64_t>(32, std::min<int64_t>(256, per_warp / 8)));
   L = std::max<int64_t>(L, 8 * Q);
   if (desc.chunk_steps > 0) L = std::min<int64_t>(L, roundQ(desc.chunk_steps));
   plan.chunk_steps = (int)L;
@@ -885,44 +884,16 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     }
   }
 
-  // ---- level-0 record slots: warp w walks chunks w, w+W, ...; one record per (warp, segment run)
+  // ---- level-0 records: one per chunk (chunks are created in segment order, so the records of
+  //      a segment are consecutive); fixed-order tree reduction afterwards
   {
-    struct Run {
-      int segment, warp, seq;
-    };
-    std::vector<Run> runs;
-    std::vector<int> run_of_chunk(n_chunks, -1);
-    const int n_slices = (int)plan.slice_begin.size() - 1;
-    std::vector<int> next_chunk(n_chunks, -1);  // the chunk the same warp processes next
-    for (int w = 0; w < W; ++w) {
-      int prev_seg = -1, prev_chunk = -1;
-      for (int sl = w; sl < n_slices; sl += W) {
-        for (int c = plan.slice_begin[sl]; c < plan.slice_begin[sl + 1]; ++c) {
-          const int s = plan.chunks[c].segment;
-          if (s != prev_seg) {
-            runs.push_back(Run{s, w, (int)runs.size()});
-            prev_seg = s;
-          }
-          run_of_chunk[c] = (int)runs.size() - 1;
-          if (prev_chunk >= 0) next_chunk[prev_chunk] = c;
-          prev_chunk = c;
-        }
-      }
-    }
-    std::vector<int> idx(runs.size());
-    std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return runs[a].segment < runs[b].segment; });
-    std::vector<int> slot_of_run(runs.size());
-    for (size_t i = 0; i < idx.size(); ++i) slot_of_run[idx[i]] = (int)i;
-    plan.n_records0 = (int)runs.size();
-    for (int c = 0; c < n_chunks; ++c) {
-      plan.chunks[c].record_slot = slot_of_run[run_of_chunk[c]];
-      const int nxt = next_chunk[c];
-      plan.chunks[c].flush = (nxt < 0 || run_of_chunk[nxt] != run_of_chunk[c]) ? 1 : 0;
-    }
-    // reduction tree, fan-in 64; the last level writes slot == segment
+    plan.n_records0 = n_chunks;
     std::vector<int> cnt(n_seg, 0), first(n_seg, 0);
-    for (auto& r : runs) cnt[r.segment]++;
+    for (int c = 0; c < n_chunks; ++c) {
+      plan.chunks[c].record_slot = c;
+      plan.chunks[c].flush = 1;
+      cnt[plan.chunks[c].segment]++;
+    }
     {
       int acc = 0;
       for (int s = 0; s < n_seg; ++s) {
@@ -930,6 +901,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         acc += cnt[s];
       }
     }
+    // reduction tree, fan-in 64; the last level writes slot == segment
     constexpr int FAN = 64;
     for (;;) {
       bool last = true;
