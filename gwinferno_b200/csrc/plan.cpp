@@ -735,10 +735,11 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   int64_t total_steps = 0;
   for (int s = 0; s < n_seg; ++s) total_steps += roundQ((plan.segments[s].n_valid + LANES - 1) / LANES);
   // Slices are pulled dynamically by the warps (stream.cuh), so they only need to be small enough
-  // for a good tail (>= ~8 per warp when the problem allows) and large enough to amortise the
-  // per-chunk record flush (~2 us): 32..256 steps.
+  // for a good tail (>= ~4 per warp when the problem allows) and large enough to amortise the
+  // per-chunk record flush and the piece changes at every lane-run start: 64..256 steps
+  // (measured optimum 64-128 on a 1.3e7-sample shard, 256 on 1e8 samples).
   const int64_t per_warp = (total_steps + W - 1) / W;
-  int64_t L = roundQ(std::max<int64_t>(32, std::min<int64_t>(256, per_warp / 8)));
+  int64_t L = roundQ(std::max<int64_t>(per_warp < 64 ? 32 : 64, std::min<int64_t>(256, per_warp / 4)));
   L = std::max<int64_t>(L, 8 * Q);
   if (desc.chunk_steps > 0) L = std::min<int64_t>(L, roundQ(desc.chunk_steps));
   plan.chunk_steps = (int)L;
