@@ -22,7 +22,7 @@ void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups,
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t aux);
 void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st);
 void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st);
-void launch_finish(const ModelDev* Md, int n_seg, cudaStream_t st);
+void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, const double* in, const ReduceTask* tasks, cudaStream_t st);
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
 void launch_partial(const ModelDev* Md, double* rec, int n_params, cudaStream_t st);
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, cudaStream_t st);
@@ -471,7 +471,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     gwi_model_destroy(m);
     return GWI_ERR_CUDA;
   }
-  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + (int)p.levels.size() + 1 + 2;
+  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
   CUDA_TRY(cudaDeviceSynchronize());
   *out = m;
   return GWI_OK;
@@ -498,12 +498,14 @@ static int run_eval(gwi_model* m, const double* lam_dev, cudaStream_t st) {
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
   }
   const double* in = H.records0;
-  for (size_t l = 0; l < m->level_tasks.size(); ++l) {
+  const size_t n_levels = m->level_tasks.size();
+  for (size_t l = 0; l + 1 < n_levels; ++l) {
     launch_reduce(in, m->level_out[l], m->level_tasks[l].first, m->level_tasks[l].second, H.rec_doubles, st);
     in = m->level_out[l];
   }
   cudaStreamWaitEvent(st, m->ev_join, 0);  // join
-  launch_finish(m->dev, H.n_segments, st);
+  // the last reduction level (one task per segment) is fused into finish_kernel
+  launch_finish(m->dev, H.n_segments, H.rec_doubles, in, m->level_tasks[n_levels - 1].first, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }

@@ -264,16 +264,24 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     M.Ksum[0] = K;
   }
   if (!M.two_pass) {
+    // stage the per-piece bounds in shared memory (the per-segment loop below reads them ~100x)
+    __shared__ double ub_s[MAX_SPLINE_DIMS * MAX_ROWS];
     __syncthreads();  // tables / piece_ub / kc written by this block are visible below
     __threadfence_block();
+    for (int r = tid; r < M.rows_total; r += nt) ub_s[r] = M.piece_ub[r];
+    __syncthreads();
     for (int s = tid; s < M.n_segments; s += nt) {
       const SegDev& S = M.segs[s];
       double sh = S.max_static;
       for (int d = 0; d < M.n_dims; ++d) {
         const DimDev& D = M.dims[d];
         double mx = -INFINITY;
-        for (int J = 0; J < D.rows; ++J)
-          if ((S.occ[d] >> J) & 1ull) mx = fmax(mx, M.piece_ub[D.row_off + J]);
+        unsigned long long occ = S.occ[d];
+        while (occ) {
+          const int J = __ffsll((long long)occ) - 1;
+          occ &= occ - 1;
+          mx = fmax(mx, ub_s[D.row_off + J]);
+        }
         if (mx > -INFINITY) sh += mx;
       }
       for (int q = 0; q < M.n_kops; ++q) {
@@ -312,11 +320,22 @@ __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict_
 // =================================================================================================
 // finish: per segment
 // =================================================================================================
-__global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp) {
+__global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ in, const ReduceTask* __restrict__ tasks) {
   const ModelDev& M = *Mp;
   const int s = blockIdx.x;
   const int P = M.n_params;
-  const double* rec = M.seg_rec + (size_t)s * M.rec_doubles;
+  // last level of the record reduction (task s sums <= 64 records of segment s), fused in here
+  extern __shared__ double srec[];
+  {
+    const ReduceTask T = tasks[s];
+    for (int i = threadIdx.x; i < M.rec_doubles; i += blockDim.x) {
+      double acc = 0.0;
+      for (int r = 0; r < T.in_count; ++r) acc += in[(size_t)(T.in_first + r) * M.rec_doubles + i];
+      srec[i] = acc;
+    }
+    __syncthreads();
+  }
+  const double* rec = srec;
   const double S1 = rec[0], S2 = rec[1];
   const double shift = M.shift[s];
   const int ngs = M.n_gslots;
@@ -558,7 +577,9 @@ void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n
   reduce_kernel<<<grid, 256, 0, st>>>(in, out, tasks, rec);
 }
 void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st) { segmax_kernel<<<n_seg, 256, 0, st>>>(Md); }
-void launch_finish(const ModelDev* Md, int n_seg, cudaStream_t st) { finish_kernel<<<n_seg, 256, 0, st>>>(Md); }
+void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, const double* in, const ReduceTask* tasks, cudaStream_t st) {
+  finish_kernel<<<n_seg, 256, (size_t)rec_doubles * sizeof(double), st>>>(Md, in, tasks);
+}
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { export_kernel<<<64, 256, 0, st>>>(Md, out); }
 void launch_partial(const ModelDev* Md, double* rec, int n_params, cudaStream_t st) { partial_kernel<<<(n_params + 7) / 8, 256, 0, st>>>(Md, rec); }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, cudaStream_t st) {
