@@ -234,7 +234,14 @@ def run_ours(args):
     mdl = eng.model
     Nobs = const["E"]
     n_steps = args.warmup + args.steps
+    chains = workloads.N_CHAINS.get(name, 1)  # cfg4: every step evaluates `chains` Lambda vectors
+    if chains > 1 and world > 1:
+        raise SystemExit("the chain-batched workload shards trivially (disjoint chain ranges per GPU); run it with --gpus 1")
     lams = np.stack([lowering.flatten_params(weights(pe, True, params_fn(s)), P) for s in range(n_steps)])
+    if chains > 1:
+        rng = np.random.default_rng(4)
+        lam_chain = torch.from_numpy(lams[0][None, :] * (1.0 + 0.02 * rng.standard_normal((chains, P)))).cuda()
+        out_chain = torch.zeros(chains * (capi.GWI_LIKE_HEADER + P), dtype=torch.float64, device="cuda")
     lam_dev = torch.from_numpy(lams).cuda()
     lam_pin = torch.from_numpy(lams).pin_memory()
     nrec = mdl.partial_size()
@@ -245,7 +252,9 @@ def run_ours(args):
 
     def step(i, lam_ptr=None):
         ptr = lam_dev[i].data_ptr() if lam_ptr is None else lam_ptr
-        if world == 1:
+        if chains > 1:
+            mdl.loglike_batch_ptr(lam_chain.data_ptr(), chains, out_chain.data_ptr(), Nobs, stream=stream)
+        elif world == 1:
             mdl.loglike(ptr, out.data_ptr(), Nobs, stream=stream)
         else:
             mdl.partial(ptr, rec.data_ptr(), stream=stream)
@@ -273,7 +282,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     kt = mdl.stream_times_ms(min(64, args.steps))
     mdl.set_timing(False)
-    res = out.cpu().numpy()
+    res = (out_chain[: capi.GWI_LIKE_HEADER + P] if chains > 1 else out).cpu().numpy()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -289,7 +298,11 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for i in range(args.warmup, n_steps):
-        if world == 1:
+        if chains > 1:
+            d = lam_chain.cpu().pin_memory().to("cuda", non_blocking=True)
+            mdl.loglike_batch_ptr(d.data_ptr(), chains, out_chain.data_ptr(), Nobs, stream=stream)
+            host = out_chain.cpu()
+        elif world == 1:
             head, grad = mdl.loglike_host(lams[i], Nobs)
         else:
             d = lam_pin[i].to("cuda", non_blocking=True)
@@ -318,20 +331,20 @@ def run_ours(args):
         except Exception:
             traffic = None
     line = {
-        "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": chains * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "model": const["family"], "E": const["E"], "S": const["S"], "I": const["I"],
-            "n_params": P, "samples_per_eval": n_total, "parallelism": (f"shard{world}: injections by (m1, q) piece bucket, whole events round-robin, one all-gather" if args.shard_by == "bucket" else f"shard{world}: injections by index range") if world > 1 else "single",
+            "n_params": P, "samples_per_eval": n_total, "chains_per_step": chains, "parallelism": (f"shard{world}: injections by (m1, q) piece bucket, whole events round-robin, one all-gather" if args.shard_by == "bucket" else f"shard{world}: injections by index range") if world > 1 else "single",
             "l2_policy": "inputs larger than L2 (plan %.2f GB per GPU)" % (info["bytes_per_eval"] / 1e9) if info["bytes_per_eval"] > 2.6e8 else "inputs fit in L2; new Lambda every step, no flush",
             "neff_grad": False, "likelihood": "marginalize_selection=False, min_neff_cut=True (reference defaults)",
         },
-        "samples_per_s": n_total * args.steps / (ms * 1e-3),
+        "samples_per_s": n_total * chains * args.steps / (ms * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "stream_kernel", "kernel_ms": k_ms, "alg_bytes_per_launch": n_local * ALG_BYTES_PER_SAMPLE,
                      "actual_bytes_per_launch": info["bytes_per_eval"], "kernel_share_of_step": k_ms / (ms / args.steps)},
-        "e2e": {"value": args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * (capi.GWI_LIKE_HEADER + P)},
-        "gpu_launches": info["kernel_launches_per_eval"] * args.steps,
+        "e2e": {"value": chains * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * P * chains, "d2h_bytes_per_step": 8 * (capi.GWI_LIKE_HEADER + P) * chains},
+        "gpu_launches": info["kernel_launches_per_eval"] * args.steps * chains,
         "clocks": clocks,
         "result": {"log_l": float(res[0]), "passed": float(res[1]), "status": float(res[7])},
         "setup_s": {"generate": t_gen, "plan_build_and_upload": t_plan},
@@ -350,7 +363,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink S and I (testing only; the reported config then differs from BASELINE's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--emulate-world", type=int, default=1, help="tuning aid: run rank 0's shard of a W-way partition on one GPU")

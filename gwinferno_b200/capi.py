@@ -116,6 +116,7 @@ SYMBOLS = [
     "gwi_eval",
     "gwi_loglike",
     "gwi_loglike_host",
+    "gwi_loglike_batch",
     "gwi_partial_size",
     "gwi_partial",
     "gwi_combine",
@@ -154,6 +155,7 @@ def load_library():
     lib.gwi_model_destroy.restype = None
     lib.gwi_eval.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(gwi_outputs), C.c_void_p]
     lib.gwi_loglike.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
+    lib.gwi_loglike_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
     lib.gwi_loglike_host.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(gwi_like_opts), C.POINTER(C.c_double)]
     lib.gwi_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gwi_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
@@ -476,6 +478,27 @@ class Model:
     def loglike(self, lam_ptr, out_ptr, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False, stream=None):
         o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
         _check(load_library().gwi_loglike(self.handle, lam_ptr, C.byref(o), out_ptr, stream))
+
+    def loglike_batch_ptr(self, lam_ptr, n_chains, out_ptr, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False, stream=None):
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        _check(load_library().gwi_loglike_batch(self.handle, lam_ptr, int(n_chains), C.byref(o), out_ptr, stream))
+
+    def loglike_batch(self, lams, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False):
+        """gwi_loglike_batch over ``lams[n_chains, P]`` (host array in, host arrays out)."""
+        lams = np.ascontiguousarray(lams, dtype=np.float64)
+        n, P = lams.shape
+        if P != self.n_params:
+            raise ValueError(f"expected {self.n_params} hyper-parameters per chain, got {P}")
+        dev = self.catalog.device
+        lam_d, out_d = DeviceBuffer(n * P, dev), DeviceBuffer(n * (GWI_LIKE_HEADER + P), dev)
+        lam_d.upload(lams)
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        _check(load_library().gwi_loglike_batch(self.handle, lam_d.ptr, n, C.byref(o), out_d.ptr, None))
+        synchronize()
+        out = out_d.download().reshape(n, GWI_LIKE_HEADER + P)
+        lam_d.free()
+        out_d.free()
+        return out[:, 0].copy(), out[:, GWI_LIKE_HEADER:].copy(), out[:, :GWI_LIKE_HEADER].copy()
 
     def close(self):
         if getattr(self, "handle", None):

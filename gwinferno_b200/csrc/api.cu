@@ -573,6 +573,19 @@ int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opt
   return gwi_combine(m, m->partial_dev, 1, opts, out_dev, stream);
 }
 
+int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, const gwi_like_opts* opts, double* out_dev, void* stream) {
+  if (!m || !lambda_dev || !out_dev || n_chains < 1) {
+    set_error("bad argument");
+    return GWI_ERR_INVALID;
+  }
+  const int P = m->plan.n_params;
+  for (int c = 0; c < n_chains; ++c) {
+    const int rc = gwi_loglike(m, lambda_dev + (size_t)c * P, opts, out_dev + (size_t)c * (GWI_LIKE_HEADER + P), stream);
+    if (rc != GWI_OK) return rc;
+  }
+  return GWI_OK;
+}
+
 int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opts* opts, double* out_host) {
   if (!m || !lambda_host || !out_host) {
     set_error("null argument");

@@ -16,8 +16,10 @@ WORKLOADS = {
     "cfg1": (0, "plpeak", 69, 3000, 100_000),
     "cfg2": (1, "bspline", 70, 4000, 500_000),
     "cfg3": (2, "bspline", 300, 10_000, 100_000_000),
+    "cfg4": (3, "bspline", 70, 4000, 500_000),  # cfg-2 catalog, 1024 chains per step (N_CHAINS)
     "cfg5": (4, "bspline_iid", 200, 8000, 20_000_000),
 }
+N_CHAINS = {"cfg4": 1024}
 
 
 def shard_catalog(name, rank=0, world=1, scale=1.0, all_reduce_minmax=None, shard_by="bucket"):
@@ -27,7 +29,7 @@ def shard_catalog(name, rank=0, world=1, scale=1.0, all_reduce_minmax=None, shar
     ``z_range`` is the redshift range of the WHOLE catalog (parametric.py:114-115), obtained with
     ``all_reduce_minmax(lo, hi) -> (min over ranks of lo, max over ranks of hi)`` when sharded."""
     cfg_idx, family, E, S, I = WORKLOADS[name]
-    cfg = int(name[3:])
+    cfg = 2 if name == "cfg4" else int(name[3:])  # cfg4 = the cfg-2 catalog
     S = max(8, int(round(S * scale)))
     I = max(64 * world, int(round(I * scale)))
     pe_all = synthetic.make_events(E, S, 1000 * cfg + 0)

@@ -185,6 +185,12 @@ enum {
  * Asynchronous on `stream`. */
 int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opts, double* out_dev, void* stream);
 
+/* Many chains (BASELINE.json configs[3]: vectorised NUTS chains): lambda_dev is [n_chains][P],
+ * out_dev is [n_chains][GWI_LIKE_HEADER + P]; chain c is evaluated exactly like gwi_loglike on
+ * lambda_dev + c*P.  The evaluations are enqueued back to back on `stream` without host
+ * synchronisation; the plan stays resident (L2-resident for the cfg-2 catalog size). */
+int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, const gwi_like_opts* opts, double* out_dev, void* stream);
+
 /* Same with HOST buffers: copies Lambda host->device, evaluates, copies the result back and
  * synchronises (this is the end-to-end call timed as `e2e` by bench.py). */
 int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opts* opts, double* out_host);
