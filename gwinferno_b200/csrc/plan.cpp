@@ -746,17 +746,27 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   std::vector<int64_t> chunk_r0, chunk_nc;  // first sorted rank / valid samples of every chunk
   plan.slice_begin.clear();
   plan.slice_begin.push_back(0);
+  // Guided scheduling: the warps pull slices in order, so the slices shrink towards the end of
+  // the stream (guided self-scheduling: slice = remaining work / 2W, clamped to [32, L]) to keep
+  // the tail short.
+  const int64_t L_full = L;
+  int64_t done_steps = 0;
   int64_t pos = 0, fill = 0;
   for (int s = 0; s < n_seg; ++s) {
     Segment& S = plan.segments[s];
     S.first_chunk = (int)plan.chunks.size();
     int64_t left = S.n_valid, r0 = 0;
     while (left > 0) {
+
       // slice full -- or a new segment that does not fit into the rest of this slice: start it on a
       // fresh slice instead of fragmenting it (every chunk boundary costs a record flush)
       if (L - fill < Q || (r0 == 0 && fill > 0 && roundQ((left + LANES - 1) / LANES) > L - fill)) {
         plan.slice_begin.push_back((int)plan.chunks.size());
         fill = 0;
+        if (desc.chunk_steps <= 0) {
+          const int64_t remaining = std::max<int64_t>(0, total_steps - done_steps);
+          L = std::max<int64_t>(32, std::min<int64_t>(L_full, roundQ(remaining / (2 * (int64_t)W))));
+        }
       }
       const int64_t steps = std::min<int64_t>(L - fill, roundQ((left + LANES - 1) / LANES));
       const int64_t n_c = std::min<int64_t>(left, steps * LANES);
@@ -769,6 +779,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       chunk_nc.push_back(n_c);
       pos += steps * LANES;
       fill += steps;
+      done_steps += steps;
       left -= n_c;
       r0 += n_c;
     }
