@@ -460,7 +460,8 @@ __global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict
       recd[PR_MIN_LOGNEFF] = min_ln;
       recd[PR_SUM_VAR] = sum_var;
       recd[PR_N_EVENTS] = (double)E;
-      recd[PR_STATUS] = fmax(status, M.seg_out[3]);
+      recd[PR_STATUS] = status;  // events only: a rank may legitimately hold no (valid) injections;
+                                 // the merged injection sum is checked in combine_kernel
     }
   }
   // one warp per hyper-parameter: sum_e J_logBF[e][i]
@@ -499,6 +500,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
     sum_var += q[PR_SUM_VAR];
     status = fmax(status, q[PR_STATUS]);
   }
+  if (!(S1 > 0.0) || !(S1 < INFINITY)) status = 1.0;  // no injection weight survived on any rank
   double K = M.Ksum[0];
   for (int g = 0; g < M.n_groups; ++g) K -= M.logZ[g];
   const double den = S2 - S1 * S1 / N;
