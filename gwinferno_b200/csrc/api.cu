@@ -18,14 +18,14 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 typedef void (*stream_fn)(const ModelDev*);
 stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, bool maxonly);
-void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, cudaStream_t st);
-void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t aux);
-void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st);
-void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st);
-void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, const double* in, const ReduceTask* tasks, cudaStream_t st);
+void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st);
+void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux);
+void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st);
+void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st);
+void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaStream_t st);
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
-void launch_partial(const ModelDev* Md, double* rec, int n_params, cudaStream_t st);
-void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, cudaStream_t st);
+void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st);
+void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st);
 
 }  // namespace gwi
 
@@ -45,8 +45,10 @@ struct gwi_model {
   ModelDev host{};      // host copy of the device descriptor
   ModelDev* dev = nullptr;
   std::vector<void*> allocs;
-  std::vector<std::pair<ReduceTask*, int>> level_tasks;  // device task arrays
-  std::vector<double*> level_out;                        // output buffer of every level
+  std::vector<std::pair<ReduceTask*, int>> level_tasks;  // device task arrays (static, shared by all chains)
+  int n_chain_alloc = 1;                                  // descriptors / scratch sets allocated (chain batch)
+  double* partial_batch = nullptr;                        // [n_chain_alloc][PR_HEADER + 3P]
+  int stream_grid_x = 1;
   stream_fn k_full = nullptr, k_max = nullptr;
   size_t smem_full = 0, smem_max = 0;
   int max_grid = 0;
@@ -239,6 +241,72 @@ static int upload(gwi_model* m, const T* src, size_t count, T** dst) {
   return GWI_OK;
 }
 
+// per-evaluation scratch of ONE chain (tables, normalisers, records, per-segment results)
+static int alloc_chain_scratch(gwi_model* m, ModelDev& H) {
+  const Plan& p = m->plan;
+  const int P = p.n_params, nseg = (int)p.segments.size();
+  int rc;
+#define UPS(expr)                \
+  do {                           \
+    rc = (expr);                 \
+    if (rc != GWI_OK) return rc; \
+  } while (0)
+  UPS(upload<double>(m, nullptr, (size_t)p.rows_total * 4, &H.tables));
+  UPS(upload<double>(m, nullptr, (size_t)p.rows_total, &H.piece_ub));
+  UPS(upload<double>(m, nullptr, (size_t)std::max(1, H.n_kops) * KC_STRIDE, &H.kc));
+  UPS(upload<double>(m, nullptr, (size_t)nseg, &H.shift));
+  UPS(upload<double>(m, nullptr, (size_t)std::max(1, H.n_groups), &H.logZ));
+  UPS(upload<double>(m, nullptr, (size_t)std::max(1, H.n_groups) * P, &H.dlogZ));
+  UPS(upload<double>(m, nullptr, (size_t)P + 1, &H.Ksum));
+  UPS(upload<double>(m, nullptr, (size_t)std::max(1, H.n_chunks), &H.chunk_max));
+  UPS(upload<int32_t>(m, nullptr, (size_t)2, &H.slice_counter));
+  UPS(upload<double>(m, nullptr, (size_t)std::max(1, p.n_records0) * p.rec_doubles, &H.records0));
+  H.seg_rec = nullptr;
+  UPS(upload<double>(m, nullptr, (size_t)nseg * 4, &H.seg_out));
+  UPS(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_J1));
+  UPS(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_Jn));
+  UPS(upload<double>(m, nullptr, (size_t)3 + 2 * P, &H.inj_raw));
+  H.n_levels = (int)p.levels.size();
+  for (int l = 0; l < 6; ++l) {
+    H.level_buf[l] = nullptr;
+    H.level_tasks[l] = nullptr;
+    H.level_ntasks[l] = 0;
+  }
+  for (int l = 0; l < H.n_levels; ++l) {
+    H.level_tasks[l] = m->level_tasks[l].first;
+    H.level_ntasks[l] = m->level_tasks[l].second;
+    if (l + 1 < H.n_levels) UPS(upload<double>(m, nullptr, p.levels[l].size() * (size_t)p.rec_doubles, &H.level_buf[l]));
+  }
+#undef UPS
+  return GWI_OK;
+}
+
+// make sure descriptors + scratch exist for `n` chains (chain 0 always exists)
+static int ensure_chains(gwi_model* m, int n) {
+  if (n <= m->n_chain_alloc) return GWI_OK;
+  std::vector<ModelDev> all(n);
+  // existing descriptors are re-read from the device (they hold the scratch pointers)
+  if (cudaMemcpy(all.data(), m->dev, sizeof(ModelDev) * m->n_chain_alloc, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("cudaMemcpy of the chain descriptors failed");
+    return GWI_ERR_CUDA;
+  }
+  for (int c = m->n_chain_alloc; c < n; ++c) {
+    all[c] = m->host;
+    const int rc = alloc_chain_scratch(m, all[c]);
+    if (rc != GWI_OK) return rc;
+  }
+  ModelDev* d = nullptr;
+  int rc = upload(m, all.data(), (size_t)n, &d);
+  if (rc != GWI_OK) return rc;
+  double* pb = nullptr;
+  rc = upload<double>(m, nullptr, (size_t)n * (PR_HEADER + 3 * m->plan.n_params), &pb);
+  if (rc != GWI_OK) return rc;
+  m->dev = d;  // the old (smaller) descriptor array stays in m->allocs until destroy
+  m->partial_batch = pb;
+  m->n_chain_alloc = n;
+  return GWI_OK;
+}
+
 extern "C" {
 
 void gwi_model_destroy(gwi_model* m) {
@@ -402,33 +470,17 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   double* d_pool;
   UP(upload(m, p.grid_pool.data(), p.grid_pool.size(), &d_pool));
   H.grid_pool = d_pool;
-  UP(upload<double>(m, nullptr, (size_t)p.rows_total * 4, &H.tables));
-  UP(upload<double>(m, nullptr, (size_t)p.rows_total, &H.piece_ub));
-  UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_kops) * KC_STRIDE, &H.kc));
-  UP(upload<double>(m, nullptr, (size_t)nseg, &H.shift));
-  UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_groups), &H.logZ));
-  UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_groups) * P, &H.dlogZ));
-  UP(upload<double>(m, nullptr, (size_t)P + 1, &H.Ksum));
-  UP(upload<double>(m, nullptr, (size_t)std::max(1, H.n_chunks), &H.chunk_max));
-  UP(upload<int32_t>(m, nullptr, (size_t)2, &H.slice_counter));
-  UP(upload<double>(m, nullptr, (size_t)std::max(1, p.n_records0) * p.rec_doubles, &H.records0));
-  UP(upload<double>(m, nullptr, (size_t)nseg * p.rec_doubles, &H.seg_rec));
-  UP(upload<double>(m, nullptr, (size_t)nseg * 4, &H.seg_out));
-  UP(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_J1));
-  UP(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_Jn));
-  UP(upload<double>(m, nullptr, (size_t)3 + 2 * P, &H.inj_raw));
+  if (p.levels.size() > 6) {
+    set_error("internal: reduction tree deeper than 6 levels");
+    gwi_model_destroy(m);
+    return GWI_ERR_UNSUPPORTED;
+  }
   for (size_t l = 0; l < p.levels.size(); ++l) {
     ReduceTask* d_t;
     UP(upload(m, p.levels[l].data(), p.levels[l].size(), &d_t));
     m->level_tasks.push_back({d_t, (int)p.levels[l].size()});
-    if (l + 1 == p.levels.size()) {
-      m->level_out.push_back(H.seg_rec);
-    } else {
-      double* buf;
-      UP(upload<double>(m, nullptr, p.levels[l].size() * (size_t)p.rec_doubles, &buf));
-      m->level_out.push_back(buf);
-    }
   }
+  UP(alloc_chain_scratch(m, H));
   UP(upload(m, &H, 1, &m->dev));
   UP(upload<double>(m, nullptr, (size_t)P, &m->lam_dev));
   UP(upload<double>(m, nullptr, (size_t)GWI_LIKE_HEADER + P, &m->out_dev));
@@ -471,41 +523,38 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     gwi_model_destroy(m);
     return GWI_ERR_CUDA;
   }
+  m->stream_grid_x = std::max(1, std::min(p.grid_blocks, ((int)p.slice_begin.size() - 1 + p.warps_per_block - 1) / p.warps_per_block));
   m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
   CUDA_TRY(cudaDeviceSynchronize());
   *out = m;
   return GWI_OK;
 }
 
-// launches prologue .. finish on `st`
-static int run_eval(gwi_model* m, const double* lam_dev, cudaStream_t st) {
+// launches prologue .. finish for `nc` chains on `st` (lam_dev: [nc][P])
+static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st) {
   const Plan& p = m->plan;
   const ModelDev& H = m->host;
   // fork: the grid normalisers (needed only by finish_kernel) overlap with the stream kernel
   cudaEventRecord(m->ev_fork, st);
   cudaStreamWaitEvent(m->aux_stream, m->ev_fork, 0);
-  launch_prologue_groups(m->dev, lam_dev, H.n_groups, m->max_grid, m->aux_stream);
+  launch_prologue_groups(m->dev, lam_dev, H.n_groups, m->max_grid, nc, m->aux_stream);
   cudaEventRecord(m->ev_join, m->aux_stream);
-  launch_prologue_tables(m->dev, lam_dev, H.n_groups, st);
-  const dim3 grid(p.grid_blocks), block(p.warps_per_block * 32);
+  launch_prologue_tables(m->dev, lam_dev, H.n_groups, nc, st);
+  const dim3 grid(m->stream_grid_x, nc), block(p.warps_per_block * 32);
   if (H.n_chunks > 0) {
     if (H.two_pass) {
       m->k_max<<<grid, block, m->smem_max, st>>>(m->dev);
-      launch_segmax(m->dev, H.n_segments, st);
+      launch_segmax(m->dev, H.n_segments, nc, st);
     }
     if (m->timing) cudaEventRecord(m->ev0[m->n_timed % 64], st);
     m->k_full<<<grid, block, m->smem_full, st>>>(m->dev);
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
   }
-  const double* in = H.records0;
-  const size_t n_levels = m->level_tasks.size();
-  for (size_t l = 0; l + 1 < n_levels; ++l) {
-    launch_reduce(in, m->level_out[l], m->level_tasks[l].first, m->level_tasks[l].second, H.rec_doubles, st);
-    in = m->level_out[l];
-  }
+  const int n_levels = (int)m->level_tasks.size();
+  for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, st);
   cudaStreamWaitEvent(st, m->ev_join, 0);  // join
   // the last reduction level (one task per segment) is fused into finish_kernel
-  launch_finish(m->dev, H.n_segments, H.rec_doubles, in, m->level_tasks[n_levels - 1].first, st);
+  launch_finish(m->dev, H.n_segments, H.rec_doubles, nc, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -521,7 +570,7 @@ int gwi_eval(gwi_model* m, const double* lambda_dev, const gwi_outputs* out, voi
   }
   CUDA_TRY(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = run_eval(m, lambda_dev, st);
+  const int rc = run_eval(m, lambda_dev, 1, st);
   if (rc != GWI_OK) return rc;
   launch_export(m->dev, *out, st);
   CUDA_TRY(cudaGetLastError());
@@ -537,9 +586,9 @@ int gwi_partial(gwi_model* m, const double* lambda_dev, double* record_dev, void
   }
   CUDA_TRY(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = run_eval(m, lambda_dev, st);
+  const int rc = run_eval(m, lambda_dev, 1, st);
   if (rc != GWI_OK) return rc;
-  launch_partial(m->dev, record_dev, m->plan.n_params, st);
+  launch_partial(m->dev, record_dev, m->plan.n_params, 1, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -558,7 +607,7 @@ int gwi_combine(gwi_model* m, const double* records_dev, int32_t n_ranks, const 
     return GWI_ERR_INVALID;
   }
   CUDA_TRY(cudaSetDevice(m->device));
-  launch_combine(m->dev, records_dev, n_ranks, *opts, out_dev, (cudaStream_t)stream);
+  launch_combine(m->dev, records_dev, n_ranks, *opts, out_dev, 1, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -574,15 +623,30 @@ int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opt
 }
 
 int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, const gwi_like_opts* opts, double* out_dev, void* stream) {
-  if (!m || !lambda_dev || !out_dev || n_chains < 1) {
-    set_error("bad argument");
+  if (!m || !lambda_dev || !out_dev || !opts || n_chains < 1 || n_chains > 65535) {
+    set_error("bad argument (1 <= n_chains <= 65535)");
     return GWI_ERR_INVALID;
   }
-  const int P = m->plan.n_params;
-  for (int c = 0; c < n_chains; ++c) {
-    const int rc = gwi_loglike(m, lambda_dev + (size_t)c * P, opts, out_dev + (size_t)c * (GWI_LIKE_HEADER + P), stream);
-    if (rc != GWI_OK) return rc;
+  if (opts->marginalize_selection && !m->plan.g2) {
+    set_error("marginalize_selection needs a model created with need_neff_grad");
+    return GWI_ERR_INVALID;
   }
+  if (opts->max_variance_cut && (opts->marginalize_selection || opts->min_neff_cut)) {
+    set_error("max_variance_cut requires marginalize_selection and min_neff_cut to be off (analysis.py:237-244)");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  if (n_chains == 1) return gwi_loglike(m, lambda_dev, opts, out_dev, stream);
+  int rc = ensure_chains(m, n_chains);
+  if (rc != GWI_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // ONE launch of every kernel covers all chains (chain = a grid coordinate): the whole machine works
+  // on the batch instead of one small catalog at a time
+  rc = run_eval(m, lambda_dev, n_chains, st);
+  if (rc != GWI_OK) return rc;
+  launch_partial(m->dev, m->partial_batch, m->plan.n_params, n_chains, st);
+  launch_combine(m->dev, m->partial_batch, 1, *opts, out_dev, n_chains, st);
+  CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
 

@@ -38,7 +38,9 @@ struct GroupDev {
   int32_t n_grid, logw_off;
 };
 
-// everything the kernels need, resident in device global memory (one copy per model)
+// everything the kernels need, resident in device global memory: one descriptor per CHAIN (the
+// static pointers are shared, the per-evaluation scratch pointers differ); kernels index the
+// descriptor array with their chain coordinate of the grid
 struct ModelDev {
   int32_t n_params, n_dims, n_deep, n_kops, n_gslots, n_sops, n_groups, n_segments;
   int32_t rows_total, rec_doubles, n_columns, col_static, g2, two_pass, n_chunks, deep_entries;
@@ -67,6 +69,10 @@ struct ModelDev {
   double* chunk_max;  // [n_chunks] (two-pass mode)
   int32_t* slice_counter;  // [2] dynamic slice scheduling: [0] full pass, [1] max-only pass; reset by the prologue
   double* records0;   // [n_records0 * rec]
+  double* level_buf[6];              // output of reduction level l (the last level is fused into finish)
+  const ReduceTask* level_tasks[6];  // static task lists
+  int32_t level_ntasks[6];
+  int32_t n_levels, pad2;
   double* seg_rec;    // [n_segments * rec]
   double* seg_out;    // [n_segments * 4] {logmean, logneff, var, status}
   double* seg_J1;     // [n_segments * P]

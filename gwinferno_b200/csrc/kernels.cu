@@ -110,8 +110,9 @@ __device__ void powerlaw_lognorm(double alpha, double lo, double hi, double& log
 // =================================================================================================
 // prologue
 // =================================================================================================
-__global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam, int role_off) {
-  const ModelDev& M = *Mp;
+__global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam0, int role_off) {
+  const ModelDev& M = Mp[blockIdx.y];  // blockIdx.y = chain
+  const double* __restrict__ Lam = Lam0 + (size_t)blockIdx.y * M.n_params;
   extern __shared__ double sm[];
   __shared__ double scratch[32];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -297,8 +298,12 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
 // =================================================================================================
 // reductions
 // =================================================================================================
-__global__ void reduce_kernel(const double* __restrict__ in, double* __restrict__ out, const ReduceTask* __restrict__ tasks, int rec) {
-  const ReduceTask T = tasks[blockIdx.x];
+__global__ void reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
+  const ModelDev& M = Mp[blockIdx.z];  // blockIdx.z = chain
+  const int rec = M.rec_doubles;
+  const double* __restrict__ in = level == 0 ? M.records0 : M.level_buf[level - 1];
+  double* __restrict__ out = M.level_buf[level];
+  const ReduceTask T = M.level_tasks[level][blockIdx.x];
   const int i = blockIdx.y * blockDim.x + threadIdx.x;
   if (i >= rec) return;
   double acc = 0.0;
@@ -307,7 +312,7 @@ __global__ void reduce_kernel(const double* __restrict__ in, double* __restrict_
 }
 
 __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict__ Mp) {
-  const ModelDev& M = *Mp;
+  const ModelDev& M = Mp[blockIdx.y];
   __shared__ double scratch[32];
   const int s = blockIdx.x;
   const SegDev& S = M.segs[s];
@@ -320,8 +325,10 @@ __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict_
 // =================================================================================================
 // finish: per segment
 // =================================================================================================
-__global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ in, const ReduceTask* __restrict__ tasks) {
-  const ModelDev& M = *Mp;
+__global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp) {
+  const ModelDev& M = Mp[blockIdx.y];
+  const double* __restrict__ in = M.n_levels > 1 ? M.level_buf[M.n_levels - 2] : M.records0;
+  const ReduceTask* __restrict__ tasks = M.level_tasks[M.n_levels - 1];
   const int s = blockIdx.x;
   const int P = M.n_params;
   // last level of the record reduction (task s sums <= 64 records of segment s), fused in here
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict_
 
 // gather the per-segment results into the caller's gwi_outputs buffers
 __global__ void export_kernel(const ModelDev* __restrict__ Mp, gwi_outputs out) {
-  const ModelDev& M = *Mp;
+  const ModelDev& M = Mp[0];
   const int P = M.n_params, E = M.n_segments - 1;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int e = tid; e < E; e += nt) {
@@ -431,8 +438,9 @@ __global__ void export_kernel(const ModelDev* __restrict__ Mp, gwi_outputs out) 
 // =================================================================================================
 // likelihood: per-rank partial record, then the rank-ordered combine (analysis.py:257-319)
 // =================================================================================================
-__global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict__ Mp, double* __restrict__ recd) {
-  const ModelDev& M = *Mp;
+__global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict__ Mp, double* __restrict__ recd0) {
+  const ModelDev& M = Mp[blockIdx.y];
+  double* __restrict__ recd = recd0 + (size_t)blockIdx.y * (PR_HEADER + 3 * M.n_params);
   const int P = M.n_params, E = M.n_segments - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   if (blockIdx.x == 0 && warp == 0) {
@@ -477,10 +485,13 @@ __global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ recs, int R, gwi_like_opts opts, double* __restrict__ out) {
-  const ModelDev& M = *Mp;
+// blockIdx.x = chain: chain c combines the R records at recs0 + c*R*stride into out0 + c*(HEADER+P)
+__global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ recs0, int R, gwi_like_opts opts, double* __restrict__ out0) {
+  const ModelDev& M = Mp[blockIdx.x];
   const int P = M.n_params;
   const int stride = PR_HEADER + 3 * P;
+  const double* __restrict__ recs = recs0 + (size_t)blockIdx.x * R * stride;
+  double* __restrict__ out = out0 + (size_t)blockIdx.x * (GWI_LIKE_HEADER + P);
   const double N = M.total_inj;
   const double SENT = -DBL_MAX;  // nan_to_num(-inf)
   // injection sums of all ranks on a common shift
@@ -567,25 +578,27 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
 // host-side launch helpers (called from api.cu)
 // =================================================================================================
 // tables + shifts (what the stream kernel needs) on `st`; the grid normalisers (only needed by
-// finish_kernel) on `aux`, concurrently with the stream kernel
-void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, cudaStream_t st) {
-  prologue_kernel<<<1, 256, 0, st>>>(Md, lam, n_groups);
+// finish_kernel) on `aux`, concurrently with the stream kernel.  `nc` = number of chains.
+void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st) {
+  prologue_kernel<<<dim3(1, nc), 256, 0, st>>>(Md, lam, n_groups);
 }
-void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, cudaStream_t aux) {
-  if (n_groups > 0) prologue_kernel<<<n_groups, 256, (size_t)max_grid * sizeof(double), aux>>>(Md, lam, 0);
+void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux) {
+  if (n_groups > 0) prologue_kernel<<<dim3(n_groups, nc), 256, (size_t)max_grid * sizeof(double), aux>>>(Md, lam, 0);
 }
-void launch_reduce(const double* in, double* out, const ReduceTask* tasks, int n_tasks, int rec, cudaStream_t st) {
-  dim3 grid(n_tasks, (rec + 255) / 256);
-  reduce_kernel<<<grid, 256, 0, st>>>(in, out, tasks, rec);
+void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st) {
+  dim3 grid(n_tasks, (rec + 255) / 256, nc);
+  reduce_kernel<<<grid, 256, 0, st>>>(Md, level);
 }
-void launch_segmax(const ModelDev* Md, int n_seg, cudaStream_t st) { segmax_kernel<<<n_seg, 256, 0, st>>>(Md); }
-void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, const double* in, const ReduceTask* tasks, cudaStream_t st) {
-  finish_kernel<<<n_seg, 256, (size_t)rec_doubles * sizeof(double), st>>>(Md, in, tasks);
+void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st) { segmax_kernel<<<dim3(n_seg, nc), 256, 0, st>>>(Md); }
+void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaStream_t st) {
+  finish_kernel<<<dim3(n_seg, nc), 256, (size_t)rec_doubles * sizeof(double), st>>>(Md);
 }
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { export_kernel<<<64, 256, 0, st>>>(Md, out); }
-void launch_partial(const ModelDev* Md, double* rec, int n_params, cudaStream_t st) { partial_kernel<<<(n_params + 7) / 8, 256, 0, st>>>(Md, rec); }
-void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, cudaStream_t st) {
-  combine_kernel<<<1, 256, 0, st>>>(Md, recs, R, o, out);
+void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st) {
+  partial_kernel<<<dim3((n_params + 7) / 8, nc), 256, 0, st>>>(Md, rec);
+}
+void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
+  combine_kernel<<<nc, 256, 0, st>>>(Md, recs, R, o, out);
 }
 
 }  // namespace gwi

@@ -186,9 +186,11 @@ enum {
 int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opts, double* out_dev, void* stream);
 
 /* Many chains (BASELINE.json configs[3]: vectorised NUTS chains): lambda_dev is [n_chains][P],
- * out_dev is [n_chains][GWI_LIKE_HEADER + P]; chain c is evaluated exactly like gwi_loglike on
- * lambda_dev + c*P.  The evaluations are enqueued back to back on `stream` without host
- * synchronisation; the plan stays resident (L2-resident for the cfg-2 catalog size). */
+ * out_dev is [n_chains][GWI_LIKE_HEADER + P]; chain c gets exactly the result gwi_loglike would
+ * give for lambda_dev + c*P (bitwise).  Every kernel is launched ONCE for the whole batch (the chain
+ * is a grid coordinate, each chain has its own scratch set, allocated on first use), so a small
+ * catalog that cannot fill the GPU for one chain fills it with many; the plan stays L2/HBM
+ * resident and is shared by all chains.  1 <= n_chains <= 65535.  Asynchronous on `stream`. */
 int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, const gwi_like_opts* opts, double* out_dev, void* stream);
 
 /* Same with HOST buffers: copies Lambda host->device, evaluates, copies the result back and
