@@ -274,10 +274,15 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     for (int s = tid; s < M.n_segments; s += nt) {
       const SegDev& S = M.segs[s];
       double sh = S.max_static;
-      for (int d = 0; d < M.n_dims; ++d) {
+      unsigned long long occ_all[MAX_SPLINE_DIMS];
+#pragma unroll
+      for (int d = 0; d < MAX_SPLINE_DIMS; ++d) occ_all[d] = S.occ[d];  // independent loads, issued together
+#pragma unroll
+      for (int d = 0; d < MAX_SPLINE_DIMS; ++d) {
+        if (d >= M.n_dims) break;
         const DimDev& D = M.dims[d];
         double mx = -INFINITY;
-        unsigned long long occ = S.occ[d];
+        unsigned long long occ = occ_all[d];
         while (occ) {
           const int J = __ffsll((long long)occ) - 1;
           occ &= occ - 1;
