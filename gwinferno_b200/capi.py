@@ -121,6 +121,7 @@ SYMBOLS = [
     "gwi_partial",
     "gwi_combine",
     "gwi_model_get_info",
+    "gwi_model_set_exact_shift",
     "gwi_model_set_timing",
     "gwi_model_stream_times",
     "gwi_last_error",
@@ -160,6 +161,7 @@ def load_library():
     lib.gwi_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gwi_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
     lib.gwi_model_get_info.argtypes = [C.c_void_p, C.POINTER(gwi_model_info)]
+    lib.gwi_model_set_exact_shift.argtypes = [C.c_void_p, C.c_int32]
     lib.gwi_model_set_timing.argtypes = [C.c_void_p, C.c_int32]
     lib.gwi_model_stream_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
     lib.gwi_debug_plan_build.argtypes = [C.c_void_p, C.POINTER(gwi_model_desc), C.c_int32, C.POINTER(C.c_void_p)]
@@ -409,6 +411,9 @@ class Model:
         i = gwi_model_info()
         _check(load_library().gwi_model_get_info(self.handle, C.byref(i)))
         return {n: getattr(i, n) for n, _ in gwi_model_info._fields_ if n != "reserved"}
+
+    def set_exact_shift(self, on=True):
+        _check(load_library().gwi_model_set_exact_shift(self.handle, int(on)))
 
     def set_timing(self, on=True):
         _check(load_library().gwi_model_set_timing(self.handle, int(on)))

@@ -47,6 +47,7 @@ struct gwi_model {
   std::vector<void*> allocs;
   std::vector<std::pair<ReduceTask*, int>> level_tasks;  // device task arrays (static, shared by all chains)
   int n_chain_alloc = 1;                                  // descriptors / scratch sets allocated (chain batch)
+  bool force_exact_shift = false;                         // gwi_model_set_exact_shift
   double* partial_batch = nullptr;                        // [n_chain_alloc][PR_HEADER + 3P]
   int stream_grid_x = 1;
   stream_fn k_full = nullptr, k_max = nullptr;
@@ -531,7 +532,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
 }
 
 // launches prologue .. finish for `nc` chains on `st` (lam_dev: [nc][P])
-static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st) {
+static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st, bool exact_shift = false) {
   const Plan& p = m->plan;
   const ModelDev& H = m->host;
   // fork: the grid normalisers (needed only by finish_kernel) overlap with the stream kernel
@@ -542,7 +543,9 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   launch_prologue_tables(m->dev, lam_dev, H.n_groups, nc, st);
   const dim3 grid(m->stream_grid_x, nc), block(p.warps_per_block * 32);
   if (H.n_chunks > 0) {
-    if (H.two_pass) {
+    if (H.two_pass || exact_shift || m->force_exact_shift) {
+      // exact per-segment maximum first (always for models with non-linear terms; as a fallback when
+      // the a-priori bound was so loose that every weight of a segment underflowed)
       m->k_max<<<grid, block, m->smem_max, st>>>(m->dev);
       launch_segmax(m->dev, H.n_segments, nc, st);
     }
@@ -664,10 +667,27 @@ int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opt
   CUDA_TRY(cudaMemcpyAsync(m->out_pinned, m->out_dev, sizeof(double) * (GWI_LIKE_HEADER + P), cudaMemcpyDeviceToHost, m->own_stream));
   CUDA_TRY(cudaStreamSynchronize(m->own_stream));
   std::memcpy(out_host, m->out_pinned, sizeof(double) * (GWI_LIKE_HEADER + P));
+  if (out_host[GWI_LIKE_STATUS] != 0.0 && !m->host.two_pass && !m->force_exact_shift) {
+    // the a-priori shift bound was too loose for this Lambda (all weights of a segment
+    // underflowed): repeat once with the exact per-segment maximum
+    m->force_exact_shift = true;
+    const int rc2 = gwi_loglike(m, m->lam_dev, opts, m->out_dev, m->own_stream);
+    m->force_exact_shift = false;
+    if (rc2 != GWI_OK) return rc2;
+    CUDA_TRY(cudaMemcpyAsync(m->out_pinned, m->out_dev, sizeof(double) * (GWI_LIKE_HEADER + P), cudaMemcpyDeviceToHost, m->own_stream));
+    CUDA_TRY(cudaStreamSynchronize(m->own_stream));
+    std::memcpy(out_host, m->out_pinned, sizeof(double) * (GWI_LIKE_HEADER + P));
+  }
   if (out_host[GWI_LIKE_STATUS] != 0.0) {
     set_error("a segment's weights all under/overflowed the fp64 range");
     return GWI_ERR_RANGE;
   }
+  return GWI_OK;
+}
+
+int gwi_model_set_exact_shift(gwi_model* m, int32_t on) {
+  if (!m) return GWI_ERR_INVALID;
+  m->force_exact_shift = on != 0;
   return GWI_OK;
 }
 

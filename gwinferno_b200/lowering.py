@@ -79,6 +79,8 @@ def flatten_params(pe_w, n_params, param_layout=None):
 def lower(pe_w, inj_w):
     if pe_w.pe_samples is False or inj_w.pe_samples is True:
         raise ValueError("first argument must be the PE-sample weights, second the injection weights")
+    if len(pe_w.terms) != len(inj_w.terms):
+        raise ValueError("PE and injection weights must be built from the same sequence of model terms")
     # ---- parameter slots (shared objects share slots) -----------------------------------------
     slot_of = {}
     layout = []

@@ -223,6 +223,13 @@ typedef struct {
 } gwi_model_info;
 int gwi_model_get_info(const gwi_model* m, gwi_model_info* info);
 
+/* Log-sum-exp reference point.  By default spline-only models use an a-priori upper bound of the
+ * per-sample log-weight per segment (single pass); if the bound is so loose for some Lambda that every
+ * weight of a segment underflows, the asynchronous calls report GWI_LIKE_STATUS = 1 and
+ * gwi_loglike_host transparently repeats the evaluation with the exact per-segment maximum (one extra
+ * forward-only pass).  gwi_model_set_exact_shift(m, 1) makes every call use the exact maximum. */
+int gwi_model_set_exact_shift(gwi_model* m, int32_t on);
+
 /* Per-launch device time of the dominant (stream) kernel, for the roofline line of bench.py:
  * after gwi_model_set_timing(m, 1) every evaluation brackets its stream-kernel launch with CUDA
  * events on the launching stream (a ring of 64 pairs).  gwi_model_stream_times synchronises those
