@@ -375,6 +375,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   H.n_padded = p.n_padded;
   H.total_inj = p.total_inj;
   H.two_pass = 0;
+  H.liny_mask = 0;
   const int mom = p.g2 ? 2 : 1;
   int deep_entries = 0;
   for (int d = 0; d < NS; ++d) {
@@ -391,6 +392,11 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     X.norm_group = D.norm_group;
     X.grid_off = D.grid_off;
     X.grid_aux = D.grid_aux;
+    X.liny = D.liny;
+    if (D.liny) {
+      H.liny_mask |= 1 << d;
+      H.two_pass = 1;  // no a-priori bound through the log of the spline: exact max first
+    }
     X.xi_lo = t.xi_lo;
     X.inv_dxi = (double)(D.rows - 1) / (t.xi_hi - t.xi_lo);
   }
@@ -414,7 +420,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   }
   // up to 2 linear terms are register-resident in the stream kernel; any other non-spline term
   // selects the generic-term variant, which then handles ALL non-spline terms
-  const bool param = H.n_kops > std::min(p.n_lin, 2);
+  const bool param = H.n_kops > std::min(p.n_lin, 2) || H.liny_mask != 0;
   H.n_lin_fast = param ? 0 : std::min(p.n_lin, 2);
   for (int q = 0; q < H.n_sops; ++q) {
     const Sop& S = p.sops[q];

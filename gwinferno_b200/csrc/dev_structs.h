@@ -10,7 +10,7 @@ struct DimDev {
   int32_t rows, row_off, slot, n_splines;
   int32_t deep, deep_off;  // deep_off: first double2 entry of this dim in the lane-private deep block
   int32_t norm_group, grid_off;
-  int32_t grid_aux, pad1;  // derived grid taps (see SplineDim::grid_aux)
+  int32_t grid_aux, liny;  // derived grid taps (see SplineDim::grid_aux); liny: SplineDim::liny
   double xi_lo, inv_dxi;
 };
 
@@ -72,7 +72,7 @@ struct ModelDev {
   double* level_buf[6];              // output of reduction level l (the last level is fused into finish)
   const ReduceTask* level_tasks[6];  // static task lists
   int32_t level_ntasks[6];
-  int32_t n_levels, pad2;
+  int32_t n_levels, liny_mask;  // bit d: spline dim d is a linear-in-y density
   double* seg_rec;    // [n_segments * rec]
   double* seg_out;    // [n_segments * 4] {logmean, logneff, var, status}
   double* seg_J1;     // [n_segments * P]

@@ -72,6 +72,7 @@ struct SplineDim {
   int32_t grid_off;  // offset of its grid xi array in the grid pool, -1 none
   int32_t grid_aux;  // offset of the derived per-grid-point taps: W[4G], J[G], then lo[n], hi[n] per basis
   int32_t outside;
+  int32_t liny;      // GWI_TERM_SPLINE_LINEAR: the spline is the density (log-weight = log of the cubic)
 };
 
 struct NormGroup {

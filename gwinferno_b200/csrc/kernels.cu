@@ -124,6 +124,53 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     const int G = M.groups[g].n_grid;
     const double* logw = M.grid_pool + M.groups[g].logw_off;
     double* li = sm;  // [G]
+    bool liny = false;
+    for (int d = 0; d < M.n_dims; ++d) liny = liny || (M.dims[d].norm_group == g && M.dims[d].liny);
+    if (liny) {
+      // spline density (BSpline.norm, interpolation.py:280-291): Z = sum_i w_i sum_k B_k(x_i) c_k
+      double s = 0.0;
+      for (int i = tid; i < G; i += nt) {
+        const double wq = exp(logw[i]);
+        double sv = 0.0;
+        for (int d = 0; d < M.n_dims; ++d) {
+          const DimDev& D = M.dims[d];
+          if (D.norm_group != g) continue;
+          const double* aux = M.grid_pool + D.grid_aux;
+          const int J = (int)aux[4 * G + i];
+          if (J >= 0) {
+            const double* w = aux + 4 * i;
+            const double* c = Lam + D.slot + J;
+            sv += w[0] * c[0] + w[1] * c[1] + w[2] * c[2] + w[3] * c[3];
+          }
+        }
+        li[i] = wq;
+        s += wq * sv;
+      }
+      s = block_sum(s, scratch);
+      if (tid == 0) M.logZ[g] = log(s);
+      const double inv = 1.0 / s;
+      for (int i = tid; i < P; i += nt) M.dlogZ[(size_t)g * P + i] = 0.0;
+      __syncthreads();
+      for (int d = 0; d < M.n_dims; ++d) {
+        const DimDev& D = M.dims[d];
+        if (D.norm_group != g) continue;
+        const double* aux = M.grid_pool + D.grid_aux;
+        for (int k = tid >> 5; k < D.n_splines; k += nt >> 5) {
+          double acc = 0.0;
+          const int lo = (int)aux[5 * G + k], hi = (int)aux[5 * G + D.n_splines + k];
+          for (int i = lo + (tid & 31); i < hi; i += 32) {
+            const int J = (int)aux[4 * G + i];
+            const int kk = k - J;
+            if (J < 0 || kk < 0 || kk > 3) continue;
+            acc += li[i] * aux[4 * i + kk];
+          }
+          acc = warp_sum(acc);
+          if ((tid & 31) == 0) M.dlogZ[(size_t)g * P + D.slot + k] += acc * inv;
+        }
+        __syncthreads();
+      }
+      return;
+    }
     for (int i = tid; i < G; i += nt) {
       double v = logw[i];
       for (int d = 0; d < M.n_dims; ++d) {

@@ -76,7 +76,7 @@ double log_dvcdz(double z) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-enum FeatKind : int { F_LOG1P = 1, F_LOG = 2, F_LOG_RATIO = 3, F_LOG_DVDZ = 4, F_NEG_LOG = 5, F_RAW = 6, F_LOG_C_OVER = 7, F_LOG_S_MINUS = 8 };
+enum FeatKind : int { F_LOG1P = 1, F_LOG = 2, F_LOG_RATIO = 3, F_LOG_DVDZ = 4, F_NEG_LOG = 5, F_RAW = 6, F_LOG_C_OVER = 7, F_LOG_S_MINUS = 8, F_NEG_LOG1P = 9, F_CONST = 10 };
 struct Feat {
   int kind;
   int col[2];
@@ -91,6 +91,8 @@ inline double eval_feat(const Feat& f, const double* const* cols, int64_t j) {
     case F_LOG_RATIO: return std::log(a / cols[f.col[1]][j]);
     case F_LOG_DVDZ: return log_dvcdz(a);
     case F_NEG_LOG: return -std::log(a);
+    case F_NEG_LOG1P: return -std::log(1.0 + a);
+    case F_CONST: return f.cst;
     case F_RAW: return a;
     case F_LOG_C_OVER: return std::log(f.cst / a);
     case F_LOG_S_MINUS: return std::log(f.cst - a);
@@ -301,7 +303,12 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     use_col(t.col[0]);
     bool ok = true;
     switch (t.kind) {
-      case GWI_TERM_SPLINE: {
+      case GWI_TERM_SPLINE:
+      case GWI_TERM_SPLINE_LINEAR: {
+        if (t.kind == GWI_TERM_SPLINE_LINEAR && t.outside != GWI_OUTSIDE_DROP) {
+          set_error("term " + std::to_string(ti) + ": a spline density must drop the samples outside its range");
+          return GWI_ERR_INVALID;
+        }
         if (t.n_splines < 4 || t.n_splines - 2 > MAX_ROWS || !slot_ok(t.slot[0], t.n_splines) || !(t.xi_hi > t.xi_lo)) {
           set_error("term " + std::to_string(ti) + ": bad spline description");
           return GWI_ERR_INVALID;
@@ -317,6 +324,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         d.slot = t.slot[0];
         d.norm_group = t.norm_group;
         d.outside = t.outside;
+        d.liny = t.kind == GWI_TERM_SPLINE_LINEAR ? 1 : 0;
         if (!add_grid(t, d.grid_off)) ok = false;
         plan.dims.push_back(d);
         SplineGeom g{};
@@ -341,6 +349,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
           case GWI_FEAT_LOG_RATIO: fk = F_LOG_RATIO; break;
           case GWI_FEAT_LOG_DVDZ: fk = F_LOG_DVDZ; break;
           case GWI_FEAT_NEG_LOG: fk = F_NEG_LOG; break;
+          case GWI_FEAT_NEG_LOG1P: fk = F_NEG_LOG1P; break;
           default: ok = false;
         }
         if (fk == F_LOG_RATIO) {
@@ -363,12 +372,14 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
           case GWI_FEAT_LOG_RATIO: fk = F_LOG_RATIO; break;
           case GWI_FEAT_LOG_DVDZ: fk = F_LOG_DVDZ; break;
           case GWI_FEAT_NEG_LOG: fk = F_NEG_LOG; break;
+          case GWI_FEAT_NEG_LOG1P: fk = F_NEG_LOG1P; break;
+          case GWI_FEAT_CONST: fk = F_CONST; break;
           default: ok = false;
         }
         if (fk == F_LOG_RATIO) {
           if (!col_ok(t.col[1])) ok = false; else use_col(t.col[1]);
         }
-        if (ok) static_feats.push_back(Feat{fk, {t.col[0], t.col[1]}, 0.0});
+        if (ok) static_feats.push_back(Feat{fk, {t.col[0], t.col[1]}, t.cst[0]});
         break;
       }
       case GWI_TERM_POWERLAW: {
@@ -472,6 +483,17 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     }
   }
 
+  // a spline density's normaliser is linear in its coefficients: its group holds that term alone
+  for (const SplineDim& D : plan.dims) {
+    if (!D.liny || D.norm_group < 0) continue;
+    int members = 0;
+    for (const SplineDim& O : plan.dims) members += O.norm_group == D.norm_group;
+    for (const Kop& k : plan.kops) members += k.norm_group == D.norm_group;
+    if (members != 1) {
+      set_error("the norm group of a SPLINE_LINEAR term must not have other members");
+      return GWI_ERR_INVALID;
+    }
+  }
   // ---- order the spline dims: most pieces first (sort key most significant), deep dims last ----
   const int NS = (int)plan.dims.size();
   {

@@ -28,6 +28,11 @@ __all__ = [
     "BSplineSpinTilt",
     "BSplineRatio",
     "BSplineMass",
+    "BSplineChiEffective",
+    "BSplineSymmetricChiEffective",
+    "BSplineChiPrecess",
+    "BSplineRedshift",
+    "BSplineEffectiveSpinDims",
     "BSplineIIDSpinMagnitudes",
     "BSplineIndependentSpinMagnitudes",
     "BSplineIIDSpinTilts",
@@ -153,11 +158,6 @@ class Base1DBSplineModel:
             raise NotImplementedError("only cubic B-splines (degree=3) are implemented on the CUDA path")
         if kwargs.get("knots") is not None or kwargs.get("interior_knots") is not None:
             raise NotImplementedError("non-uniform knot vectors are not implemented on the CUDA path")
-        if not getattr(basis, "logy", False):
-            raise NotImplementedError(
-                "linear-in-y bases (BSpline/LogXBSpline as a density) are not implemented on the CUDA path; "
-                "use LogYBSpline / LogXLogYBSpline"
-            )
         self.n_splines = int(n_splines)
         self.xmin, self.xmax = float(xrange[0]), float(xrange[1])
         self.degree = degree
@@ -191,7 +191,8 @@ class Base1DBSplineModel:
                 groups = [S.NormGroup(model.grid_log_w, name=f"Z[{cols[0]}]")]
                 g = group_base
             term = S.Term(
-                S.TERM_SPLINE,
+                # LogY bases: exp(B.c) (interpolation.py:381-394); BSpline/LogXBSpline: B.c itself (:293-317)
+                S.TERM_SPLINE if model.basis.logy else S.TERM_SPLINE_LINEAR,
                 [cols[0]],
                 slots=[slots[0]],
                 n_splines=model.n_splines,
@@ -237,6 +238,103 @@ class BSplineMass(Base1DBSplineModel):
         super().__init__(n_splines, m, m_inj, basis=basis, xrange=xrange, **kwargs)
 
 
+class BSplineChiEffective(Base1DBSplineModel):
+    """single.py:199-230 (default basis: the spline itself is the density)."""
+
+    def __init__(self, n_splines, chieff, chieff_inj, basis=BSpline, **kwargs):
+        xrange = kwargs.pop("xrange", (-1.0, 1.0))
+        super().__init__(n_splines, chieff, chieff_inj, basis=basis, xrange=xrange, **kwargs)
+
+
+def _const_factor(value, column, pe_samples, tag):
+    """A constant factor of the weight as a lazy static term."""
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_STATIC, [cols[0]], cst=[float(np.log(value))], feature=S.FEAT_CONST, name=f"const[{tag}]")], [], []
+
+    return LazyWeight([_LazyTerm(("const", tag, float(value), id(column)), [column], [], build)], pe_samples)
+
+
+class BSplineSymmetricChiEffective(Base1DBSplineModel):
+    """single.py:233-284: a spline in |chi_eff| on [0, 1], times 1/2."""
+
+    def __init__(self, n_splines, chieff, chieff_inj, basis=BSpline, **kwargs):
+        xrange = kwargs.pop("xrange", (0.0, 1.0))
+        super().__init__(n_splines, np.abs(chieff), np.abs(chieff_inj), basis=basis, xrange=xrange, **kwargs)
+
+    def __call__(self, coefs, pe_samples=True):
+        return self._lazy(coefs, pe_samples) * _const_factor(0.5, self.column, pe_samples, "symmetric")
+
+
+class BSplineChiPrecess(Base1DBSplineModel):
+    """single.py:287-318."""
+
+    def __init__(self, n_splines, chip, chip_inj, basis=BSpline, **kwargs):
+        xrange = kwargs.pop("xrange", (0.0, 1.0))
+        super().__init__(n_splines, chip, chip_inj, basis=basis, xrange=xrange, **kwargs)
+
+
+class BSplineRedshift(Base1DBSplineModel):
+    """single.py:398-492: ``R(z) = exp(B(log z).c) dVc/dz / (1+z) / Z(c)``, ``Z`` by trapezoid over
+    1000 points between the data's redshift extremes.
+
+    The reference builds the LogXBSpline basis with its DEFAULT ``normalize=True``, which makes the
+    exponent ``(B.c) / trapezoid(B.c)`` (single.py:77-92 -> interpolation.py:293-317); that coupling
+    is not expressible as a sum of terms, so this mirror requires ``normalize=False`` (the exponent
+    is then the plain spline, as in ``PowerlawSplineRedshiftModel``, spline_perturbation.py:317)."""
+
+    def __init__(self, n_splines, z, z_inj, dVdc, dVdc_inj, zmax=2.3, basis=LogXBSpline, z_range=None, **kwargs):
+        if basis is not LogXBSpline:
+            raise NotImplementedError("only the LogXBSpline basis is implemented for BSplineRedshift")
+        if kwargs.get("normalize", basis.default_normalize):
+            raise NotImplementedError(
+                "BSplineRedshift with a normalised basis (the LogXBSpline default) divides the EXPONENT by "
+                "trapezoid(B.c); pass normalize=False for exp(B.c) dVc/dz/(1+z)/Z(c)"
+            )
+        xrange = kwargs.pop("xrange", (1e-4, zmax))
+        super().__init__(n_splines, z, z_inj, xrange=xrange, basis=basis, **kwargs)
+        self.dvdc_column = _Column(dVdc, dVdc_inj)
+        if z_range is None:
+            self.zmin = float(max(np.min(self.column.pe), np.min(self.column.inj)))  # single.py:445
+            self.zmax = float(min(np.max(self.column.pe), np.max(self.column.inj)))  # :446
+        else:  # a process holding a SHARD passes the whole catalog's range
+            self.zmin, self.zmax = float(z_range[0]), float(z_range[1])
+        self.zgrid = np.linspace(self.zmin, self.zmax, 1000)  # :447
+        with np.errstate(divide="ignore"):
+            self._grid_log_w = np.log(S.trapezoid_weights(self.zgrid) * Planck15.dVcdz(self.zgrid) / (1.0 + self.zgrid))  # :465-468
+        gxi = np.log(self.zgrid)
+        inside = (gxi >= self.xi_range[0]) & (gxi <= self.xi_range[1])
+        self._grid_xi = np.where(inside, np.clip(gxi, *self.xi_range), np.nan)  # LogX bases are 0 outside (:175)
+
+    def __call__(self, coefs, pe_samples=True):
+        model = self
+
+        def build(slots, group_base, cols):
+            t = S.Term(
+                S.TERM_SPLINE, [cols[0]], slots=[slots[0]], n_splines=model.n_splines, logx=True,
+                outside=S.OUTSIDE_ZERO,  # funcs() is 0 outside the mask => exp(0) = 1 (single.py:90-92, 488)
+                xrange=(model.xmin, model.xmax), norm_group=group_base, grid_xi=model._grid_xi, name="spline[log z]",
+            )
+            t.xi_range = model.xi_range
+            terms = [
+                t,
+                S.Term(S.TERM_STATIC, [cols[1]], feature=S.FEAT_LOG, name="dVc/dz (given)"),
+                S.Term(S.TERM_STATIC, [cols[0]], feature=S.FEAT_NEG_LOG1P, name="1/(1+z)"),
+            ]
+            return terms, [S.NormGroup(model._grid_log_w, name="Z[redshift]")], []
+
+        if np.shape(coefs) != (self.n_splines,):
+            raise ValueError(f"expected {self.n_splines} coefficients, got shape {np.shape(coefs)}")
+        return LazyWeight([_LazyTerm((id(self), "bsz"), [self.column, self.dvdc_column], [coefs], build)], pe_samples)
+
+    def normalization(self, cs):
+        """Host-side ``Z(cs)`` (single.py:453-469), e.g. for the merger rate."""
+        from .lowering import host_spline_on_grid
+
+        s = host_spline_on_grid(self._grid_xi, self.xi_range, self.n_splines, np.asarray(cs, dtype=np.float64))
+        return float(np.sum(np.exp(self._grid_log_w + s)))
+
+
 # ================================================================================================
 # separable products (gwinferno/models/bsplines/separable.py)
 # ================================================================================================
@@ -277,6 +375,17 @@ class BSplineIIDSpinTilts(_IIDPair):
 
 class BSplineIndependentSpinTilts(_IndependentPair):
     _cls = BSplineSpinTilt
+
+
+class BSplineEffectiveSpinDims:
+    """separable.py:706-778."""
+
+    def __init__(self, n_splines_e, n_splines_p, chieff, chip, chieff_inj, chip_inj, kwargs_e={}, kwargs_p={}, **kwargs):
+        self.chi_eff_model = BSplineChiEffective(n_splines_e, chieff, chieff_inj, **kwargs_e, **kwargs)
+        self.chi_p_model = BSplineChiPrecess(n_splines_p, chip, chip_inj, **kwargs_p, **kwargs)
+
+    def __call__(self, ecoefs, pcoefs, pe_samples=True):
+        return self.chi_eff_model(ecoefs, pe_samples=pe_samples) * self.chi_p_model(pcoefs, pe_samples=pe_samples)
 
 
 class BSplinePrimaryBSplineRatio:

@@ -29,6 +29,7 @@ TERM_PLPEAK = 6  # log[(1-lam) PL(m1) + lam TN(m1)]                  parametric.
 TERM_BETA = 7  # log betadist(col; alpha, beta, scale)               distributions.py:146-162
 TERM_ISOALIGN = 8  # log[(1-xi)/2 + xi TN(ct; 1, sigma, -1, 1)]      parametric.py:84-86
 TERM_TRUNCNORM = 9  # log truncnorm_pdf(col; mu, sig, lo, hi)        distributions.py:122-143
+TERM_SPLINE_LINEAR = 10  # log sum_k B_k(xi) c_k : the spline is the density  interpolation.py:280-317
 
 # ---- gwi_feature --------------------------------------------------------------------------
 FEAT_LOG1P = 1  # log(1 + col0)
@@ -36,6 +37,8 @@ FEAT_LOG = 2  # log(col0)
 FEAT_LOG_RATIO = 3  # log(col0 / col1)
 FEAT_LOG_DVDZ = 4  # log dVc/dz(col0)   (Planck15-LVK table, cosmology.py:95-120)
 FEAT_NEG_LOG = 5  # -log(col0)          (division by the sampling prior)
+FEAT_NEG_LOG1P = 6  # -log(1 + col0)    (the 1/(1+z) of BSplineRedshift, single.py:488-491)
+FEAT_CONST = 7  # cst[0]                (a constant factor, e.g. the 0.5 of single.py:284)
 
 # ---- gwi_outside (SPLINE only) ------------------------------------------------------------
 OUTSIDE_DROP = 0  # LogY-type bases are -inf outside xrange => pdf 0 (interpolation.py:407,449)

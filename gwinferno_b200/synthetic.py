@@ -148,3 +148,14 @@ def bspline_lambda(nsplines, seed, scale=1.0):
         out["redshift"][0] = 0.0
     out["lamb"] = 2.7
     return out
+
+
+def effective_spins(d):
+    """``(chi_eff, chi_p)`` of a sample dictionary (component spins -> effective spin and effective
+    precession), the coordinates of ``BSplineEffectiveSpinDims`` (separable.py:706-778)."""
+    q, a1, a2, c1, c2 = d["mass_ratio"], d["a_1"], d["a_2"], d["cos_tilt_1"], d["cos_tilt_2"]
+    chi_eff = (a1 * c1 + q * a2 * c2) / (1.0 + q)
+    s1 = np.sqrt(np.clip(1.0 - c1 * c1, 0.0, None))
+    s2 = np.sqrt(np.clip(1.0 - c2 * c2, 0.0, None))
+    chi_p = np.maximum(a1 * s1, q * (4.0 * q + 3.0) / (4.0 + 3.0 * q) * a2 * s2)
+    return np.ascontiguousarray(chi_eff), np.ascontiguousarray(chi_p)

@@ -56,7 +56,11 @@ typedef enum {
   GWI_TERM_PLPEAK = 6,         /* log[(1-lam) PL + lam TN](col0); slots alpha,mu,sigma,lam; cst mmin,mmax  parametric.py:49-53 */
   GWI_TERM_BETA = 7,           /* log betadist(col0; alpha, beta, scale=cst0)               distributions.py:146-162 */
   GWI_TERM_ISOALIGN = 8,       /* log[(1-xi)/2 + xi TN(col0; 1, sigma, -1, 1)]              parametric.py:84-86      */
-  GWI_TERM_TRUNCNORM = 9       /* log truncnorm_pdf(col0; mu, sigma, lo=cst0, hi=cst1)      distributions.py:122-143 */
+  GWI_TERM_TRUNCNORM = 9,      /* log truncnorm_pdf(col0; mu, sigma, lo=cst0, hi=cst1)      distributions.py:122-143 */
+  GWI_TERM_SPLINE_LINEAR = 10  /* log sum_k B_k(xi) c_k : the spline IS the density (BSpline / LogXBSpline projection,
+                                  interpolation.py:280-317; BSplineChiEffective etc., single.py:199-318).  Same fields as
+                                  SPLINE; outside must be DROP; a density <= 0 gives the sample zero weight.  Its norm
+                                  group holds this term alone and is Z = sum_g w_g sum_k B_k(xi_g) c_k (linear in c). */
 } gwi_term_kind;
 
 typedef enum {
@@ -64,7 +68,9 @@ typedef enum {
   GWI_FEAT_LOG = 2,       /* log(col0)          */
   GWI_FEAT_LOG_RATIO = 3, /* log(col0 / col1)   */
   GWI_FEAT_LOG_DVDZ = 4,  /* log dVc/dz(col0), flat LCDM Planck15-LVK table (cosmology.py:48-120) */
-  GWI_FEAT_NEG_LOG = 5    /* -log(col0)         */
+  GWI_FEAT_NEG_LOG = 5,   /* -log(col0)         */
+  GWI_FEAT_NEG_LOG1P = 6, /* -log(1 + col0)     (the 1/(1+z) of BSplineRedshift, single.py:488-491) */
+  GWI_FEAT_CONST = 7      /* cst[0] (STATIC only): a constant factor, e.g. the 0.5 of single.py:284   */
 } gwi_feature;
 
 typedef enum {

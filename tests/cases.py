@@ -10,6 +10,7 @@ from gwinferno_b200 import models as M
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 COLS = ["mass_1", "mass_ratio", "mass_2", "a_1", "a_2", "cos_tilt_1", "cos_tilt_2", "redshift", "prior"]
+EXTRA_COLS = ["chi_eff", "chi_p", "dVdc"]  # derived coordinates stored by the cases that use them
 GOLDEN_CASES = [
     "bspline_full",
     "bspline_full_margsel",
@@ -19,6 +20,9 @@ GOLDEN_CASES = [
     "inference_test_bspline",
     "inference_test_parametric",
     "plpeak",
+    "bspline_effspin",
+    "bspline_effspin_margsel",
+    "bspline_symchieff",
 ]
 LIKE_KW = {
     "bspline_full": dict(marginalize_selection=False, min_neff_cut=True),
@@ -29,6 +33,9 @@ LIKE_KW = {
     "inference_test_bspline": dict(marginalize_selection=False, min_neff_cut=False),
     "inference_test_parametric": dict(marginalize_selection=False, min_neff_cut=False),
     "plpeak": dict(min_neff_cut=True),
+    "bspline_effspin": dict(min_neff_cut=False),
+    "bspline_effspin_margsel": dict(marginalize_selection=True, min_neff_cut=False),
+    "bspline_symchieff": dict(min_neff_cut=False),
 }
 
 
@@ -99,6 +106,27 @@ def build_weight_fn(model, pe, inj, meta):
             return p_m1q * p_a * p_ct * mz(d["redshift"], p["lamb"]) / d["prior"]
 
         return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
+    if model == "bspline_effspin":
+        mm = M.BSplinePrimaryBSplineRatio(int(meta["n_m1"]), int(meta["n_q"]), pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax)
+        ms = M.BSplineEffectiveSpinDims(int(meta["n_e"]), int(meta["n_p"]), pe["chi_eff"], pe["chi_p"], inj["chi_eff"], inj["chi_p"], normalize=True)
+        mz = M.BSplineRedshift(int(meta["n_z"]), pe["redshift"], inj["redshift"], pe["dVdc"], inj["dVdc"], zmax=float(meta["zmax"]), normalize=False)
+
+        def weights(d, pe_samples, p):
+            w = mm(p["mass_cs"], p["q_cs"], pe_samples=pe_samples) * ms(p["chieff_cs"], p["chip_cs"], pe_samples=pe_samples)
+            return w * mz(p["z_cs"], pe_samples=pe_samples) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(p["z_cs"]))
+    if model == "bspline_symchieff":
+        mm = M.BSplineMass(int(meta["n_m1"]), pe["mass_1"], inj["mass_1"], mmin=mmin, mmax=mmax, basis=M.LogXBSpline)
+        me = M.BSplineSymmetricChiEffective(int(meta["n_e"]), pe["chi_eff"], inj["chi_eff"], normalize=True)
+        mp = M.BSplineChiPrecess(int(meta["n_p"]), pe["chi_p"], inj["chi_p"], basis=M.LogYBSpline)
+        mz = M.PowerlawSplineRedshiftModel(int(meta["n_z"]), pe["redshift"], inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            w = mm(p["mass_cs"], pe_samples=pe_samples) * me(p["chieff_cs"], pe_samples=pe_samples) * mp(p["chip_cs"], pe_samples=pe_samples)
+            return w * mz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(p["lamb"], p["z_cs"]))
     raise KeyError(model)
 
 
@@ -107,8 +135,9 @@ def load_case(name):
     d = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
     c = Case()
     c.name = name
-    c.pe = {k: d[f"pe_{k}"] for k in COLS}
-    c.inj = {k: d[f"inj_{k}"] for k in COLS}
+    cols = COLS + [k for k in EXTRA_COLS if f"pe_{k}" in d.files]
+    c.pe = {k: d[f"pe_{k}"] for k in cols}
+    c.inj = {k: d[f"inj_{k}"] for k in cols}
     c.total_inj = float(d["const_total_inj"])
     c.Nobs = int(d["const_nObs"])
     c.Tobs = float(d["const_obs_time"])

@@ -35,6 +35,9 @@ PAR = R["parametric"]
 INT = R["interpolation"]
 
 COLS = ["mass_1", "mass_ratio", "mass_2", "a_1", "a_2", "cos_tilt_1", "cos_tilt_2", "redshift", "prior"]
+EXTRA_COLS = ["chi_eff", "chi_p", "dVdc"]  # derived coordinates, stored only by the cases that use them
+SGL = R["single"]
+COSMO = R["cosmology"]
 
 
 def _record_likelihood(pe_w, inj_w, total_inj, Nobs, Tobs, vt, **kw):
@@ -92,7 +95,7 @@ def _complex_step(weights_fn, pe, inj, const, params, names, vt_fn, like_kw):
 
 def _save(name, pe, inj, const, params, names, base, jac, meta):
     out = {}
-    for c in COLS:
+    for c in COLS + [c for c in EXTRA_COLS if c in pe]:
         out[f"pe_{c}"] = pe[c]
         out[f"inj_{c}"] = inj[c]
     for k, v in const.items():
@@ -270,13 +273,86 @@ def case_plpeak():
     _save("plpeak", pe, inj, const, params, names, base, jac, dict(model="plpeak", mmin=mmin, mmax=mmax))
 
 
+def _with_derived(pe, inj):
+    for d in (pe, inj):
+        d["chi_eff"], d["chi_p"] = synthetic.effective_spins(d)
+        d["dVdc"] = np.asarray(COSMO.PLANCK_2015_LVK_Cosmology.dVcdz(d["redshift"]), dtype=np.float64)
+
+
+def case_bspline_effspin():
+    """Effective-spin model: B-spline m1+q, ``BSplineEffectiveSpinDims`` (the chi_eff / chi_p splines
+    ARE the densities: default ``BSpline`` basis, single.py:199-230,287-318; separable.py:706-778)
+    and ``BSplineRedshift`` (single.py:398-492; ``normalize=False`` so that the exponent is the plain
+    spline)."""
+    E, S, I = 7, 220, 5000
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=130)
+    _with_derived(pe, inj)
+    ns = dict(m1=14, q=8, e=12, p=9, z=7)
+    mmin, mmax, zmax = 3.0, 100.0, 2.3
+    rm = SEP.BSplinePrimaryBSplineRatio(ns["m1"], ns["q"], pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax)
+    rs = SEP.BSplineEffectiveSpinDims(ns["e"], ns["p"], pe["chi_eff"], pe["chi_p"], inj["chi_eff"], inj["chi_p"], normalize=True)
+    rz = SGL.BSplineRedshift(ns["z"], pe["redshift"], inj["redshift"], pe["dVdc"], inj["dVdc"], zmax=zmax, normalize=False)
+    rng = np.random.default_rng(130002)
+    params = dict(
+        mass_cs=0.4 * rng.standard_normal(ns["m1"]), q_cs=0.4 * rng.standard_normal(ns["q"]),
+        chieff_cs=np.exp(0.6 * rng.standard_normal(ns["e"])), chip_cs=np.exp(0.6 * rng.standard_normal(ns["p"])),
+        z_cs=0.4 * rng.standard_normal(ns["z"]),
+    )
+    names = ["mass_cs", "q_cs", "chieff_cs", "chip_cs", "z_cs"]
+
+    def weights(d, pe_samples, p):
+        w = rm(p["mass_cs"], p["q_cs"], pe_samples=pe_samples) * rs(p["chieff_cs"], p["chip_cs"], pe_samples=pe_samples)
+        return w * rz(p["z_cs"], pe_samples=pe_samples) / d["prior"]
+
+    vt = lambda p: rz.normalization(p["z_cs"])  # noqa: E731
+    for name, kw in (("bspline_effspin", dict(min_neff_cut=False)), ("bspline_effspin_margsel", dict(marginalize_selection=True, min_neff_cut=False))):
+        base, jac = _complex_step(weights, pe, inj, const, params, names, vt, kw)
+        _save(name, pe, inj, const, params, names, base, jac, dict(model="bspline_effspin", mmin=mmin, mmax=mmax, zmax=zmax, **{f"n_{k}": v for k, v in ns.items()}))
+
+
+def case_bspline_symchieff():
+    """``BSplineSymmetricChiEffective`` (spline density in |chi_eff|, x 1/2, single.py:233-284), chi_p
+    with a LogY basis, the primary mass as a ``LogXBSpline`` DENSITY (linear in y, log in x) and the
+    power-law x spline redshift model."""
+    E, S, I = 6, 200, 4000
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=131)
+    _with_derived(pe, inj)
+    ns = dict(m1=12, e=8, p=7, z=6)
+    mmin, mmax = 3.0, 100.0
+    rm = SGL.BSplineMass(ns["m1"], pe["mass_1"], inj["mass_1"], mmin=mmin, mmax=mmax, basis=INT.LogXBSpline)
+    re_ = SGL.BSplineSymmetricChiEffective(ns["e"], pe["chi_eff"], inj["chi_eff"], normalize=True)
+    rp = SGL.BSplineChiPrecess(ns["p"], pe["chi_p"], inj["chi_p"], basis=INT.LogYBSpline)
+    rz = SPL.PowerlawSplineRedshiftModel(ns["z"], pe["redshift"], inj["redshift"])
+    rng = np.random.default_rng(131002)
+    params = dict(
+        mass_cs=np.exp(0.8 * rng.standard_normal(ns["m1"])), chieff_cs=np.exp(0.5 * rng.standard_normal(ns["e"])),
+        chip_cs=0.5 * rng.standard_normal(ns["p"]), lamb=np.float64(2.2), z_cs=0.3 * rng.standard_normal(ns["z"]),
+    )
+    names = ["mass_cs", "chieff_cs", "chip_cs", "lamb", "z_cs"]
+
+    def weights(d, pe_samples, p):
+        w = rm(p["mass_cs"], pe_samples=pe_samples) * re_(p["chieff_cs"], pe_samples=pe_samples) * rp(p["chip_cs"], pe_samples=pe_samples)
+        return w * rz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+
+    vt = lambda p: rz.normalization(p["lamb"], p["z_cs"])  # noqa: E731
+    base, jac = _complex_step(weights, pe, inj, const, params, names, vt, dict(min_neff_cut=False))
+    _save("bspline_symchieff", pe, inj, const, params, names, base, jac, dict(model="bspline_symchieff", mmin=mmin, mmax=mmax, **{f"n_{k}": v for k, v in ns.items()}))
+
+
+CASES = dict(
+    bspline_full=case_bspline_full,
+    bspline_iid=case_bspline_iid,
+    bspline_indep_masses=case_bspline_indep_masses,
+    inference_test_bspline=case_inference_test_bspline,
+    inference_test_parametric=case_inference_test_parametric,
+    plpeak=case_plpeak,
+    bspline_effspin=case_bspline_effspin,
+    bspline_symchieff=case_bspline_symchieff,
+)
+
 if __name__ == "__main__":
     import warnings
 
     warnings.filterwarnings("ignore")
-    case_bspline_full()
-    case_bspline_iid()
-    case_bspline_indep_masses()
-    case_inference_test_bspline()
-    case_inference_test_parametric()
-    case_plpeak()
+    for name in sys.argv[1:] or list(CASES):  # optional: only the named cases
+        CASES[name]()

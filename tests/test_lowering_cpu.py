@@ -69,7 +69,8 @@ def test_weight_products_must_match(cat):
 def test_unsupported_reference_options_fail_loudly(cat):
     pe, inj, _ = cat
     with pytest.raises(NotImplementedError):
-        M.Base1DBSplineModel(8, pe["a_1"], inj["a_1"], basis=M.BSpline)  # linear-in-y density
+        # the reference's default (normalised LogXBSpline) divides the EXPONENT by trapezoid(B.c)
+        M.BSplineRedshift(8, pe["redshift"], inj["redshift"], pe["redshift"], inj["redshift"])
     with pytest.raises(NotImplementedError):
         M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], degree=2)
     with pytest.raises(NotImplementedError):
@@ -109,3 +110,20 @@ def test_sharded_catalog_is_an_exact_partition():
         assert np.array_equal(np.sort(np.concatenate([key(p) for p in parts])), key(full))
     ev = [workloads.shard_catalog("cfg2", r, 4, all_reduce_minmax=lambda a, b: (a, b))[0]["mass_1"].shape[0] for r in range(4)]
     assert sum(ev) == 70
+
+
+def test_spline_density_bases_lower_to_linear_spline_terms(cat):
+    """BSpline / LogXBSpline bases: the spline itself is the density (interpolation.py:293-317)."""
+    pe, inj, _ = cat
+    a = M.BSplineChiEffective(8, pe["cos_tilt_1"], inj["cos_tilt_1"], normalize=True)
+    b = M.BSplineSymmetricChiEffective(6, pe["cos_tilt_2"], inj["cos_tilt_2"])
+    z = M.BSplineRedshift(7, pe["redshift"], inj["redshift"], pe["prior"], inj["prior"], normalize=False)
+    ca, cb, cz = np.ones(8), np.ones(6), np.zeros(7)
+    low = lowering.lower(a(ca, pe_samples=True) * b(cb, pe_samples=True) * z(cz, pe_samples=True),
+                         a(ca, pe_samples=False) * b(cb, pe_samples=False) * z(cz, pe_samples=False))
+    kinds = [t.kind for t in low.spec.terms]
+    assert kinds.count(S.TERM_SPLINE_LINEAR) == 2 and kinds.count(S.TERM_SPLINE) == 1 and kinds.count(S.TERM_STATIC) == 3
+    assert low.spec.n_params == 21 and len(low.spec.groups) == 2  # chi_eff normalised, symmetric one not, redshift Z
+    t = [t for t in low.spec.terms if t.kind == S.TERM_SPLINE][0]
+    assert t.outside == S.OUTSIDE_ZERO and t.logx and t.xrange == (1e-4, 2.3)
+    assert np.array_equal(low.pe_cols[[t for t in low.spec.terms if t.kind == S.TERM_SPLINE_LINEAR][1].cols[0]], np.abs(pe["cos_tilt_2"]))

@@ -18,7 +18,7 @@ from tests import cases
 
 MANT = np.uint64(0x000FFFFFFFFFFFFF)
 ONE = np.uint64(0x3FF0000000000000)
-SPLINE_CASES = ["bspline_full", "bspline_iid", "bspline_indep_masses", "inference_test_bspline"]
+SPLINE_CASES = ["bspline_full", "bspline_iid", "bspline_indep_masses", "inference_test_bspline", "bspline_effspin", "bspline_symchieff"]
 
 
 def test_library_exports_every_declared_symbol():
@@ -64,6 +64,10 @@ def _decode(case, plan):
         w = np.stack([(1 - u) ** 3, 3 * u**3 - 6 * u**2 + 4, -3 * u**3 + 3 * u**2 + 3 * u + 1, u**3], -1) / 6.0
         c = Lam[term.slots[0] : term.slots[0] + term.n_splines]
         f = np.einsum("nk,nk->n", w, c[Jc[:, None] + np.arange(4)])
+        if term.kind == popmodel.TERM_SPLINE_LINEAR:  # the spline is the density: log of the cubic
+            assert real.all()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                f = np.where(f > 0, np.log(np.where(f > 0, f, 1.0)), -np.inf)
         x += np.where(real, f, 0.0)
     for k in range(n_kops):
         kind, c0, _, s0 = (int(v) for v in kops[k, :4])
