@@ -746,8 +746,8 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   plan.warps_per_block = wpb;
   plan.grid_blocks = std::max(1, sm_count);
   const int W = plan.grid_blocks * plan.warps_per_block;
-  // Balanced slicing: the piece-sorted sample stream of all segments (injections first, then the
-  // events) is cut into SLICES of L steps (32 samples per step); slice i belongs to warp i % W.
+  // Balanced slicing: the piece-sorted sample stream of all segments (the events first, then the
+  // injections) is cut into SLICES of L steps (32 samples per step); slice i belongs to warp i % W.
   // By default L = ceil(total steps / W): every warp gets exactly one slice, i.e. the same amount
   // of work.  A slice is split into CHUNKS at segment boundaries; the lanes of the warp own
   // contiguous sorted runs inside each chunk.  (desc.chunk_steps > 0 caps L: tests use it to force
@@ -770,12 +770,18 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   plan.slice_begin.clear();
   plan.slice_begin.push_back(0);
   // Guided scheduling: the warps pull slices in order, so the slices shrink towards the end of
-  // the stream (guided self-scheduling: slice = remaining work / 2W, clamped to [32, L]) to keep
+  // the stream (guided self-scheduling: slice = remaining work / 2W, clamped to [8, L]) to keep
   // the tail short.
   const int64_t L_full = L;
+  // one warp step takes ~2500 cycles of latency (8 resident warps/SM), so a 32-step final slice is a
+  // 40 us tail; 8-step slices at the very end cut it to ~10 us for ~2W extra record flushes
+  const int64_t L_MIN = 8;
   int64_t done_steps = 0;
   int64_t pos = 0, fill = 0;
-  for (int s = 0; s < n_seg; ++s) {
+  for (int si = 0; si < n_seg; ++si) {
+    // events first, the injection set (segment 0) last: the small final slices of the guided
+    // schedule are then cheap injection slices, not spill-heavy PE slices (shorter tail)
+    const int s = (si + 1) % n_seg;
     Segment& S = plan.segments[s];
     S.first_chunk = (int)plan.chunks.size();
     int64_t left = S.n_valid, r0 = 0;
@@ -788,7 +794,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         fill = 0;
         {
           const int64_t remaining = std::max<int64_t>(0, total_steps - done_steps);
-          L = std::max<int64_t>(std::min<int64_t>(32, L_full), std::min<int64_t>(L_full, roundQ(remaining / (2 * (int64_t)W))));
+          L = std::max<int64_t>(std::min<int64_t>(L_MIN, L_full), std::min<int64_t>(L_full, roundQ(remaining / (2 * (int64_t)W))));
         }
       }
       const int64_t steps = std::min<int64_t>(L - fill, roundQ((left + LANES - 1) / LANES));
@@ -919,8 +925,8 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     }
   }
 
-  // ---- level-0 records: one per chunk (chunks are created in segment order, so the records of
-  //      a segment are consecutive); fixed-order tree reduction afterwards
+  // ---- level-0 records: one per chunk (the chunks, hence the records, of a segment are
+  //      consecutive); fixed-order tree reduction afterwards
   {
     plan.n_records0 = n_chunks;
     std::vector<int> cnt(n_seg, 0), first(n_seg, 0);
@@ -929,13 +935,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       plan.chunks[c].flush = 1;
       cnt[plan.chunks[c].segment]++;
     }
-    {
-      int acc = 0;
-      for (int s = 0; s < n_seg; ++s) {
-        first[s] = acc;
-        acc += cnt[s];
-      }
-    }
+    for (int s = 0; s < n_seg; ++s) first[s] = plan.segments[s].first_chunk;  // chunks of a segment are consecutive
     // reduction tree, fan-in 64; the last level writes slot == segment
     constexpr int FAN = 64;
     for (;;) {
