@@ -30,7 +30,7 @@ class gwi_term(C.Structure):
         ("outside", C.c_int32),
         ("logx", C.c_int32),
         ("col", C.c_int32 * 2),
-        ("slot", C.c_int32 * 4),
+        ("slot", C.c_int32 * 6),
         ("cst", C.c_double * 4),
         ("n_splines", C.c_int32),
         ("norm_group", C.c_int32),
@@ -260,8 +260,8 @@ class _Desc:
             ct.logx = int(bool(t.logx))
             cols = [col_index[c] for c in t.cols] + [-1, -1]
             ct.col[0], ct.col[1] = cols[0], cols[1]
-            slots = list(t.slots) + [-1] * 4
-            for k in range(4):
+            slots = list(t.slots) + [-1] * 6
+            for k in range(6):
                 ct.slot[k] = int(slots[k])
             cst = list(t.cst) + [0.0] * 4
             for k in range(4):

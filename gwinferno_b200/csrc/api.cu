@@ -411,10 +411,8 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     X.n_gslots = K.n_gslots;
     X.norm_group = K.norm_group;
     X.grid_off = K.grid_off;
-    for (int i = 0; i < 4; ++i) {
-      X.slot[i] = K.slot[i];
-      X.cst[i] = K.cst[i];
-    }
+    for (int i = 0; i < 6; ++i) X.slot[i] = K.slot[i];
+    for (int i = 0; i < 4; ++i) X.cst[i] = K.cst[i];
     for (int i = 0; i < K.n_gslots; ++i) H.gslot_slot[K.gslot + i] = K.slot[i];
     if (K.kind != KOP_LIN) H.two_pass = 1;  // no a-priori bound for the non-linear terms: exact max first
   }

@@ -17,7 +17,7 @@ struct DimDev {
 struct KopDev {
   int32_t kind, col0, col1, gslot;
   int32_t n_gslots, norm_group, grid_off, pad;
-  int32_t slot[4];
+  int32_t slot[6], pad2[2];
   double cst[4];
 };
 

@@ -32,9 +32,10 @@ constexpr uint64_t ONE_BITS = 0x3FF0000000000000ull;
 enum KopKind : int32_t {
   KOP_LIN = 1,       // x += theta * F                       gslots: theta
   KOP_PLRATIO = 2,   // powerlaw in q with per-sample lower bound: cols (log q, log lo)   gslots: beta
-  KOP_PLPEAK = 3,    // cols (log m1, m1)                     gslots: alpha, mu, sigma, lam
+  KOP_PLPEAK = 3,    // cols (log m1, m1)                     gslots: alpha, mu, sigma, lam [, delta]
   KOP_ISOALIGN = 4,  // col (cos tilt)                        gslots: xi, sigma
-  KOP_QUAD = 5       // truncated normal body: col (x)        gslots: mu, sigma
+  KOP_QUAD = 5,      // truncated normal body: col (x)        gslots: mu, sigma
+  KOP_SMOOTH = 6     // low-mass window: col (x - xmin)       gslots: delta
 };
 
 struct Kop {
@@ -42,7 +43,7 @@ struct Kop {
   int32_t col[2];     // stream-column indices of its features
   int32_t gslot;      // first generic gradient slot
   int32_t n_gslots;
-  int32_t slot[4];    // Lambda slots
+  int32_t slot[6];    // Lambda slots
   double cst[4];      // LIN: cst[0] = offset added to Lambda[slot]; PLPEAK/QUAD: lo, hi
   int32_t norm_group; // LIN only
   int32_t grid_off;   // offset of its grid feature in the grid pool (doubles), -1 none

@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
       truncnorm_consts(mu, sig, K.cst[0], K.cst[1], lt, dmu, dsg);
       kc[0] = alpha; kc[1] = ln; kc[2] = mu; kc[3] = 0.5 / (sig * sig); kc[4] = lt; kc[5] = lam;
       kc[6] = dn; kc[7] = sig; kc[8] = dmu; kc[9] = dsg;
+      kc[10] = K.slot[4] >= 0 ? Lam[K.slot[4]] : 0.0;  // delta_m (0 = no low-mass window)
+      kc[11] = K.cst[0];                                // mmin
     } else if (K.kind == KOP_ISOALIGN) {
       const double xi = Lam[K.slot[0]], sig = Lam[K.slot[1]];
       double lt, dmu, dsg;
@@ -281,6 +283,8 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     } else if (K.kind == KOP_QUAD) {
       const double mu = Lam[K.slot[0]], sig = Lam[K.slot[1]];
       kc[0] = mu; kc[1] = sig; kc[2] = 0.5 / (sig * sig);
+    } else if (K.kind == KOP_SMOOTH) {
+      kc[0] = Lam[K.slot[0]];
     }
   }
   for (int i = tid; i < P + 1; i += nt) M.Ksum[i] = 0.0;

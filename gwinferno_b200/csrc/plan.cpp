@@ -76,7 +76,7 @@ double log_dvcdz(double z) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-enum FeatKind : int { F_LOG1P = 1, F_LOG = 2, F_LOG_RATIO = 3, F_LOG_DVDZ = 4, F_NEG_LOG = 5, F_RAW = 6, F_LOG_C_OVER = 7, F_LOG_S_MINUS = 8, F_NEG_LOG1P = 9, F_CONST = 10 };
+enum FeatKind : int { F_LOG1P = 1, F_LOG = 2, F_LOG_RATIO = 3, F_LOG_DVDZ = 4, F_NEG_LOG = 5, F_RAW = 6, F_LOG_C_OVER = 7, F_LOG_S_MINUS = 8, F_NEG_LOG1P = 9, F_CONST = 10, F_MINUS_C = 11, F_PROD_MINUS_C = 12 };
 struct Feat {
   int kind;
   int col[2];
@@ -93,6 +93,8 @@ inline double eval_feat(const Feat& f, const double* const* cols, int64_t j) {
     case F_NEG_LOG: return -std::log(a);
     case F_NEG_LOG1P: return -std::log(1.0 + a);
     case F_CONST: return f.cst;
+    case F_MINUS_C: return a - f.cst;
+    case F_PROD_MINUS_C: return a * cols[f.col[1]][j] - f.cst;
     case F_RAW: return a;
     case F_LOG_C_OVER: return std::log(f.cst / a);
     case F_LOG_S_MINUS: return std::log(f.cst - a);
@@ -283,10 +285,8 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     k.col[1] = f1;
     k.gslot = plan.n_gslots;
     k.n_gslots = n_gs;
-    for (int i = 0; i < 4; ++i) {
-      k.slot[i] = i < n_gs ? slots[i] : -1;
-      k.cst[i] = cst ? cst[i] : 0.0;
-    }
+    for (int i = 0; i < 6; ++i) k.slot[i] = i < n_gs ? slots[i] : -1;
+    for (int i = 0; i < 4; ++i) k.cst[i] = cst ? cst[i] : 0.0;
     k.norm_group = group;
     k.grid_off = grid_off;
     plan.n_gslots += n_gs;
@@ -409,12 +409,25 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         for (int i = 0; i < 4; ++i)
           if (!slot_ok(t.slot[i], 1)) ok = false;
         if (!(t.cst[0] > 0.0) || !(t.cst[1] > t.cst[0])) ok = false;
+        const bool tapered = t.slot[4] >= 0;  // delta_m given: PL part x smooth(delta, m1, mmin)
+        if (tapered && !slot_ok(t.slot[4], 1)) ok = false;
         if (ok) {
           const int f0 = add_feat(F_LOG, t.col[0], -1, 0.0);
           const int f1 = add_feat(F_RAW, t.col[0], -1, 0.0);
           const double cst[4] = {t.cst[0], t.cst[1], 0, 0};
-          ok = add_kop(KOP_PLPEAK, f0, f1, 4, t.slot, cst, -1, -1);
+          ok = add_kop(KOP_PLPEAK, f0, f1, tapered ? 5 : 4, t.slot, cst, -1, -1);
           cuts.push_back(RangeCut{1, {t.col[0], -1}, t.cst[0], t.cst[1]});
+        }
+        break;
+      }
+      case GWI_TERM_SMOOTH: {
+        if (!slot_ok(t.slot[0], 1)) ok = false;
+        const bool prod = t.col[1] >= 0;
+        if (prod && !col_ok(t.col[1])) ok = false;
+        if (ok) {
+          if (prod) use_col(t.col[1]);
+          const int f0 = add_feat(prod ? F_PROD_MINUS_C : F_MINUS_C, t.col[0], prod ? t.col[1] : -1, t.cst[0]);
+          ok = add_kop(KOP_SMOOTH, f0, -1, 1, t.slot, nullptr, -1, -1);
         }
         break;
       }

@@ -478,20 +478,34 @@ def powerlaw_primary_ratio_pdf(m1, q, alpha, beta, mmin, mmax):
 
 
 def plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=None):
-    """parametric.py:49-53 (``delta`` smoothing is not implemented on the CUDA path)."""
-    if delta is not None:
-        raise NotImplementedError("low-mass smoothing (delta) is not implemented on the CUDA path")
+    """parametric.py:49-53; with ``delta`` the power-law part carries the low-mass window
+    ``smooth(delta, m1, mmin)`` exactly as the reference evaluates it (distributions.py:16-21)."""
     col = _col_of(m1)
+    tapered = delta is not None
 
     def build(slots, group_base, cols):
-        return [S.Term(S.TERM_PLPEAK, [cols[0]], slots=list(slots[:4]), cst=[float(mmin), float(mmax)], name="plpeak[m1]")], [], []
+        return [S.Term(S.TERM_PLPEAK, [cols[0]], slots=list(slots[: 5 if tapered else 4]), cst=[float(mmin), float(mmax)], name="plpeak[m1]")], [], []
 
-    return LazyWeight([_LazyTerm(("plpeak", id(m1), float(mmin), float(mmax)), [col], [alpha, mpp, sigpp, lam], build)], _is_pe(m1))
+    params = [alpha, mpp, sigpp, lam] + ([delta] if tapered else [])
+    return LazyWeight([_LazyTerm(("plpeak", id(m1), float(mmin), float(mmax), tapered), [col], params, build)], _is_pe(m1))
+
+
+def _smooth_term(delta, x, x2, xmin):
+    """``smooth(delta, x [* x2], xmin)`` (distributions.py:16-21) as a lazy factor."""
+    cx = [_col_of(x)] + ([_col_of(x2)] if x2 is not None else [])
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_SMOOTH, list(cols), slots=[slots[0]], cst=[float(xmin)], name="smooth")], [], []
+
+    return LazyWeight([_LazyTerm(("smooth", id(x), id(x2), float(xmin)), cx, [delta], build)], _is_pe(x))
 
 
 def plpeak_primary_ratio_pdf(m1, q, alpha, beta, mmin, mmax, mpp, sigpp, lam, delta=None):
     """parametric.py:39-46."""
-    return _powerlaw_ratio_term(q, m1, beta, mmin) * plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=delta)
+    w = _powerlaw_ratio_term(q, m1, beta, mmin) * plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=delta)
+    if delta is not None:
+        w = w * _smooth_term(delta, q, m1, mmin)  # smooth(delta, q * m1, mmin)   (:46)
+    return w
 
 
 def beta_spin_magnitude(a, alpha, beta, amax=1):

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GWI_VERSION 1
+#define GWI_VERSION 2
 
 typedef enum {
   GWI_OK = 0,
@@ -53,14 +53,18 @@ typedef enum {
   GWI_TERM_STATIC = 3,         /* F(col), no parameter             e.g. log dVc/dz, -log prior            */
   GWI_TERM_POWERLAW = 4,       /* log powerlaw_pdf(col0; alpha=L[slot0], lo=cst0, hi=cst1)  distributions.py:100-119 */
   GWI_TERM_POWERLAW_RATIO = 5, /* log powerlaw_pdf(q=col0; beta=L[slot0], lo=cst0/col1, hi=1) parametric.py:28,40    */
-  GWI_TERM_PLPEAK = 6,         /* log[(1-lam) PL + lam TN](col0); slots alpha,mu,sigma,lam; cst mmin,mmax  parametric.py:49-53 */
+  GWI_TERM_PLPEAK = 6,         /* log[(1-lam) PL + lam TN](col0); slots alpha,mu,sigma,lam; cst mmin,mmax  parametric.py:49-53;
+                                  slot[4] >= 0: delta_m, the PL part is multiplied by smooth(delta, col0, mmin)  (:52-53) */
   GWI_TERM_BETA = 7,           /* log betadist(col0; alpha, beta, scale=cst0)               distributions.py:146-162 */
   GWI_TERM_ISOALIGN = 8,       /* log[(1-xi)/2 + xi TN(col0; 1, sigma, -1, 1)]              parametric.py:84-86      */
   GWI_TERM_TRUNCNORM = 9,      /* log truncnorm_pdf(col0; mu, sigma, lo=cst0, hi=cst1)      distributions.py:122-143 */
-  GWI_TERM_SPLINE_LINEAR = 10  /* log sum_k B_k(xi) c_k : the spline IS the density (BSpline / LogXBSpline projection,
+  GWI_TERM_SPLINE_LINEAR = 10, /* log sum_k B_k(xi) c_k : the spline IS the density (BSpline / LogXBSpline projection,
                                   interpolation.py:280-317; BSplineChiEffective etc., single.py:199-318).  Same fields as
                                   SPLINE; outside must be DROP; a density <= 0 gives the sample zero weight.  Its norm
                                   group holds this term alone and is Z = sum_g w_g sum_k B_k(xi_g) c_k (linear in c). */
+  GWI_TERM_SMOOTH = 11         /* log smooth(delta=L[slot0], x, xmin=cst0), x = col0 (col1 < 0) or col0*col1: the low-mass
+                                  window AS THE REFERENCE EVALUATES IT, 1/(1 + exp(d/(x-xmin) + d/(x-xmin-d))) for every x
+                                  (distributions.py:16-21; parametric.py:43-46) */
 } gwi_term_kind;
 
 typedef enum {
@@ -89,7 +93,7 @@ typedef struct {
   int32_t outside;    /* gwi_outside (SPLINE) */
   int32_t logx;       /* SPLINE: spline coordinate xi = log(col0) instead of col0 */
   int32_t col[2];     /* catalog column indices, -1 if unused */
-  int32_t slot[4];    /* offsets into Lambda, -1 if unused; SPLINE: slot[0] = first coefficient */
+  int32_t slot[6];    /* offsets into Lambda, -1 if unused; SPLINE: slot[0] = first coefficient */
   double cst[4];      /* constants, see gwi_term_kind */
   int32_t n_splines;  /* SPLINE: number of basis functions (>= 4, <= 256) */
   int32_t norm_group; /* index into groups[], -1 = term has no grid normaliser */

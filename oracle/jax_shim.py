@@ -98,6 +98,20 @@ def _wrapping(fn):
     return inner
 
 
+def _exp(x, *a, **k):
+    """``exp`` that stays usable for complex-step differentiation: where a COMPLEX argument overflows
+    (Re > 709.78) NumPy returns ``inf + nan j`` and everything downstream becomes NaN, although the real
+    function is +inf there with every derivative lost to the same overflow.  Return ``inf + 0j`` at
+    those points (real arguments are passed through untouched)."""
+    if np.iscomplexobj(x):
+        x = np.asarray(x)
+        over = np.real(x) > 709.78
+        if np.any(over):
+            out = np.exp(np.where(over, 0.0, x), *a, **k)
+            return np.where(over, complex(np.inf, 0.0), out)
+    return np.exp(x, *a, **k)
+
+
 def _build_jnp():
     jnp = types.ModuleType("jax.numpy")
     for name in dir(np):
@@ -108,6 +122,7 @@ def _build_jnp():
             setattr(jnp, name, _wrapping(obj))
         else:
             setattr(jnp, name, obj)
+    jnp.exp = _wrapping(_exp)
     jnp.ndarray = np.ndarray
     jnp.linalg = np.linalg
     jnp.inf = np.inf

@@ -23,6 +23,7 @@ GOLDEN_CASES = [
     "bspline_effspin",
     "bspline_effspin_margsel",
     "bspline_symchieff",
+    "plpeak_smooth",
 ]
 LIKE_KW = {
     "bspline_full": dict(marginalize_selection=False, min_neff_cut=True),
@@ -36,6 +37,7 @@ LIKE_KW = {
     "bspline_effspin": dict(min_neff_cut=False),
     "bspline_effspin_margsel": dict(marginalize_selection=True, min_neff_cut=False),
     "bspline_symchieff": dict(min_neff_cut=False),
+    "plpeak_smooth": dict(min_neff_cut=False),
 }
 
 
@@ -104,6 +106,14 @@ def build_weight_fn(model, pe, inj, meta):
             p_a = M.independent_spin_magnitude_beta_dist(d["a_1"], d["a_2"], p["alpha_a1"], p["beta_a1"], p["alpha_a2"], p["beta_a2"])
             p_ct = M.independent_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["lambda_ct1"], p["lambda_ct2"], p["sig_ct1"], p["sig_ct2"])
             return p_m1q * p_a * p_ct * mz(d["redshift"], p["lamb"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
+    if model == "plpeak_smooth":
+        mz = M.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            p_m1q = M.plpeak_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], p["alpha"], p["beta"], mmin, mmax, p["mu_peak"], p["sig_peak"], p["lambda_m"], delta=p["delta_m"])
+            return p_m1q * mz(d["redshift"], p["lamb"]) / d["prior"]
 
         return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
     if model == "bspline_effspin":

@@ -273,6 +273,26 @@ def case_plpeak():
     _save("plpeak", pe, inj, const, params, names, base, jac, dict(model="plpeak", mmin=mmin, mmax=mmax))
 
 
+def case_plpeak_smooth():
+    """PL+Peak with the low-mass window ``delta`` (parametric.py:39-53 -> distributions.py:16-21, as
+    the reference evaluates it) x power-law redshift."""
+    E, S, I = 7, 200, 5000
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=141)
+    mmin, mmax = 4.0, 100.0
+    rz = PAR.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+    params = dict(alpha=np.float64(-2.3), beta=np.float64(1.1), mu_peak=np.float64(33.0), sig_peak=np.float64(5.0), lambda_m=np.float64(0.1),
+                  delta_m=np.float64(4.7), lamb=np.float64(2.6))
+    names = list(params.keys())
+
+    def weights(d, pe_samples, p):
+        p_m1q = PAR.plpeak_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], p["alpha"], p["beta"], mmin, mmax, p["mu_peak"], p["sig_peak"], p["lambda_m"], delta=p["delta_m"])
+        return p_m1q * rz(d["redshift"], p["lamb"]) / d["prior"]
+
+    vt = lambda p: rz.normalization(lamb=p["lamb"])  # noqa: E731
+    base, jac = _complex_step(weights, pe, inj, const, params, names, vt, dict(min_neff_cut=False))
+    _save("plpeak_smooth", pe, inj, const, params, names, base, jac, dict(model="plpeak_smooth", mmin=mmin, mmax=mmax))
+
+
 def _with_derived(pe, inj):
     for d in (pe, inj):
         d["chi_eff"], d["chi_p"] = synthetic.effective_spins(d)
@@ -348,6 +368,7 @@ CASES = dict(
     plpeak=case_plpeak,
     bspline_effspin=case_bspline_effspin,
     bspline_symchieff=case_bspline_symchieff,
+    plpeak_smooth=case_plpeak_smooth,
 )
 
 if __name__ == "__main__":

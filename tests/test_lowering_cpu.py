@@ -75,8 +75,6 @@ def test_unsupported_reference_options_fail_loudly(cat):
         M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], degree=2)
     with pytest.raises(NotImplementedError):
         M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], knots=np.linspace(0, 1, 12))
-    with pytest.raises(NotImplementedError):
-        M.plpeak_primary_pdf(pe["mass_1"], -2.0, 3.0, 100.0, 30.0, 5.0, 0.1, delta=4.0)
 
 
 def test_parametric_free_functions_lower_to_parametric_terms(cat):
