@@ -35,7 +35,8 @@ enum KopKind : int32_t {
   KOP_PLPEAK = 3,    // cols (log m1, m1)                     gslots: alpha, mu, sigma, lam [, delta]
   KOP_ISOALIGN = 4,  // col (cos tilt)                        gslots: xi, sigma
   KOP_QUAD = 5,      // truncated normal body: col (x)        gslots: mu, sigma
-  KOP_SMOOTH = 6     // low-mass window: col (x - xmin)       gslots: delta
+  KOP_SMOOTH = 6,    // low-mass window: col (x - xmin)       gslots: delta
+  KOP_ISOALIGN2 = 7  // cols (cos tilt 1, cos tilt 2)         gslots: xi, sigma
 };
 
 struct Kop {

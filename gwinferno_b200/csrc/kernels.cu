@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
       kc[6] = dn; kc[7] = sig; kc[8] = dmu; kc[9] = dsg;
       kc[10] = K.slot[4] >= 0 ? Lam[K.slot[4]] : 0.0;  // delta_m (0 = no low-mass window)
       kc[11] = K.cst[0];                                // mmin
-    } else if (K.kind == KOP_ISOALIGN) {
+    } else if (K.kind == KOP_ISOALIGN || K.kind == KOP_ISOALIGN2) {
       const double xi = Lam[K.slot[0]], sig = Lam[K.slot[1]];
       double lt, dmu, dsg;
       truncnorm_consts(1.0, sig, -1.0, 1.0, lt, dmu, dsg);

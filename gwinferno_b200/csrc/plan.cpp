@@ -453,6 +453,18 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         }
         break;
       }
+      case GWI_TERM_ISOALIGN_PAIR: {
+        if (!slot_ok(t.slot[0], 1) || !slot_ok(t.slot[1], 1) || !col_ok(t.col[1])) ok = false;
+        if (ok) {
+          use_col(t.col[1]);
+          const int f0 = add_feat(F_RAW, t.col[0], -1, 0.0);
+          const int f1 = add_feat(F_RAW, t.col[1], -1, 0.0);
+          ok = add_kop(KOP_ISOALIGN2, f0, f1, 2, t.slot, nullptr, -1, -1);
+          cuts.push_back(RangeCut{1, {t.col[0], -1}, -1.0, 1.0});
+          cuts.push_back(RangeCut{1, {t.col[1], -1}, -1.0, 1.0});
+        }
+        break;
+      }
       case GWI_TERM_TRUNCNORM: {
         if (!slot_ok(t.slot[0], 1) || !slot_ok(t.slot[1], 1) || !(t.cst[1] > t.cst[0])) ok = false;
         if (ok) {

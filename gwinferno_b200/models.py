@@ -52,6 +52,7 @@ __all__ = [
     "independent_spin_magnitude_beta_dist",
     "mixture_isoalign_spin_tilt",
     "iid_spin_tilt",
+    "default_spin_tilt",
     "independent_spin_tilt",
     "weight_from_prior",
 ]
@@ -534,6 +535,16 @@ def mixture_isoalign_spin_tilt(ct, xi_tilt, sigma_tilt):
         return [S.Term(S.TERM_ISOALIGN, [cols[0]], slots=list(slots[:2]), name=f"isoalign[{cols[0]}]")], [], []
 
     return LazyWeight([_LazyTerm(("isoalign", id(ct)), [col], [xi_tilt, sigma_tilt], build)], _is_pe(ct))
+
+
+def default_spin_tilt(ct1, ct2, xi_tilt, sigma_tilt):
+    """parametric.py:97-102: ``(1 - xi)/4 + xi TN(ct1) TN(ct2)`` (both tilts aligned together)."""
+    c1, c2 = _col_of(ct1), _col_of(ct2)
+
+    def build(slots, group_base, cols):
+        return [S.Term(S.TERM_ISOALIGN_PAIR, [cols[0], cols[1]], slots=list(slots[:2]), name=f"isoalign2[{cols[0]},{cols[1]}]")], [], []
+
+    return LazyWeight([_LazyTerm(("isoalign2", id(ct1), id(ct2)), [c1, c2], [xi_tilt, sigma_tilt], build)], _is_pe(ct1))
 
 
 def iid_spin_tilt(ct1, ct2, xi_tilt, sigma_tilt):

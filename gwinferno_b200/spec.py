@@ -30,6 +30,7 @@ TERM_BETA = 7  # log betadist(col; alpha, beta, scale)               distributio
 TERM_ISOALIGN = 8  # log[(1-xi)/2 + xi TN(ct; 1, sigma, -1, 1)]      parametric.py:84-86
 TERM_TRUNCNORM = 9  # log truncnorm_pdf(col; mu, sig, lo, hi)        distributions.py:122-143
 TERM_SPLINE_LINEAR = 10  # log sum_k B_k(xi) c_k : the spline is the density  interpolation.py:280-317
+TERM_ISOALIGN_PAIR = 12  # log[(1-xi)/4 + xi TN(ct1) TN(ct2)]   (default_spin_tilt, parametric.py:97-102)
 TERM_SMOOTH = 11  # log smooth(delta; col0 [* col1], xmin)           distributions.py:16-21
 
 # ---- gwi_feature --------------------------------------------------------------------------

@@ -62,6 +62,8 @@ typedef enum {
                                   interpolation.py:280-317; BSplineChiEffective etc., single.py:199-318).  Same fields as
                                   SPLINE; outside must be DROP; a density <= 0 gives the sample zero weight.  Its norm
                                   group holds this term alone and is Z = sum_g w_g sum_k B_k(xi_g) c_k (linear in c). */
+  GWI_TERM_ISOALIGN_PAIR = 12, /* log[(1-xi)/4 + xi TN(col0; 1, sigma, -1, 1) TN(col1; 1, sigma, -1, 1)]  (default_spin_tilt,
+                                  parametric.py:97-102); slots xi, sigma */
   GWI_TERM_SMOOTH = 11         /* log smooth(delta=L[slot0], x, xmin=cst0), x = col0 (col1 < 0) or col0*col1: the low-mass
                                   window AS THE REFERENCE EVALUATES IT, 1/(1 + exp(d/(x-xmin) + d/(x-xmin-d))) for every x
                                   (distributions.py:16-21; parametric.py:43-46) */

@@ -24,6 +24,9 @@ GOLDEN_CASES = [
     "bspline_effspin_margsel",
     "bspline_symchieff",
     "plpeak_smooth",
+    "default_spin",
+    "mixed_bspline_m1",
+    "mixed_plpeak_m1",
 ]
 LIKE_KW = {
     "bspline_full": dict(marginalize_selection=False, min_neff_cut=True),
@@ -38,6 +41,9 @@ LIKE_KW = {
     "bspline_effspin_margsel": dict(marginalize_selection=True, min_neff_cut=False),
     "bspline_symchieff": dict(min_neff_cut=False),
     "plpeak_smooth": dict(min_neff_cut=False),
+    "default_spin": dict(min_neff_cut=False),
+    "mixed_bspline_m1": dict(min_neff_cut=False),
+    "mixed_plpeak_m1": dict(min_neff_cut=False),
 }
 
 
@@ -114,6 +120,33 @@ def build_weight_fn(model, pe, inj, meta):
         def weights(d, pe_samples, p):
             p_m1q = M.plpeak_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], p["alpha"], p["beta"], mmin, mmax, p["mu_peak"], p["sig_peak"], p["lambda_m"], delta=p["delta_m"])
             return p_m1q * mz(d["redshift"], p["lamb"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
+    if model == "default_spin":
+        mz = M.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            w = M.powerlaw_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], alpha=p["alpha"], beta=p["beta"], mmin=mmin, mmax=mmax)
+            w = w * M.iid_spin_magnitude(d["a_1"], d["a_2"], p["alpha_a"], p["beta_a"]) * M.default_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["xi"], p["sig_t"])
+            return w * mz(d["redshift"], p["lamb"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
+    if model == "mixed_bspline_m1":
+        mm = M.BSplinePrimaryPowerlawRatio(int(meta["n_m1"]), pe["mass_1"], inj["mass_1"], mmin=mmin, mmax=mmax)
+        mz = M.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            w = mm(d["mass_1"], d["mass_ratio"], p["beta"], mmin, p["mass_cs"], pe_samples=pe_samples)
+            return w * M.iid_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["xi"], p["sig_t"]) * mz(d["redshift"], p["lamb"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
+    if model == "mixed_plpeak_m1":
+        mm = M.PLPeakPrimaryBSplineRatio(int(meta["n_q"]), pe["mass_ratio"], inj["mass_ratio"])
+        mz = M.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            w = mm(d["mass_1"], p["alpha"], mmin, mmax, p["mu_peak"], p["sig_peak"], p["lambda_m"], p["q_cs"], pe_samples=pe_samples)
+            return w * M.iid_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["xi"], p["sig_t"]) * mz(d["redshift"], p["lamb"]) / d["prior"]
 
         return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
     if model == "bspline_effspin":

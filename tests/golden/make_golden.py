@@ -293,6 +293,61 @@ def case_plpeak_smooth():
     _save("plpeak_smooth", pe, inj, const, params, names, base, jac, dict(model="plpeak_smooth", mmin=mmin, mmax=mmax))
 
 
+def case_default_spin():
+    """PL primary/ratio x IID Beta spin magnitudes x ``default_spin_tilt`` (both tilts aligned together,
+    parametric.py:67-68,97-102) x power-law redshift."""
+    E, S, I = 6, 200, 4000
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=142)
+    mmin, mmax = 3.0, 100.0
+    rz = PAR.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+    params = dict(alpha=np.float64(-2.1), beta=np.float64(0.9), alpha_a=np.float64(1.7), beta_a=np.float64(3.9), xi=np.float64(0.55), sig_t=np.float64(0.9), lamb=np.float64(2.8))
+    names = list(params.keys())
+
+    def weights(d, pe_samples, p):
+        w = PAR.powerlaw_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], alpha=p["alpha"], beta=p["beta"], mmin=mmin, mmax=mmax)
+        w = w * PAR.iid_spin_magnitude(d["a_1"], d["a_2"], p["alpha_a"], p["beta_a"]) * PAR.default_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["xi"], p["sig_t"])
+        return w * rz(d["redshift"], p["lamb"]) / d["prior"]
+
+    vt = lambda p: rz.normalization(lamb=p["lamb"])  # noqa: E731
+    base, jac = _complex_step(weights, pe, inj, const, params, names, vt, dict(min_neff_cut=False))
+    _save("default_spin", pe, inj, const, params, names, base, jac, dict(model="default_spin", mmin=mmin, mmax=mmax))
+
+
+def case_mixed_mass():
+    """The two semi-parametric mass models (separable.py:295-365, 368-443):
+    ``mixed_bspline_m1``: B-spline primary x power-law ratio; ``mixed_plpeak_m1``: PL+Peak primary x
+    B-spline ratio; both x IID spin-tilt mixture x power-law redshift."""
+    E, S, I = 6, 200, 4000
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=143)
+    mmin, mmax = 3.0, 100.0
+    rz = PAR.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+    vt = lambda p: rz.normalization(lamb=p["lamb"])  # noqa: E731
+    rng = np.random.default_rng(143002)
+    # (1) B-spline primary x power-law ratio
+    r1 = SEP.BSplinePrimaryPowerlawRatio(16, pe["mass_1"], inj["mass_1"], mmin=mmin, mmax=mmax)
+    params = dict(mass_cs=0.5 * rng.standard_normal(16), beta=np.float64(1.2), xi=np.float64(0.4), sig_t=np.float64(1.1), lamb=np.float64(2.5))
+    names = list(params.keys())
+
+    def weights1(d, pe_samples, p):
+        w = r1(d["mass_1"], d["mass_ratio"], p["beta"], mmin, p["mass_cs"], pe_samples=pe_samples)
+        return w * PAR.iid_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["xi"], p["sig_t"]) * rz(d["redshift"], p["lamb"]) / d["prior"]
+
+    base, jac = _complex_step(weights1, pe, inj, const, params, names, vt, dict(min_neff_cut=False))
+    _save("mixed_bspline_m1", pe, inj, const, params, names, base, jac, dict(model="mixed_bspline_m1", mmin=mmin, mmax=mmax, n_m1=16))
+    # (2) PL+Peak primary x B-spline ratio
+    r2 = SEP.PLPeakPrimaryBSplineRatio(9, pe["mass_ratio"], inj["mass_ratio"])
+    params = dict(alpha=np.float64(-2.6), mu_peak=np.float64(35.0), sig_peak=np.float64(4.0), lambda_m=np.float64(0.12), q_cs=0.5 * rng.standard_normal(9),
+                  xi=np.float64(0.7), sig_t=np.float64(0.6), lamb=np.float64(3.0))
+    names = list(params.keys())
+
+    def weights2(d, pe_samples, p):
+        w = r2(d["mass_1"], p["alpha"], mmin, mmax, p["mu_peak"], p["sig_peak"], p["lambda_m"], p["q_cs"], pe_samples=pe_samples)
+        return w * PAR.iid_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["xi"], p["sig_t"]) * rz(d["redshift"], p["lamb"]) / d["prior"]
+
+    base, jac = _complex_step(weights2, pe, inj, const, params, names, vt, dict(min_neff_cut=False))
+    _save("mixed_plpeak_m1", pe, inj, const, params, names, base, jac, dict(model="mixed_plpeak_m1", mmin=mmin, mmax=mmax, n_q=9))
+
+
 def _with_derived(pe, inj):
     for d in (pe, inj):
         d["chi_eff"], d["chi_p"] = synthetic.effective_spins(d)
@@ -369,6 +424,8 @@ CASES = dict(
     bspline_effspin=case_bspline_effspin,
     bspline_symchieff=case_bspline_symchieff,
     plpeak_smooth=case_plpeak_smooth,
+    default_spin=case_default_spin,
+    mixed_mass=case_mixed_mass,
 )
 
 if __name__ == "__main__":
