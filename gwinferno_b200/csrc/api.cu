@@ -262,7 +262,6 @@ static int alloc_chain_scratch(gwi_model* m, ModelDev& H) {
   UPS(upload<double>(m, nullptr, (size_t)std::max(1, H.n_chunks), &H.chunk_max));
   UPS(upload<int32_t>(m, nullptr, (size_t)2, &H.slice_counter));
   UPS(upload<double>(m, nullptr, (size_t)std::max(1, p.n_records0) * p.rec_doubles, &H.records0));
-  H.seg_rec = nullptr;
   UPS(upload<double>(m, nullptr, (size_t)nseg * 4, &H.seg_out));
   UPS(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_J1));
   UPS(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_Jn));

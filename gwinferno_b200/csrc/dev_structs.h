@@ -73,7 +73,6 @@ struct ModelDev {
   const ReduceTask* level_tasks[6];  // static task lists
   int32_t level_ntasks[6];
   int32_t n_levels, liny_mask;  // bit d: spline dim d is a linear-in-y density
-  double* seg_rec;    // [n_segments * rec]
   double* seg_out;    // [n_segments * 4] {logmean, logneff, var, status}
   double* seg_J1;     // [n_segments * P]
   double* seg_Jn;     // [n_segments * P]

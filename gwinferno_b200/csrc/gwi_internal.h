@@ -87,7 +87,7 @@ struct Chunk {
   int32_t steps;        // samples per lane (multiple of 2*UNROLL)
   int64_t first;        // first padded sample index (multiple of 32*UNROLL)
   int32_t record_slot;  // level-0 record receiving this chunk's sums
-  int32_t flush;        // 1 = the warp must write + clear its record after this chunk
+  int32_t pad;          // (every chunk writes and clears its own record)
 };
 
 struct Segment {

@@ -12,7 +12,10 @@
 // keeps the per-piece gradient moments in registers and only spills when a piece index changes.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -167,8 +170,8 @@ inline uint64_t pack_word(int J, double u) {
 }
 
 template <class F>
-void parallel_for(int64_t n, int n_workers, F&& fn) {
-  if (n_workers <= 1 || n < 4096) {
+void parallel_for(int64_t n, int n_workers, F&& fn, int64_t min_n = 4096) {
+  if (n_workers <= 1 || n < min_n) {
     fn(0, n, 0);
     return;
   }
@@ -183,7 +186,7 @@ void parallel_for(int64_t n, int n_workers, F&& fn) {
 }
 
 // LSD radix sort of (key, index) pairs by the low `bits` bits of the key, 11-bit digits
-void radix_sort_pairs(std::vector<uint64_t>& keys, std::vector<uint32_t>& idx, int bits) {
+void radix_sort_pairs(std::vector<uint64_t>& keys, std::vector<uint32_t>& idx, int bits, int n_workers = 1) {
   const size_t n = keys.size();
   if (n < 2) return;
   if (n < 4096) {
@@ -200,23 +203,41 @@ void radix_sort_pairs(std::vector<uint64_t>& keys, std::vector<uint32_t>& idx, i
     idx.swap(i2);
     return;
   }
-  constexpr int RB = 11;
+  constexpr int RB = 11, NB = 1 << RB;
   std::vector<uint64_t> k2(n);
   std::vector<uint32_t> i2(n);
+  // every pass: per-thread histograms of contiguous blocks, one exclusive scan over
+  // (bucket, thread), then a stable scatter of every block (the result does not depend on T)
+  const int T = (n_workers > 1 && n >= (size_t)1 << 20) ? n_workers : 1;
+  const size_t per = (n + T - 1) / T;
+  std::vector<size_t> cnt((size_t)T * NB);
   for (int shift = 0; shift < bits; shift += RB) {
-    size_t cnt[1 << RB] = {0};
-    for (size_t i = 0; i < n; ++i) ++cnt[(keys[i] >> shift) & ((1 << RB) - 1)];
+    std::fill(cnt.begin(), cnt.end(), 0);
+    parallel_for((int64_t)T, T, [&](int64_t ta, int64_t tb, int) {
+      for (int64_t t = ta; t < tb; ++t) {
+        size_t* c = cnt.data() + (size_t)t * NB;
+        const size_t a = (size_t)t * per, b = std::min(n, a + per);
+        for (size_t i = a; i < b; ++i) ++c[(keys[i] >> shift) & (NB - 1)];
+      }
+    }, 1);
     size_t acc = 0;
-    for (int b = 0; b < (1 << RB); ++b) {
-      const size_t c = cnt[b];
-      cnt[b] = acc;
-      acc += c;
-    }
-    for (size_t i = 0; i < n; ++i) {
-      const size_t p = cnt[(keys[i] >> shift) & ((1 << RB) - 1)]++;
-      k2[p] = keys[i];
-      i2[p] = idx[i];
-    }
+    for (int b = 0; b < NB; ++b)
+      for (int t = 0; t < T; ++t) {
+        const size_t c = cnt[(size_t)t * NB + b];
+        cnt[(size_t)t * NB + b] = acc;
+        acc += c;
+      }
+    parallel_for((int64_t)T, T, [&](int64_t ta, int64_t tb, int) {
+      for (int64_t t = ta; t < tb; ++t) {
+        size_t* c = cnt.data() + (size_t)t * NB;
+        const size_t a = (size_t)t * per, b = std::min(n, a + per);
+        for (size_t i = a; i < b; ++i) {
+          const size_t p = c[(keys[i] >> shift) & (NB - 1)]++;
+          k2[p] = keys[i];
+          i2[p] = idx[i];
+        }
+      }
+    }, 1);
     keys.swap(k2);
     idx.swap(i2);
   }
@@ -241,6 +262,15 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   auto col_ok = [&](int c) { return c >= 0 && c < cat.n_columns; };
   auto slot_ok = [&](int s, int n) { return s >= 0 && s + n <= desc.n_params; };
 
+  // GWI_PLAN_TIMING=1: print the wall time of every build phase to stderr
+  const bool timing = std::getenv("GWI_PLAN_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[gwi plan] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
   // ---- norm groups --------------------------------------------------------------------------
   for (int g = 0; g < desc.n_groups; ++g) {
     const gwi_norm_group& G = desc.groups[g];
@@ -600,6 +630,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   }
   plan.rec_doubles = rec_size(plan.n_gslots, plan.g2, plan.rows_total);
 
+  tick("terms, grids");
   // ---- pass 1: validity + sort key per sample -----------------------------------------------
   const int E = cat.n_events;
   const int64_t n_pe = E > 0 ? cat.pe_offsets[E] : 0;
@@ -653,18 +684,39 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     parallel_for(n_inj, n_workers, [&](int64_t a, int64_t b, int) {
       for (int64_t j = a; j < b; ++j) keys[j] = sample_key(cat.inj_columns.data(), j);
     });
+    // compaction of the valid samples, order-preserving: per-block counts, scan, per-block copy
     std::vector<uint64_t> vk;
     std::vector<uint32_t>& vi = order[0];
-    vk.reserve(n_inj);
-    vi.reserve(n_inj);
-    for (int64_t j = 0; j < n_inj; ++j)
-      if (keys[j] != INVALID) {
-        vk.push_back(keys[j]);
-        vi.push_back((uint32_t)j);
-      }
+    {
+      const int T = std::max(1, n_workers);
+      const int64_t per = (n_inj + T - 1) / T;
+      std::vector<int64_t> cnt(T + 1, 0);
+      parallel_for((int64_t)T, T, [&](int64_t ta, int64_t tb, int) {
+        for (int64_t t = ta; t < tb; ++t) {
+          int64_t n = 0;
+          for (int64_t j = t * per; j < std::min(n_inj, (t + 1) * per); ++j) n += keys[j] != INVALID;
+          cnt[t + 1] = n;
+        }
+      }, 1);
+      for (int t = 0; t < T; ++t) cnt[t + 1] += cnt[t];
+      vk.resize(cnt[T]);
+      vi.resize(cnt[T]);
+      parallel_for((int64_t)T, T, [&](int64_t ta, int64_t tb, int) {
+        for (int64_t t = ta; t < tb; ++t) {
+          int64_t o = cnt[t];
+          for (int64_t j = t * per; j < std::min(n_inj, (t + 1) * per); ++j)
+            if (keys[j] != INVALID) {
+              vk[o] = keys[j];
+              vi[o++] = (uint32_t)j;
+            }
+        }
+      }, 1);
+    }
     keys.clear();
     keys.shrink_to_fit();
-    radix_sort_pairs(vk, vi, key_bits);
+    tick("injection keys + compaction");
+    radix_sort_pairs(vk, vi, key_bits, n_workers);
+    tick("injection sort");
     plan.segments[0].n_total = n_inj;
     plan.segments[0].n_valid = (int64_t)vi.size();
   }
@@ -696,6 +748,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   for (int s = 1; s < n_seg; ++s) plan.n_valid_pe += plan.segments[s].n_valid;
   plan.n_valid_inj = plan.segments[0].n_valid;
 
+  tick("event keys + sorts");
   // ---- deep dims: how often does each dim's piece index change along the sorted order? -------
   // Leading sort keys change rarely (register-resident moments, spilled on change); a dim whose
   // piece changes more than about once per 100 consecutive samples would make some lane of every
@@ -704,23 +757,33 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   {
     // per segment: fraction of consecutive sorted samples whose piece index differs, per dim
     std::vector<std::vector<double>> rate(n_seg, std::vector<double>(NS, 0.0));
-    for (int s = 0; s < n_seg; ++s) {
-      const double* const* cols = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
-      const std::vector<uint32_t>& ord = order[s];
-      const size_t n = ord.size();
-      const size_t stride = std::max<size_t>(1, n / 200000);  // sample long segments
-      double pairs = 0.0;
-      for (size_t i = 0; i + 1 < n; i += stride) {
-        for (int d = 0; d < NS; ++d) {
-          int J0, J1;
-          double u;
-          spline_locate(geom[d], cols[geom[d].col][ord[i]], J0, u);
-          spline_locate(geom[d], cols[geom[d].col][ord[i + 1]], J1, u);
-          if (J0 != J1) rate[s][d] += 1.0;
+    std::atomic<int> next_seg{0};
+    auto rate_work = [&]() {
+      for (;;) {
+        const int s = next_seg.fetch_add(1);
+        if (s >= n_seg) break;
+        const double* const* cols = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
+        const std::vector<uint32_t>& ord = order[s];
+        const size_t n = ord.size();
+        const size_t stride = std::max<size_t>(1, n / 50000);  // sample long segments
+        double pairs = 0.0;
+        for (size_t i = 0; i + 1 < n; i += stride) {
+          for (int d = 0; d < NS; ++d) {
+            int J0, J1;
+            double u;
+            spline_locate(geom[d], cols[geom[d].col][ord[i]], J0, u);
+            spline_locate(geom[d], cols[geom[d].col][ord[i + 1]], J1, u);
+            if (J0 != J1) rate[s][d] += 1.0;
+          }
+          pairs += 1.0;
         }
-        pairs += 1.0;
+        for (int d = 0; d < NS; ++d) rate[s][d] = pairs > 0 ? rate[s][d] / pairs : 0.0;
       }
-      for (int d = 0; d < NS; ++d) rate[s][d] = pairs > 0 ? rate[s][d] / pairs : 0.0;
+    };
+    {
+      std::vector<std::thread> th;
+      for (int w = 0; w < std::min(n_workers, n_seg); ++w) th.emplace_back(rate_work);
+      for (auto& t : th) t.join();
     }
     // cost model (issue slots per sample): a register-resident dim pays the warp-wide spill path
     // whenever ANY of its 32 lanes changes piece (~60 slots incl. the shared-memory atomics); a
@@ -757,12 +820,13 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     for (int d = 0; d < NS; ++d) plan.dims[d].deep = d >= NS - nd;
   }
 
+  tick("piece-change rates");
   // ---- launch geometry + chunking -----------------------------------------------------------
   // shared memory per warp: shallow accumulators + deep lane-private arrays + generic slots
   const int mom = plan.g2 ? 2 : 1;
-  int rows_shallow = 0, rows_deep = 0;
-  for (int d = 0; d < NS; ++d) (plan.dims[d].deep ? rows_deep : rows_shallow) += plan.dims[d].rows;
-  (void)rows_shallow;
+  int rows_deep = 0;
+  for (int d = 0; d < NS; ++d)
+    if (plan.dims[d].deep) rows_deep += plan.dims[d].rows;
   const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * DEEP_LANES * 8 +
                              (int64_t)plan.n_gslots * (1 + mom) * LANES * 8;
   const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
@@ -848,6 +912,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   plan.n_padded = pos;
   const int n_chunks = (int)plan.chunks.size();
 
+  tick("slicing");
   // ---- pass 2: fill the stream columns ------------------------------------------------------
   try {
     plan.columns.assign((size_t)plan.n_columns * (size_t)std::max<int64_t>(1, plan.n_padded), 0ull);
@@ -869,17 +934,30 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   {
     std::atomic<int> next{0};
     auto work = [&]() {
+      // The sorted order gathers from random rows of the caller's columns.  Gather first, in tight
+      // loops with nothing but independent loads (many cache/TLB misses in flight), into a
+      // chunk-local copy in sorted order; everything below then reads sequentially.
+      std::vector<std::vector<double>> gathered(cat.n_columns);
+      std::vector<const double*> tcols(cat.n_columns, nullptr);
       for (;;) {
         const int c = next.fetch_add(1);
         if (c >= n_chunks) break;
         const Chunk& C = plan.chunks[c];
         const int s = C.segment;
-        const Segment& S = plan.segments[s];
-        const double* const* cols = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
+        const double* const* src = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
         const std::vector<uint32_t>& ord = order[s];
         const int64_t r0 = chunk_r0[c];  // first sorted rank of this chunk
         const int64_t n_c = chunk_nc[c];
-        (void)S;
+        for (int cc : used_cols) {
+          std::vector<double>& g = gathered[cc];
+          if ((int64_t)g.size() < n_c) g.resize(n_c);
+          const double* sc = src[cc];
+          const uint32_t* o = ord.data() + r0;
+          double* gp = g.data();
+          for (int64_t r = 0; r < n_c; ++r) gp[r] = sc[o[r]];
+          tcols[cc] = gp;
+        }
+        const double* const* cols = tcols.data();
         SegStat st;
         st.max_static = NEG_INF;
         for (int d = 0; d < MAX_SPLINE_DIMS; ++d) st.occ[d] = 0;
@@ -892,7 +970,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
             const int64_t r = (int64_t)lane * C.steps + k;
             const int64_t p = C.first + (int64_t)(k / UNROLL) * (LANES * UNROLL) + lane * UNROLL + (k % UNROLL);
             if (r < n_c) {
-              const int64_t j = ord[r0 + r];
+              const int64_t j = r;  // row of the chunk-local sorted copy
               for (int d = 0; d < NS; ++d) {
                 int J;
                 double u;
@@ -918,7 +996,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
             } else {
               // lane padding: a copy of the chunk's last valid sample (so every term evaluates to
               // finite values and no piece index changes) with static log-weight -inf => weight 0
-              const int64_t j = ord[r0 + n_c - 1];
+              const int64_t j = n_c - 1;
               for (int d = 0; d < NS; ++d) {
                 int J;
                 double u;
@@ -950,6 +1028,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     }
   }
 
+  tick("column fill");
   // ---- level-0 records: one per chunk (the chunks, hence the records, of a segment are
   //      consecutive); fixed-order tree reduction afterwards
   {
@@ -957,7 +1036,6 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     std::vector<int> cnt(n_seg, 0), first(n_seg, 0);
     for (int c = 0; c < n_chunks; ++c) {
       plan.chunks[c].record_slot = c;
-      plan.chunks[c].flush = 1;
       cnt[plan.chunks[c].segment]++;
     }
     for (int s = 0; s < n_seg; ++s) first[s] = plan.segments[s].first_chunk;  // chunks of a segment are consecutive
