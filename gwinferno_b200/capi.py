@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GWI_LIBRARY", os.path.join(_HERE, "libgwi.so"))  # override: tuning experiments only
 
+GWI_VERSION = 2  # include/gwi.h: GWI_VERSION (6 Lambda slots per term)
 GWI_LIKE_HEADER = 8
 LIKE_FIELDS = ("log_l", "passed", "log_mu", "logNeff_inj", "min_logNeff", "sum_logBF", "variance", "status")
 PARTIAL_HEADER = 8
@@ -143,6 +144,8 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise GwiError(-2, f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` " "(there is no CPU fallback)")
     lib = C.CDLL(LIB_PATH)
+    if lib.gwi_version() != GWI_VERSION:  # the structs below would not match the library's
+        raise GwiError(-1, f"{LIB_PATH} has ABI version {lib.gwi_version()}, this binding expects {GWI_VERSION}: rebuild it")
     lib.gwi_last_error.restype = C.c_char_p
     lib.gwi_partial_size.restype = C.c_int64
     lib.gwi_partial_size.argtypes = [C.c_void_p]

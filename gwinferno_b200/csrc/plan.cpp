@@ -799,6 +799,16 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
           for (int d = 0; d < NS - cand; ++d) cost += n * std::min(1.0, 32.0 * rate[s][d]) * 60.0;
           cost += n * cand * 17.0;
         }
+        if (timing) {
+          double ci = 0.0, cp = 0.0, np_ = 0.0;
+          for (int s = 0; s < n_seg; ++s) {
+            const double n = (double)order[s].size();
+            double c = cand * 17.0;
+            for (int d = 0; d < NS - cand; ++d) c += std::min(1.0, 32.0 * rate[s][d]) * 60.0;
+            if (s == 0) ci = c; else { cp += n * c; np_ += n; }
+          }
+          std::fprintf(stderr, "[gwi plan] n_deep=%d: modelled extra issue slots per sample: injections %.1f, events %.1f\n", cand, ci, np_ > 0 ? cp / np_ : 0.0);
+        }
         if (best < 0.0 || cost < best) {
           best = cost;
           nd = cand;
