@@ -187,7 +187,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "setup_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -352,12 +352,32 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(name)
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def _protect_stdout():
+    """stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 on their own
+    (NCCL prints its version banner there when NCCL_DEBUG is set in the environment) are sent to
+    stderr instead, and the result line goes to the original stdout."""
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(text):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
