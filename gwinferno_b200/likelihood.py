@@ -126,7 +126,26 @@ def hierarchical_likelihood(
         lowered = lowering.Lowered(eng.spec, eng.lowered.pe_cols, eng.lowered.inj_cols, eng.lowered.param_layout, _slot_map(pe_weights))
     lam = lowering.flatten_params(pe_weights, eng.n_params)
     log_l, grad, head = eng.loglike(lam, Nobs=Nobs, marginalize_selection=marginalize_selection, min_neff_cut=min_neff_cut, max_variance_cut=max_variance_cut)
+    # O(P) host glue: chain rule through parameter maps; per-sample constants kept off the device
+    grad = lowering.pull_back(pe_weights, grad)
+    log_l, grad, head = apply_host_norm(log_l, grad, head, *lowering.host_log_norm(pe_weights, eng.n_params), n_events=eng.n_events, Nobs=Nobs)
     return LikelihoodResult(log_l, grad, head, lowered, pe_weights, surveyed_hypervolume, Tobs, Nobs)
+
+
+def apply_host_norm(log_l, grad, head, logZ, dlogZ, n_events, Nobs):
+    """Every sample weight is ``exp(-logZ)`` times what the device model evaluated: shift the sites
+    (``logBF_i`` and ``log mu`` by ``-logZ``; N_eff and the variances are scale-free) and the
+    likelihood ``log_l = sum_i logBF_i - Nobs log mu`` (analysis.py:257-319) by ``(Nobs - E) logZ``
+    -- nothing when ``Nobs`` equals the number of events, as in every reference example."""
+    if logZ == 0.0 and not np.any(dlogZ):
+        return log_l, grad, head
+    head = dict(head)
+    head["log_mu"] = head["log_mu"] - logZ
+    head["sum_logBF"] = head["sum_logBF"] - n_events * logZ
+    if head["passed"]:
+        log_l = log_l + (Nobs - n_events) * logZ
+        grad = grad + (Nobs - n_events) * dlogZ
+    return log_l, grad, head
 
 
 def _slot_map(pe_w):

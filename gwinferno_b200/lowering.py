@@ -28,6 +28,24 @@ def host_spline_on_grid(grid_xi, xi_range, n_splines, coefs):
     return np.where(ok, s, 0.0)
 
 
+def host_spline_design(grid_xi, xi_range, n_splines):
+    """Dense ``[G, n_splines]`` design matrix of the cubic B-spline basis on a normalisation grid
+    (host-side O(P) glue only: parameter maps and host normalisers; NaN grid entries => zero row)."""
+    lo, hi = xi_range
+    n_int = n_splines - 2
+    dx = (hi - lo) / (n_int - 1)
+    ok = np.isfinite(grid_xi)
+    t = (np.where(ok, grid_xi, lo) - lo) / dx
+    j = np.clip(np.floor(t), 0, n_int - 2).astype(np.int64)
+    u = t - j
+    w = np.stack([(1 - u) ** 3, 3 * u**3 - 6 * u**2 + 4, -3 * u**3 + 3 * u**2 + 3 * u + 1, u**3], axis=-1) / 6.0
+    D = np.zeros((grid_xi.size, n_splines))
+    rows = np.arange(grid_xi.size)
+    for k in range(4):
+        D[rows, j + k] = np.where(ok, w[:, k], 0.0)
+    return D
+
+
 class Lowered:
     """Static lowering result: spec, column arrays, and the recipe to flatten parameters."""
 
@@ -59,21 +77,68 @@ def _structure(pe_w, inj_w):
     return keys, tuple(pattern)
 
 
-def flatten_params(pe_w, n_params, param_layout=None):
-    """Flat ``Lambda`` from the parameter values carried by the PE-side lazy terms."""
-    Lam = np.zeros(n_params)
-    seen = {}
-    off = 0
+def _param_blocks(pe_w):
+    """``[(offset, value, ParamMap or None)]`` per distinct parameter object, in Lambda order."""
+    blocks, seen, off = [], {}, 0
     for t in pe_w.terms:
-        for p, k in zip(t.params, t.param_keys):
+        for i, (p, k) in enumerate(zip(t.params, t.param_keys)):
+            m = getattr(t, "maps", {}).get(i)
             if k in seen:
+                if blocks[seen[k]][2] is not m:
+                    raise ValueError("a parameter object shared between terms must use the same parameter map in all of them")
                 continue
-            seen[k] = off
-            Lam[off : off + p.size] = p
+            seen[k] = len(blocks)
+            blocks.append((off, p, m))
             off += p.size
+    return blocks, off
+
+
+def flatten_params(pe_w, n_params, param_layout=None):
+    """Flat ``Lambda`` from the parameter values carried by the PE-side lazy terms (after their
+    host-side parameter maps, if any)."""
+    blocks, off = _param_blocks(pe_w)
     if off != n_params:
         raise ValueError("parameter structure changed between calls")
+    Lam = np.zeros(n_params)
+    for o, p, m in blocks:
+        Lam[o : o + p.size] = p if m is None else m.fwd(p)
     return Lam
+
+
+def pull_back(pe_w, grad):
+    """Gradient (or Jacobian rows, last axis = Lambda) with respect to the kernel's Lambda -> with
+    respect to the parameter values the caller passed (chain rule through the parameter maps)."""
+    blocks, _ = _param_blocks(pe_w)
+    if all(m is None for _, _, m in blocks):
+        return grad
+    out = np.array(grad, dtype=np.float64, copy=True)
+    flat = out.reshape(-1, out.shape[-1])
+    for o, p, m in blocks:
+        if m is not None:
+            for r in range(flat.shape[0]):
+                flat[r, o : o + p.size] = m.vjp(p, flat[r, o : o + p.size])
+    return out
+
+
+def host_log_norm(pe_w, n_params):
+    """``(log Z, dlog Z/dLambda[P])`` of the host-side normalisers: every sample's log-weight is
+    lower by ``log Z`` than what the device model evaluates (the derivative is with respect to the
+    parameter values the caller passed)."""
+    slot, off = {}, 0
+    for t in pe_w.terms:
+        for p, k in zip(t.params, t.param_keys):
+            if k not in slot:
+                slot[k] = off
+                off += p.size
+    logZ, dlogZ = 0.0, np.zeros(n_params)
+    for t in pe_w.terms:
+        if getattr(t, "host_norm", None) is None:
+            continue
+        z, dz = t.host_norm(t.params)
+        logZ += z
+        for p, k, d in zip(t.params, t.param_keys, dz):
+            dlogZ[slot[k] : slot[k] + p.size] += d
+    return logZ, dlogZ
 
 
 def lower(pe_w, inj_w):

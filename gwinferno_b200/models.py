@@ -88,7 +88,14 @@ class _LazyTerm:
     """One additive log-density term; ``params`` are the hyper-parameter VALUES of this call,
     ``build(slots, group_base)`` produces the static spec entries (terms, groups, cuts)."""
 
-    def __init__(self, key, columns, params, build):
+    def __init__(self, key, columns, params, build, maps=None, host_norm=None):
+        # ``maps``: {index in params: ParamMap} -- an O(P) host-side change of variables applied when
+        # Lambda is assembled; gradients are pulled back through it (lowering.pull_back)
+        self.maps = dict(maps or {})
+        # ``host_norm(params) -> (log Z, [dlog Z/dparam_i])``: a per-sample CONSTANT -log Z that is
+        # not part of the device model (it cancels in log L when Nobs = number of events); the
+        # front-end applies it to the reported sites (lowering.host_log_norm)
+        self.host_norm = host_norm
         self.key = key  # hashable identity of the STATIC part (model object id, dimension)
         self.columns = columns  # list[_Column]
         # parameter OBJECTS passed by the caller: the same object given to two terms (IID models,
@@ -97,6 +104,14 @@ class _LazyTerm:
         self.param_keys = [id(p) for p in self._orig]
         self.params = [np.atleast_1d(np.asarray(p, dtype=np.float64)) for p in params]
         self.build = build
+
+
+class ParamMap:
+    """Host-side change of variables for one parameter block: ``fwd(value) -> value seen by the
+    kernel`` and ``vjp(value, grad_wrt_mapped) -> grad_wrt_value``."""
+
+    def __init__(self, fwd, vjp):
+        self.fwd, self.vjp = fwd, vjp
 
 
 class LazyWeight:
@@ -276,24 +291,35 @@ class BSplineChiPrecess(Base1DBSplineModel):
 
 
 class BSplineRedshift(Base1DBSplineModel):
-    """single.py:398-492: ``R(z) = exp(B(log z).c) dVc/dz / (1+z) / Z(c)``, ``Z`` by trapezoid over
-    1000 points between the data's redshift extremes.
+    """single.py:398-492: ``R(z) = exp(f(z)) dVc/dz / (1+z) / Z(c)``, ``Z`` by trapezoid over 1000
+    points between the data's redshift extremes, ``f`` = the projection of the LogXBSpline basis.
 
-    The reference builds the LogXBSpline basis with its DEFAULT ``normalize=True``, which makes the
-    exponent ``(B.c) / trapezoid(B.c)`` (single.py:77-92 -> interpolation.py:293-317); that coupling
-    is not expressible as a sum of terms, so this mirror requires ``normalize=False`` (the exponent
-    is then the plain spline, as in ``PowerlawSplineRedshiftModel``, spline_perturbation.py:317)."""
+    The reference builds that basis with its DEFAULT ``normalize=True``, so ``f(z) = B(log z).c /
+    trapezoid(B.c)`` (single.py:77-92 -> interpolation.py:280-317): the exponent is the spline of the
+    RESCALED coefficients ``c' = c / (a.c)``, ``a_k = trapezoid(B_k)`` over the basis' own 1000-point
+    grid.  The kernel evaluates the plain spline of ``c'``; the rescaling and its chain rule are an
+    O(P) host-side :class:`ParamMap`.  With ``normalize=False`` the map is the identity."""
 
     def __init__(self, n_splines, z, z_inj, dVdc, dVdc_inj, zmax=2.3, basis=LogXBSpline, z_range=None, **kwargs):
         if basis is not LogXBSpline:
             raise NotImplementedError("only the LogXBSpline basis is implemented for BSplineRedshift")
-        if kwargs.get("normalize", basis.default_normalize):
-            raise NotImplementedError(
-                "BSplineRedshift with a normalised basis (the LogXBSpline default) divides the EXPONENT by "
-                "trapezoid(B.c); pass normalize=False for exp(B.c) dVc/dz/(1+z)/Z(c)"
-            )
         xrange = kwargs.pop("xrange", (1e-4, zmax))
         super().__init__(n_splines, z, z_inj, xrange=xrange, basis=basis, **kwargs)
+        self._coef_map = None
+        if self.normalize:
+            from .lowering import host_spline_design  # tiny, grid-only helper
+
+            # BSpline.norm (interpolation.py:280-291): 1 / trapezoid(grid_bases . c, grid)
+            a = np.exp(self.grid_log_w) @ host_spline_design(self.grid_xi, self.xi_range, self.n_splines)
+
+            def fwd(c, a=a):
+                return c / (a @ c)
+
+            def vjp(c, g, a=a):
+                n = a @ c
+                return g / n - a * ((g @ c) / (n * n))
+
+            self._coef_map = ParamMap(fwd, vjp)
         self.dvdc_column = _Column(dVdc, dVdc_inj)
         if z_range is None:
             self.zmin = float(max(np.min(self.column.pe), np.min(self.column.inj)))  # single.py:445
@@ -311,10 +337,12 @@ class BSplineRedshift(Base1DBSplineModel):
         model = self
 
         def build(slots, group_base, cols):
+            rescaled = model._coef_map is not None
             t = S.Term(
                 S.TERM_SPLINE, [cols[0]], slots=[slots[0]], n_splines=model.n_splines, logx=True,
                 outside=S.OUTSIDE_ZERO,  # funcs() is 0 outside the mask => exp(0) = 1 (single.py:90-92, 488)
-                xrange=(model.xmin, model.xmax), norm_group=group_base, grid_xi=model._grid_xi, name="spline[log z]",
+                xrange=(model.xmin, model.xmax), norm_group=-1 if rescaled else group_base,
+                grid_xi=None if rescaled else model._grid_xi, name="spline[log z]",
             )
             t.xi_range = model.xi_range
             terms = [
@@ -322,14 +350,37 @@ class BSplineRedshift(Base1DBSplineModel):
                 S.Term(S.TERM_STATIC, [cols[1]], feature=S.FEAT_LOG, name="dVc/dz (given)"),
                 S.Term(S.TERM_STATIC, [cols[0]], feature=S.FEAT_NEG_LOG1P, name="1/(1+z)"),
             ]
-            return terms, [S.NormGroup(model._grid_log_w, name="Z[redshift]")], []
+            return terms, ([] if rescaled else [S.NormGroup(model._grid_log_w, name="Z[redshift]")]), []
 
         if np.shape(coefs) != (self.n_splines,):
             raise ValueError(f"expected {self.n_splines} coefficients, got shape {np.shape(coefs)}")
-        return LazyWeight([_LazyTerm((id(self), "bsz"), [self.column, self.dvdc_column], [coefs], build)], pe_samples)
+        if self._coef_map is None:
+            return LazyWeight([_LazyTerm((id(self), "bsz"), [self.column, self.dvdc_column], [coefs], build)], pe_samples)
+        # normalised basis: the exponent uses c' = c / (a.c) (device, through the ParamMap) while the
+        # reference's normaliser uses the raw c (single.py:465-468): a per-sample constant, kept on the host
+        return LazyWeight(
+            [_LazyTerm((id(self), "bsz-rescaled"), [self.column, self.dvdc_column], [coefs], build, maps={0: self._coef_map},
+                       host_norm=self._host_norm)],
+            pe_samples,
+        )
+
+    def _host_norm(self, params):
+        logZ, dlogZ = self._log_normalization(params[0])
+        return logZ, [dlogZ]
+
+    def _log_normalization(self, cs):
+        """``(log Z(cs), dlog Z/dcs)`` of single.py:453-469 on the host (1000-point sum)."""
+        from .lowering import host_spline_design
+
+        D = host_spline_design(self._grid_xi, self.xi_range, self.n_splines)
+        li = self._grid_log_w + D @ np.asarray(cs, dtype=np.float64)
+        m = np.max(li)
+        e = np.exp(li - m)
+        return float(m + np.log(np.sum(e))), (e / np.sum(e)) @ D
 
     def normalization(self, cs):
-        """Host-side ``Z(cs)`` (single.py:453-469), e.g. for the merger rate."""
+        """Host-side ``Z(cs)`` (single.py:453-469), e.g. for the merger rate.  As in the reference
+        this is the trapezoid of ``dVc/dz / (1+z) exp(B.cs)`` with the UN-rescaled coefficients."""
         from .lowering import host_spline_on_grid
 
         s = host_spline_on_grid(self._grid_xi, self.xi_range, self.n_splines, np.asarray(cs, dtype=np.float64))

@@ -28,6 +28,10 @@ GOLDEN_CASES = [
     "mixed_bspline_m1",
     "mixed_plpeak_m1",
 ]
+# Cases whose model carries host-side glue (a parameter map / a host normaliser, lowering.pull_back and
+# lowering.host_log_norm): the DEVICE model is an ordinary one, so they are checked on the CPU with the
+# oracle standing in for the device (tests/test_host_glue_cpu.py), not in the GPU-parametrised list.
+HOST_GLUE_CASES = ["bspline_redshift_default"]
 LIKE_KW = {
     "bspline_full": dict(marginalize_selection=False, min_neff_cut=True),
     "bspline_full_margsel": dict(marginalize_selection=True, min_neff_cut=True),
@@ -44,6 +48,7 @@ LIKE_KW = {
     "default_spin": dict(min_neff_cut=False),
     "mixed_bspline_m1": dict(min_neff_cut=False),
     "mixed_plpeak_m1": dict(min_neff_cut=False),
+    "bspline_redshift_default": dict(min_neff_cut=False),
 }
 
 
@@ -149,6 +154,14 @@ def build_weight_fn(model, pe, inj, meta):
             return w * M.iid_spin_tilt(d["cos_tilt_1"], d["cos_tilt_2"], p["xi"], p["sig_t"]) * mz(d["redshift"], p["lamb"]) / d["prior"]
 
         return weights, (lambda p: mz.normalization(lamb=p["lamb"]))
+    if model == "bspline_redshift_default":
+        mz = M.BSplineRedshift(8, pe["redshift"], inj["redshift"], pe["dVdc"], inj["dVdc"], zmax=float(meta["zmax"]))
+
+        def weights(d, pe_samples, p):
+            w = M.powerlaw_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], alpha=p["alpha"], beta=p["beta"], mmin=mmin, mmax=mmax)
+            return w * mz(p["z_cs"], pe_samples=pe_samples) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(p["z_cs"]))
     if model == "bspline_effspin":
         mm = M.BSplinePrimaryBSplineRatio(int(meta["n_m1"]), int(meta["n_q"]), pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax)
         ms = M.BSplineEffectiveSpinDims(int(meta["n_e"]), int(meta["n_p"]), pe["chi_eff"], pe["chi_p"], inj["chi_eff"], inj["chi_p"], normalize=True)

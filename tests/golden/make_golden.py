@@ -348,6 +348,28 @@ def case_mixed_mass():
     _save("mixed_plpeak_m1", pe, inj, const, params, names, base, jac, dict(model="mixed_plpeak_m1", mmin=mmin, mmax=mmax, n_q=9))
 
 
+def case_bspline_redshift_default():
+    """``BSplineRedshift`` exactly as the reference constructs it by default (single.py:398-492): the
+    LogXBSpline basis is normalised, so the exponent is ``B.c / trapezoid(B.c)`` while ``Z`` uses the
+    raw coefficients; masses from the parametric power law."""
+    E, S, I = 6, 200, 4000
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=144)
+    _with_derived(pe, inj)
+    mmin, mmax, zmax = 3.0, 100.0, 2.3
+    rz = SGL.BSplineRedshift(8, pe["redshift"], inj["redshift"], pe["dVdc"], inj["dVdc"], zmax=zmax)
+    rng = np.random.default_rng(144002)
+    params = dict(alpha=np.float64(-2.4), beta=np.float64(1.3), z_cs=np.exp(0.4 * rng.standard_normal(8)))
+    names = list(params.keys())
+
+    def weights(d, pe_samples, p):
+        w = PAR.powerlaw_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], alpha=p["alpha"], beta=p["beta"], mmin=mmin, mmax=mmax)
+        return w * rz(p["z_cs"], pe_samples=pe_samples) / d["prior"]
+
+    vt = lambda p: rz.normalization(p["z_cs"])  # noqa: E731
+    base, jac = _complex_step(weights, pe, inj, const, params, names, vt, dict(min_neff_cut=False))
+    _save("bspline_redshift_default", pe, inj, const, params, names, base, jac, dict(model="bspline_redshift_default", mmin=mmin, mmax=mmax, zmax=zmax))
+
+
 def _with_derived(pe, inj):
     for d in (pe, inj):
         d["chi_eff"], d["chi_p"] = synthetic.effective_spins(d)
@@ -426,6 +448,7 @@ CASES = dict(
     plpeak_smooth=case_plpeak_smooth,
     default_spin=case_default_spin,
     mixed_mass=case_mixed_mass,
+    bspline_redshift_default=case_bspline_redshift_default,
 )
 
 if __name__ == "__main__":

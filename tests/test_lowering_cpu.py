@@ -69,8 +69,7 @@ def test_weight_products_must_match(cat):
 def test_unsupported_reference_options_fail_loudly(cat):
     pe, inj, _ = cat
     with pytest.raises(NotImplementedError):
-        # the reference's default (normalised LogXBSpline) divides the EXPONENT by trapezoid(B.c)
-        M.BSplineRedshift(8, pe["redshift"], inj["redshift"], pe["redshift"], inj["redshift"])
+        M.BSplineRedshift(8, pe["redshift"], inj["redshift"], pe["redshift"], inj["redshift"], basis=M.LogYBSpline)
     with pytest.raises(NotImplementedError):
         M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], degree=2)
     with pytest.raises(NotImplementedError):
