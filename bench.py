@@ -179,7 +179,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps * n_full / n_sample, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "E": E, "S": S, "I": I},
+        "config": {"workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "model": family, "E": E, "S": S, "I": I,
+                   "samples_per_eval": n_full, "chains_per_step": 1, "parallelism": f"{cores} host processes (CPU)",
+                   "neff_grad": False, "likelihood": "marginalize_selection=False, min_neff_cut=True (reference defaults)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n_sample} of {n_full} samples ({cores} worker processes x ({n_events} events x {S} + {n_inj_each} injections)), "
                                    f"{1e3 * t / args.steps:.1f} ms per sampled step, extrapolated linearly in samples; NumPy oracle port (JAX unavailable)"},
