@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from gwinferno_b200 import nuts, workloads  # noqa: E402
+from gwinferno_b200 import nuts, pipeline, workloads  # noqa: E402
 from gwinferno_b200.likelihood import PopulationLikelihood  # noqa: E402
 
 
@@ -37,17 +37,7 @@ def main():
         log_l, grad, head = eng.loglike(lam, Nobs=Nobs)
         return log_l, grad
 
-    S = low.slots_for
-    blocks = [
-        (S(p0["mass_cs"]), 15.0, 1.0, 1, False),
-        (S(p0["q_cs"]), 5.0, 1.0, 1, False),
-        (S(p0["a1_cs"]), 5.0, 25.0, 2, False),
-        (S(p0["a2_cs"]), 5.0, 25.0, 2, False),
-        (S(p0["tilt1_cs"]), 5.0, 25.0, 2, False),
-        (S(p0["tilt2_cs"]), 5.0, 25.0, 2, False),
-        (S(p0["z_cs"]), 1.0, 1.0, 2, True),
-        (S(p0["lamb"]), 3.0, None, 0, False),
-    ]
+    blocks = pipeline.bspline_prior_blocks(low.slots_for, p0)  # pipeline/utils.py:163-216 defaults, example taus
     post = nuts.BSplinePosterior(loglike, low.spec.n_params, blocks)
     rng = np.random.default_rng(0)
     theta0 = 0.1 * rng.standard_normal(post.dim)
