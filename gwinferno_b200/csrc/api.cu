@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <string>
 #include <vector>
@@ -30,6 +31,20 @@ void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_lik
 }  // namespace gwi
 
 using namespace gwi;
+
+// nothing may throw across the C boundary: the plan builder allocates several arrays of the
+// catalog's size on the host
+static int build_plan_noexcept(const CatalogView& cat, const gwi_model_desc& desc, int sm_count, int n_workers, Plan& plan) {
+  try {
+    return build_plan(cat, desc, sm_count, n_workers, plan);
+  } catch (const std::bad_alloc&) {
+    set_error("out of host memory building the plan");
+    return GWI_ERR_ALLOC;
+  } catch (const std::exception& e) {
+    set_error(std::string("plan builder failed: ") + e.what());
+    return GWI_ERR_INVALID;
+  }
+}
 
 struct gwi_catalog {
   CatalogView view;
@@ -97,6 +112,11 @@ int gwi_catalog_create(const gwi_catalog_desc* d, gwi_catalog** out) {
     set_error("total_inj must be positive and at least the number of found injections");
     return GWI_ERR_INVALID;
   }
+  // the plan builder indexes samples with 32 bits (a rank's shard; 180 GB of HBM hold ~2.5e9 samples)
+  if (d->n_inj > (int64_t)UINT32_MAX || (d->n_events > 0 && d->pe_offsets && d->pe_offsets[d->n_events] > (int64_t)UINT32_MAX)) {
+    set_error("more than 2^32 - 1 samples in one catalog shard: split it across ranks");
+    return GWI_ERR_UNSUPPORTED;
+  }
   gwi_catalog* c = new (std::nothrow) gwi_catalog();
   if (!c) return GWI_ERR_ALLOC;
   c->view.n_columns = d->n_columns;
@@ -138,7 +158,7 @@ int gwi_debug_plan_build(const gwi_catalog* cat, const gwi_model_desc* desc, int
   }
   gwi_plan* p = new (std::nothrow) gwi_plan();
   if (!p) return GWI_ERR_ALLOC;
-  const int rc = build_plan(cat->view, *desc, 148, n_workers, p->plan);
+  const int rc = build_plan_noexcept(cat->view, *desc, 148, n_workers, p->plan);
   if (rc != GWI_OK) {
     delete p;
     return rc;
@@ -349,7 +369,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   gwi_model* m = new (std::nothrow) gwi_model();
   if (!m) return GWI_ERR_ALLOC;
   m->device = cat->view.device;
-  int rc = build_plan(cat->view, *desc, prop.multiProcessorCount, 0, m->plan);
+  int rc = build_plan_noexcept(cat->view, *desc, prop.multiProcessorCount, 0, m->plan);
   if (rc != GWI_OK) {
     delete m;
     return rc;
