@@ -13,9 +13,9 @@ Multi-GPU: injections sharded by (m1, q) piece bucket, whole events dealt round-
 all-gather of ~4 KB partial records per step; total work is fixed => "scaling": "strong".
 
 PyTorch is used only as plumbing (NCCL all-gather, CUDA events, device scratch tensors); every
-kernel in the timed region is from libgwi.so.  ``--impl reference`` times the CPU arm: the oracle
-port of the reference algorithm (NumPy) on all host cores, on a bounded sample (the reference
-itself needs JAX, which this image does not have).
+kernel in the timed region is from libgwi.so.  ``--impl reference`` times the CPU arm: the plain-C
+oracle port of the reference algorithm (oracle/c/gwi_oracle.c) on all host cores, on a bounded
+sample (the reference itself needs JAX, which this image does not have).
 """
 
 import argparse
@@ -83,111 +83,91 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(name, n_events=8, n_inj=400_000):
-    """Oracle port on ONE host core, bounded sample of the same workload; extrapolated linearly in
-    the number of samples to the full workload."""
-    from gwinferno_b200 import workloads
-    from oracle import popmodel
+def _cpu_arm(name, seconds_per_step, steps, warmup):
+    """The CPU implementation of the path: the plain-C oracle (oracle/c/gwi_oracle.c, a port of the
+    reference algorithm working from raw coordinates; the reference itself needs JAX, which is not
+    installed) on ALL host cores, on a bounded sample of the workload -- every event of the first
+    ``n_ev`` and the first ``n_inj`` found injections, sized from a calibration run so that one step
+    takes about ``seconds_per_step`` -- extrapolated linearly in samples to the full workload.
+    Each step evaluates a different Lambda and includes the likelihood glue (analysis.py:257-319)."""
+    from gwinferno_b200 import lowering, synthetic, workloads
+    from oracle import c_oracle, popmodel
 
-    _, family, E, S, I = workloads.WORKLOADS[name]
-    scale = min(1.0, n_inj / I)
-    pe, inj, const, z_range = workloads.shard_catalog(name, 0, 1, scale=scale)
-    S_full = S
-    # keep full-length events but only a few of them
-    from gwinferno_b200 import synthetic
+    cfg_idx, family, E, S, I = workloads.WORKLOADS[name]
+    cfg = 2 if name == "cfg4" else int(name[3:])
+    cores = os.cpu_count() or 1
+    n_full = E * S + I
 
-    pe_full = synthetic.make_events(E, S_full, 1000 * int(name[3:]) + 0)
-    pe = {k: np.ascontiguousarray(v[:n_events]) for k, v in pe_full.items()}
-    weights, params_fn = workloads.build_model(family, pe, inj, z_range=z_range)
-    low, lam, _ = workloads.lower_workload(weights, params_fn, pe, inj)
-    n_sample = pe["redshift"].size + inj["redshift"].size
-    popmodel.partial_record(low.spec, low.pe_cols, low.inj_cols, lam)  # warm-up (cosmology table, caches)
+    def build(n_ev, n_inj):
+        pe_all = synthetic.make_events(E, S, 1000 * cfg + 0)
+        zpe = (float(pe_all["redshift"].min()), float(pe_all["redshift"].max()))
+        pe = {k: np.ascontiguousarray(v[:n_ev]) for k, v in pe_all.items()}
+        inj = synthetic.make_injections(I, 1000 * cfg + 1, 0, n_inj)
+        z_range = (max(zpe[0], synthetic.ZLO), min(zpe[1], synthetic.ZHI))
+        weights, params_fn = workloads.build_model(family, pe, inj, z_range=z_range)
+        low, lam, _ = workloads.lower_workload(weights, params_fn, pe, inj)
+        return low, weights, params_fn, pe, n_ev * S + n_inj
+
+    def one(low, lam, n_ev):
+        ev = c_oracle.evaluate(low.spec, low.pe_cols, low.inj_cols, 4.0 * I, lam, want_jac=True, want_neff_jac=False, n_threads=cores)
+        return popmodel.hierarchical_log_likelihood(ev, n_ev, min_neff_cut=True)[0]
+
+    # calibration on a small sample
+    n_ev0, n_inj0 = min(E, 2 * cores), min(I, 200_000)
+    low, weights, params_fn, pe, n0 = build(n_ev0, n_inj0)
+    lam = lowering.flatten_params(weights(pe, True, params_fn(0)), low.spec.n_params)
+    one(low, lam, n_ev0)  # warm-up: cosmology table, page faults
     t0 = time.perf_counter()
-    reps = 0
-    while True:
-        rec = popmodel.partial_record(low.spec, low.pe_cols, low.inj_cols, lam)
-        popmodel.combine_records(low.spec, [rec], const["total_inj"], lam, n_events)
-        reps += 1
-        if time.perf_counter() - t0 > 8.0 or reps >= 5:
-            break
-    dt = (time.perf_counter() - t0) / reps
-    n_full = E * S_full + I
-    return {
-        "value": (1.0 / dt) * n_sample / n_full,
-        "unit": UNIT,
-        "cores": 1,
-        "kind": "port",
-        "sample": f"{n_events} events x {S_full} samples + {inj['redshift'].size} injections ({n_sample} of {n_full} samples), {dt:.3f} s per eval, "
-        "extrapolated linearly in samples; NumPy oracle port of the reference algorithm (JAX unavailable)",
-        "samples_per_s": n_sample / dt,
-    }
-
-
-def _ref_worker(args):
-    name, family, widx, nworkers, n_events, n_inj_each, seed_steps = args
-    from gwinferno_b200 import synthetic, workloads
-    from oracle import popmodel
-
-    _, _, E, S, I = workloads.WORKLOADS[name]
-    cfg = int(name[3:])
-    pe_full = synthetic.make_events(E, S, 1000 * cfg + 0)
-    ev_idx = [e for e in range(n_events * nworkers) if e % nworkers == widx and e < E]
-    pe = {k: np.ascontiguousarray(v[ev_idx]) for k, v in pe_full.items()}
-    zpe = (float(pe_full["redshift"].min()), float(pe_full["redshift"].max()))
-    inj = synthetic.make_injections(I, 1000 * cfg + 1, widx * n_inj_each, (widx + 1) * n_inj_each)
-    z_range = (max(zpe[0], synthetic.ZLO), min(zpe[1], synthetic.ZHI))
-    weights, params_fn = workloads.build_model(family, pe, inj, z_range=z_range)
-    low, lam, _ = workloads.lower_workload(weights, params_fn, pe, inj)
+    one(low, lam, n_ev0)
+    rate = n0 / (time.perf_counter() - t0)  # samples per second on all cores
+    frac = min(1.0, rate * seconds_per_step / n_full)
+    n_ev, n_inj = max(1, int(round(E * frac))), max(1000, int(round(I * frac)))
+    low, weights, params_fn, pe, n_sample = build(n_ev, n_inj)
     times = []
-    for s in seed_steps:
-        p = params_fn(s)
-        from gwinferno_b200 import lowering
-
-        lam = lowering.flatten_params(weights(pe, True, p), low.spec.n_params)
+    for s_ in range(warmup + steps):
+        lam = lowering.flatten_params(weights(pe, True, params_fn(s_)), low.spec.n_params)
         t0 = time.perf_counter()
-        rec = popmodel.partial_record(low.spec, low.pe_cols, low.inj_cols, lam)
+        one(low, lam, n_ev)
         times.append(time.perf_counter() - t0)
-    return times, pe["redshift"].size + inj["redshift"].size
+    t = float(np.sum(times[warmup:]))
+    value = (steps / t) * n_sample / n_full
+    return {
+        "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{n_ev} events x {S} samples + {n_inj} injections ({n_sample} of {n_full} samples), {1e3 * t / steps:.0f} ms per sampled step on {cores} threads, "
+                  "extrapolated linearly in samples; plain-C port of the reference algorithm (oracle/c/gwi_oracle.c; the reference needs JAX, not installed)",
+        "samples_per_s": n_sample * steps / t,
+    }, t, n_sample, n_full
+
+
+def cpu_baseline(name):
+    """cpu_baseline object of the GPU arm's line: about 10 s of CPU work on rank 0."""
+    return _cpu_arm(name, seconds_per_step=2.0, steps=4, warmup=1)[0]
 
 
 def run_reference(args):
-    """CPU arm: the oracle port on all host cores (one worker process per core, each evaluating its
-    shard of a bounded sample; the records combine exactly like the multi-GPU path)."""
+    """CPU arm (``--impl reference``): same metric, config and unit as the GPU arm, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
-
     from gwinferno_b200 import workloads
 
     name = args.workload
     _, family, E, S, I = workloads.WORKLOADS[name]
-    cores = os.cpu_count() or 1
-    n_inj_each = max(1000, min(I // cores, 250_000))
-    n_events = max(1, min(E // cores, 4))
-    steps = list(range(args.warmup + args.steps))
-    ctx = mp.get_context("fork")
     t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_ref_worker, [(name, family, w, cores, n_events, n_inj_each, steps) for w in range(cores)])
-    n_sample = sum(r[1] for r in res)
-    # per step: all workers run concurrently; the step takes as long as the slowest worker
-    per_step = np.max(np.array([r[0] for r in res]), axis=0)[args.warmup :]
-    t = float(np.sum(per_step))
-    n_full = E * S + I
-    value = (args.steps / t) * n_sample / n_full
+    # bounded steps: the whole run ends within a few minutes whatever --steps is
+    per_step = max(0.25, min(3.0, 150.0 / max(1, args.steps + args.warmup)))
+    base, t, n_sample, n_full = _cpu_arm(name, seconds_per_step=per_step, steps=args.steps, warmup=args.warmup)
+    value = base["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps * n_full / n_sample, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "model": family, "E": E, "S": S, "I": I,
-                   "samples_per_eval": n_full, "chains_per_step": 1, "parallelism": f"{cores} host processes (CPU)",
+                   "samples_per_eval": n_full, "chains_per_step": 1, "parallelism": f"{base['cores']} host threads (CPU)",
                    "neff_grad": False, "likelihood": "marginalize_selection=False, min_neff_cut=True (reference defaults)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_sample} of {n_full} samples ({cores} worker processes x ({n_events} events x {S} + {n_inj_each} injections)), "
-                                   f"{1e3 * t / args.steps:.1f} ms per sampled step, extrapolated linearly in samples; NumPy oracle port (JAX unavailable)"},
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "setup_s": time.perf_counter() - t0,
+        "setup_s": time.perf_counter() - t0 - t,
     }
     emit(json.dumps(line))
 
