@@ -104,14 +104,17 @@ def hierarchical_likelihood(
     device=0,
 ):
     """Drop-in for ``gwinferno.pipeline.analysis.hierarchical_likelihood`` (analysis.py:139-356)
-    on lazy weights.  ``log`` is accepted for signature compatibility (the fused path always works
-    in log space).  The categorical sub-population branch (:246-254) and posterior-predictive
+    on lazy weights.  ``log=True`` takes lazy LOG-weights (``log_prob`` terms combined with ``+`` and
+    ``- jnp.log(prior)``, analysis.py:401-421); the fused path always works in log space, so both forms
+    lower to the same device model.  The categorical sub-population branch (:246-254) and posterior-predictive
     resampling (:321-355) are outside the fused hot path and raise NotImplementedError."""
     if max_variance_cut and (marginalize_selection or min_neff_cut):
         raise ValueError(
             "max_variance_cut is True which requires marginalize_selection and min_neff_cut to be False but got "
             f"marginalize_selection = {marginalize_selection} and min_neff_cut = {min_neff_cut}"
         )
+    if bool(log) != bool(getattr(pe_weights, "log_domain", False)) or bool(log) != bool(getattr(inj_weights, "log_domain", False)):
+        raise ValueError("log=True expects log-weights (built from log_prob with + / -), log=False expects weights (built with * and /)")
     if categorical or marginal_qs:
         raise NotImplementedError("the categorical sub-population branch is not part of the fused path")
     keys, pattern = lowering._structure(pe_weights, inj_weights)

@@ -118,9 +118,12 @@ class LazyWeight:
     """Symbolic per-sample weight  prod_d p_d(theta_d; Lambda) / prior  for one sample set
     (``pe_samples=True`` or ``False``)."""
 
-    def __init__(self, terms, pe_samples):
+    def __init__(self, terms, pe_samples, log_domain=False):
         self.terms = list(terms)
         self.pe_samples = pe_samples
+        # log_domain: the object stands for the LOG of the weight (what the reference passes with
+        # ``hierarchical_likelihood(..., log=True)``, analysis.py:401-421): factors combine with + / -
+        self.log_domain = bool(log_domain)
 
     def _merge(self, other):
         if self.pe_samples is None:
@@ -131,6 +134,8 @@ class LazyWeight:
 
     def __mul__(self, other):
         if isinstance(other, LazyWeight):
+            if self.log_domain or other.log_domain:
+                raise TypeError("log-weights combine with + and -, not *")
             return LazyWeight(self.terms + other.terms, self._merge(other))
         return NotImplemented
 
@@ -139,9 +144,28 @@ class LazyWeight:
     def __truediv__(self, other):
         if isinstance(other, LazyWeight):
             raise TypeError("division by a population term is not supported")
+        if self.log_domain:
+            raise TypeError("log-weights combine with + and -, not /")
         # division by the sampling-prior array (examples/simple_bspline_example.py:66)
         arr = np.asarray(other, dtype=np.float64)
         return self * weight_from_prior(arr, pe_samples=self.pe_samples)
+
+    def __add__(self, other):
+        if isinstance(other, LazyWeight) and self.log_domain and other.log_domain:
+            return LazyWeight(self.terms + other.terms, self._merge(other), log_domain=True)
+        if isinstance(other, LazyWeight):
+            raise TypeError("only log-weights (log_prob) can be added")
+        return NotImplemented
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        """``log_weight - jnp.log(prior)`` (analysis.py:401-402)."""
+        if not self.log_domain or isinstance(other, LazyWeight):
+            raise TypeError("only the log of the sampling prior can be subtracted, and only from a log-weight")
+        prior = np.exp(np.asarray(other, dtype=np.float64))
+        w = weight_from_prior(prior, pe_samples=self.pe_samples)
+        return LazyWeight(self.terms + w.terms, self._merge(w), log_domain=True)
 
 
 def weight_from_prior(prior, pe_samples=None):
@@ -674,6 +698,12 @@ class PowerlawRedshiftModel:
             return model._terms(slots, group_base, cols)
 
         return LazyWeight([_LazyTerm((id(self), "plz"), [self.column], [lamb], build)], pe_samples)
+
+    def log_prob(self, z, lamb):
+        """parametric.py:129-136: the same density as ``__call__`` in the log domain (combine with
+        ``+`` and ``- jnp.log(prior)``, evaluate with ``hierarchical_likelihood(..., log=True)``)."""
+        w = self(z, lamb)
+        return LazyWeight(w.terms, w.pe_samples, log_domain=True)
 
     # host-side value of the normaliser (a 1000-point sum; used for ``surveyed_hypervolume``)
     def normalization(self, lamb):

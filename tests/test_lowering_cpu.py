@@ -124,3 +124,25 @@ def test_spline_density_bases_lower_to_linear_spline_terms(cat):
     t = [t for t in low.spec.terms if t.kind == S.TERM_SPLINE][0]
     assert t.outside == S.OUTSIDE_ZERO and t.logx and t.xrange == (1e-4, 2.3)
     assert np.array_equal(low.pe_cols[[t for t in low.spec.terms if t.kind == S.TERM_SPLINE_LINEAR][1].cols[0]], np.abs(pe["cos_tilt_2"]))
+
+
+def test_log_domain_weights_lower_to_the_same_model(cat):
+    """``log_prob`` terms combined with + / - log(prior) (analysis.py:401-402, log=True) give the same
+    device model as the product form."""
+    pe, inj, _ = cat
+    z = M.PowerlawRedshiftModel(pe["redshift"], inj["redshift"])
+    lamb = np.float64(2.3)
+    prod = lowering.lower(z(pe["redshift"], lamb) / pe["prior"], z(inj["redshift"], lamb) / inj["prior"])
+    lw_pe = z.log_prob(pe["redshift"], lamb) - np.log(pe["prior"])
+    lw_inj = z.log_prob(inj["redshift"], lamb) - np.log(inj["prior"])
+    assert lw_pe.log_domain and lw_inj.log_domain
+    logd = lowering.lower(lw_pe, lw_inj)
+    assert [(t.kind, t.feature) for t in logd.spec.terms] == [(t.kind, t.feature) for t in prod.spec.terms]
+    prior_col = [t for t in logd.spec.terms if t.feature == S.FEAT_NEG_LOG][0].cols[0]
+    assert np.allclose(logd.pe_cols[prior_col], pe["prior"], rtol=1e-15)
+    with pytest.raises(TypeError):
+        _ = lw_pe * z(pe["redshift"], lamb)
+    with pytest.raises(TypeError):
+        _ = z(pe["redshift"], lamb) + z(pe["redshift"], lamb)
+    s = z.log_prob(pe["redshift"], lamb) + z.log_prob(pe["redshift"], lamb)
+    assert s.log_domain and len(s.terms) == 2
