@@ -163,3 +163,62 @@ def test_model_create_fails_loudly_without_gpu():
     with pytest.raises(capi.GwiError) as e:
         capi.Model(cat, case.low.spec)
     assert "no CPU fallback" in str(e.value)
+
+
+class _Adhoc:
+    pass
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_plan_reproduces_oracle_on_random_small_models(seed):
+    """Randomised edge cases of the host plan builder: tiny and single-sample events, events whose
+    samples are all masked, few or no valid injections, narrow supports, minimal spline counts, every
+    basis flavour, several chunk lengths -- the decoded plan must give the oracle's per-segment sums."""
+    from gwinferno_b200 import lowering, synthetic
+    from gwinferno_b200 import models as M
+
+    rng = np.random.default_rng(1000 + seed)
+    E, S, I = int(rng.integers(1, 6)), int(rng.integers(1, 40)), int(rng.integers(40, 400))
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=200 + seed)
+    mmin = float(rng.choice([3.0, 8.0, 20.0]))  # the larger values mask many samples (all of some events)
+    mmax = float(rng.choice([60.0, 100.0]))
+    nm, nq, na = int(rng.integers(4, 14)), int(rng.integers(4, 9)), int(rng.integers(4, 8))
+    mass = M.BSplinePrimaryBSplineRatio(nm, nq, pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax)
+    flavour = seed % 3
+    if flavour == 0:
+        spin = M.BSplineSpinMagnitude(na, pe["a_1"], inj["a_1"], normalize=True)
+    elif flavour == 1:
+        spin = M.BSplineChiPrecess(na, pe["a_1"], inj["a_1"], normalize=True)  # the spline is the density
+    else:
+        spin = M.BSplineSpinTilt(na, pe["cos_tilt_1"], inj["cos_tilt_1"], xrange=(-0.5, 0.7), normalize=True)  # narrow support
+    zmod = M.PowerlawSplineRedshiftModel(int(rng.integers(4, 8)), pe["redshift"], inj["redshift"])
+    p = dict(m=0.5 * rng.standard_normal(nm), q=0.5 * rng.standard_normal(nq), a=np.exp(0.4 * rng.standard_normal(na)), lamb=np.float64(rng.uniform(-1, 4)),
+             z=0.4 * rng.standard_normal(zmod.n_splines))
+
+    def w(d, pe_samples):
+        return mass(p["m"], p["q"], pe_samples=pe_samples) * spin(p["a"], pe_samples=pe_samples) * zmod(d["redshift"], p["lamb"], p["z"]) / d["prior"]
+
+    case = _Adhoc()
+    case.low = lowering.lower(w(pe, True), w(inj, False))
+    case.Lam = lowering.flatten_params(w(pe, True), case.low.spec.n_params)
+    cat = capi.Catalog(case.low.pe_cols, case.low.inj_cols, const["total_inj"])
+    plan = capi.HostPlan(cat, case.low.spec, chunk_steps=int(rng.choice([0, 4, 8, 32])))
+    x, seg_of, segs, chunks, cols, dimt = _decode(case, plan)
+    ev = popmodel.evaluate(case.low.spec, case.low.pe_cols, case.low.inj_cols, const["total_inj"], case.Lam, want_jac=False)
+    sumZ = np.sum(ev["logZ"])
+    assert segs.shape[0] == E + 1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for s in range(E + 1):
+            xs = x[seg_of == s]
+            n_total, n_valid = int(segs[s, 0]), int(segs[s, 1])
+            assert np.isfinite(xs).sum() == n_valid
+            want = ev["log_mu"] if s == 0 else ev["logBF"][s - 1]
+            if n_valid == 0:
+                assert not np.isfinite(want)  # the oracle agrees that the segment has no weight
+                continue
+            m = xs.max()
+            S1, S2 = np.exp(xs - m).sum(), np.exp(2 * (xs - m)).sum()
+            denom = const["total_inj"] if s == 0 else n_total
+            assert abs(m + np.log(S1) - np.log(denom) - sumZ - want) < 1e-11
+            if s > 0:
+                assert abs(2 * np.log(S1) - np.log(S2) - ev["logNeff"][s - 1]) < 1e-11
