@@ -3,9 +3,11 @@
 # Also prints the per-launch DRAM traffic that bench.py reads from profiles/traffic.json ("cfg3_n1").
 set -eu
 REP="$1"
-ncu -i "$REP" --page raw --csv | python - <<'PY'
+CSV="${REP%.ncu-rep}.raw.csv"
+ncu -i "$REP" --page raw --csv > "$CSV"
+python - "$CSV" <<'PY'
 import csv, sys
-rows = list(csv.reader(sys.stdin))
+rows = list(csv.reader(open(sys.argv[1])))
 hdr, units, vals = rows[0], rows[1], rows[2]
 keep = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
