@@ -874,7 +874,15 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   const int64_t L_full = L;
   // one warp step takes ~2500 cycles of latency (8 resident warps/SM), so a 32-step final slice is a
   // 40 us tail; 8-step slices at the very end cut it to ~10 us for ~2W extra record flushes
-  const int64_t L_MIN = 8;
+  // tuning experiments only (defaults = the measured choice): GWI_TUNE_LMIN, GWI_TUNE_GUIDED_DIV
+  auto env_int = [](const char* name, int64_t dflt, int64_t lo, int64_t hi) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    const long long x = std::atoll(v);
+    return (int64_t)std::min<long long>(hi, std::max<long long>(lo, x));
+  };
+  const int64_t L_MIN = roundQ(env_int("GWI_TUNE_LMIN", 8, Q, 1024));
+  const int64_t GUIDED_DIV = env_int("GWI_TUNE_GUIDED_DIV", 2, 1, 16);  // slice = remaining / (DIV * W)
   int64_t done_steps = 0;
   int64_t pos = 0, fill = 0;
   for (int si = 0; si < n_seg; ++si) {
@@ -893,7 +901,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         fill = 0;
         {
           const int64_t remaining = std::max<int64_t>(0, total_steps - done_steps);
-          L = std::max<int64_t>(std::min<int64_t>(L_MIN, L_full), std::min<int64_t>(L_full, roundQ(remaining / (2 * (int64_t)W))));
+          L = std::max<int64_t>(std::min<int64_t>(L_MIN, L_full), std::min<int64_t>(L_full, roundQ(remaining / (GUIDED_DIV * (int64_t)W))));
         }
       }
       const int64_t steps = std::min<int64_t>(L - fill, roundQ((left + LANES - 1) / LANES));
