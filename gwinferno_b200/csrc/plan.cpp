@@ -949,6 +949,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     double fmin[MAX_KOPS], fmax[MAX_KOPS];
   };
   std::vector<SegStat> cstat(n_chunks);
+  std::atomic<int64_t> gather_seconds{0};  // (microseconds, summed over the workers; timing only)
   {
     std::atomic<int> next{0};
     auto work = [&]() {
@@ -957,9 +958,11 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       // chunk-local copy in sorted order; everything below then reads sequentially.
       std::vector<std::vector<double>> gathered(cat.n_columns);
       std::vector<const double*> tcols(cat.n_columns, nullptr);
+      double t_gather = 0.0;
       for (;;) {
         const int c = next.fetch_add(1);
         if (c >= n_chunks) break;
+        const auto tg0 = std::chrono::steady_clock::now();
         const Chunk& C = plan.chunks[c];
         const int s = C.segment;
         const double* const* src = s == 0 ? cat.inj_columns.data() : cat.pe_columns.data();
@@ -975,6 +978,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
           for (int64_t r = 0; r < n_c; ++r) gp[r] = sc[o[r]];
           tcols[cc] = gp;
         }
+        if (timing) t_gather += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg0).count();
         const double* const* cols = tcols.data();
         SegStat st;
         st.max_static = NEG_INF;
@@ -1031,6 +1035,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         }
         cstat[c] = st;
       }
+      if (timing) gather_seconds.fetch_add((int64_t)(t_gather * 1e6));
     };
     std::vector<std::thread> th;
     for (int w = 0; w < std::min(n_workers, std::max(1, n_chunks)); ++w) th.emplace_back(work);
@@ -1047,6 +1052,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   }
 
   tick("column fill");
+  if (timing) std::fprintf(stderr, "[gwi plan]   of which gather (thread-seconds) %8.3f s over %d workers\n", gather_seconds.load() * 1e-6, n_workers);
   // ---- level-0 records: one per chunk (the chunks, hence the records, of a segment are
   //      consecutive); fixed-order tree reduction afterwards
   {
