@@ -136,7 +136,7 @@ _lib = None
 _cudart = None
 
 
-def load_library():
+def load_library(_allow_emulator=False):
     """Load libgwi.so (built in-tree by ``__graft_entry__.build()`` / ``make -C gwinferno_b200/csrc``)."""
     global _lib
     if _lib is not None:
@@ -144,6 +144,9 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise GwiError(-2, f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` " "(there is no CPU fallback)")
     lib = C.CDLL(LIB_PATH)
+    if hasattr(lib, "gwi_emu_marker") and not _allow_emulator:
+        # tests/emu builds the kernel sources for a host warp emulator (CPU test suite only)
+        raise GwiError(-2, f"{LIB_PATH} is the test suite's host-emulator build, not the CUDA library (there is no CPU path)")
     if lib.gwi_version() != GWI_VERSION:  # the structs below would not match the library's
         raise GwiError(-1, f"{LIB_PATH} has ABI version {lib.gwi_version()}, this binding expects {GWI_VERSION}: rebuild it")
     lib.gwi_last_error.restype = C.c_char_p

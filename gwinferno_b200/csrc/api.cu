@@ -569,11 +569,11 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
     if (H.two_pass || exact_shift || m->force_exact_shift) {
       // exact per-segment maximum first (always for models with non-linear terms; as a fallback when
       // the a-priori bound was so loose that every weight of a segment underflowed)
-      m->k_max<<<grid, block, m->smem_max, st>>>(m->dev);
+      GWI_LAUNCH(m->k_max, grid, block, m->smem_max, st)(m->dev);
       launch_segmax(m->dev, H.n_segments, nc, st);
     }
     if (m->timing) cudaEventRecord(m->ev0[m->n_timed % 64], st);
-    m->k_full<<<grid, block, m->smem_full, st>>>(m->dev);
+    GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev);
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
   }
   const int n_levels = (int)m->level_tasks.size();

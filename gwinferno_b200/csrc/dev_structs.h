@@ -4,6 +4,15 @@
 
 #include "gwi_internal.h"
 
+// kernel<<<grid, block, dynamic shared bytes, stream>>>(args...).  The only other expansion is the
+// host warp emulator of the CPU test suite (tests/emu/cuda_runtime.h: test infrastructure that
+// compiles these same kernel sources with g++; it is never part of libgwi.so).
+#ifdef GWI_HOST_EMULATION
+#define GWI_LAUNCH(kernel, grid, block, smem, stream) GWI_EMU_LAUNCH(kernel, grid, block, smem, stream)
+#else
+#define GWI_LAUNCH(kernel, grid, block, smem, stream) kernel<<<(grid), (block), (smem), (stream)>>>
+#endif
+
 namespace gwi {
 
 struct DimDev {

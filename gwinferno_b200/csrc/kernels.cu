@@ -636,25 +636,25 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
 // tables + shifts (what the stream kernel needs) on `st`; the grid normalisers (only needed by
 // finish_kernel) on `aux`, concurrently with the stream kernel.  `nc` = number of chains.
 void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st) {
-  prologue_kernel<<<dim3(1, nc), 256, 0, st>>>(Md, lam, n_groups);
+  GWI_LAUNCH(prologue_kernel, dim3(1, nc), 256, 0, st)(Md, lam, n_groups);
 }
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux) {
-  if (n_groups > 0) prologue_kernel<<<dim3(n_groups, nc), 256, (size_t)max_grid * sizeof(double), aux>>>(Md, lam, 0);
+  if (n_groups > 0) GWI_LAUNCH(prologue_kernel, dim3(n_groups, nc), 256, (size_t)max_grid * sizeof(double), aux)(Md, lam, 0);
 }
 void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st) {
   dim3 grid(n_tasks, (rec + 255) / 256, nc);
-  reduce_kernel<<<grid, 256, 0, st>>>(Md, level);
+  GWI_LAUNCH(reduce_kernel, grid, 256, 0, st)(Md, level);
 }
-void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st) { segmax_kernel<<<dim3(n_seg, nc), 256, 0, st>>>(Md); }
+void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st) { GWI_LAUNCH(segmax_kernel, dim3(n_seg, nc), 256, 0, st)(Md); }
 void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaStream_t st) {
-  finish_kernel<<<dim3(n_seg, nc), 256, (size_t)rec_doubles * sizeof(double), st>>>(Md);
+  GWI_LAUNCH(finish_kernel, dim3(n_seg, nc), 256, (size_t)rec_doubles * sizeof(double), st)(Md);
 }
-void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { export_kernel<<<64, 256, 0, st>>>(Md, out); }
+void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { GWI_LAUNCH(export_kernel, 64, 256, 0, st)(Md, out); }
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st) {
-  partial_kernel<<<dim3((n_params + 7) / 8, nc), 256, 0, st>>>(Md, rec);
+  GWI_LAUNCH(partial_kernel, dim3((n_params + 7) / 8, nc), 256, 0, st)(Md, rec);
 }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
-  combine_kernel<<<nc, 256, 0, st>>>(Md, recs, R, o, out);
+  GWI_LAUNCH(combine_kernel, nc, 256, 0, st)(Md, recs, R, o, out);
 }
 
 }  // namespace gwi
