@@ -223,6 +223,7 @@ class DeviceBuffer:
         p = C.c_void_p()
         _cuda_check(rt.cudaMalloc(C.byref(p), max(1, self.n) * 8), "cudaMalloc")
         self.ptr = p.value
+        self._rt = rt  # freed by the runtime that allocated it
 
     def upload(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
@@ -236,7 +237,7 @@ class DeviceBuffer:
 
     def free(self):
         if self.ptr:
-            cudart().cudaFree(self.ptr)
+            self._rt.cudaFree(self.ptr)
             self.ptr = None
 
     def __del__(self):
@@ -352,10 +353,11 @@ class Catalog:
         h = C.c_void_p()
         _check(lib.gwi_catalog_create(C.byref(d), C.byref(h)))
         self.handle = h
+        self._owner = lib  # a handle is destroyed by the library that created it
 
     def close(self):
         if getattr(self, "handle", None):
-            load_library().gwi_catalog_destroy(self.handle)
+            self._owner.gwi_catalog_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -374,6 +376,7 @@ class HostPlan:
         h = C.c_void_p()
         _check(lib.gwi_debug_plan_build(catalog.handle, C.byref(self._d.desc), int(n_workers), C.byref(h)))
         self.handle = h
+        self._owner = lib
 
     def read(self, what, dtype=np.int64):
         lib = load_library()
@@ -386,7 +389,7 @@ class HostPlan:
 
     def close(self):
         if getattr(self, "handle", None):
-            load_library().gwi_debug_plan_destroy(self.handle)
+            self._owner.gwi_debug_plan_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -410,6 +413,7 @@ class Model:
         h = C.c_void_p()
         _check(lib.gwi_model_create(catalog.handle, C.byref(self._d.desc), C.byref(h)))
         self.handle = h
+        self._owner = lib
         self._bufs = None
 
     # -- introspection ---------------------------------------------------------------------
@@ -513,7 +517,7 @@ class Model:
 
     def close(self):
         if getattr(self, "handle", None):
-            load_library().gwi_model_destroy(self.handle)
+            self._owner.gwi_model_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

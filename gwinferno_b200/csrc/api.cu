@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <new>
@@ -27,6 +28,7 @@ void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaS
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st);
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st);
+void launch_epilogue(const ModelDev* Md, int n_tasks0, int rec_doubles, int mode, double* rec, const gwi_like_opts& o, double* out, int nc, cudaStream_t st);
 
 }  // namespace gwi
 
@@ -63,6 +65,9 @@ struct gwi_model {
   std::vector<std::pair<ReduceTask*, int>> level_tasks;  // device task arrays (static, shared by all chains)
   int n_chain_alloc = 1;                                  // descriptors / scratch sets allocated (chain batch)
   bool force_exact_shift = false;                         // gwi_model_set_exact_shift
+  // GWI_FUSED_EPILOGUE=1 (tuning switch, default off until measured on the GPU): reduction tree,
+  // per-segment finish, partial record and single-rank combine in ONE launch (epilogue_kernel)
+  bool fused_epilogue = false;
   double* partial_batch = nullptr;                        // [n_chain_alloc][PR_HEADER + 3P]
   int stream_grid_x = 1;
   stream_fn k_full = nullptr, k_max = nullptr;
@@ -286,6 +291,18 @@ static int alloc_chain_scratch(gwi_model* m, ModelDev& H) {
   UPS(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_J1));
   UPS(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_Jn));
   UPS(upload<double>(m, nullptr, (size_t)3 + 2 * P, &H.inj_raw));
+  {
+    // arrival counters of the fused epilogue (zeroed here; the kernel leaves them zero)
+    int n_counters = 0;
+    for (int l = 0; l < 6; ++l) H.epi_level_off[l] = 0;
+    for (size_t l = 1; l < p.levels.size(); ++l) {
+      H.epi_level_off[l] = n_counters;
+      n_counters += (int)p.levels[l].size();
+    }
+    H.epi_seg_counter = n_counters++;
+    H.epi_pad = 0;
+    UPS(upload<int32_t>(m, nullptr, (size_t)n_counters, &H.epi_counters));
+  }
   H.n_levels = (int)p.levels.size();
   for (int l = 0; l < 6; ++l) {
     H.level_buf[l] = nullptr;
@@ -547,15 +564,22 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     gwi_model_destroy(m);
     return GWI_ERR_CUDA;
   }
+  {
+    const char* e = std::getenv("GWI_FUSED_EPILOGUE");
+    m->fused_epilogue = e && e[0] == '1';
+  }
   m->stream_grid_x = std::max(1, std::min(p.grid_blocks, ((int)p.slice_begin.size() - 1 + p.warps_per_block - 1) / p.warps_per_block));
-  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
+  m->launches_per_eval = m->fused_epilogue ? 2 + (H.two_pass ? 2 : 0) + 1 + 1 : 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
   CUDA_TRY(cudaDeviceSynchronize());
   *out = m;
   return GWI_OK;
 }
 
-// launches prologue .. finish for `nc` chains on `st` (lam_dev: [nc][P])
-static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st, bool exact_shift = false) {
+// launches prologue .. finish for `nc` chains on `st` (lam_dev: [nc][P]).  epi_mode (fused epilogue
+// only): 0 = per-segment results, 1 = + partial record into `rec`, 2 = + single-rank combine into `out`;
+// returns with *epi_done = true when the fused kernel has already produced what epi_mode asks for.
+static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st, bool exact_shift = false, int epi_mode = 0, double* rec = nullptr,
+                    const gwi_like_opts* opts = nullptr, double* out = nullptr, bool* epi_done = nullptr) {
   const Plan& p = m->plan;
   const ModelDev& H = m->host;
   // fork: the grid normalisers (needed only by finish_kernel) overlap with the stream kernel
@@ -577,6 +601,15 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
   }
   const int n_levels = (int)m->level_tasks.size();
+  if (epi_done) *epi_done = false;
+  if (m->fused_epilogue) {
+    cudaStreamWaitEvent(st, m->ev_join, 0);  // join
+    gwi_like_opts none{};
+    launch_epilogue(m->dev, m->level_tasks[0].second, H.rec_doubles, epi_mode, rec, opts ? *opts : none, out, nc, st);
+    if (epi_done) *epi_done = true;
+    CUDA_TRY(cudaGetLastError());
+    return GWI_OK;
+  }
   for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, st);
   cudaStreamWaitEvent(st, m->ev_join, 0);  // join
   // the last reduction level (one task per segment) is fused into finish_kernel
@@ -612,9 +645,10 @@ int gwi_partial(gwi_model* m, const double* lambda_dev, double* record_dev, void
   }
   CUDA_TRY(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = run_eval(m, lambda_dev, 1, st);
+  bool done = false;
+  const int rc = run_eval(m, lambda_dev, 1, st, false, 1, record_dev, nullptr, nullptr, &done);
   if (rc != GWI_OK) return rc;
-  launch_partial(m->dev, record_dev, m->plan.n_params, 1, st);
+  if (!done) launch_partial(m->dev, record_dev, m->plan.n_params, 1, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -643,6 +677,23 @@ int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opt
     set_error("null argument");
     return GWI_ERR_INVALID;
   }
+  if (m->fused_epilogue) {
+    // same argument checks as gwi_partial + gwi_combine, then ONE epilogue launch does both
+    if (!lambda_dev || !opts || !out_dev) {
+      set_error("null argument");
+      return GWI_ERR_INVALID;
+    }
+    if (opts->marginalize_selection && !m->plan.g2) {
+      set_error("marginalize_selection needs a model created with need_neff_grad");
+      return GWI_ERR_INVALID;
+    }
+    if (opts->max_variance_cut && (opts->marginalize_selection || opts->min_neff_cut)) {
+      set_error("max_variance_cut requires marginalize_selection and min_neff_cut to be off (analysis.py:237-244)");
+      return GWI_ERR_INVALID;
+    }
+    CUDA_TRY(cudaSetDevice(m->device));
+    return run_eval(m, lambda_dev, 1, (cudaStream_t)stream, false, 2, m->partial_dev, opts, out_dev, nullptr);
+  }
   int rc = gwi_partial(m, lambda_dev, m->partial_dev, stream);
   if (rc != GWI_OK) return rc;
   return gwi_combine(m, m->partial_dev, 1, opts, out_dev, stream);
@@ -668,10 +719,13 @@ int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, 
   cudaStream_t st = (cudaStream_t)stream;
   // ONE launch of every kernel covers all chains (chain = a grid coordinate): the whole machine works
   // on the batch instead of one small catalog at a time
-  rc = run_eval(m, lambda_dev, n_chains, st);
+  bool done = false;
+  rc = run_eval(m, lambda_dev, n_chains, st, false, 2, m->partial_batch, opts, out_dev, &done);
   if (rc != GWI_OK) return rc;
-  launch_partial(m->dev, m->partial_batch, m->plan.n_params, n_chains, st);
-  launch_combine(m->dev, m->partial_batch, 1, *opts, out_dev, n_chains, st);
+  if (!done) {
+    launch_partial(m->dev, m->partial_batch, m->plan.n_params, n_chains, st);
+    launch_combine(m->dev, m->partial_batch, 1, *opts, out_dev, n_chains, st);
+  }
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }

@@ -86,6 +86,12 @@ struct ModelDev {
   double* seg_J1;     // [n_segments * P]
   double* seg_Jn;     // [n_segments * P]
   double* inj_raw;    // [3 + 2P] {shift, S1, S2, G1raw[P], G2raw[P]}
+  // fused epilogue (epilogue_kernel): arrival counters, one per reduction task of the levels >= 1
+  // (level l starts at epi_level_off[l]) and one for the finished segments at [epi_seg_counter];
+  // zero between evaluations (the last arriver resets the counter it consumed)
+  int32_t* epi_counters;
+  int32_t epi_level_off[6];
+  int32_t epi_seg_counter, epi_pad;
 };
 
 // partial (per-rank) likelihood record: 8 header doubles + 3P

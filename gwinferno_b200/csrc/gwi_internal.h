@@ -103,7 +103,7 @@ struct ReduceTask {
   int32_t out_slot;  // slot in the output buffer of this level
   int32_t in_first;  // first slot in the input buffer
   int32_t in_count;
-  int32_t pad;
+  int32_t parent;    // index (within the next level's task list) of the task that consumes out_slot; -1 on the last level
 };
 
 // Host-side evaluation plan ("what the stream kernel reads")

@@ -381,24 +381,9 @@ __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict_
 // =================================================================================================
 // finish: per segment
 // =================================================================================================
-__global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp) {
-  const ModelDev& M = Mp[blockIdx.y];
-  const double* __restrict__ in = M.n_levels > 1 ? M.level_buf[M.n_levels - 2] : M.records0;
-  const ReduceTask* __restrict__ tasks = M.level_tasks[M.n_levels - 1];
-  const int s = blockIdx.x;
+// per-segment results from the segment's summed record `rec` (in shared memory): all threads of the block
+__device__ void finish_segment(const ModelDev& M, int s, const double* rec) {
   const int P = M.n_params;
-  // last level of the record reduction (task s sums <= 64 records of segment s), fused in here
-  extern __shared__ double srec[];
-  {
-    const ReduceTask T = tasks[s];
-    for (int i = threadIdx.x; i < M.rec_doubles; i += blockDim.x) {
-      double acc = 0.0;
-      for (int r = 0; r < T.in_count; ++r) acc += in[(size_t)(T.in_first + r) * M.rec_doubles + i];
-      srec[i] = acc;
-    }
-    __syncthreads();
-  }
-  const double* rec = srec;
   const double S1 = rec[0], S2 = rec[1];
   const double shift = M.shift[s];
   const int ngs = M.n_gslots;
@@ -466,6 +451,25 @@ __global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp) {
+  const ModelDev& M = Mp[blockIdx.y];
+  const double* __restrict__ in = M.n_levels > 1 ? M.level_buf[M.n_levels - 2] : M.records0;
+  const ReduceTask* __restrict__ tasks = M.level_tasks[M.n_levels - 1];
+  const int s = blockIdx.x;
+  // last level of the record reduction (task s sums <= 64 records of segment s), fused in here
+  extern __shared__ double srec[];
+  {
+    const ReduceTask T = tasks[s];
+    for (int i = threadIdx.x; i < M.rec_doubles; i += blockDim.x) {
+      double acc = 0.0;
+      for (int r = 0; r < T.in_count; ++r) acc += in[(size_t)(T.in_first + r) * M.rec_doubles + i];
+      srec[i] = acc;
+    }
+    __syncthreads();
+  }
+  finish_segment(M, s, srec);
+}
+
 // gather the per-segment results into the caller's gwi_outputs buffers
 __global__ void export_kernel(const ModelDev* __restrict__ Mp, gwi_outputs out) {
   const ModelDev& M = Mp[0];
@@ -494,32 +498,39 @@ __global__ void export_kernel(const ModelDev* __restrict__ Mp, gwi_outputs out) 
 // =================================================================================================
 // likelihood: per-rank partial record, then the rank-ordered combine (analysis.py:257-319)
 // =================================================================================================
-__global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict__ Mp, double* __restrict__ recd0) {
-  const ModelDev& M = Mp[blockIdx.y];
-  double* __restrict__ recd = recd0 + (size_t)blockIdx.y * (PR_HEADER + 3 * M.n_params);
+template <bool CG>
+__device__ __forceinline__ double ldd(const double* p) {
+  return CG ? __ldcg(p) : *p;
+}
+
+// The rank's partial record.  Warp `gwarp` of `n_gwarps` takes the hyper-parameters gwarp, gwarp +
+// n_gwarps, ...; warp 0 also writes the header.  CG: the per-segment results were written by other
+// blocks of the SAME kernel (fused epilogue) and must be read through L2.
+template <bool CG>
+__device__ __forceinline__ void partial_rows(const ModelDev& M, double* recd, int gwarp, int n_gwarps) {
   const int P = M.n_params, E = M.n_segments - 1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  if (blockIdx.x == 0 && warp == 0) {
+  const int lane = threadIdx.x & 31;
+  if (gwarp == 0) {
     // header: fixed-order (lane-strided, then butterfly) sums over this rank's events
     double sum_logBF = 0.0, min_ln = INFINITY, sum_var = 0.0, status = 0.0;
     for (int e = 1 + lane; e <= E; e += 32) {
       const double* o = M.seg_out + (size_t)e * 4;
-      sum_logBF += o[0];
-      double ln = o[1];  // analysis.py:296: min over nan_to_num(logn_effs)
+      sum_logBF += ldd<CG>(o + 0);
+      double ln = ldd<CG>(o + 1);  // analysis.py:296: min over nan_to_num(logn_effs)
       if (ln != ln) ln = 0.0;
       ln = fmin(fmax(ln, -DBL_MAX), DBL_MAX);
       min_ln = fmin(min_ln, ln);
-      sum_var += o[2];
-      status = fmax(status, o[3]);
+      sum_var += ldd<CG>(o + 2);
+      status = fmax(status, ldd<CG>(o + 3));
     }
     sum_logBF = warp_sum(sum_logBF);
     sum_var = warp_sum(sum_var);
     min_ln = -warp_max(-min_ln);
     status = warp_max(status);
     if (lane == 0) {
-      recd[PR_SHIFT] = M.inj_raw[0];
-      recd[PR_S1] = M.inj_raw[1];
-      recd[PR_S2] = M.inj_raw[2];
+      recd[PR_SHIFT] = ldd<CG>(M.inj_raw + 0);
+      recd[PR_S1] = ldd<CG>(M.inj_raw + 1);
+      recd[PR_S2] = ldd<CG>(M.inj_raw + 2);
       recd[PR_SUM_LOGBF] = sum_logBF;
       recd[PR_MIN_LOGNEFF] = min_ln;
       recd[PR_SUM_VAR] = sum_var;
@@ -529,25 +540,31 @@ __global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict
     }
   }
   // one warp per hyper-parameter: sum_e J_logBF[e][i]
-  for (int i = blockIdx.x * wpb + warp; i < P; i += gridDim.x * wpb) {
+  for (int i = gwarp; i < P; i += n_gwarps) {
     double acc = 0.0;
-    for (int e = 1 + lane; e <= E; e += 32) acc += M.seg_J1[(size_t)e * P + i];
+    for (int e = 1 + lane; e <= E; e += 32) acc += ldd<CG>(M.seg_J1 + (size_t)e * P + i);
     acc = warp_sum(acc);
     if (lane == 0) {
-      recd[PR_HEADER + i] = M.inj_raw[3 + i];
-      recd[PR_HEADER + P + i] = M.inj_raw[3 + P + i];
+      recd[PR_HEADER + i] = ldd<CG>(M.inj_raw + 3 + i);
+      recd[PR_HEADER + P + i] = ldd<CG>(M.inj_raw + 3 + P + i);
       recd[PR_HEADER + 2 * P + i] = acc;
     }
   }
 }
 
-// blockIdx.x = chain: chain c combines the R records at recs0 + c*R*stride into out0 + c*(HEADER+P)
-__global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ recs0, int R, gwi_like_opts opts, double* __restrict__ out0) {
-  const ModelDev& M = Mp[blockIdx.x];
+__global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict__ Mp, double* __restrict__ recd0) {
+  const ModelDev& M = Mp[blockIdx.y];
+  double* __restrict__ recd = recd0 + (size_t)blockIdx.y * (PR_HEADER + 3 * M.n_params);
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  partial_rows<false>(M, recd, blockIdx.x * wpb + warp, gridDim.x * wpb);
+}
+
+// rank-ordered merge of R partial records + the likelihood glue: all threads of one block.  (`recs`
+// is deliberately not __restrict__/const-qualified for the read-only cache: the fused epilogue calls
+// this on a record the same block has just written.)
+__device__ void combine_records(const ModelDev& M, const double* recs, int R, const gwi_like_opts& opts, double* out) {
   const int P = M.n_params;
   const int stride = PR_HEADER + 3 * P;
-  const double* __restrict__ recs = recs0 + (size_t)blockIdx.x * R * stride;
-  double* __restrict__ out = out0 + (size_t)blockIdx.x * (GWI_LIKE_HEADER + P);
   const double N = M.total_inj;
   const double SENT = -DBL_MAX;  // nan_to_num(-inf)
   // injection sums of all ranks on a common shift
@@ -630,6 +647,90 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
   }
 }
 
+// blockIdx.x = chain: chain c combines the R records at recs0 + c*R*stride into out0 + c*(HEADER+P)
+__global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict__ Mp, const double* recs0, int R, gwi_like_opts opts, double* __restrict__ out0) {
+  const ModelDev& M = Mp[blockIdx.x];
+  const int P = M.n_params;
+  const int stride = PR_HEADER + 3 * P;
+  combine_records(M, recs0 + (size_t)blockIdx.x * R * stride, R, opts, out0 + (size_t)blockIdx.x * (GWI_LIKE_HEADER + P));
+}
+
+// =================================================================================================
+// fused epilogue: record reduction tree + per-segment finish + partial record (+ single-rank combine)
+// in ONE launch.  Block b starts with task b of reduction level 0; the block that delivers the LAST
+// input of a next-level task (arrival counter) goes on to execute that task, and so on up to the
+// segment's root, where it runs the per-segment finish; the block that finishes the last segment
+// writes the partial record and, for the single-rank likelihood, combines it.  Every task still sums
+// its inputs in the fixed order of the plan, so the results are bitwise those of the separate
+// reduce / finish / partial / combine kernels whichever block ends up doing the work.
+// mode: 0 = stop after the per-segment results, 1 = + partial record, 2 = + combine (R = 1).
+// =================================================================================================
+__global__ void __launch_bounds__(256) epilogue_kernel(const ModelDev* __restrict__ Mp, int mode, double* recd0, gwi_like_opts opts, double* out0) {
+  const ModelDev& M = Mp[blockIdx.y];  // blockIdx.y = chain
+  extern __shared__ double srec[];
+  __shared__ int ticket_s;
+  const int rec = M.rec_doubles;
+  const int last_level = M.n_levels - 1;
+  int level = 0, t = blockIdx.x;
+  for (;;) {
+    const ReduceTask T = M.level_tasks[level][t];
+    const double* in = level == 0 ? M.records0 : M.level_buf[level - 1];
+    if (level == last_level) {
+      // root of segment T.out_slot: sum into shared memory, then the per-segment results
+      for (int i = threadIdx.x; i < rec; i += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < T.in_count; ++r) acc += __ldcg(in + (size_t)(T.in_first + r) * rec + i);
+        srec[i] = acc;
+      }
+      __syncthreads();
+      finish_segment(M, T.out_slot, srec);
+      break;
+    }
+    double* out = M.level_buf[level];
+    for (int i = threadIdx.x; i < rec; i += blockDim.x) {
+      double acc = 0.0;
+      for (int r = 0; r < T.in_count; ++r) acc += __ldcg(in + (size_t)(T.in_first + r) * rec + i);
+      out[(size_t)T.out_slot * rec + i] = acc;
+    }
+    // publish, then count this input in at the consuming task
+    __threadfence();
+    __syncthreads();
+    const int parent_count = M.level_tasks[level + 1][T.parent].in_count;
+    int* counter = M.epi_counters + M.epi_level_off[level + 1] + T.parent;
+    if (threadIdx.x == 0) {
+      const int k = atomicAdd(counter, 1);
+      if (k == parent_count - 1) *counter = 0;  // last arriver: nobody else touches it in this evaluation
+      ticket_s = k;
+    }
+    __syncthreads();
+    const int k = ticket_s;
+    __syncthreads();  // ticket_s is rewritten on the next level
+    if (k != parent_count - 1) return;
+    __threadfence();
+    t = T.parent;
+    ++level;
+  }
+  if (mode == 0) return;
+  // ---- this block finished a segment: the last such block assembles the likelihood record ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* counter = M.epi_counters + M.epi_seg_counter;
+    const int k = atomicAdd(counter, 1);
+    if (k == M.n_segments - 1) *counter = 0;
+    ticket_s = k;
+  }
+  __syncthreads();
+  if (ticket_s != M.n_segments - 1) return;
+  __threadfence();
+  const int P = M.n_params;
+  double* recd = recd0 + (size_t)blockIdx.y * (PR_HEADER + 3 * P);
+  partial_rows<true>(M, recd, threadIdx.x >> 5, blockDim.x >> 5);
+  if (mode == 1) return;
+  __syncthreads();  // the record written above is read by other threads of this block below
+  combine_records(M, recd, 1, opts, out0 + (size_t)blockIdx.y * (GWI_LIKE_HEADER + P));
+}
+
 // =================================================================================================
 // host-side launch helpers (called from api.cu)
 // =================================================================================================
@@ -652,6 +753,9 @@ void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaS
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { GWI_LAUNCH(export_kernel, 64, 256, 0, st)(Md, out); }
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st) {
   GWI_LAUNCH(partial_kernel, dim3((n_params + 7) / 8, nc), 256, 0, st)(Md, rec);
+}
+void launch_epilogue(const ModelDev* Md, int n_tasks0, int rec_doubles, int mode, double* rec, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
+  GWI_LAUNCH(epilogue_kernel, dim3(n_tasks0, nc), 256, (size_t)rec_doubles * sizeof(double), st)(Md, mode, rec, o, out);
 }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
   GWI_LAUNCH(combine_kernel, nc, 256, 0, st)(Md, recs, R, o, out);

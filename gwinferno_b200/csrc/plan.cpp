@@ -1090,6 +1090,18 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       first.swap(nfirst);
       if (last) break;
     }
+    // parent links (used by the fused epilogue, where the block that delivers the last input of a
+    // task goes on to execute it): the consumer of out_slot o is the next-level task whose input
+    // range contains o
+    for (size_t l = 0; l < plan.levels.size(); ++l) {
+      for (auto& T : plan.levels[l]) T.parent = -1;
+      if (l + 1 == plan.levels.size()) break;
+      const auto& up = plan.levels[l + 1];
+      std::vector<int32_t> owner(plan.levels[l].size(), -1);
+      for (size_t t = 0; t < up.size(); ++t)
+        for (int i = 0; i < up[t].in_count; ++i) owner[up[t].in_first + i] = (int32_t)t;
+      for (auto& T : plan.levels[l]) T.parent = owner[T.out_slot];
+    }
   }
   return GWI_OK;
 }

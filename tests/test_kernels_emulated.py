@@ -31,11 +31,13 @@ del _name
 
 @pytest.fixture(scope="module", autouse=True)
 def _emulated_device():
+    variant = os.environ.get("GWI_EMU_VARIANT", "")  # an experiment build (tests/emu/Makefile VARIANT=), built by hand
     try:
-        emu.build()
+        if not variant:
+            emu.build()
     except Exception as e:  # no g++ / not x86-64
         pytest.skip(f"host emulator build failed: {e}")
-    emu.activate()
+    emu.activate(variant)
     yield
     emu.deactivate()
 
