@@ -51,6 +51,29 @@ class gwi_cut(C.Structure):
     _fields_ = [("kind", C.c_int32), ("col", C.c_int32 * 2), ("lo", C.c_double), ("hi", C.c_double)]
 
 
+class gwi_nuts_opts(C.Structure):
+    _fields_ = [("n_warmup", C.c_int32), ("n_samples", C.c_int32), ("max_depth", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_int64), ("target_accept", C.c_double)]
+
+
+class gwi_nuts_info(C.Structure):
+    _fields_ = [
+        ("step_size", C.c_double),
+        ("mean_accept", C.c_double),
+        ("sampling_seconds", C.c_double),
+        ("leapfrogs_sampling", C.c_int64),
+        ("leapfrogs_total", C.c_int64),
+        ("n_evals", C.c_int64),
+    ]
+
+
+class gwi_prior_block(C.Structure):
+    _fields_ = [("first", C.c_int32), ("count", C.c_int32), ("sigma", C.c_double), ("tau", C.c_double), ("diff_degree", C.c_int32), ("fix_first_zero", C.c_int32)]
+
+
+# double (*)(void* ctx, const double* theta, double* grad)
+POTENTIAL_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
 class gwi_model_desc(C.Structure):
     _fields_ = [
         ("n_terms", C.c_int32),
@@ -130,6 +153,12 @@ SYMBOLS = [
     "gwi_debug_plan_build",
     "gwi_debug_plan_destroy",
     "gwi_debug_plan_read",
+    "gwi_nuts_sample",
+    "gwi_posterior_create",
+    "gwi_posterior_destroy",
+    "gwi_posterior_dim",
+    "gwi_posterior_potential",
+    "gwi_nuts_sample_posterior",
 ]
 
 _lib = None
@@ -173,6 +202,14 @@ def load_library(_allow_emulator=False):
     lib.gwi_debug_plan_build.argtypes = [C.c_void_p, C.POINTER(gwi_model_desc), C.c_int32, C.POINTER(C.c_void_p)]
     lib.gwi_debug_plan_destroy.argtypes = [C.c_void_p]
     lib.gwi_debug_plan_destroy.restype = None
+    lib.gwi_nuts_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(gwi_nuts_opts), C.POINTER(C.c_double), C.POINTER(gwi_nuts_info)]
+    lib.gwi_posterior_create.argtypes = [C.c_void_p, C.POINTER(gwi_like_opts), C.POINTER(gwi_prior_block), C.c_int32, C.POINTER(C.c_void_p)]
+    lib.gwi_posterior_destroy.argtypes = [C.c_void_p]
+    lib.gwi_posterior_destroy.restype = None
+    lib.gwi_posterior_dim.argtypes = [C.c_void_p]
+    lib.gwi_posterior_potential.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.gwi_posterior_potential.restype = C.c_double
+    lib.gwi_nuts_sample_posterior.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(gwi_nuts_opts), C.POINTER(C.c_double), C.POINTER(gwi_nuts_info)]
     _lib = lib
     return lib
 
@@ -518,6 +555,82 @@ class Model:
     def close(self):
         if getattr(self, "handle", None):
             self._owner.gwi_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- native NUTS driver (csrc/nuts.cpp) ----------------------------------------------------------
+def _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept):
+    return gwi_nuts_opts(int(n_warmup), int(n_samples), int(max_depth), 0, int(seed), float(target_accept))
+
+
+def _nuts_info(i):
+    return {n: getattr(i, n) for n, _ in gwi_nuts_info._fields_}
+
+
+def nuts_sample(potential, theta0, n_warmup, n_samples, seed=0, target_accept=0.8, max_depth=8):
+    """gwi_nuts_sample on a Python potential ``theta -> (U, dU/dtheta)`` (tests, small problems: the
+    callback re-enters the interpreter once per leapfrog step).  Returns ``(samples, info)``."""
+    lib = load_library()
+    theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
+    dim = theta0.size
+
+    def _cb(_ctx, th, g):
+        u, grad = potential(np.ctypeslib.as_array(th, shape=(dim,)).copy())
+        np.ctypeslib.as_array(g, shape=(dim,))[:] = grad
+        return float(u)
+
+    cb = POTENTIAL_FN(_cb)
+    samples = np.empty((int(n_samples), dim), dtype=np.float64)
+    info = gwi_nuts_info()
+    o = _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept)
+    _check(lib.gwi_nuts_sample(C.cast(cb, C.c_void_p), None, dim, _dptr(theta0), C.byref(o), _dptr(samples), C.byref(info)))
+    return samples, _nuts_info(info)
+
+
+class Posterior:
+    """gwi_posterior: U(theta) = -(log L + log prior) of one Model, evaluated and sampled natively.
+    ``blocks``: iterable of ``(lambda_slice, prior_sigma, smoothing_tau or None, difference_degree,
+    fix_first_zero)`` -- the format of ``pipeline.bspline_prior_blocks`` / ``nuts.BSplinePosterior``."""
+
+    def __init__(self, model, blocks, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False):
+        lib = load_library()
+        self.model = model
+        blocks = list(blocks)
+        arr = (gwi_prior_block * max(1, len(blocks)))()
+        for i, (sl, sig, tau, deg, fix0) in enumerate(blocks):
+            arr[i] = gwi_prior_block(int(sl.start), int(sl.stop - sl.start), float(sig), -1.0 if tau is None else float(tau), int(deg), int(bool(fix0)))
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        h = C.c_void_p()
+        _check(lib.gwi_posterior_create(model.handle, C.byref(o), arr, len(blocks), C.byref(h)))
+        self.handle = h
+        self._owner = lib
+        self.dim = int(lib.gwi_posterior_dim(h))
+
+    def potential(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        assert theta.size == self.dim
+        grad = np.empty(self.dim, dtype=np.float64)
+        u = self._owner.gwi_posterior_potential(self.handle, _dptr(theta), _dptr(grad))
+        return float(u), grad
+
+    def sample(self, theta0, n_warmup, n_samples, seed=0, target_accept=0.8, max_depth=8):
+        theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
+        assert theta0.size == self.dim
+        samples = np.empty((int(n_samples), self.dim), dtype=np.float64)
+        info = gwi_nuts_info()
+        o = _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept)
+        _check(self._owner.gwi_nuts_sample_posterior(self.handle, _dptr(theta0), C.byref(o), _dptr(samples), C.byref(info)))
+        return samples, _nuts_info(info)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._owner.gwi_posterior_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

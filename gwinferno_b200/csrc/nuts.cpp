@@ -1,0 +1,453 @@
+// Host-side No-U-Turn sampler over the fused likelihood.
+//
+// The reference hands its likelihood to NumPyro: `NUTS(numpyro_model)` + `MCMC(...).run(...)`
+// (examples/utils.py:63-84; kernel table gwinferno/pipeline/analysis.py:21).  NumPyro/JAX do not exist
+// in this environment, and with a 0.1 ms GPU evaluation an interpreted sampler loop costs more than
+// the likelihood it drives, so the loop lives here: O(P) host arithmetic per leapfrog step around one
+// gwi_loglike_host call, no Python in between.  Two layers:
+//   * gwi_nuts_sample    -- the sampler for ANY potential given as a C callback (tests use it on
+//                           analytic targets; a JAX/NumPyro-free caller can plug its own model in);
+//   * gwi_posterior_*    -- the potential of the reference's B-spline analyses: -(log L + log prior)
+//                           with the Gaussian coefficient priors and the P-spline difference penalty
+//                           (gwinferno/models/bsplines/smoothing.py:8-28, pipeline/utils.py:163-216;
+//                           `fix_first_zero`: pipeline/utils.py:213-214).
+// Algorithm: Hoffman & Gelman (2014) Algorithm 6 -- slice-variant NUTS, dual-averaging step size,
+// diagonal mass matrix estimated once in the middle of warm-up -- the same as gwinferno_b200/nuts.py
+// (the NumPy implementation, kept as the readable specification and cross-check).
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "gwi_internal.h"
+
+namespace gwi {
+namespace {
+
+// xoshiro256++ seeded through splitmix64; normals by the polar method
+struct Rng {
+  uint64_t s[4];
+  bool have_spare = false;
+  double spare = 0.0;
+  explicit Rng(uint64_t seed) {
+    uint64_t z = seed;
+    for (int i = 0; i < 4; ++i) {
+      z += 0x9E3779B97F4A7C15ull;
+      uint64_t x = z;
+      x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+      x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+      s[i] = x ^ (x >> 31);
+    }
+  }
+  static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+  uint64_t next() {
+    const uint64_t r = rotl(s[0] + s[3], 23) + s[0];
+    const uint64_t t = s[1] << 17;
+    s[2] ^= s[0];
+    s[3] ^= s[1];
+    s[1] ^= s[2];
+    s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl(s[3], 45);
+    return r;
+  }
+  double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }  // [0, 1)
+  double normal() {
+    if (have_spare) {
+      have_spare = false;
+      return spare;
+    }
+    double u, v, q;
+    do {
+      u = 2.0 * uniform() - 1.0;
+      v = 2.0 * uniform() - 1.0;
+      q = u * u + v * v;
+    } while (q >= 1.0 || q == 0.0);
+    const double f = std::sqrt(-2.0 * std::log(q) / q);
+    spare = v * f;
+    have_spare = true;
+    return u * f;
+  }
+};
+
+typedef std::vector<double> Vec;
+
+struct Sampler {
+  gwi_potential_fn fn;
+  void* ctx;
+  int dim;
+  Vec inv_mass;
+  Rng rng;
+  int64_t n_evals = 0, n_leapfrog = 0;
+
+  Sampler(gwi_potential_fn f, void* c, int d, uint64_t seed) : fn(f), ctx(c), dim(d), inv_mass(d, 1.0), rng(seed) {}
+
+  double U(const Vec& theta, Vec& grad) {
+    ++n_evals;
+    double u = fn(ctx, theta.data(), grad.data());
+    if (!(u == u)) u = std::numeric_limits<double>::infinity();
+    return u;
+  }
+  double kinetic(const Vec& r) const {
+    double k = 0.0;
+    for (int i = 0; i < dim; ++i) k += inv_mass[i] * r[i] * r[i];
+    return 0.5 * k;
+  }
+  void draw_momentum(Vec& r) {
+    for (int i = 0; i < dim; ++i) r[i] = rng.normal() / std::sqrt(inv_mass[i]);
+  }
+  // one leapfrog step from (theta, r, grad) in place; returns the new potential
+  double leapfrog(Vec& theta, Vec& r, Vec& grad, double eps) {
+    for (int i = 0; i < dim; ++i) {
+      r[i] -= 0.5 * eps * grad[i];
+      theta[i] += eps * inv_mass[i] * r[i];
+    }
+    const double u = U(theta, grad);
+    for (int i = 0; i < dim; ++i) r[i] -= 0.5 * eps * grad[i];
+    return u;
+  }
+  static double finite_or_inf(double h) { return std::isfinite(h) ? h : std::numeric_limits<double>::infinity(); }
+
+  double find_reasonable_eps(const Vec& theta, double u0, const Vec& g0) {
+    double eps = 0.05;
+    Vec r(dim);
+    draw_momentum(r);
+    const double h0 = u0 + kinetic(r);
+    Vec th1 = theta, r1 = r, g1 = g0;
+    double u1 = leapfrog(th1, r1, g1, eps);
+    double h1 = u1 + kinetic(r1);
+    const double a = (std::isfinite(h1) && h0 - h1 > std::log(0.5)) ? 1.0 : -1.0;
+    for (int it = 0; it < 30; ++it) {
+      th1 = theta;
+      r1 = r;
+      g1 = g0;
+      u1 = leapfrog(th1, r1, g1, eps);
+      h1 = finite_or_inf(u1 + kinetic(r1));
+      if (a * (h0 - h1) <= -a * std::log(2.0)) break;
+      eps *= std::pow(2.0, a);
+    }
+    return eps;
+  }
+
+  struct Tree {
+    Vec thm, rm, gm, thp, rp, gp, th1, g1;
+    double u1 = 0.0;
+    int64_t n1 = 0;
+    int s1 = 0;
+    double alpha = 0.0;
+    int64_t n_alpha = 0;
+  };
+
+  bool no_uturn(const Vec& thm, const Vec& rm, const Vec& thp, const Vec& rp) const {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < dim; ++i) {
+      const double d = thp[i] - thm[i];
+      a += d * inv_mass[i] * rm[i];
+      b += d * inv_mass[i] * rp[i];
+    }
+    return a >= 0.0 && b >= 0.0;
+  }
+
+  // Algorithm 6, BuildTree(theta, r, u, v, j, eps, theta0, r0) with the joint log-density -H
+  void build_tree(const Vec& theta, const Vec& r, const Vec& grad, double logu, int v, int j, double eps, double h0, Tree& T) {
+    if (j == 0) {
+      T.th1 = theta;
+      T.thm = r;  // scratch: momentum
+      T.g1 = grad;
+      T.u1 = leapfrog(T.th1, T.thm, T.g1, v * eps);
+      ++n_leapfrog;
+      const double h1 = finite_or_inf(T.u1 + kinetic(T.thm));
+      T.rm = T.thm;
+      T.rp = T.thm;
+      T.thm = T.th1;
+      T.thp = T.th1;
+      T.gm = T.g1;
+      T.gp = T.g1;
+      T.n1 = logu <= -h1 ? 1 : 0;
+      T.s1 = logu < 1000.0 - h1 ? 1 : 0;
+      T.alpha = std::isfinite(h1) ? std::fmin(1.0, std::exp(std::fmin(0.0, h0 - h1))) : 0.0;
+      T.n_alpha = 1;
+      return;
+    }
+    build_tree(theta, r, grad, logu, v, j - 1, eps, h0, T);
+    if (T.s1 == 1) {
+      Tree T2;
+      if (v == -1) {
+        build_tree(T.thm, T.rm, T.gm, logu, v, j - 1, eps, h0, T2);
+        T.thm.swap(T2.thm);
+        T.rm.swap(T2.rm);
+        T.gm.swap(T2.gm);
+      } else {
+        build_tree(T.thp, T.rp, T.gp, logu, v, j - 1, eps, h0, T2);
+        T.thp.swap(T2.thp);
+        T.rp.swap(T2.rp);
+        T.gp.swap(T2.gp);
+      }
+      if (T.n1 + T2.n1 > 0 && rng.uniform() < (double)T2.n1 / (double)(T.n1 + T2.n1)) {
+        T.th1.swap(T2.th1);
+        T.g1.swap(T2.g1);
+        T.u1 = T2.u1;
+      }
+      T.alpha += T2.alpha;
+      T.n_alpha += T2.n_alpha;
+      T.s1 = T2.s1 * (no_uturn(T.thm, T.rm, T.thp, T.rp) ? 1 : 0);
+      T.n1 += T2.n1;
+    }
+  }
+
+  int run(const double* theta0, const gwi_nuts_opts& o, double* samples, gwi_nuts_info* info) {
+    Vec theta(theta0, theta0 + dim), grad(dim);
+    double u = U(theta, grad);
+    if (!std::isfinite(u)) {
+      set_error("NUTS: the potential is not finite at the starting point");
+      return GWI_ERR_INVALID;
+    }
+    double eps = find_reasonable_eps(theta, u, grad);
+    double mu = std::log(10.0 * eps);
+    const double gamma = 0.05, t0 = 10.0, kappa = 0.75;
+    double eps_bar = 1.0, Hbar = 0.0;
+    std::vector<Vec> warm;
+    double accept_sum = 0.0;
+    int64_t leapfrog_sampling0 = 0;
+    auto t_sampling = std::chrono::steady_clock::now();
+    Vec r0(dim), thm, thp, rm, rp, gm, gp;
+    const int n_total = o.n_warmup + o.n_samples;
+    for (int m = 0; m < n_total; ++m) {
+      if (m == o.n_warmup) {
+        t_sampling = std::chrono::steady_clock::now();
+        leapfrog_sampling0 = n_leapfrog;
+      }
+      draw_momentum(r0);
+      const double h0 = u + kinetic(r0);
+      const double logu = std::log(rng.uniform()) - h0;
+      thm = thp = theta;
+      rm = rp = r0;
+      gm = gp = grad;
+      int j = 0, s = 1;
+      int64_t n = 1;
+      const double step = m < o.n_warmup ? eps : eps_bar;
+      double a = 0.0;
+      int64_t na = 1;
+      while (s == 1 && j < o.max_depth) {
+        const int v = rng.uniform() < 0.5 ? -1 : 1;
+        Tree T;
+        if (v == -1) {
+          build_tree(thm, rm, gm, logu, v, j, step, h0, T);
+          thm.swap(T.thm);
+          rm.swap(T.rm);
+          gm.swap(T.gm);
+        } else {
+          build_tree(thp, rp, gp, logu, v, j, step, h0, T);
+          thp.swap(T.thp);
+          rp.swap(T.rp);
+          gp.swap(T.gp);
+        }
+        if (T.s1 == 1 && rng.uniform() < std::fmin(1.0, (double)T.n1 / (double)n)) {
+          theta.swap(T.th1);
+          grad.swap(T.g1);
+          u = T.u1;
+        }
+        n += T.n1;
+        s = T.s1 * (no_uturn(thm, rm, thp, rp) ? 1 : 0);
+        a = T.alpha;
+        na = T.n_alpha;
+        ++j;
+      }
+      const double acc = a / (double)(na > 0 ? na : 1);
+      if (m < o.n_warmup) {
+        const double mm = (double)(m + 1);
+        Hbar = (1.0 - 1.0 / (mm + t0)) * Hbar + (o.target_accept - acc) / (mm + t0);
+        eps = std::exp(mu - std::sqrt(mm) / gamma * Hbar);
+        const double eta = std::pow(mm, -kappa);
+        eps_bar = std::exp(eta * std::log(eps) + (1.0 - eta) * std::log(eps_bar));
+        warm.push_back(theta);
+        // one mass-matrix update in the middle of warm-up (diagonal, regularised sample variance)
+        if (m + 1 == o.n_warmup / 2 && warm.size() >= 20) {
+          const size_t first = warm.size() / 4, nn = warm.size() - first;
+          for (int i = 0; i < dim; ++i) {
+            double mean = 0.0;
+            for (size_t k = first; k < warm.size(); ++k) mean += warm[k][i];
+            mean /= (double)nn;
+            double var = 0.0;
+            for (size_t k = first; k < warm.size(); ++k) var += (warm[k][i] - mean) * (warm[k][i] - mean);
+            var /= (double)nn;
+            inv_mass[i] = ((double)nn / ((double)nn + 5.0)) * var + 1e-3 * (5.0 / ((double)nn + 5.0));
+          }
+          u = U(theta, grad);
+          eps = find_reasonable_eps(theta, u, grad);
+          mu = std::log(10.0 * eps);
+          eps_bar = 1.0;
+          Hbar = 0.0;
+        }
+      } else {
+        std::memcpy(samples + (size_t)(m - o.n_warmup) * dim, theta.data(), sizeof(double) * dim);
+        accept_sum += acc;
+      }
+    }
+    if (info) {
+      info->step_size = eps_bar;
+      info->mean_accept = o.n_samples > 0 ? accept_sum / o.n_samples : 0.0;
+      info->sampling_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sampling).count();
+      info->leapfrogs_sampling = n_leapfrog - leapfrog_sampling0;
+      info->leapfrogs_total = n_leapfrog;
+      info->n_evals = n_evals;
+    }
+    return GWI_OK;
+  }
+};
+
+}  // namespace
+}  // namespace gwi
+
+using namespace gwi;
+
+// -(log L + log prior) of one gwi_model: Lambda = theta scattered into the free slots
+struct gwi_posterior {
+  gwi_model* model = nullptr;
+  gwi_like_opts opts{};
+  int n_params = 0, dim = 0;
+  std::vector<int> free_slot;  // free_slot[i] = Lambda index of theta[i]
+  struct Block {
+    int first, count;
+    std::vector<double> Q;  // count x count: I / sigma^2 + tau D^T D
+  };
+  std::vector<Block> blocks;
+  std::vector<double> lam, out, gp;
+  int last_rc = GWI_OK;
+  int64_t n_evals = 0;
+};
+
+extern "C" {
+
+int gwi_nuts_sample(gwi_potential_fn fn, void* ctx, int32_t dim, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info) {
+  if (!fn || dim < 1 || !theta0 || !opts || (!samples && opts->n_samples > 0) || opts->n_warmup < 0 || opts->n_samples < 0 || opts->max_depth < 1 ||
+      opts->max_depth > 20 || !(opts->target_accept > 0.0 && opts->target_accept < 1.0)) {
+    set_error("gwi_nuts_sample: bad argument");
+    return GWI_ERR_INVALID;
+  }
+  try {
+    Sampler S(fn, ctx, dim, (uint64_t)opts->seed);
+    return S.run(theta0, *opts, samples, info);
+  } catch (const std::bad_alloc&) {
+    set_error("out of host memory in the sampler");
+    return GWI_ERR_ALLOC;
+  }
+}
+
+int gwi_posterior_create(gwi_model* m, const gwi_like_opts* opts, const gwi_prior_block* blocks, int32_t n_blocks, gwi_posterior** out) {
+  if (!m || !opts || !out || n_blocks < 0 || (n_blocks > 0 && !blocks)) {
+    set_error("gwi_posterior_create: null argument");
+    return GWI_ERR_INVALID;
+  }
+  const int64_t psize = gwi_partial_size(m);
+  if (psize < 0) return GWI_ERR_INVALID;
+  const int P = (int)((psize - 8) / 3);  // PR_HEADER + 3P
+  gwi_posterior* p = new (std::nothrow) gwi_posterior();
+  if (!p) return GWI_ERR_ALLOC;
+  try {
+    p->model = m;
+    p->opts = *opts;
+    p->n_params = P;
+    std::vector<char> is_free(P, 1);
+    for (int b = 0; b < n_blocks; ++b) {
+      const gwi_prior_block& B = blocks[b];
+      if (B.first < 0 || B.count < 1 || B.first + B.count > P || !(B.sigma > 0.0) || B.diff_degree < 0) {
+        delete p;
+        set_error("gwi_posterior_create: prior block outside the parameter vector, or sigma <= 0");
+        return GWI_ERR_INVALID;
+      }
+      if (B.fix_first_zero) is_free[B.first] = 0;
+      gwi_posterior::Block X;
+      X.first = B.first;
+      X.count = B.count;
+      const int n = B.count;
+      X.Q.assign((size_t)n * n, 0.0);
+      for (int i = 0; i < n; ++i) X.Q[(size_t)i * n + i] = 1.0 / (B.sigma * B.sigma);
+      if (B.tau >= 0.0 && n > B.diff_degree) {
+        // D = diff(I, n = degree): rows of binomial coefficients with alternating sign
+        const int deg = B.diff_degree, rows = n - deg;
+        std::vector<double> coef(deg + 1, 0.0);
+        coef[0] = 1.0;
+        for (int k = 0; k < deg; ++k) {
+          for (int i = k + 1; i >= 1; --i) coef[i] = coef[i - 1] - coef[i];
+          coef[0] = -coef[0];
+        }
+        for (int r = 0; r < rows; ++r)
+          for (int a = 0; a <= deg; ++a)
+            for (int c = 0; c <= deg; ++c) X.Q[(size_t)(r + a) * n + (r + c)] += B.tau * coef[a] * coef[c];
+      }
+      p->blocks.push_back(std::move(X));
+    }
+    for (int i = 0; i < P; ++i)
+      if (is_free[i]) p->free_slot.push_back(i);
+    p->dim = (int)p->free_slot.size();
+    p->lam.assign(P, 0.0);
+    p->gp.assign(P, 0.0);
+    p->out.assign((size_t)GWI_LIKE_HEADER + P, 0.0);
+  } catch (const std::bad_alloc&) {
+    delete p;
+    return GWI_ERR_ALLOC;
+  }
+  *out = p;
+  return GWI_OK;
+}
+
+void gwi_posterior_destroy(gwi_posterior* p) { delete p; }
+
+int gwi_posterior_dim(const gwi_posterior* p) { return p ? p->dim : (int)GWI_ERR_INVALID; }
+
+// matches gwi_potential_fn (ctx = the gwi_posterior); +inf where the likelihood's cuts fail (the
+// reference's nan_to_num(-inf) sentinel, analysis.py:272-277) or the evaluation reports an error
+double gwi_posterior_potential(void* ctx, const double* theta, double* grad) {
+  gwi_posterior* p = static_cast<gwi_posterior*>(ctx);
+  const int P = p->n_params;
+  const double inf = std::numeric_limits<double>::infinity();
+  std::fill(p->lam.begin(), p->lam.end(), 0.0);
+  for (int i = 0; i < p->dim; ++i) p->lam[p->free_slot[i]] = theta[i];
+  ++p->n_evals;
+  const int rc = gwi_loglike_host(p->model, p->lam.data(), &p->opts, p->out.data());
+  for (int i = 0; i < p->dim; ++i) grad[i] = 0.0;
+  if (rc != GWI_OK) {
+    if (rc != GWI_ERR_RANGE) p->last_rc = rc;
+    return inf;
+  }
+  const double log_l = p->out[GWI_LIKE_LOG_L];
+  if (!std::isfinite(log_l) || log_l < -1e300) return inf;
+  double lp = 0.0;
+  std::fill(p->gp.begin(), p->gp.end(), 0.0);
+  for (const auto& B : p->blocks) {
+    const double* c = p->lam.data() + B.first;
+    const int n = B.count;
+    for (int i = 0; i < n; ++i) {
+      double qc = 0.0;
+      const double* row = B.Q.data() + (size_t)i * n;
+      for (int j = 0; j < n; ++j) qc += row[j] * c[j];
+      lp -= 0.5 * c[i] * qc;
+      p->gp[B.first + i] -= qc;
+    }
+  }
+  for (int i = 0; i < p->dim; ++i) {
+    const int s = p->free_slot[i];
+    grad[i] = -(p->out[GWI_LIKE_HEADER + s] + p->gp[s]);
+  }
+  return -(log_l + lp);
+}
+
+int gwi_nuts_sample_posterior(gwi_posterior* p, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info) {
+  if (!p) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  p->last_rc = GWI_OK;
+  const int64_t before = p->n_evals;
+  const int rc = gwi_nuts_sample(gwi_posterior_potential, p, p->dim, theta0, opts, samples, info);
+  if (info) info->n_evals = p->n_evals - before;
+  if (rc != GWI_OK) return rc;
+  return p->last_rc;  // a CUDA / argument error inside an evaluation surfaces here
+}
+
+}  // extern "C"

@@ -13,6 +13,8 @@ import time
 
 import numpy as np
 
+from . import capi
+
 
 class BSplinePosterior:
     """Potential energy U(theta) = -(log L + log prior) of the cfg-2/3 B-spline model
@@ -29,6 +31,15 @@ class BSplinePosterior:
                 self.free[sl.start] = False  # z_cs = concatenate([0], sampled)  (pipeline/utils.py:213-214)
         self.dim = int(self.free.sum())
         self.n_evals = 0
+        # per block Q = I / sigma^2 + tau D^T D (D = difference matrix), so that log prior = -c.Q.c / 2
+        self._Q = []
+        for sl, sig, tau, deg, _ in blocks:
+            n = sl.stop - sl.start
+            Q = np.eye(n) / sig**2
+            if tau is not None and n > deg:
+                D = np.diff(np.eye(n), n=deg, axis=0)
+                Q = Q + tau * (D.T @ D)  # apply_difference_prior (smoothing.py:26-28)
+            self._Q.append(Q)
 
     def to_lambda(self, theta):
         lam = np.zeros(self.n_params)
@@ -37,15 +48,11 @@ class BSplinePosterior:
 
     def log_prior(self, lam):
         lp, g = 0.0, np.zeros(self.n_params)
-        for sl, sig, tau, deg, _ in self.blocks:
+        for (sl, _, _, _, _), Q in zip(self.blocks, self._Q):
             c = lam[sl]
-            lp += -0.5 * np.sum(c * c) / sig**2
-            g[sl] += -c / sig**2
-            if tau is not None and c.size > deg:
-                D = np.diff(np.eye(c.size), n=deg, axis=0)
-                d = D @ c
-                lp += -0.5 * tau * d @ d  # apply_difference_prior (smoothing.py:26-28)
-                g[sl] += -tau * (D.T @ d)
+            qc = Q @ c
+            lp += -0.5 * (c @ qc)
+            g[sl] -= qc
         return lp, g
 
     def __call__(self, theta):
@@ -174,6 +181,19 @@ def nuts(U, theta0, n_warmup, n_samples, rng, target_accept=0.8, max_depth=8):
     info = dict(step_size=float(eps_bar), mean_accept=float(np.mean(accept_stat)), sampling_seconds=dt,
                 leapfrogs_sampling=int(n_leapfrog - n_leapfrog_sampling0), leapfrogs_total=int(n_leapfrog))
     return samples, info
+
+
+def nuts_native(engine, blocks, theta0, n_warmup, n_samples, Nobs=None, seed=0, target_accept=0.8, max_depth=8, **like_kw):
+    """The same sampler with the whole transition loop in native code (csrc/nuts.cpp,
+    gwi_nuts_sample_posterior): ``engine`` is a :class:`~gwinferno_b200.likelihood.PopulationLikelihood`,
+    ``blocks`` as for :class:`BSplinePosterior`.  One gwi_loglike_host call per leapfrog step and no
+    interpreter in between -- use this when the likelihood is cheaper than ~1 ms.  Returns
+    ``(samples[n_samples, dim], info)``; ``info`` has the keys of :func:`nuts` plus ``n_evals``."""
+    post = capi.Posterior(engine.model, blocks, engine.n_events if Nobs is None else Nobs, **like_kw)
+    try:
+        return post.sample(theta0, n_warmup, n_samples, seed=seed, target_accept=target_accept, max_depth=max_depth)
+    finally:
+        post.close()
 
 
 def effective_sample_size(x):

@@ -250,6 +250,55 @@ int gwi_model_set_exact_shift(gwi_model* m, int32_t on);
 int gwi_model_set_timing(gwi_model* m, int32_t on);
 int gwi_model_stream_times(gwi_model* m, float* ms_out, int32_t cap);
 
+/* ---- sampler: the host-side NUTS loop around gwi_loglike_host ------------------------------
+ * The reference gives its likelihood to NumPyro -- `NUTS(numpyro_model)`, `MCMC(kernel, num_warmup,
+ * num_samples).run(...)` (examples/utils.py:63-84, gwinferno/pipeline/analysis.py:21).  These entry
+ * points are what that pair is replaced by where JAX/NumPyro do not exist: the whole transition loop
+ * (Hoffman & Gelman 2014, Algorithm 6: slice-variant NUTS, dual-averaging step size, diagonal mass
+ * matrix estimated once in the middle of warm-up) runs in native code, so an evaluation that takes
+ * 0.1 ms on the GPU is not throttled by an interpreter between leapfrog steps.
+ *
+ * gwi_nuts_sample works on ANY potential U(theta) = -log p(theta) given as a callback that writes
+ * dU/dtheta and returns U (+inf = reject); samples is [n_samples][dim], row-major. */
+typedef double (*gwi_potential_fn)(void* ctx, const double* theta, double* grad);
+typedef struct {
+  int32_t n_warmup, n_samples;
+  int32_t max_depth;     /* maximum tree depth (NumPyro: max_tree_depth), 1..20 */
+  int32_t reserved;
+  int64_t seed;
+  double target_accept;  /* dual-averaging target of the mean acceptance statistic, e.g. 0.8 */
+} gwi_nuts_opts;
+typedef struct {
+  double step_size;      /* the adapted (averaged) step size used after warm-up */
+  double mean_accept;
+  double sampling_seconds;   /* wall time of the post-warm-up transitions */
+  int64_t leapfrogs_sampling, leapfrogs_total;
+  int64_t n_evals;       /* potential + gradient evaluations, warm-up included */
+} gwi_nuts_info;
+int gwi_nuts_sample(gwi_potential_fn fn, void* ctx, int32_t dim, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info);
+
+/* The potential of the reference's B-spline analyses, U = -(log L(Lambda) + log prior(Lambda)):
+ * log L from gwi_loglike_host with `opts`; per coefficient block c = Lambda[first : first+count] a
+ * Normal(0, sigma) prior plus, when tau >= 0, the P-spline smoothing penalty -tau/2 |D c|^2 with D the
+ * diff_degree-th difference matrix (gwinferno/models/bsplines/smoothing.py:8-28; the prior helpers
+ * of gwinferno/pipeline/utils.py:163-216).  fix_first_zero pins the block's first coefficient at 0
+ * and removes it from theta (pipeline/utils.py:213-214).  Slots outside every block have a flat
+ * prior.  theta = the free slots of Lambda in increasing order (gwi_posterior_dim of them).
+ * gwi_posterior_potential has the gwi_potential_fn signature (ctx = the gwi_posterior). */
+typedef struct {
+  int32_t first, count;
+  double sigma;
+  double tau;            /* < 0: no smoothing penalty */
+  int32_t diff_degree;
+  int32_t fix_first_zero;
+} gwi_prior_block;
+typedef struct gwi_posterior gwi_posterior;
+int gwi_posterior_create(gwi_model* m, const gwi_like_opts* opts, const gwi_prior_block* blocks, int32_t n_blocks, gwi_posterior** out);
+void gwi_posterior_destroy(gwi_posterior* p);
+int gwi_posterior_dim(const gwi_posterior* p);
+double gwi_posterior_potential(void* posterior, const double* theta, double* grad);
+int gwi_nuts_sample_posterior(gwi_posterior* p, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info);
+
 const char* gwi_last_error(void);
 int gwi_version(void);
 

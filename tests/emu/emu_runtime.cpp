@@ -197,15 +197,27 @@ static void prepare_fiber(Fiber& f) {
   f.sp = s;
 }
 
+// fiber stacks are recycled between launches (a fresh mapping would page-fault on every first touch)
+static std::mutex g_stack_mutex;
+static std::vector<char*> g_free_stacks;
+
 struct Worker {
   Block block;
   std::vector<char*> stacks;
   ~Worker() {
-    for (char* s : stacks) munmap(s, STACK_BYTES);
+    std::lock_guard<std::mutex> lock(g_stack_mutex);
+    for (char* s : stacks) g_free_stacks.push_back(s);
   }
   void run_block(dim3 grid, dim3 bdim, uint3 bidx, Body& body) {
     const int n = (int)(bdim.x * bdim.y * bdim.z);
     Block& b = block;
+    if ((int)stacks.size() < n) {
+      std::lock_guard<std::mutex> lock(g_stack_mutex);
+      while ((int)stacks.size() < n && !g_free_stacks.empty()) {
+        stacks.push_back(g_free_stacks.back());
+        g_free_stacks.pop_back();
+      }
+    }
     while ((int)stacks.size() < n) {
       void* p = mmap(nullptr, STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
       if (p == MAP_FAILED) {

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     import os, re
 
     hdr = open(os.path.join(os.path.dirname(capi._HERE), "include", "gwi.h")).read()
-    declared = set(re.findall(r"^(?:int|void|int64_t|const char\*)\s+(gwi_[a-z_]+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|void|int64_t|double|const char\*)\s+(gwi_[a-z_]+)\s*\(", hdr, flags=re.M))
     assert declared == set(capi.SYMBOLS)
 
 

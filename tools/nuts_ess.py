@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=150)
     ap.add_argument("--samples", type=int, default=200)
     ap.add_argument("--max-depth", type=int, default=8)
+    ap.add_argument("--driver", choices=["native", "numpy"], default="native",
+                    help="native: the whole NUTS loop in libgwi (csrc/nuts.cpp); numpy: gwinferno_b200/nuts.py around gwi_loglike_host")
     args = ap.parse_args()
     pe, inj, const, z_range = workloads.shard_catalog(args.workload, 0, 1, scale=args.scale)
     weights, params_fn = workloads.build_model(const["family"], pe, inj, z_range=z_range)
@@ -42,7 +44,11 @@ def main():
     rng = np.random.default_rng(0)
     theta0 = 0.1 * rng.standard_normal(post.dim)
     t0 = time.perf_counter()
-    samples, info = nuts.nuts(post, theta0, args.warmup, args.samples, rng, max_depth=args.max_depth)
+    if args.driver == "native":
+        samples, info = nuts.nuts_native(eng, blocks, theta0, args.warmup, args.samples, Nobs=Nobs, seed=0, max_depth=args.max_depth)
+        post.n_evals = info["n_evals"]
+    else:
+        samples, info = nuts.nuts(post, theta0, args.warmup, args.samples, rng, max_depth=args.max_depth)
     wall = time.perf_counter() - t0
     ess = np.array([nuts.effective_sample_size(samples[:, i]) for i in range(samples.shape[1])])
     out = {
@@ -51,7 +57,8 @@ def main():
         "ess_min": float(ess.min()), "ess_median": float(np.median(ess)),
         "ess_min_per_s": float(ess.min() / info["sampling_seconds"]), "ess_median_per_s": float(np.median(ess) / info["sampling_seconds"]),
         "grad_evals_total": post.n_evals, "grad_evals_per_s_overall": post.n_evals / wall, "wall_s": wall, **info,
-        "sampler": "gwinferno_b200/nuts.py (NumPy NUTS, diagonal mass); likelihood+gradient on the GPU via gwi_loglike_host",
+        "sampler": ("csrc/nuts.cpp (native NUTS loop, diagonal mass)" if args.driver == "native" else "gwinferno_b200/nuts.py (NumPy NUTS, diagonal mass)")
+        + "; likelihood+gradient on the GPU via gwi_loglike_host",
     }
     print(json.dumps(out))
 
