@@ -52,7 +52,7 @@ class gwi_cut(C.Structure):
 
 
 class gwi_nuts_opts(C.Structure):
-    _fields_ = [("n_warmup", C.c_int32), ("n_samples", C.c_int32), ("max_depth", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_int64), ("target_accept", C.c_double)]
+    _fields_ = [("n_warmup", C.c_int32), ("n_samples", C.c_int32), ("max_depth", C.c_int32), ("flags", C.c_int32), ("seed", C.c_int64), ("target_accept", C.c_double)]
 
 
 class gwi_nuts_info(C.Structure):
@@ -565,15 +565,18 @@ class Model:
 
 
 # ---- native NUTS driver (csrc/nuts.cpp) ----------------------------------------------------------
-def _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept):
-    return gwi_nuts_opts(int(n_warmup), int(n_samples), int(max_depth), 0, int(seed), float(target_accept))
+NUTS_MULTINOMIAL, NUTS_WINDOWED_ADAPT, NUTS_DENSE_MASS = 1, 2, 4  # include/gwi.h: GWI_NUTS_*
+
+
+def _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept, flags=0):
+    return gwi_nuts_opts(int(n_warmup), int(n_samples), int(max_depth), int(flags), int(seed), float(target_accept))
 
 
 def _nuts_info(i):
     return {n: getattr(i, n) for n, _ in gwi_nuts_info._fields_}
 
 
-def nuts_sample(potential, theta0, n_warmup, n_samples, seed=0, target_accept=0.8, max_depth=8):
+def nuts_sample(potential, theta0, n_warmup, n_samples, seed=0, target_accept=0.8, max_depth=8, flags=0):
     """gwi_nuts_sample on a Python potential ``theta -> (U, dU/dtheta)`` (tests, small problems: the
     callback re-enters the interpreter once per leapfrog step).  Returns ``(samples, info)``."""
     lib = load_library()
@@ -588,7 +591,7 @@ def nuts_sample(potential, theta0, n_warmup, n_samples, seed=0, target_accept=0.
     cb = POTENTIAL_FN(_cb)
     samples = np.empty((int(n_samples), dim), dtype=np.float64)
     info = gwi_nuts_info()
-    o = _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept)
+    o = _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept, flags)
     _check(lib.gwi_nuts_sample(C.cast(cb, C.c_void_p), None, dim, _dptr(theta0), C.byref(o), _dptr(samples), C.byref(info)))
     return samples, _nuts_info(info)
 
@@ -619,12 +622,12 @@ class Posterior:
         u = self._owner.gwi_posterior_potential(self.handle, _dptr(theta), _dptr(grad))
         return float(u), grad
 
-    def sample(self, theta0, n_warmup, n_samples, seed=0, target_accept=0.8, max_depth=8):
+    def sample(self, theta0, n_warmup, n_samples, seed=0, target_accept=0.8, max_depth=8, flags=0):
         theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
         assert theta0.size == self.dim
         samples = np.empty((int(n_samples), self.dim), dtype=np.float64)
         info = gwi_nuts_info()
-        o = _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept)
+        o = _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept, flags)
         _check(self._owner.gwi_nuts_sample_posterior(self.handle, _dptr(theta0), C.byref(o), _dptr(samples), C.byref(info)))
         return samples, _nuts_info(info)
 

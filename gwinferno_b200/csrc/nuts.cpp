@@ -14,6 +14,7 @@
 // Algorithm: Hoffman & Gelman (2014) Algorithm 6 -- slice-variant NUTS, dual-averaging step size,
 // diagonal mass matrix estimated once in the middle of warm-up -- the same as gwinferno_b200/nuts.py
 // (the NumPy implementation, kept as the readable specification and cross-check).
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -80,7 +81,12 @@ struct Sampler {
   gwi_potential_fn fn;
   void* ctx;
   int dim;
-  Vec inv_mass;
+  Vec inv_mass;  // diagonal of the inverse mass matrix (= variance estimate of the target)
+  // dense variant (GWI_NUTS_DENSE_MASS): inverse mass = covariance estimate `cov` (row-major), its lower
+  // Cholesky factor `chol` for the momentum draws; used once the first slow window has been estimated
+  bool dense = false, want_dense = false;
+  Vec cov, chol;
+  mutable Vec tmp_v;
   Rng rng;
   int64_t n_evals = 0, n_leapfrog = 0;
 
@@ -92,19 +98,51 @@ struct Sampler {
     if (!(u == u)) u = std::numeric_limits<double>::infinity();
     return u;
   }
+  // v = M^-1 r
+  void velocity(const Vec& r, Vec& v) const {
+    v.resize(dim);
+    if (!dense) {
+      for (int i = 0; i < dim; ++i) v[i] = inv_mass[i] * r[i];
+      return;
+    }
+    for (int i = 0; i < dim; ++i) {
+      const double* row = cov.data() + (size_t)i * dim;
+      double a = 0.0;
+      for (int j = 0; j < dim; ++j) a += row[j] * r[j];
+      v[i] = a;
+    }
+  }
   double kinetic(const Vec& r) const {
     double k = 0.0;
-    for (int i = 0; i < dim; ++i) k += inv_mass[i] * r[i] * r[i];
+    if (!dense) {
+      for (int i = 0; i < dim; ++i) k += inv_mass[i] * r[i] * r[i];
+      return 0.5 * k;
+    }
+    velocity(r, tmp_v);
+    for (int i = 0; i < dim; ++i) k += r[i] * tmp_v[i];
     return 0.5 * k;
   }
+  // r ~ N(0, M), M = cov^-1 = (L L^T)^-1  =>  r = L^-T z
   void draw_momentum(Vec& r) {
-    for (int i = 0; i < dim; ++i) r[i] = rng.normal() / std::sqrt(inv_mass[i]);
+    if (!dense) {
+      for (int i = 0; i < dim; ++i) r[i] = rng.normal() / std::sqrt(inv_mass[i]);
+      return;
+    }
+    for (int i = 0; i < dim; ++i) r[i] = rng.normal();
+    for (int i = dim - 1; i >= 0; --i) {
+      double a = r[i];
+      for (int j = i + 1; j < dim; ++j) a -= chol[(size_t)j * dim + i] * r[j];
+      r[i] = a / chol[(size_t)i * dim + i];
+    }
   }
   // one leapfrog step from (theta, r, grad) in place; returns the new potential
   double leapfrog(Vec& theta, Vec& r, Vec& grad, double eps) {
-    for (int i = 0; i < dim; ++i) {
-      r[i] -= 0.5 * eps * grad[i];
-      theta[i] += eps * inv_mass[i] * r[i];
+    for (int i = 0; i < dim; ++i) r[i] -= 0.5 * eps * grad[i];
+    if (!dense) {
+      for (int i = 0; i < dim; ++i) theta[i] += eps * inv_mass[i] * r[i];
+    } else {
+      velocity(r, tmp_v);
+      for (int i = 0; i < dim; ++i) theta[i] += eps * tmp_v[i];
     }
     const double u = U(theta, grad);
     for (int i = 0; i < dim; ++i) r[i] -= 0.5 * eps * grad[i];
@@ -144,10 +182,13 @@ struct Sampler {
 
   bool no_uturn(const Vec& thm, const Vec& rm, const Vec& thp, const Vec& rp) const {
     double a = 0.0, b = 0.0;
+    Vec vm, vp;
+    velocity(rm, vm);
+    velocity(rp, vp);
     for (int i = 0; i < dim; ++i) {
       const double d = thp[i] - thm[i];
-      a += d * inv_mass[i] * rm[i];
-      b += d * inv_mass[i] * rp[i];
+      a += d * vm[i];
+      b += d * vp[i];
     }
     return a >= 0.0 && b >= 0.0;
   }
@@ -199,6 +240,223 @@ struct Sampler {
     }
   }
 
+  // ---- multinomial NUTS (Betancourt 2017; the scheme of Stan's base_nuts and of NumPyro's default
+  //      kernel): states of a trajectory are drawn with weights exp(-H), biased towards the newer
+  //      subtree at the top level; the U-turn criterion uses the summed momentum rho and is also
+  //      demanded across the junction of the two half-trees.
+  struct Point {
+    Vec theta, r, grad;
+    double u = 0.0;
+  };
+  static double log_add_exp(double a, double b) {
+    if (a == -std::numeric_limits<double>::infinity()) return b;
+    if (b == -std::numeric_limits<double>::infinity()) return a;
+    const double m = a > b ? a : b;
+    return m + std::log(std::exp(a - m) + std::exp(b - m));
+  }
+  void sharp(const Vec& r, Vec& out) const { velocity(r, out); }
+  bool criterion(const Vec& sharp_minus, const Vec& sharp_plus, const Vec& rho) const {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < dim; ++i) {
+      a += sharp_plus[i] * rho[i];
+      b += sharp_minus[i] * rho[i];
+    }
+    return a > 0.0 && b > 0.0;
+  }
+  struct MultiState {
+    Point z;  // the integrator's moving end
+    double H0 = 0.0, eps = 0.0;
+    int64_t n_leapfrog = 0;
+    double sum_metro = 0.0;
+    bool divergent = false;
+  };
+  bool build_multi(MultiState& S, int depth, Point& z_propose, Vec& sharp_beg, Vec& sharp_end, Vec& rho, Vec& p_beg, Vec& p_end, int sign,
+                   double& log_sum_weight) {
+    if (depth == 0) {
+      S.z.u = leapfrog(S.z.theta, S.z.r, S.z.grad, sign * S.eps);
+      ++S.n_leapfrog;
+      ++n_leapfrog;
+      const double h = finite_or_inf(S.z.u + kinetic(S.z.r));
+      if (h - S.H0 > 1000.0) S.divergent = true;
+      log_sum_weight = log_add_exp(log_sum_weight, S.H0 - h);
+      S.sum_metro += S.H0 - h > 0.0 ? 1.0 : std::exp(S.H0 - h);
+      z_propose = S.z;
+      sharp(S.z.r, sharp_beg);
+      sharp_end = sharp_beg;
+      for (int i = 0; i < dim; ++i) rho[i] += S.z.r[i];
+      p_beg = S.z.r;
+      p_end = S.z.r;
+      return !S.divergent;
+    }
+    const double ninf = -std::numeric_limits<double>::infinity();
+    double lsw_init = ninf;
+    Vec p_init_end(dim), sharp_init_end(dim), rho_init(dim, 0.0);
+    if (!build_multi(S, depth - 1, z_propose, sharp_beg, sharp_init_end, rho_init, p_beg, p_init_end, sign, lsw_init)) return false;
+    Point z_propose_final = S.z;
+    double lsw_final = ninf;
+    Vec p_final_beg(dim), sharp_final_beg(dim), rho_final(dim, 0.0);
+    if (!build_multi(S, depth - 1, z_propose_final, sharp_final_beg, sharp_end, rho_final, p_final_beg, p_end, sign, lsw_final)) return false;
+    const double lsw_subtree = log_add_exp(lsw_init, lsw_final);
+    log_sum_weight = log_add_exp(log_sum_weight, lsw_subtree);
+    if (lsw_final > lsw_subtree) {
+      z_propose = z_propose_final;
+    } else if (rng.uniform() < std::exp(lsw_final - lsw_subtree)) {
+      z_propose = z_propose_final;
+    }
+    Vec rho_subtree(dim), ext(dim);
+    for (int i = 0; i < dim; ++i) {
+      rho_subtree[i] = rho_init[i] + rho_final[i];
+      rho[i] += rho_subtree[i];
+    }
+    bool persist = criterion(sharp_beg, sharp_end, rho_subtree);
+    for (int i = 0; i < dim; ++i) ext[i] = rho_init[i] + p_final_beg[i];
+    persist = persist && criterion(sharp_beg, sharp_final_beg, ext);
+    for (int i = 0; i < dim; ++i) ext[i] = rho_final[i] + p_init_end[i];
+    persist = persist && criterion(sharp_init_end, sharp_end, ext);
+    return persist;
+  }
+  // one transition from (theta, grad, u); returns the mean acceptance statistic of the trajectory
+  double transition_multi(Vec& theta, Vec& grad, double& u, double eps, int max_depth) {
+    MultiState S;
+    S.eps = eps;
+    S.z.theta = theta;
+    S.z.grad = grad;
+    S.z.u = u;
+    S.z.r.resize(dim);
+    draw_momentum(S.z.r);
+    S.H0 = u + kinetic(S.z.r);
+    Point z_fwd = S.z, z_bck = S.z, z_sample = S.z, z_propose = S.z;
+    Vec p_fwd_fwd = S.z.r, p_fwd_bck = S.z.r, p_bck_fwd = S.z.r, p_bck_bck = S.z.r;
+    Vec sharp_fwd_fwd;
+    sharp(S.z.r, sharp_fwd_fwd);
+    Vec sharp_fwd_bck = sharp_fwd_fwd, sharp_bck_fwd = sharp_fwd_fwd, sharp_bck_bck = sharp_fwd_fwd;
+    Vec rho = S.z.r, rho_fwd(dim), rho_bck(dim), ext(dim);
+    double log_sum_weight = 0.0;
+    int depth = 0;
+    while (depth < max_depth) {
+      std::fill(rho_fwd.begin(), rho_fwd.end(), 0.0);
+      std::fill(rho_bck.begin(), rho_bck.end(), 0.0);
+      bool valid;
+      double lsw_subtree = -std::numeric_limits<double>::infinity();
+      if (rng.uniform() > 0.5) {
+        S.z = z_fwd;
+        rho_bck = rho;
+        p_bck_fwd = p_fwd_fwd;
+        sharp_bck_fwd = sharp_fwd_fwd;
+        valid = build_multi(S, depth, z_propose, sharp_fwd_bck, sharp_fwd_fwd, rho_fwd, p_fwd_bck, p_fwd_fwd, +1, lsw_subtree);
+        z_fwd = S.z;
+      } else {
+        S.z = z_bck;
+        rho_fwd = rho;
+        p_fwd_bck = p_bck_bck;
+        sharp_fwd_bck = sharp_bck_bck;
+        valid = build_multi(S, depth, z_propose, sharp_bck_fwd, sharp_bck_bck, rho_bck, p_bck_fwd, p_bck_bck, -1, lsw_subtree);
+        z_bck = S.z;
+      }
+      if (!valid) break;
+      ++depth;
+      if (lsw_subtree > log_sum_weight) {
+        z_sample = z_propose;
+      } else if (rng.uniform() < std::exp(lsw_subtree - log_sum_weight)) {
+        z_sample = z_propose;
+      }
+      log_sum_weight = log_add_exp(log_sum_weight, lsw_subtree);
+      for (int i = 0; i < dim; ++i) rho[i] = rho_bck[i] + rho_fwd[i];
+      bool persist = criterion(sharp_bck_bck, sharp_fwd_fwd, rho);
+      for (int i = 0; i < dim; ++i) ext[i] = rho_bck[i] + p_fwd_bck[i];
+      persist = persist && criterion(sharp_bck_bck, sharp_fwd_bck, ext);
+      for (int i = 0; i < dim; ++i) ext[i] = rho_fwd[i] + p_bck_fwd[i];
+      persist = persist && criterion(sharp_bck_fwd, sharp_fwd_fwd, ext);
+      if (!persist) break;
+    }
+    theta = z_sample.theta;
+    grad = z_sample.grad;
+    u = z_sample.u;
+    return S.n_leapfrog > 0 ? S.sum_metro / (double)S.n_leapfrog : 0.0;
+  }
+
+  // Dense inverse mass from warm[first:]: sample covariance shrunk towards its diagonal with the
+  // analytic intensity of Schaefer & Strimmer (2005) (off-diagonal entries that the window cannot
+  // resolve are damped; with few draws this degrades gracefully to the diagonal estimate), then Stan's
+  // regularisation towards 1e-3 I.  Falls back to the diagonal estimate if the factorisation fails.
+  bool estimate_dense(const std::vector<Vec>& warm, size_t first) {
+    const size_t nn = warm.size() - first;
+    if (nn < 10) return false;
+    const size_t D = (size_t)dim;
+    Vec mean(D, 0.0);
+    for (size_t k = first; k < warm.size(); ++k)
+      for (size_t i = 0; i < D; ++i) mean[i] += warm[k][i];
+    for (size_t i = 0; i < D; ++i) mean[i] /= (double)nn;
+    Vec S(D * D, 0.0), W2(D * D, 0.0), x(D);
+    for (size_t k = first; k < warm.size(); ++k) {
+      for (size_t i = 0; i < D; ++i) x[i] = warm[k][i] - mean[i];
+      for (size_t i = 0; i < D; ++i)
+        for (size_t j = 0; j <= i; ++j) {
+          const double w = x[i] * x[j];
+          S[i * D + j] += w;
+          W2[i * D + j] += w * w;
+        }
+    }
+    const double n = (double)nn;
+    double num = 0.0, den = 0.0;
+    for (size_t i = 0; i < D; ++i)
+      for (size_t j = 0; j < i; ++j) {
+        const double wbar = S[i * D + j] / n;
+        const double var_w = (W2[i * D + j] / n - wbar * wbar) * n / (n - 1.0);  // variance of w_k
+        const double sij = S[i * D + j] / (n - 1.0);
+        num += var_w * n / ((n - 1.0) * (n - 1.0));  // Var(s_ij)
+        den += sij * sij;
+      }
+    double lambda = den > 0.0 ? num / den : 1.0;
+    lambda = std::fmin(1.0, std::fmax(0.0, lambda));
+    cov.assign(D * D, 0.0);
+    const double a = n / (n + 5.0), b = 1e-3 * (5.0 / (n + 5.0));
+    for (size_t i = 0; i < D; ++i)
+      for (size_t j = 0; j <= i; ++j) {
+        double c = S[i * D + j] / (n - 1.0);
+        if (i != j) c *= 1.0 - lambda;
+        c *= a;
+        if (i == j) c += b;
+        cov[i * D + j] = c;
+        cov[j * D + i] = c;
+      }
+    // Cholesky cov = L L^T
+    chol.assign(D * D, 0.0);
+    for (size_t i = 0; i < D; ++i)
+      for (size_t j = 0; j <= i; ++j) {
+        double acc = cov[i * D + j];
+        for (size_t k = 0; k < j; ++k) acc -= chol[i * D + k] * chol[j * D + k];
+        if (i == j) {
+          if (!(acc > 0.0)) return false;
+          chol[i * D + i] = std::sqrt(acc);
+        } else {
+          chol[i * D + j] = acc / chol[j * D + j];
+        }
+      }
+    for (size_t i = 0; i < D; ++i) inv_mass[i] = cov[i * D + i];
+    shrinkage = lambda;
+    return true;
+  }
+  double shrinkage = 1.0;
+
+  // regularised diagonal variance of warm[first:] (Stan's shrinkage towards 1e-3)
+  void estimate_mass(const std::vector<Vec>& warm, size_t first) {
+    if (want_dense) {
+      dense = estimate_dense(warm, first);
+      if (dense) return;
+    }
+    const size_t nn = warm.size() - first;
+    for (int i = 0; i < dim; ++i) {
+      double mean = 0.0;
+      for (size_t k = first; k < warm.size(); ++k) mean += warm[k][i];
+      mean /= (double)nn;
+      double var = 0.0;
+      for (size_t k = first; k < warm.size(); ++k) var += (warm[k][i] - mean) * (warm[k][i] - mean);
+      var /= (double)nn;
+      inv_mass[i] = ((double)nn / ((double)nn + 5.0)) * var + 1e-3 * (5.0 / ((double)nn + 5.0));
+    }
+  }
+
   int run(const double* theta0, const gwi_nuts_opts& o, double* samples, gwi_nuts_info* info) {
     Vec theta(theta0, theta0 + dim), grad(dim);
     double u = U(theta, grad);
@@ -211,6 +469,21 @@ struct Sampler {
     const double gamma = 0.05, t0 = 10.0, kappa = 0.75;
     double eps_bar = 1.0, Hbar = 0.0;
     std::vector<Vec> warm;
+    const bool multinomial = (o.flags & GWI_NUTS_MULTINOMIAL) != 0, windowed = (o.flags & GWI_NUTS_WINDOWED_ADAPT) != 0;
+    want_dense = (o.flags & GWI_NUTS_DENSE_MASS) != 0;
+    // windowed adaptation (Stan's schedule): a fast initial buffer (15 % of warm-up), slow windows that
+    // double in length and each end with a mass-matrix update + step-size restart, a final fast buffer (10 %)
+    int slow_start = -1, slow_end = -1, win_end = -1, win_len = 0;
+    if (windowed && o.n_warmup >= 20) {
+      slow_start = std::max(1, (int)(0.15 * o.n_warmup));
+      slow_end = o.n_warmup - std::max(1, (int)(0.10 * o.n_warmup));
+      win_len = std::max(5, (slow_end - slow_start) / 7);  // window lengths ~ 1 : 2 : 4
+      win_end = slow_start + win_len;
+      if (win_end + 2 * win_len > slow_end) win_end = slow_end;  // no room for a second window
+      warm.reserve(o.n_warmup);
+    }
+    size_t win_first = 0;  // first warm-up draw of the current slow window
+    int adapt_origin = 0;  // windowed adaptation restarts the dual-averaging iteration count with every window
     double accept_sum = 0.0;
     int64_t leapfrog_sampling0 = 0;
     auto t_sampling = std::chrono::steady_clock::now();
@@ -232,6 +505,10 @@ struct Sampler {
       const double step = m < o.n_warmup ? eps : eps_bar;
       double a = 0.0;
       int64_t na = 1;
+      if (multinomial) {
+        a = transition_multi(theta, grad, u, step, o.max_depth);
+        s = 0;
+      }
       while (s == 1 && j < o.max_depth) {
         const int v = rng.uniform() < 0.5 ? -1 : 1;
         Tree T;
@@ -259,29 +536,41 @@ struct Sampler {
       }
       const double acc = a / (double)(na > 0 ? na : 1);
       if (m < o.n_warmup) {
-        const double mm = (double)(m + 1);
+        const double mm = (double)(m + 1 - adapt_origin);
         Hbar = (1.0 - 1.0 / (mm + t0)) * Hbar + (o.target_accept - acc) / (mm + t0);
         eps = std::exp(mu - std::sqrt(mm) / gamma * Hbar);
         const double eta = std::pow(mm, -kappa);
         eps_bar = std::exp(eta * std::log(eps) + (1.0 - eta) * std::log(eps_bar));
         warm.push_back(theta);
-        // one mass-matrix update in the middle of warm-up (diagonal, regularised sample variance)
-        if (m + 1 == o.n_warmup / 2 && warm.size() >= 20) {
-          const size_t first = warm.size() / 4, nn = warm.size() - first;
-          for (int i = 0; i < dim; ++i) {
-            double mean = 0.0;
-            for (size_t k = first; k < warm.size(); ++k) mean += warm[k][i];
-            mean /= (double)nn;
-            double var = 0.0;
-            for (size_t k = first; k < warm.size(); ++k) var += (warm[k][i] - mean) * (warm[k][i] - mean);
-            var /= (double)nn;
-            inv_mass[i] = ((double)nn / ((double)nn + 5.0)) * var + 1e-3 * (5.0 / ((double)nn + 5.0));
+        bool update = false;
+        size_t first = 0;
+        if (windowed && slow_start > 0) {
+          if (m + 1 == slow_start) win_first = warm.size();
+          if (m + 1 == win_end) {
+            update = warm.size() - win_first >= 5;
+            first = win_first;
+            win_first = warm.size();
+            if (win_end >= slow_end) {
+              win_end = -1;  // the final fast buffer only tunes the step size
+            } else {
+              win_len *= 2;
+              win_end += win_len;
+              if (win_end + 2 * win_len > slow_end) win_end = slow_end;  // the last window absorbs the remainder
+            }
           }
+        } else if (m + 1 == o.n_warmup / 2 && warm.size() >= 20) {
+          // one mass-matrix update in the middle of warm-up (diagonal, regularised sample variance)
+          update = true;
+          first = warm.size() / 4;
+        }
+        if (update) {
+          estimate_mass(warm, first);
           u = U(theta, grad);
           eps = find_reasonable_eps(theta, u, grad);
           mu = std::log(10.0 * eps);
           eps_bar = 1.0;
           Hbar = 0.0;
+          if (windowed) adapt_origin = m + 1;
         }
       } else {
         std::memcpy(samples + (size_t)(m - o.n_warmup) * dim, theta.data(), sizeof(double) * dim);

@@ -183,15 +183,17 @@ def nuts(U, theta0, n_warmup, n_samples, rng, target_accept=0.8, max_depth=8):
     return samples, info
 
 
-def nuts_native(engine, blocks, theta0, n_warmup, n_samples, Nobs=None, seed=0, target_accept=0.8, max_depth=8, **like_kw):
+def nuts_native(engine, blocks, theta0, n_warmup, n_samples, Nobs=None, seed=0, target_accept=0.8, max_depth=8, flags=0, **like_kw):
     """The same sampler with the whole transition loop in native code (csrc/nuts.cpp,
     gwi_nuts_sample_posterior): ``engine`` is a :class:`~gwinferno_b200.likelihood.PopulationLikelihood`,
     ``blocks`` as for :class:`BSplinePosterior`.  One gwi_loglike_host call per leapfrog step and no
-    interpreter in between -- use this when the likelihood is cheaper than ~1 ms.  Returns
+    interpreter in between -- use this when the likelihood is cheaper than ~1 ms.  ``flags``: 0 = this
+    module's algorithm; ``capi.NUTS_MULTINOMIAL | capi.NUTS_WINDOWED_ADAPT | capi.NUTS_DENSE_MASS``
+    select multinomial trajectory sampling, Stan-style windowed warm-up and a dense mass matrix.  Returns
     ``(samples[n_samples, dim], info)``; ``info`` has the keys of :func:`nuts` plus ``n_evals``."""
     post = capi.Posterior(engine.model, blocks, engine.n_events if Nobs is None else Nobs, **like_kw)
     try:
-        return post.sample(theta0, n_warmup, n_samples, seed=seed, target_accept=target_accept, max_depth=max_depth)
+        return post.sample(theta0, n_warmup, n_samples, seed=seed, target_accept=target_accept, max_depth=max_depth, flags=flags)
     finally:
         post.close()
 

@@ -261,10 +261,18 @@ int gwi_model_stream_times(gwi_model* m, float* ms_out, int32_t cap);
  * gwi_nuts_sample works on ANY potential U(theta) = -log p(theta) given as a callback that writes
  * dU/dtheta and returns U (+inf = reject); samples is [n_samples][dim], row-major. */
 typedef double (*gwi_potential_fn)(void* ctx, const double* theta, double* grad);
+enum {
+  GWI_NUTS_MULTINOMIAL = 1,    /* multinomial trajectory sampling with the generalised U-turn criterion
+                                  (Betancourt 2017; NumPyro's and Stan's default kernel) instead of slice sampling */
+  GWI_NUTS_WINDOWED_ADAPT = 2, /* Stan-style warm-up: doubling slow windows, mass matrix re-estimated after each */
+  GWI_NUTS_DENSE_MASS = 4      /* dense mass matrix (NumPyro: dense_mass=True): inverse mass = shrunk sample covariance
+                                  of the warm-up window; spline coefficients under a smoothing prior are strongly
+                                  correlated, which a diagonal metric cannot follow.  Use with a warm-up of >= ~5 dim */
+};
 typedef struct {
   int32_t n_warmup, n_samples;
   int32_t max_depth;     /* maximum tree depth (NumPyro: max_tree_depth), 1..20 */
-  int32_t reserved;
+  int32_t flags;         /* 0 = Algorithm 6 as in gwinferno_b200/nuts.py; GWI_NUTS_* below */
   int64_t seed;
   double target_accept;  /* dual-averaging target of the mean acceptance statistic, e.g. 0.8 */
 } gwi_nuts_opts;

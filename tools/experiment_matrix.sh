@@ -1,0 +1,75 @@
+#!/usr/bin/env bash
+# One gpurun call that measures every prepared, default-off switch against the product build
+# (all of them pass the full parity suite on the host warp emulator, tests/emu; none has run on a GPU):
+#
+#   # here (no GPU): build the variants, they travel with the snapshot
+#   bash tools/experiment_matrix.sh build
+#   # on the box
+#   gpurun --timeout 1500 -- 'bash tools/experiment_matrix.sh run r02'
+#
+# `run` prints and stores (gpurun_out/<tag>_matrix.jsonl) one line per (library, environment, workload):
+# parity (pytest -m gpu, tail), evals/s, ms/step, stream-kernel ms and roofline fraction, e2e evals/s.
+# Workloads: cfg3 (headline), cfg3 rank-0 shard of an 8-way run (--emulate-world 8), cfg2 (launch-bound).
+set -u
+MODE="${1:-run}"
+TAG="${2:-rXX}"
+CSRC=gwinferno_b200/csrc
+declare -A VARIANTS=(
+  [exp1]="-DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1"
+  [exp2]="-DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
+  [exp3]="-DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
+  [exp4]="-DGWI_EXP_RED_SPILL=1 -DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
+)
+if [ "$MODE" = build ]; then
+  make -C $CSRC -j8 > /dev/null || exit 1
+  for v in "${!VARIANTS[@]}"; do
+    make -C $CSRC -j8 VARIANT=$v EXTRA="${VARIANTS[$v]}" > /dev/null || exit 1
+    echo "built $CSRC/../libgwi_$v.so  (${VARIANTS[$v]})"
+  done
+  exit 0
+fi
+OUT=gpurun_out
+mkdir -p $OUT
+: > $OUT/${TAG}_matrix.jsonl
+run_one() {  # label, library ("" = product), extra env (KEY=VAL ...), bench args
+  local label="$1" lib="$2" envs="$3"; shift 3
+  local line
+  line=$(env $envs ${lib:+GWI_LIBRARY=$lib} python bench.py --no-cpu-baseline "$@" 2> $OUT/${TAG}_matrix_err.txt | tail -1)
+  python - "$label" "$line" <<'PY' | tee -a $OUT/${TAG}_matrix.jsonl
+import json, sys
+label, line = sys.argv[1], sys.argv[2]
+try:
+    d = json.loads(line)
+    r = d.get("roofline", {})
+    print(json.dumps({"label": label, "workload": d["config"]["workload"].split(":")[0], "value": round(d["value"], 2), "ms_per_step": round(d["ms_per_step"], 4),
+                      "kernel_ms": round(r.get("kernel_ms", float("nan")), 4), "frac": round(r.get("frac", float("nan")), 4), "e2e": round(d["e2e"]["value"], 2),
+                      "log_l": d["result"]["log_l"], "n_chunks": d["plan"]["n_chunks"], "sm_mhz": d["clocks"]["sm_mhz"]}))
+except Exception as e:
+    print(json.dumps({"label": label, "error": str(e), "raw": line[:200]}))
+PY
+}
+# parity first: a variant whose GPU tests fail is not timed
+for v in "" "${!VARIANTS[@]}"; do
+  lib=""; [ -n "$v" ] && lib=gwinferno_b200/libgwi_$v.so
+  [ -n "$v" ] && [ ! -f "$lib" ] && continue
+  res=$(env ${lib:+GWI_LIBRARY=$lib} python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
+  echo "{\"label\": \"${v:-product}\", \"pytest_gpu\": \"$res\"}" | tee -a $OUT/${TAG}_matrix.jsonl
+  case "$res" in *failed*|*error*) continue ;; esac
+  run_one "${v:-product}" "$lib" "" --workload cfg3
+  run_one "${v:-product} shard8" "$lib" "" --workload cfg3 --emulate-world 8
+  run_one "${v:-product} cfg2" "$lib" "" --workload cfg2 --steps 200 --warmup 20
+done
+# runtime switches on the product build
+run_one "product fused-epilogue" "" "GWI_FUSED_EPILOGUE=1" --workload cfg3
+run_one "product fused-epilogue shard8" "" "GWI_FUSED_EPILOGUE=1" --workload cfg3 --emulate-world 8
+run_one "product fused-epilogue cfg2" "" "GWI_FUSED_EPILOGUE=1" --workload cfg2 --steps 200 --warmup 20
+res=$(GWI_FUSED_EPILOGUE=1 python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
+echo "{\"label\": \"product fused-epilogue\", \"pytest_gpu\": \"$res\"}" | tee -a $OUT/${TAG}_matrix.jsonl
+for tune in "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=16" "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=8" "GWI_TUNE_GUIDED_DIV=2 GWI_TUNE_LMIN=16"; do
+  run_one "product $tune shard8" "" "$tune" --workload cfg3 --emulate-world 8
+  run_one "product $tune" "" "$tune" --workload cfg3
+done
+# NUTS ESS/s (the second half of the metric): NumPy driver vs native driver vs native + windowed dense mass
+for args in "--driver numpy" "--driver native" "--driver native --flags 7 --warmup 1000 --samples 500"; do
+  python tools/nuts_ess.py $args 2>> $OUT/${TAG}_matrix_err.txt | tail -1 | tee -a $OUT/${TAG}_matrix.jsonl
+done

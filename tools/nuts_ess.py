@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--max-depth", type=int, default=8)
     ap.add_argument("--driver", choices=["native", "numpy"], default="native",
                     help="native: the whole NUTS loop in libgwi (csrc/nuts.cpp); numpy: gwinferno_b200/nuts.py around gwi_loglike_host")
+    ap.add_argument("--flags", type=int, default=0,
+                    help="native driver only: GWI_NUTS_* bits (1 multinomial, 2 windowed adaptation, 4 dense mass matrix)")
     args = ap.parse_args()
     pe, inj, const, z_range = workloads.shard_catalog(args.workload, 0, 1, scale=args.scale)
     weights, params_fn = workloads.build_model(const["family"], pe, inj, z_range=z_range)
@@ -45,7 +47,7 @@ def main():
     theta0 = 0.1 * rng.standard_normal(post.dim)
     t0 = time.perf_counter()
     if args.driver == "native":
-        samples, info = nuts.nuts_native(eng, blocks, theta0, args.warmup, args.samples, Nobs=Nobs, seed=0, max_depth=args.max_depth)
+        samples, info = nuts.nuts_native(eng, blocks, theta0, args.warmup, args.samples, Nobs=Nobs, seed=0, max_depth=args.max_depth, flags=args.flags)
         post.n_evals = info["n_evals"]
     else:
         samples, info = nuts.nuts(post, theta0, args.warmup, args.samples, rng, max_depth=args.max_depth)
@@ -53,7 +55,7 @@ def main():
     ess = np.array([nuts.effective_sample_size(samples[:, i]) for i in range(samples.shape[1])])
     out = {
         "metric": "NUTS ESS/s", "workload": args.workload, "E": const["E"], "S": const["S"], "I": const["I"], "dim": post.dim,
-        "warmup": args.warmup, "samples": args.samples, "max_tree_depth": args.max_depth,
+        "warmup": args.warmup, "samples": args.samples, "max_tree_depth": args.max_depth, "driver": args.driver, "flags": args.flags,
         "ess_min": float(ess.min()), "ess_median": float(np.median(ess)),
         "ess_min_per_s": float(ess.min() / info["sampling_seconds"]), "ess_median_per_s": float(np.median(ess) / info["sampling_seconds"]),
         "grad_evals_total": post.n_evals, "grad_evals_per_s_overall": post.n_evals / wall, "wall_s": wall, **info,
