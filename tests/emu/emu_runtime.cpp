@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <string>
+#include <algorithm>
 #include <thread>
 #include <vector>
 
@@ -201,6 +203,14 @@ static void prepare_fiber(Fiber& f) {
 static std::mutex g_stack_mutex;
 static std::vector<char*> g_free_stacks;
 
+static bool lane_order_reversed() {
+  static const bool r = [] {
+    const char* e = std::getenv("GWI_EMU_LANE_ORDER");
+    return e && std::string(e) == "reverse";
+  }();
+  return r;
+}
+
 struct Worker {
   Block block;
   std::vector<char*> stacks;
@@ -254,7 +264,11 @@ struct Worker {
         progress = progress || w.gen != w.gen_next;
         w.gen = w.gen_next;
       }
-      for (int i = 0; i < n; ++i) {
+      for (int ii = 0; ii < n; ++ii) {
+        // GWI_EMU_LANE_ORDER=reverse: lanes of a warp run 31..0 between synchronisation points (a result
+        // that depends on the lane order beyond atomic-add rounding points at a missing barrier)
+        const int i = lane_order_reversed() ? (ii & ~31) + std::min(31, n - 1 - (ii & ~31)) - (ii & 31) : ii;
+        if (i < 0 || i >= n) continue;
         Fiber& f = b.fibers[i];
         if (f.done) continue;
         if (f.wait_ptr) {
