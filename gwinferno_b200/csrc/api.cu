@@ -68,6 +68,12 @@ struct gwi_model {
   // GWI_FUSED_EPILOGUE=1 (tuning switch, default off until measured on the GPU): reduction tree,
   // per-segment finish, partial record and single-rank combine in ONE launch (epilogue_kernel)
   bool fused_epilogue = false;
+  // GWI_GRAPH=1 (tuning switch, default off until measured on the GPU): gwi_loglike_host replays ONE
+  // captured CUDA graph (H2D copy of Lambda, every kernel of the evaluation with its aux-stream fork /
+  // join, D2H copy of the result) instead of issuing ~10 stream operations per call
+  bool use_graph = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  gwi_like_opts graph_opts{};
   double* partial_batch = nullptr;                        // [n_chain_alloc][PR_HEADER + 3P]
   int stream_grid_x = 1;
   stream_fn k_full = nullptr, k_max = nullptr;
@@ -356,6 +362,7 @@ void gwi_model_destroy(gwi_model* m) {
   if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
   for (auto e : m->ev0) cudaEventDestroy(e);
   for (auto e : m->ev1) cudaEventDestroy(e);
   delete m;
@@ -567,6 +574,8 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   {
     const char* e = std::getenv("GWI_FUSED_EPILOGUE");
     m->fused_epilogue = e && e[0] == '1';
+    const char* g = std::getenv("GWI_GRAPH");
+    m->use_graph = g && g[0] == '1';
   }
   m->stream_grid_x = std::max(1, std::min(p.grid_blocks, ((int)p.slice_begin.size() - 1 + p.warps_per_block - 1) / p.warps_per_block));
   m->launches_per_eval = m->fused_epilogue ? 2 + (H.two_pass ? 2 : 0) + 1 + 1 : 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
@@ -738,10 +747,43 @@ int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opt
   CUDA_TRY(cudaSetDevice(m->device));
   const int P = m->plan.n_params;
   std::memcpy(m->lam_pinned, lambda_host, sizeof(double) * P);
-  CUDA_TRY(cudaMemcpyAsync(m->lam_dev, m->lam_pinned, sizeof(double) * P, cudaMemcpyHostToDevice, m->own_stream));
-  const int rc = gwi_loglike(m, m->lam_dev, opts, m->out_dev, m->own_stream);
-  if (rc != GWI_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(m->out_pinned, m->out_dev, sizeof(double) * (GWI_LIKE_HEADER + P), cudaMemcpyDeviceToHost, m->own_stream));
+  if (m->use_graph && opts && !m->timing && !m->force_exact_shift) {
+    // the kernels take `opts` by value: a graph is valid for the options it was captured with
+    if (m->graph_exec && std::memcmp(&m->graph_opts, opts, sizeof(gwi_like_opts)) != 0) {
+      cudaGraphExecDestroy(m->graph_exec);
+      m->graph_exec = nullptr;
+    }
+    if (!m->graph_exec) {
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(m->own_stream, cudaStreamCaptureModeThreadLocal));
+      cudaMemcpyAsync(m->lam_dev, m->lam_pinned, sizeof(double) * P, cudaMemcpyHostToDevice, m->own_stream);
+      const int rc_cap = gwi_loglike(m, m->lam_dev, opts, m->out_dev, m->own_stream);
+      cudaMemcpyAsync(m->out_pinned, m->out_dev, sizeof(double) * (GWI_LIKE_HEADER + P), cudaMemcpyDeviceToHost, m->own_stream);
+      const cudaError_t e_end = cudaStreamEndCapture(m->own_stream, &graph);  // always ends the capture, also after an error
+      if (rc_cap != GWI_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc_cap;
+      }
+      if (e_end != cudaSuccess || !graph) {
+        set_error(std::string("stream capture of the evaluation failed: ") + cudaGetErrorString(e_end));
+        return GWI_ERR_CUDA;
+      }
+      const cudaError_t e_inst = cudaGraphInstantiate(&m->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e_inst != cudaSuccess) {
+        m->graph_exec = nullptr;
+        set_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(e_inst));
+        return GWI_ERR_CUDA;
+      }
+      m->graph_opts = *opts;
+    }
+    CUDA_TRY(cudaGraphLaunch(m->graph_exec, m->own_stream));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(m->lam_dev, m->lam_pinned, sizeof(double) * P, cudaMemcpyHostToDevice, m->own_stream));
+    const int rc = gwi_loglike(m, m->lam_dev, opts, m->out_dev, m->own_stream);
+    if (rc != GWI_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(m->out_pinned, m->out_dev, sizeof(double) * (GWI_LIKE_HEADER + P), cudaMemcpyDeviceToHost, m->own_stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(m->own_stream));
   std::memcpy(out_host, m->out_pinned, sizeof(double) * (GWI_LIKE_HEADER + P));
   if (out_host[GWI_LIKE_STATUS] != 0.0 && !m->host.two_pass && !m->force_exact_shift) {

@@ -21,6 +21,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <tuple>
 #include <utility>
 
@@ -68,6 +69,10 @@ struct gwi_emu_stream;
 struct gwi_emu_event;
 typedef gwi_emu_stream* cudaStream_t;
 typedef gwi_emu_event* cudaEvent_t;
+struct gwi_emu_graph;
+typedef gwi_emu_graph* cudaGraph_t;
+typedef gwi_emu_graph* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
 struct cudaDeviceProp {
   char name[256];
   int multiProcessorCount;
@@ -99,6 +104,13 @@ cudaError_t cudaDeviceSynchronize(void);
 cudaError_t cudaGetLastError(void);
 cudaError_t cudaFuncSetAttribute(const void* fn, int attr, int value);
 const char* cudaGetErrorString(cudaError_t e);
+/* stream capture: between Begin and End every launch / async copy is recorded instead of executed */
+cudaError_t cudaStreamBeginCapture(cudaStream_t s, int mode);
+cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* graph);
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* exec, cudaGraph_t graph, unsigned long long flags);
+cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t s);
+cudaError_t cudaGraphDestroy(cudaGraph_t graph);
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t exec);
 int gwi_emu_marker(void);  // identifies the emulator build (the product binding refuses it)
 }
 
@@ -113,7 +125,7 @@ struct Body {
   virtual void run() = 0;
   virtual ~Body() {}
 };
-void run_grid(dim3 grid, dim3 block, size_t dyn_smem, Body& body);
+void run_grid(dim3 grid, dim3 block, size_t dyn_smem, std::shared_ptr<Body> body);  // executes now, or records during stream capture
 
 template <class F>
 struct Launcher {
@@ -127,8 +139,8 @@ struct Launcher {
       std::tuple<A...> a;
       B(F f, A... x) : fn(f), a(x...) {}
       void run() override { std::apply(fn, a); }
-    } body(fn, args...);
-    run_grid(grid, block, smem, body);
+    };
+    run_grid(grid, block, smem, std::make_shared<B>(fn, args...));
   }
 };
 template <class F>

@@ -16,6 +16,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <algorithm>
@@ -299,7 +300,27 @@ static int pool_size() {
   return n;
 }
 
-void run_grid(dim3 grid, dim3 block, size_t dyn_smem, Body& body) {
+}  // namespace gwi_emu
+
+// a captured stream: the recorded operations, replayed in order by cudaGraphLaunch
+struct gwi_emu_graph {
+  std::vector<std::function<void()>> ops;
+};
+static thread_local gwi_emu_graph* t_capture = nullptr;
+
+namespace gwi_emu {
+
+static void run_grid_now(dim3 grid, dim3 block, size_t dyn_smem, Body& body);
+
+void run_grid(dim3 grid, dim3 block, size_t dyn_smem, std::shared_ptr<Body> body) {
+  if (t_capture) {
+    t_capture->ops.push_back([=]() { run_grid_now(grid, block, dyn_smem, *body); });
+    return;
+  }
+  run_grid_now(grid, block, dyn_smem, *body);
+}
+
+static void run_grid_now(dim3 grid, dim3 block, size_t dyn_smem, Body& body) {
   if (dyn_smem > gwi::EMU_SMEM_DOUBLES * 8) {
     std::fprintf(stderr, "gwi_emu: %zu bytes of dynamic shared memory requested\n", dyn_smem);
     std::abort();
@@ -406,7 +427,40 @@ cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, int) {
   std::memmove(dst, src, bytes);
   return cudaSuccess;
 }
-cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, int kind, cudaStream_t) { return cudaMemcpy(dst, src, bytes, kind); }
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, int kind, cudaStream_t) {
+  if (t_capture) {
+    t_capture->ops.push_back([=]() { std::memmove(dst, src, bytes); });
+    return cudaSuccess;
+  }
+  return cudaMemcpy(dst, src, bytes, kind);
+}
+cudaError_t cudaStreamBeginCapture(cudaStream_t, int) {
+  if (t_capture) return cudaErrorInvalidValue;
+  t_capture = new gwi_emu_graph();
+  return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* graph) {
+  if (!t_capture) return cudaErrorInvalidValue;
+  *graph = t_capture;
+  t_capture = nullptr;
+  return cudaSuccess;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* exec, cudaGraph_t graph, unsigned long long) {
+  *exec = new gwi_emu_graph(*graph);
+  return cudaSuccess;
+}
+cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t) {
+  for (auto& op : exec->ops) op();
+  return cudaSuccess;
+}
+cudaError_t cudaGraphDestroy(cudaGraph_t graph) {
+  delete graph;
+  return cudaSuccess;
+}
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t exec) {
+  delete exec;
+  return cudaSuccess;
+}
 cudaError_t cudaMemset(void* p, int v, size_t bytes) {
   std::memset(p, v, bytes);
   return cudaSuccess;

@@ -63,6 +63,12 @@ done
 run_one "product fused-epilogue" "" "GWI_FUSED_EPILOGUE=1" --workload cfg3
 run_one "product fused-epilogue shard8" "" "GWI_FUSED_EPILOGUE=1" --workload cfg3 --emulate-world 8
 run_one "product fused-epilogue cfg2" "" "GWI_FUSED_EPILOGUE=1" --workload cfg2 --steps 200 --warmup 20
+# CUDA graph replay of gwi_loglike_host: shows in the `e2e` column (host buffers), not in `value`
+run_one "product graph cfg2" "" "GWI_GRAPH=1" --workload cfg2 --steps 200 --warmup 20
+run_one "product graph+fused cfg2" "" "GWI_GRAPH=1 GWI_FUSED_EPILOGUE=1" --workload cfg2 --steps 200 --warmup 20
+run_one "product graph+fused cfg3" "" "GWI_GRAPH=1 GWI_FUSED_EPILOGUE=1" --workload cfg3
+res=$(GWI_GRAPH=1 GWI_FUSED_EPILOGUE=1 python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
+echo "{\"label\": \"product graph+fused\", \"pytest_gpu\": \"$res\"}" | tee -a $OUT/${TAG}_matrix.jsonl
 res=$(GWI_FUSED_EPILOGUE=1 python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
 echo "{\"label\": \"product fused-epilogue\", \"pytest_gpu\": \"$res\"}" | tee -a $OUT/${TAG}_matrix.jsonl
 for tune in "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=16" "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=8" "GWI_TUNE_GUIDED_DIV=2 GWI_TUNE_LMIN=16"; do
@@ -73,3 +79,4 @@ done
 for args in "--driver numpy" "--driver native" "--driver native --flags 7 --warmup 1000 --samples 500"; do
   python tools/nuts_ess.py $args 2>> $OUT/${TAG}_matrix_err.txt | tail -1 | tee -a $OUT/${TAG}_matrix.jsonl
 done
+GWI_GRAPH=1 GWI_FUSED_EPILOGUE=1 python tools/nuts_ess.py --driver native --flags 7 --warmup 1000 --samples 500 2>> $OUT/${TAG}_matrix_err.txt | tail -1 | tee -a $OUT/${TAG}_matrix.jsonl
