@@ -31,6 +31,7 @@ fi
 OUT=gpurun_out
 mkdir -p $OUT
 : > $OUT/${TAG}_matrix.jsonl
+export GWI_TEST_EXPERIMENTAL=1  # include the tests of the default-off switches in every pytest -m gpu below
 run_one() {  # label, library ("" = product), extra env (KEY=VAL ...), bench args
   local label="$1" lib="$2" envs="$3"; shift 3
   local line
