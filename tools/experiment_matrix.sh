@@ -5,7 +5,8 @@
 #   # here (no GPU): build the variants, they travel with the snapshot
 #   bash tools/experiment_matrix.sh build
 #   # on the box
-#   gpurun --timeout 1500 -- 'bash tools/experiment_matrix.sh run r02'
+#   gpurun --timeout 2400 -- 'bash tools/experiment_matrix.sh run r02'          # everything, ~35 GPU-minutes
+#   gpurun --timeout 1200 -- 'ONLY="uni exp5" bash tools/experiment_matrix.sh run r02'   # a subset of the builds
 #
 # `run` prints and stores (gpurun_out/<tag>_matrix.jsonl) one line per (library, environment, workload):
 # parity (pytest -m gpu, tail), evals/s, ms/step, stream-kernel ms and roofline fraction, e2e evals/s.
@@ -52,8 +53,10 @@ except Exception as e:
     print(json.dumps({"label": label, "error": str(e), "raw": line[:200]}))
 PY
 }
-# parity first: a variant whose GPU tests fail is not timed
+# parity first: a variant whose GPU tests fail is not timed.  ONLY="uni exp5" restricts the compile-time
+# variants (the product build is always included); budget ~2.5 GPU-minutes per variant.
 for v in "" "${!VARIANTS[@]}"; do
+  if [ -n "$v" ] && [ -n "${ONLY:-}" ]; then case " $ONLY " in *" $v "*) ;; *) continue ;; esac; fi
   lib=""; [ -n "$v" ] && lib=gwinferno_b200/libgwi_$v.so
   [ -n "$v" ] && [ ! -f "$lib" ] && continue
   res=$(env ${lib:+GWI_LIBRARY=$lib} python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
