@@ -117,6 +117,9 @@ int gwi_emu_marker(void);  // identifies the emulator build (the product binding
 // ---- fibers: synchronisation points ------------------------------------------------------------
 namespace gwi_emu {
 void warp_barrier();                              // all live lanes of the calling lane's warp
+void warp_barrier_mask(unsigned mask);            // __syncwarp(mask): the live lanes named in `mask` (all of them must call it with the same mask)
+void named_barrier(int id, int n_threads);        // bar.sync id, n_threads (n_threads a multiple of 32; ids 1..15)
+unsigned warp_alive_mask();
 void block_barrier();                             // all live threads of the block
 uint64_t warp_exchange(uint64_t mine, int from);  // publish `mine`, return lane `from`'s value (one barrier)
 unsigned warp_ballot(bool pred);
@@ -171,7 +174,12 @@ inline int lane_id() { return (int)(threadIdx.x & 31u); }
 
 // ---- device intrinsics -------------------------------------------------------------------------
 inline void __syncthreads() { gwi_emu::block_barrier(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { gwi_emu::warp_barrier(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) {
+  if (mask == 0xffffffffu) gwi_emu::warp_barrier();
+  else gwi_emu::warp_barrier_mask(mask);
+}
+// bar.sync id, n: kernels call this wrapper (under nvcc it is one line of inline PTX)
+inline void gwi_named_barrier_sync(int id, int n_threads) { gwi_emu::named_barrier(id, n_threads); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
@@ -194,6 +202,18 @@ inline T __shfl_down_sync(unsigned, T v, int delta) {
   return gwi_emu::from_bits<T>(gwi_emu::warp_exchange(gwi_emu::to_bits(v), l + delta <= 31 ? l + delta : l));
 }
 inline unsigned __ballot_sync(unsigned, int pred) { return gwi_emu::warp_ballot(pred != 0); }
+inline int __any_sync(unsigned, int pred) { return gwi_emu::warp_ballot(pred != 0) != 0u; }
+inline int __all_sync(unsigned, int pred) { return gwi_emu::warp_ballot(pred == 0) == 0u; }
+inline unsigned __activemask() { return gwi_emu::warp_alive_mask(); }  // fibers of a warp are never "diverged": every live lane
+template <class T>
+inline unsigned __match_any_sync(unsigned, T v) {
+  // lanes holding the same value: 32 broadcasts (this is a test emulator, not a fast one)
+  unsigned r = 0;
+  const uint64_t mine = gwi_emu::to_bits(v);
+  for (int l = 0; l < 32; ++l)
+    if (gwi_emu::warp_exchange(mine, l) == mine && ((gwi_emu::warp_alive_mask() >> l) & 1u)) r |= 1u << l;
+  return r;
+}
 
 template <class T>
 inline T __ldg(const T* p) {
@@ -215,6 +235,31 @@ inline double atomicAdd(double* p, double v) {
     if (__atomic_compare_exchange_n(q, &old, gwi_emu::to_bits(nv), false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return gwi_emu::from_bits<double>(old);
   }
 }
+
+inline int atomicMax(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+  return old;
+}
+inline int atomicMin(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+  return old;
+}
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicCAS(int* p, int cmp, int v) {
+  __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return cmp;
+}
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
+  __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return cmp;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
 
 inline double __hiloint2double(int hi, int lo) { return gwi_emu::from_bits<double>(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo); }
 inline int __double2loint(double v) { return (int)(uint32_t)gwi_emu::to_bits(v); }

@@ -73,9 +73,16 @@ constexpr size_t STACK_BYTES = 256 * 1024;
 // sweep (gen = gen_next), and the fiber that completed it waits like the others: between two
 // synchronisation points the lanes of a warp therefore always run in lane order 0..31, whatever the
 // warp did before -- the emulation is deterministic even when blocks race for work items.
+struct PartialBarrier {  // __syncwarp(mask) with a proper subset of the lanes
+  unsigned mask = 0;
+  uint64_t gen = 0, gen_next = 0;
+  unsigned arrived = 0;
+};
 struct Warp {
   uint64_t gen = 0, gen_next = 0;
   int arrived = 0, alive = 0;
+  unsigned alive_mask = 0;
+  PartialBarrier partial[4];
   uint64_t xbuf[2][32];
   unsigned ballot[4] = {0, 0, 0, 0};
 };
@@ -91,9 +98,14 @@ struct Fiber {
   Warp* warp = nullptr;
 };
 
+struct NamedBarrier {  // bar.sync id, n
+  uint64_t gen = 0, gen_next = 0;
+  int arrived = 0;
+};
 struct Block {
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
+  NamedBarrier named[16];
   uint64_t gen = 0, gen_next = 0;
   int arrived = 0, alive = 0;
   void* sched_sp = nullptr;
@@ -132,6 +144,54 @@ void warp_barrier() {
   }
   f->wait_ptr = &w.gen;
   f->wait_val = w.gen;
+  yield_to_scheduler();
+}
+
+unsigned warp_alive_mask() { return t_block->current->warp->alive_mask; }
+
+void warp_barrier_mask(unsigned mask) {
+  Block& b = *t_block;
+  Fiber* f = b.current;
+  Warp& w = *f->warp;
+  mask &= w.alive_mask;
+  PartialBarrier* pb = nullptr;
+  for (auto& c : w.partial)
+    if (c.mask == mask && c.arrived != 0) pb = &c;  // a barrier of this lane set is already forming
+  if (!pb)
+    for (auto& c : w.partial)
+      if (c.arrived == 0 && c.gen == c.gen_next) {
+        pb = &c;
+        pb->mask = mask;
+        break;
+      }
+  if (!pb) {
+    std::fprintf(stderr, "gwi_emu: more than 4 concurrent partial-mask __syncwarp barriers in one warp\n");
+    std::abort();
+  }
+  pb->arrived |= 1u << (f->tid.x & 31u);
+  if (pb->arrived == mask) {
+    pb->arrived = 0;
+    ++pb->gen_next;
+  }
+  f->wait_ptr = &pb->gen;
+  f->wait_val = pb->gen;
+  yield_to_scheduler();
+}
+
+void named_barrier(int id, int n_threads) {
+  Block& b = *t_block;
+  Fiber* f = b.current;
+  if (id < 0 || id > 15 || n_threads <= 0) {
+    std::fprintf(stderr, "gwi_emu: bad named barrier (%d, %d)\n", id, n_threads);
+    std::abort();
+  }
+  NamedBarrier& nb = b.named[id];
+  if (++nb.arrived == n_threads) {
+    nb.arrived = 0;
+    ++nb.gen_next;
+  }
+  f->wait_ptr = &nb.gen;
+  f->wait_val = nb.gen;
   yield_to_scheduler();
 }
 
@@ -182,6 +242,7 @@ extern "C" void gwi_emu_fiber_main() {
   // a finished thread no longer takes part in barriers
   Warp& w = *f->warp;
   --w.alive;
+  w.alive_mask &= ~(1u << (f->tid.x & 31u));
   release_warp_if_complete(w);
   --b.alive;
   release_block_if_complete(b);
@@ -240,6 +301,7 @@ struct Worker {
     b.fibers.assign(n, Fiber());
     b.warps.assign((n + 31) / 32, Warp());
     b.gen = b.gen_next = 0;
+    for (auto& nb : b.named) nb = NamedBarrier();
     b.arrived = 0;
     b.alive = n;
     b.body = &body;
@@ -250,6 +312,7 @@ struct Worker {
       f.done = false;
       f.warp = &b.warps[i / 32];
       f.warp->alive++;
+      f.warp->alive_mask |= 1u << (i & 31);
       prepare_fiber(f);
     }
     for (auto& w : b.warps) std::memset(w.xbuf, 0, sizeof(w.xbuf));
@@ -264,6 +327,14 @@ struct Worker {
       for (auto& w : b.warps) {
         progress = progress || w.gen != w.gen_next;
         w.gen = w.gen_next;
+        for (auto& c : w.partial) {
+          progress = progress || c.gen != c.gen_next;
+          c.gen = c.gen_next;
+        }
+      }
+      for (auto& nb : b.named) {
+        progress = progress || nb.gen != nb.gen_next;
+        nb.gen = nb.gen_next;
       }
       for (int ii = 0; ii < n; ++ii) {
         // GWI_EMU_LANE_ORDER=reverse: lanes of a warp run 31..0 between synchronisation points (a result
