@@ -844,7 +844,14 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   wpb = std::max(1, std::min(wpb, 8));
   plan.warps_per_block = wpb;
   plan.grid_blocks = std::max(1, sm_count);
-  const int W = plan.grid_blocks * plan.warps_per_block;
+  // GWI_TUNE_BATCH_HINT=n (tuning experiment, default 1): the model will be evaluated for ~n chains per
+  // launch (gwi_loglike_batch), so the machine is filled by chains and ONE chain only needs W/n warps:
+  // slices get n times longer (up to the cap), i.e. fewer record flushes and longer piece-sorted lane
+  // runs.  The emulator's path statistics for the config-2 catalog: 2 701 chunks of 8 steps and 88 % of
+  // the warp iterations with lanes on the piece-change path at n = 1.
+  int batch_hint = 1;
+  if (const char* e = std::getenv("GWI_TUNE_BATCH_HINT")) batch_hint = std::max(1, std::atoi(e));
+  const int W = std::max(plan.warps_per_block, plan.grid_blocks * plan.warps_per_block / batch_hint);
   // Balanced slicing: the piece-sorted sample stream of all segments (the events first, then the
   // injections) is cut into SLICES of L steps (32 samples per step); slice i belongs to warp i % W.
   // By default L = ceil(total steps / W): every warp gets exactly one slice, i.e. the same amount

@@ -82,6 +82,11 @@ for tune in "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=16" "GWI_TUNE_GUIDED_DIV=1 GWI_
   run_one "product $tune shard8" "" "$tune" --workload cfg3 --emulate-world 8
   run_one "product $tune" "" "$tune" --workload cfg3
 done
+# cfg4 (1024 chains per launch on the config-2 catalog): batch geometry, alone and with the unified pair path
+run_one "product cfg4" "" "" --workload cfg4 --steps 5 --warmup 3
+run_one "product batch-hint cfg4" "" "GWI_TUNE_BATCH_HINT=1024" --workload cfg4 --steps 5 --warmup 3
+[ -f gwinferno_b200/libgwi_uni.so ] && run_one "uni cfg4" gwinferno_b200/libgwi_uni.so "" --workload cfg4 --steps 5 --warmup 3
+[ -f gwinferno_b200/libgwi_uni.so ] && run_one "uni batch-hint cfg4" gwinferno_b200/libgwi_uni.so "GWI_TUNE_BATCH_HINT=1024" --workload cfg4 --steps 5 --warmup 3
 # NUTS ESS/s (the second half of the metric): NumPy driver vs native driver vs native + windowed dense mass
 for args in "--driver numpy" "--driver native" "--driver native --flags 7 --warmup 1000 --samples 500"; do
   python tools/nuts_ess.py $args 2>> $OUT/${TAG}_matrix_err.txt | tail -1 | tee -a $OUT/${TAG}_matrix.jsonl
