@@ -769,8 +769,8 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         double pairs = 0.0;
         for (size_t i = 0; i + 1 < n; i += stride) {
           for (int d = 0; d < NS; ++d) {
-            int J0, J1;
-            double u;
+            int J0 = 0, J1 = 0;  // (every sample of the plan is inside the support: spline_locate succeeds)
+            double u = 0.0;
             spline_locate(geom[d], cols[geom[d].col][ord[i]], J0, u);
             spline_locate(geom[d], cols[geom[d].col][ord[i + 1]], J1, u);
             if (J0 != J1) rate[s][d] += 1.0;
@@ -1001,8 +1001,8 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
             if (r < n_c) {
               const int64_t j = r;  // row of the chunk-local sorted copy
               for (int d = 0; d < NS; ++d) {
-                int J;
-                double u;
+                int J = 0;
+                double u = 0.0;
                 spline_locate(geom[d], cols[geom[d].col][j], J, u);
                 plan.columns[col_index(d, p)] = pack_word(J, u);
                 st.occ[d] |= 1ull << J;
@@ -1027,8 +1027,8 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
               // finite values and no piece index changes) with static log-weight -inf => weight 0
               const int64_t j = n_c - 1;
               for (int d = 0; d < NS; ++d) {
-                int J;
-                double u;
+                int J = 0;
+                double u = 0.0;
                 spline_locate(geom[d], cols[geom[d].col][j], J, u);
                 plan.columns[col_index(d, p)] = pack_word(J, u);
               }

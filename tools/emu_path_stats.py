@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--scale", type=float, default=0.05)
     ap.add_argument("--emulate-world", type=int, default=1)
     ap.add_argument("--sms", type=int, default=148)
+    ap.add_argument("--n-deep", type=int, default=-1, help="force the number of deep dims (-1 = the plan's cost model)")
     args = ap.parse_args()
     os.environ.setdefault("GWI_EMU_SMS", str(args.sms))
     from tests import emu
@@ -40,7 +41,7 @@ def main():
     pe, inj, const, z_range = workloads.shard_catalog(args.workload, 0, args.emulate_world, scale=args.scale, all_reduce_minmax=lambda lo, hi: (lo, hi))
     weights, params_fn = workloads.build_model(const["family"], pe, inj, z_range=z_range)
     low, lam, _ = workloads.lower_workload(weights, params_fn, pe, inj)
-    eng = PopulationLikelihood(low, const["total_inj"])
+    eng = PopulationLikelihood(low, const["total_inj"], n_deep=args.n_deep)
     info = eng.info()
     t1 = time.time()
     for i in range(16):

@@ -82,6 +82,10 @@ for tune in "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=16" "GWI_TUNE_GUIDED_DIV=1 GWI_
   run_one "product $tune shard8" "" "$tune" --workload cfg3 --emulate-world 8
   run_one "product $tune" "" "$tune" --workload cfg3
 done
+# deep-dim split with the unified pair path (the plan's cost model was calibrated for the old path)
+for nd in 2 4; do
+  [ -f gwinferno_b200/libgwi_uni2.so ] && run_one "uni2 n_deep=$nd" gwinferno_b200/libgwi_uni2.so "" --workload cfg3 --n-deep $nd
+done
 # cfg4 (1024 chains per launch on the config-2 catalog): batch geometry, alone and with the unified pair path
 run_one "product cfg4" "" "" --workload cfg4 --steps 5 --warmup 3
 run_one "product batch-hint cfg4" "" "GWI_TUNE_BATCH_HINT=1024" --workload cfg4 --steps 5 --warmup 3
