@@ -20,6 +20,26 @@
 
 #include "dev_structs.h"
 
+// GWI_EXP_STAGE_DESC (experiment switch, default 0): the small kernels read dozens of ModelDev fields,
+// each a dependent global load (the cold prologue takes 33 us under ncu, mostly load latency).  With
+// the switch a block first copies its chain's descriptor (~3 KB) into shared memory with coalesced
+// 8-byte loads and works from that copy.
+#ifndef GWI_EXP_STAGE_DESC
+#define GWI_EXP_STAGE_DESC 0
+#endif
+#if GWI_EXP_STAGE_DESC
+#define GWI_STAGED_DESC(M, src)                                                                              \
+  __shared__ __align__(16) unsigned long long gwi_desc_stage[(sizeof(ModelDev) + 7) / 8];                    \
+  {                                                                                                          \
+    const unsigned long long* gwi_desc_src = reinterpret_cast<const unsigned long long*>(&(src));            \
+    for (unsigned i = threadIdx.x; i < (sizeof(ModelDev) + 7) / 8; i += blockDim.x) gwi_desc_stage[i] = gwi_desc_src[i]; \
+    __syncthreads();                                                                                         \
+  }                                                                                                          \
+  const ModelDev& M = *reinterpret_cast<const ModelDev*>(gwi_desc_stage)
+#else
+#define GWI_STAGED_DESC(M, src) const ModelDev& M = (src)
+#endif
+
 namespace gwi {
 
 // cubic B-spline piece basis in w = u - 1/2 :  b_k(u) = sum_n BETA[k][n] w^n
@@ -111,7 +131,7 @@ __device__ void powerlaw_lognorm(double alpha, double lo, double hi, double& log
 // prologue
 // =================================================================================================
 __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam0, int role_off) {
-  const ModelDev& M = Mp[blockIdx.y];  // blockIdx.y = chain
+  GWI_STAGED_DESC(M, Mp[blockIdx.y]);  // blockIdx.y = chain
   const double* __restrict__ Lam = Lam0 + (size_t)blockIdx.y * M.n_params;
   extern __shared__ double sm[];
   __shared__ double scratch[32];
@@ -452,7 +472,7 @@ __device__ void finish_segment(const ModelDev& M, int s, const double* rec) {
 }
 
 __global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp) {
-  const ModelDev& M = Mp[blockIdx.y];
+  GWI_STAGED_DESC(M, Mp[blockIdx.y]);
   const double* __restrict__ in = M.n_levels > 1 ? M.level_buf[M.n_levels - 2] : M.records0;
   const ReduceTask* __restrict__ tasks = M.level_tasks[M.n_levels - 1];
   const int s = blockIdx.x;
@@ -649,7 +669,7 @@ __device__ void combine_records(const ModelDev& M, const double* recs, int R, co
 
 // blockIdx.x = chain: chain c combines the R records at recs0 + c*R*stride into out0 + c*(HEADER+P)
 __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict__ Mp, const double* recs0, int R, gwi_like_opts opts, double* __restrict__ out0) {
-  const ModelDev& M = Mp[blockIdx.x];
+  GWI_STAGED_DESC(M, Mp[blockIdx.x]);
   const int P = M.n_params;
   const int stride = PR_HEADER + 3 * P;
   combine_records(M, recs0 + (size_t)blockIdx.x * R * stride, R, opts, out0 + (size_t)blockIdx.x * (GWI_LIKE_HEADER + P));
@@ -666,7 +686,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
 // mode: 0 = stop after the per-segment results, 1 = + partial record, 2 = + combine (R = 1).
 // =================================================================================================
 __global__ void __launch_bounds__(256) epilogue_kernel(const ModelDev* __restrict__ Mp, int mode, double* recd0, gwi_like_opts opts, double* out0) {
-  const ModelDev& M = Mp[blockIdx.y];  // blockIdx.y = chain
+  GWI_STAGED_DESC(M, Mp[blockIdx.y]);  // blockIdx.y = chain
   extern __shared__ double srec[];
   __shared__ int ticket_s;
   const int rec = M.rec_doubles;

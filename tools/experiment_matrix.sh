@@ -20,6 +20,7 @@ declare -A VARIANTS=(
   [exp2]="-DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
   [exp3]="-DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
   [exp4]="-DGWI_EXP_RED_SPILL=1 -DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
+  [stage]="-DGWI_EXP_STAGE_DESC=1"
   [uni]="-DGWI_EXP_UNIFIED_PAIR=1"
   [uni2]="-DGWI_EXP_UNIFIED_PAIR=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_RED_SPILL=1"
   [exp5]="-DGWI_EXP_UNIFIED_PAIR=1 -DGWI_EXP_RED_SPILL=1 -DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
