@@ -127,7 +127,7 @@ class gwi_model_info(C.Structure):
         ("grid_blocks", C.c_int32),
         ("block_threads", C.c_int32),
         ("kernel_launches_per_eval", C.c_int32),
-        ("reserved", C.c_int32),
+        ("active_switches", C.c_int32),
     ]
 
 

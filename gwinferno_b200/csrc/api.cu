@@ -20,6 +20,8 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 typedef void (*stream_fn)(const ModelDev*);
 stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, bool maxonly);
+stream_fn pick_stream_split_kernel(int ns, int ndeep, int nlin, bool g2);  // experiment builds only (else nullptr)
+size_t stream_split_extra_smem(int npairs);
 void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st);
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux);
 void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st);
@@ -78,6 +80,10 @@ struct gwi_model {
   int stream_grid_x = 1;
   stream_fn k_full = nullptr, k_max = nullptr;
   size_t smem_full = 0, smem_max = 0;
+  // GWI_SPLIT=1 on a -DGWI_EXP_SPLIT=1 build: producer / consumer warp pairs (stream_split.cuh)
+  stream_fn k_split = nullptr;
+  size_t smem_split = 0;
+  int split_pairs = 0;
   int max_grid = 0;
   int launches_per_eval = 0;
   // scratch for the host-buffer call and single-rank likelihood
@@ -577,6 +583,19 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     const char* g = std::getenv("GWI_GRAPH");
     m->use_graph = g && g[0] == '1';
   }
+  {
+    const char* e = std::getenv("GWI_SPLIT");
+    if (e && e[0] == '1' && !param) {
+      m->k_split = pick_stream_split_kernel(NS, p.n_deep, H.n_lin_fast, p.g2);
+      // as many producer / consumer pairs as fit (the ring needs room next to the consumers' accumulators)
+      m->split_pairs = wpb;
+      while (m->split_pairs > 1 && (fixed + per_warp * m->split_pairs) * 8 + stream_split_extra_smem(m->split_pairs) > (size_t)prop.sharedMemPerBlockOptin) --m->split_pairs;
+      m->smem_split = (fixed + per_warp * m->split_pairs) * 8 + stream_split_extra_smem(m->split_pairs);
+      if (m->k_split && (m->smem_split > (size_t)prop.sharedMemPerBlockOptin ||
+                         cudaFuncSetAttribute((const void*)m->k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_split) != cudaSuccess))
+        m->k_split = nullptr;  // does not fit: keep the regular kernel
+    }
+  }
   m->stream_grid_x = std::max(1, std::min(p.grid_blocks, ((int)p.slice_begin.size() - 1 + p.warps_per_block - 1) / p.warps_per_block));
   m->launches_per_eval = m->fused_epilogue ? 2 + (H.two_pass ? 2 : 0) + 1 + 1 : 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
   CUDA_TRY(cudaDeviceSynchronize());
@@ -606,7 +625,12 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
       launch_segmax(m->dev, H.n_segments, nc, st);
     }
     if (m->timing) cudaEventRecord(m->ev0[m->n_timed % 64], st);
-    GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev);
+    if (m->k_split) {
+      const dim3 block2(m->split_pairs * 64);  // a producer and a consumer warp per slice stream
+      GWI_LAUNCH(m->k_split, grid, block2, m->smem_split, st)(m->dev);
+    } else {
+      GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev);
+    }
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
   }
   const int n_levels = (int)m->level_tasks.size();
@@ -857,6 +881,7 @@ int gwi_model_get_info(const gwi_model* m, gwi_model_info* info) {
   info->grid_blocks = p.grid_blocks;
   info->block_threads = p.warps_per_block * 32;
   info->kernel_launches_per_eval = m->launches_per_eval;
+  info->active_switches = (m->fused_epilogue ? 1 : 0) | (m->use_graph ? 2 : 0) | (m->k_split ? 4 : 0);
   return GWI_OK;
 }
 

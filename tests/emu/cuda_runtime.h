@@ -120,6 +120,7 @@ void warp_barrier();                              // all live lanes of the calli
 void warp_barrier_mask(unsigned mask);            // __syncwarp(mask): the live lanes named in `mask` (all of them must call it with the same mask)
 void named_barrier(int id, int n_threads);        // bar.sync id, n_threads (n_threads a multiple of 32; ids 1..15)
 unsigned warp_alive_mask();
+void warp_yield();                                // spin-wait hint: let the other fibers of the block run
 void block_barrier();                             // all live threads of the block
 uint64_t warp_exchange(uint64_t mine, int from);  // publish `mine`, return lane `from`'s value (one barrier)
 unsigned warp_ballot(bool pred);
@@ -181,6 +182,7 @@ inline void __syncwarp(unsigned mask = 0xffffffffu) {
 // bar.sync id, n: kernels call this wrapper (under nvcc it is one line of inline PTX)
 inline void gwi_named_barrier_sync(int id, int n_threads) { gwi_emu::named_barrier(id, n_threads); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __nanosleep(unsigned) { gwi_emu::warp_yield(); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <class T>

@@ -147,6 +147,8 @@ void warp_barrier() {
   yield_to_scheduler();
 }
 
+void warp_yield() { yield_to_scheduler(); }  // stays runnable: resumed on the next sweep
+
 unsigned warp_alive_mask() { return t_block->current->warp->alive_mask; }
 
 void warp_barrier_mask(unsigned mask) {

@@ -20,6 +20,7 @@ declare -A VARIANTS=(
   [exp2]="-DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
   [exp3]="-DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
   [exp4]="-DGWI_EXP_RED_SPILL=1 -DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
+  [split]="-DGWI_EXP_SPLIT=1"
   [stage]="-DGWI_EXP_STAGE_DESC=1"
   [uni]="-DGWI_EXP_UNIFIED_PAIR=1"
   [uni2]="-DGWI_EXP_UNIFIED_PAIR=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_RED_SPILL=1"
@@ -58,6 +59,7 @@ PY
 # variants (the product build is always included); budget ~2.5 GPU-minutes per variant.
 for v in "" "${!VARIANTS[@]}"; do
   if [ -n "$v" ] && [ -n "${ONLY:-}" ]; then case " $ONLY " in *" $v "*) ;; *) continue ;; esac; fi
+  [ "$v" = split ] && continue  # needs GWI_SPLIT=1: measured separately below
   lib=""; [ -n "$v" ] && lib=gwinferno_b200/libgwi_$v.so
   [ -n "$v" ] && [ ! -f "$lib" ] && continue
   res=$(env ${lib:+GWI_LIBRARY=$lib} python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
@@ -83,6 +85,15 @@ for tune in "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=16" "GWI_TUNE_GUIDED_DIV=1 GWI_
   run_one "product $tune shard8" "" "$tune" --workload cfg3 --emulate-world 8
   run_one "product $tune" "" "$tune" --workload cfg3
 done
+# role-split stream kernel (producer / consumer warp pairs, 128 registers): needs its build AND GWI_SPLIT=1
+if [ -f gwinferno_b200/libgwi_split.so ]; then
+  res=$(GWI_SPLIT=1 GWI_LIBRARY=gwinferno_b200/libgwi_split.so python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
+  echo "{\"label\": \"split GWI_SPLIT=1\", \"pytest_gpu\": \"$res\"}" | tee -a $OUT/${TAG}_matrix.jsonl
+  run_one "split GWI_SPLIT=1" gwinferno_b200/libgwi_split.so "GWI_SPLIT=1" --workload cfg3
+  run_one "split GWI_SPLIT=1 n_deep=4" gwinferno_b200/libgwi_split.so "GWI_SPLIT=1" --workload cfg3 --n-deep 4
+  run_one "split GWI_SPLIT=1 shard8" gwinferno_b200/libgwi_split.so "GWI_SPLIT=1" --workload cfg3 --emulate-world 8
+  run_one "split GWI_SPLIT=1 cfg2" gwinferno_b200/libgwi_split.so "GWI_SPLIT=1" --workload cfg2 --steps 200 --warmup 20
+fi
 # deep-dim split with the unified pair path (the plan's cost model was calibrated for the old path)
 for nd in 2 4; do
   [ -f gwinferno_b200/libgwi_uni2.so ] && run_one "uni2 n_deep=$nd" gwinferno_b200/libgwi_uni2.so "" --workload cfg3 --n-deep $nd
