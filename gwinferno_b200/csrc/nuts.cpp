@@ -693,7 +693,6 @@ int gwi_posterior_dim(const gwi_posterior* p) { return p ? p->dim : (int)GWI_ERR
 // reference's nan_to_num(-inf) sentinel, analysis.py:272-277) or the evaluation reports an error
 double gwi_posterior_potential(void* ctx, const double* theta, double* grad) {
   gwi_posterior* p = static_cast<gwi_posterior*>(ctx);
-  const int P = p->n_params;
   const double inf = std::numeric_limits<double>::infinity();
   std::fill(p->lam.begin(), p->lam.end(), 0.0);
   for (int i = 0; i < p->dim; ++i) p->lam[p->free_slot[i]] = theta[i];
