@@ -85,6 +85,10 @@ for tune in "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=16" "GWI_TUNE_GUIDED_DIV=1 GWI_
   run_one "product $tune shard8" "" "$tune" --workload cfg3 --emulate-world 8
   run_one "product $tune" "" "$tune" --workload cfg3
 done
+# config-2 size: one flush (~1 700 instructions) per 8-step chunk today; longer minimum slices halve / quarter that
+for tune in "GWI_TUNE_LMIN=16" "GWI_TUNE_LMIN=32" "GWI_TUNE_GUIDED_DIV=1 GWI_TUNE_LMIN=32"; do
+  run_one "product $tune cfg2" "" "$tune" --workload cfg2 --steps 200 --warmup 20
+done
 # role-split stream kernel (producer / consumer warp pairs, 128 registers): needs its build AND GWI_SPLIT=1
 if [ -f gwinferno_b200/libgwi_split.so ]; then
   res=$(GWI_SPLIT=1 GWI_LIBRARY=gwinferno_b200/libgwi_split.so python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
