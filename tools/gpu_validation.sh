@@ -27,4 +27,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --lo
 # full capture of the dominant kernel
 ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 3 -c 1 -f -o "$OUT/${TAG}_stream_kernel" \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2> "$OUT/${TAG}_ncu_full_err.txt"
+# the second half of the metric: NUTS ESS/s on config 2, sampler loop in native code (csrc/nuts.cpp)
+python tools/nuts_ess.py --driver native --warmup 200 --samples 300 > "$OUT/${TAG}_nuts_cfg2.json" 2> "$OUT/${TAG}_nuts_err.txt"
+tail -c 600 "$OUT/${TAG}_nuts_cfg2.json"; echo
 ls -la "$OUT" | tail -12
