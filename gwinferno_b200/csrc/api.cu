@@ -22,7 +22,8 @@ typedef void (*stream_fn)(const ModelDev*);
 stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, bool maxonly);
 stream_fn pick_stream_split_kernel(int ns, int ndeep, int nlin, bool g2);  // experiment builds only (else nullptr)
 size_t stream_split_extra_smem(int npairs);
-void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st);
+void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st, int use_learned_shift);
+void launch_segmax_learn(const ModelDev* Md, int n_seg, int nc, cudaStream_t st);
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux);
 void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st);
 void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st);
@@ -81,6 +82,11 @@ struct gwi_model {
   stream_fn k_full = nullptr, k_max = nullptr;
   size_t smem_full = 0, smem_max = 0;
   // GWI_SPLIT=1 on a -DGWI_EXP_SPLIT=1 build: producer / consumer warp pairs (stream_split.cuh)
+  // GWI_SPECULATIVE_SHIFT=1 on a -DGWI_EXP_TRACK_MAX=1 build (host call only, one chain): models that need
+  // the exact per-segment maximum take it from the previous evaluation's full pass instead of a max-only pass
+  bool spec_shift = false;      // switch
+  bool spec_learned = false;    // shift_next holds maxima of an earlier evaluation
+  bool spec_allowed_now = false;  // set by gwi_loglike_host around its first attempt
   stream_fn k_split = nullptr;
   size_t smem_split = 0;
   int split_pairs = 0;
@@ -303,6 +309,8 @@ static int alloc_chain_scratch(gwi_model* m, ModelDev& H) {
   UPS(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_J1));
   UPS(upload<double>(m, nullptr, (size_t)nseg * P, &H.seg_Jn));
   UPS(upload<double>(m, nullptr, (size_t)3 + 2 * P, &H.inj_raw));
+  UPS(upload<double>(m, nullptr, (size_t)nseg, &H.shift_next));
+  UPS(upload<double>(m, nullptr, (size_t)nseg, &H.spec_bad));
   {
     // arrival counters of the fused epilogue (zeroed here; the kernel leaves them zero)
     int n_counters = 0;
@@ -582,6 +590,11 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     m->fused_epilogue = e && e[0] == '1';
     const char* g = std::getenv("GWI_GRAPH");
     m->use_graph = g && g[0] == '1';
+#if GWI_EXP_TRACK_MAX
+    const char* sp = std::getenv("GWI_SPECULATIVE_SHIFT");
+    m->spec_shift = sp && sp[0] == '1' && H.two_pass;
+    if (m->spec_shift) m->use_graph = false;  // the launch sequence differs from call to call
+#endif
   }
   {
     const char* e = std::getenv("GWI_SPLIT");
@@ -615,10 +628,11 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   cudaStreamWaitEvent(m->aux_stream, m->ev_fork, 0);
   launch_prologue_groups(m->dev, lam_dev, H.n_groups, m->max_grid, nc, m->aux_stream);
   cudaEventRecord(m->ev_join, m->aux_stream);
-  launch_prologue_tables(m->dev, lam_dev, H.n_groups, nc, st);
+  const bool speculate = m->spec_shift && m->spec_allowed_now && m->spec_learned && nc == 1 && !exact_shift && !m->force_exact_shift;
+  launch_prologue_tables(m->dev, lam_dev, H.n_groups, nc, st, speculate ? 1 : 0);
   const dim3 grid(m->stream_grid_x, nc), block(p.warps_per_block * 32);
   if (H.n_chunks > 0) {
-    if (H.two_pass || exact_shift || m->force_exact_shift) {
+    if ((H.two_pass && !speculate) || exact_shift || m->force_exact_shift) {
       // exact per-segment maximum first (always for models with non-linear terms; as a fallback when
       // the a-priori bound was so loose that every weight of a segment underflowed)
       GWI_LAUNCH(m->k_max, grid, block, m->smem_max, st)(m->dev);
@@ -632,6 +646,10 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
       GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev);
     }
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
+    if (m->spec_shift && nc == 1) {
+      launch_segmax_learn(m->dev, H.n_segments, nc, st);  // next evaluation's shift; flags this one if its shift was off
+      m->spec_learned = true;
+    }
   }
   const int n_levels = (int)m->level_tasks.size();
   if (epi_done) *epi_done = false;
@@ -771,6 +789,11 @@ int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opt
   CUDA_TRY(cudaSetDevice(m->device));
   const int P = m->plan.n_params;
   std::memcpy(m->lam_pinned, lambda_host, sizeof(double) * P);
+  m->spec_allowed_now = m->spec_shift;
+  struct SpecGuard {
+    gwi_model* m;
+    ~SpecGuard() { m->spec_allowed_now = false; }
+  } spec_guard{m};
   if (m->use_graph && opts && !m->timing && !m->force_exact_shift) {
     // the kernels take `opts` by value: a graph is valid for the options it was captured with
     if (m->graph_exec && std::memcmp(&m->graph_opts, opts, sizeof(gwi_like_opts)) != 0) {
@@ -810,7 +833,8 @@ int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opt
   }
   CUDA_TRY(cudaStreamSynchronize(m->own_stream));
   std::memcpy(out_host, m->out_pinned, sizeof(double) * (GWI_LIKE_HEADER + P));
-  if (out_host[GWI_LIKE_STATUS] != 0.0 && !m->host.two_pass && !m->force_exact_shift) {
+  if (out_host[GWI_LIKE_STATUS] != 0.0 && (!m->host.two_pass || m->spec_shift) && !m->force_exact_shift) {
+    m->spec_allowed_now = false;
     // the a-priori shift bound was too loose for this Lambda (all weights of a segment
     // underflowed): repeat once with the exact per-segment maximum
     m->force_exact_shift = true;
@@ -881,7 +905,7 @@ int gwi_model_get_info(const gwi_model* m, gwi_model_info* info) {
   info->grid_blocks = p.grid_blocks;
   info->block_threads = p.warps_per_block * 32;
   info->kernel_launches_per_eval = m->launches_per_eval;
-  info->active_switches = (m->fused_epilogue ? 1 : 0) | (m->use_graph ? 2 : 0) | (m->k_split ? 4 : 0);
+  info->active_switches = (m->fused_epilogue ? 1 : 0) | (m->use_graph ? 2 : 0) | (m->k_split ? 4 : 0) | (m->spec_shift ? 8 : 0);
   return GWI_OK;
 }
 

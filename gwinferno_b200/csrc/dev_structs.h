@@ -13,7 +13,18 @@
 #define GWI_LAUNCH(kernel, grid, block, smem, stream) kernel<<<(grid), (block), (smem), (stream)>>>
 #endif
 
+// GWI_EXP_TRACK_MAX (experiment switch, default 0; run-time side: GWI_SPECULATIVE_SHIFT=1): the full pass of
+// the stream kernel also records every chunk's max x, so that models without an a-priori bound (parametric
+// terms, spline densities) can take the NEXT evaluation's log-sum-exp shift from THIS evaluation's exact
+// maxima instead of running a max-only pass first; an evaluation whose maxima moved by more than
+// SPEC_SHIFT_TOL from the shift it used is flagged and repeated with the exact maximum by the host call.
+#ifndef GWI_EXP_TRACK_MAX
+#define GWI_EXP_TRACK_MAX 0
+#endif
+
 namespace gwi {
+
+constexpr double SPEC_SHIFT_TOL = 500.0;  // e^-500 .. e^+500 around the shift: no under/overflow, full fp64 precision
 
 struct DimDev {
   int32_t rows, row_off, slot, n_splines;
@@ -92,6 +103,9 @@ struct ModelDev {
   int32_t* epi_counters;
   int32_t epi_level_off[6];
   int32_t epi_seg_counter, epi_pad;
+  // speculative shift (GWI_EXP_TRACK_MAX): maxima learned from the last full pass; 1.0 where the shift used was too far off
+  double* shift_next;  // [n_segments]
+  double* spec_bad;    // [n_segments], zero unless a speculative evaluation has to be repeated
 };
 
 // partial (per-rank) likelihood record: 8 header doubles + 3P

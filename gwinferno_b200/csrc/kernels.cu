@@ -130,7 +130,7 @@ __device__ void powerlaw_lognorm(double alpha, double lo, double hi, double& log
 // =================================================================================================
 // prologue
 // =================================================================================================
-__global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam0, int role_off) {
+__global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam0, int role_off, int use_learned_shift) {
   GWI_STAGED_DESC(M, Mp[blockIdx.y]);  // blockIdx.y = chain
   const double* __restrict__ Lam = Lam0 + (size_t)blockIdx.y * M.n_params;
   extern __shared__ double sm[];
@@ -260,6 +260,8 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     M.slice_counter[0] = 0;
     M.slice_counter[1] = 0;
   }
+  if (use_learned_shift)  // speculative shift: the maxima of the previous evaluation's full pass
+    for (int sg = tid; sg < M.n_segments; sg += nt) M.shift[sg] = M.shift_next[sg];
   for (int r = tid; r < M.rows_total; r += nt) {
     int d = 0;
     while (d + 1 < M.n_dims && r >= M.dims[d + 1].row_off) ++d;
@@ -398,6 +400,23 @@ __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict_
   if (threadIdx.x == 0) M.shift[s] = (mx > -INFINITY && mx < INFINITY) ? mx : 0.0;
 }
 
+// after a full pass that recorded the chunk maxima (GWI_EXP_TRACK_MAX): learn the next evaluation's shift and
+// flag the segments whose maximum is too far from the shift this evaluation used
+__global__ void __launch_bounds__(256) segmax_learn_kernel(const ModelDev* __restrict__ Mp) {
+  const ModelDev& M = Mp[blockIdx.y];
+  __shared__ double scratch[32];
+  const int s = blockIdx.x;
+  const SegDev& S = M.segs[s];
+  double mx = -INFINITY;
+  for (int c = threadIdx.x; c < S.n_chunks; c += blockDim.x) mx = fmax(mx, M.chunk_max[S.first_chunk + c]);
+  mx = block_max(mx, scratch);
+  if (threadIdx.x == 0) {
+    const bool finite = mx > -INFINITY && mx < INFINITY;
+    M.shift_next[s] = finite ? mx : 0.0;
+    M.spec_bad[s] = (finite && !(fabs(mx - M.shift[s]) < SPEC_SHIFT_TOL)) ? 1.0 : 0.0;
+  }
+}
+
 // =================================================================================================
 // finish: per segment
 // =================================================================================================
@@ -414,7 +433,10 @@ __device__ void finish_segment(const ModelDev& M, int s, const double* rec) {
   const double* M2 = M1 + M.rows_total * 4;
   double K = M.Ksum[0];
   for (int g = 0; g < M.n_groups; ++g) K -= M.logZ[g];
-  const bool ok = (S1 > 0.0) && (S1 < INFINITY) && (S2 > 0.0) && (S2 < INFINITY);
+  bool ok = (S1 > 0.0) && (S1 < INFINITY) && (S2 > 0.0) && (S2 < INFINITY);
+#if GWI_EXP_TRACK_MAX
+  ok = ok && M.spec_bad[s] == 0.0;  // the learned shift was too far from this evaluation's maximum
+#endif
   const double N = M.total_inj;
   const double den_inj = S2 - S1 * S1 / N;
   if (threadIdx.x == 0) {
@@ -756,11 +778,12 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const ModelDev* __restric
 // =================================================================================================
 // tables + shifts (what the stream kernel needs) on `st`; the grid normalisers (only needed by
 // finish_kernel) on `aux`, concurrently with the stream kernel.  `nc` = number of chains.
-void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st) {
-  GWI_LAUNCH(prologue_kernel, dim3(1, nc), 256, 0, st)(Md, lam, n_groups);
+void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st, int use_learned_shift) {
+  GWI_LAUNCH(prologue_kernel, dim3(1, nc), 256, 0, st)(Md, lam, n_groups, use_learned_shift);
 }
+void launch_segmax_learn(const ModelDev* Md, int n_seg, int nc, cudaStream_t st) { GWI_LAUNCH(segmax_learn_kernel, dim3(n_seg, nc), 256, 0, st)(Md); }
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux) {
-  if (n_groups > 0) GWI_LAUNCH(prologue_kernel, dim3(n_groups, nc), 256, (size_t)max_grid * sizeof(double), aux)(Md, lam, 0);
+  if (n_groups > 0) GWI_LAUNCH(prologue_kernel, dim3(n_groups, nc), 256, (size_t)max_grid * sizeof(double), aux)(Md, lam, 0, 0);
 }
 void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st) {
   dim3 grid(n_tasks, (rec + 255) / 256, nc);

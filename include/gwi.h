@@ -231,7 +231,7 @@ typedef struct {
   int32_t n_spline_dims, n_deep, n_linear, n_param_terms;
   int32_t grid_blocks, block_threads;
   int32_t kernel_launches_per_eval; /* kernels launched by one gwi_loglike call */
-  int32_t active_switches;  /* tuning switches in effect: 1 fused epilogue, 2 CUDA-graph host call, 4 role-split stream kernel */
+  int32_t active_switches;  /* tuning switches in effect: 1 fused epilogue, 2 CUDA-graph host call, 4 role-split stream kernel, 8 speculative shift */
 } gwi_model_info;
 int gwi_model_get_info(const gwi_model* m, gwi_model_info* info);
 

@@ -21,6 +21,7 @@ declare -A VARIANTS=(
   [exp3]="-DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
   [exp4]="-DGWI_EXP_RED_SPILL=1 -DGWI_EXP_DEEP_GROUPED=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_SINGLE_BUF=1"
   [split]="-DGWI_EXP_SPLIT=1"
+  [track]="-DGWI_EXP_TRACK_MAX=1"
   [stage]="-DGWI_EXP_STAGE_DESC=1"
   [uni]="-DGWI_EXP_UNIFIED_PAIR=1"
   [uni2]="-DGWI_EXP_UNIFIED_PAIR=1 -DGWI_EXP_RESET_CUR=1 -DGWI_EXP_RED_SPILL=1"
@@ -60,6 +61,7 @@ PY
 for v in "" "${!VARIANTS[@]}"; do
   if [ -n "$v" ] && [ -n "${ONLY:-}" ]; then case " $ONLY " in *" $v "*) ;; *) continue ;; esac; fi
   [ "$v" = split ] && continue  # needs GWI_SPLIT=1: measured separately below
+  [ "$v" = track ] && continue  # needs GWI_SPECULATIVE_SHIFT=1: measured separately below
   lib=""; [ -n "$v" ] && lib=gwinferno_b200/libgwi_$v.so
   [ -n "$v" ] && [ ! -f "$lib" ] && continue
   res=$(env ${lib:+GWI_LIBRARY=$lib} python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
@@ -97,6 +99,13 @@ if [ -f gwinferno_b200/libgwi_split.so ]; then
   run_one "split GWI_SPLIT=1 n_deep=4" gwinferno_b200/libgwi_split.so "GWI_SPLIT=1" --workload cfg3 --n-deep 4
   run_one "split GWI_SPLIT=1 shard8" gwinferno_b200/libgwi_split.so "GWI_SPLIT=1" --workload cfg3 --emulate-world 8
   run_one "split GWI_SPLIT=1 cfg2" gwinferno_b200/libgwi_split.so "GWI_SPLIT=1" --workload cfg2 --steps 200 --warmup 20
+fi
+# parametric models (cfg1): one pass instead of two with the shift learned from the previous evaluation (e2e column)
+if [ -f gwinferno_b200/libgwi_track.so ]; then
+  res=$(GWI_SPECULATIVE_SHIFT=1 GWI_LIBRARY=gwinferno_b200/libgwi_track.so python -m pytest tests -m gpu -x -q 2>&1 | tail -1)
+  echo "{\"label\": \"track GWI_SPECULATIVE_SHIFT=1\", \"pytest_gpu\": \"$res\"}" | tee -a $OUT/${TAG}_matrix.jsonl
+  run_one "product cfg1" "" "" --workload cfg1 --steps 200 --warmup 20
+  run_one "track speculative cfg1" gwinferno_b200/libgwi_track.so "GWI_SPECULATIVE_SHIFT=1" --workload cfg1 --steps 200 --warmup 20
 fi
 # deep-dim split with the unified pair path (the plan's cost model was calibrated for the old path)
 for nd in 2 4; do
