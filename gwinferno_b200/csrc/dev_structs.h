@@ -24,7 +24,7 @@
 
 namespace gwi {
 
-constexpr double SPEC_SHIFT_TOL = 500.0;  // e^-500 .. e^+500 around the shift: no under/overflow, full fp64 precision
+constexpr double SPEC_SHIFT_TOL = 300.0;  // p = e^(x - shift) within e^+-300 at the maximum: p and p^2 (N_eff sums) stay far from the fp64 limits
 
 struct DimDev {
   int32_t rows, row_off, slot, n_splines;
