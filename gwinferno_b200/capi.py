@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GWI_LIBRARY", os.path.join(_HERE, "libgwi.so"))  # override: tuning experiments only
 
-GWI_VERSION = 2  # include/gwi.h: GWI_VERSION (6 Lambda slots per term)
+GWI_VERSION = 3  # include/gwi.h: GWI_VERSION (gwi_model_last_sites, library-owned exchange)
 GWI_LIKE_HEADER = 8
 LIKE_FIELDS = ("log_l", "passed", "log_mu", "logNeff_inj", "min_logNeff", "sum_logBF", "variance", "status")
 PARTIAL_HEADER = 8
@@ -133,6 +133,7 @@ class gwi_model_info(C.Structure):
 
 # every symbol include/gwi.h declares (tests check that the library exports all of them)
 SYMBOLS = [
+    "gwi_model_last_sites",
     "gwi_catalog_create",
     "gwi_catalog_destroy",
     "gwi_model_create",
@@ -196,6 +197,8 @@ def load_library(_allow_emulator=False):
     lib.gwi_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gwi_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
     lib.gwi_model_get_info.argtypes = [C.c_void_p, C.POINTER(gwi_model_info)]
+    lib.gwi_model_last_sites.restype = C.c_int64
+    lib.gwi_model_last_sites.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int64]
     lib.gwi_model_set_exact_shift.argtypes = [C.c_void_p, C.c_int32]
     lib.gwi_model_set_timing.argtypes = [C.c_void_p, C.c_int32]
     lib.gwi_model_stream_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
@@ -458,6 +461,18 @@ class Model:
         i = gwi_model_info()
         _check(load_library().gwi_model_get_info(self.handle, C.byref(i)))
         return {n: getattr(i, n) for n, _ in gwi_model_info._fields_ if n != "reserved"}
+
+    def last_sites(self):
+        """``[E + 1, 4]`` {log mean weight, log N_eff, variance, status} of the last evaluation; row 0 = injections."""
+        lib = load_library()
+        n = lib.gwi_model_last_sites(self.handle, None, 0)
+        if n < 0:
+            _check(int(n))
+        out = np.zeros(int(n))
+        got = lib.gwi_model_last_sites(self.handle, _dptr(out), int(n))
+        if got < 0:
+            _check(int(got))
+        return out.reshape(-1, 4)
 
     def set_exact_shift(self, on=True):
         _check(load_library().gwi_model_set_exact_shift(self.handle, int(on)))

@@ -886,6 +886,22 @@ int gwi_model_stream_times(gwi_model* m, float* ms_out, int32_t cap) {
   return (int)n;
 }
 
+int64_t gwi_model_last_sites(gwi_model* m, double* dst_host, int64_t cap) {
+  if (!m) return GWI_ERR_INVALID;
+  const int64_t n = 4 * (int64_t)m->plan.segments.size();
+  if (!dst_host) return n;
+  if (cap < n) {
+    set_error("gwi_model_last_sites: destination too small");
+    return GWI_ERR_INVALID;
+  }
+  if (cudaSetDevice(m->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(dst_host, m->host.seg_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error(std::string("gwi_model_last_sites: ") + cudaGetErrorString(cudaGetLastError()));
+    return GWI_ERR_CUDA;
+  }
+  return n;
+}
+
 int gwi_model_get_info(const gwi_model* m, gwi_model_info* info) {
   if (!m || !info) return GWI_ERR_INVALID;
   const Plan& p = m->plan;

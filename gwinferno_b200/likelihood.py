@@ -11,11 +11,20 @@ NumPyro in the loop the "sites" the reference records with ``numpyro.determinist
 There is no CPU fallback: a missing library or GPU raises :class:`gwinferno_b200.capi.GwiError`.
 """
 
+import collections
+import os
+import warnings
+
 import numpy as np
 
 from . import capi, lowering
 
-_ENGINES = {}
+# device-resident plans, keyed by the uids of the model objects / sample arrays of a weight product
+# (models._uid_of: never re-used, unlike id()); least-recently-used plans are closed when more than
+# GWI_MAX_ENGINES (default 8) are alive -- a cfg-3 plan is 7.4 GB of device memory
+_ENGINES = collections.OrderedDict()
+_MAX_ENGINES = max(1, int(os.environ.get("GWI_MAX_ENGINES", "8")))
+_BUILDS = collections.Counter()  # (term kinds, sharing pattern) -> plans built; warns when one model shape keeps missing the cache
 
 
 class PopulationLikelihood:
@@ -48,6 +57,12 @@ class PopulationLikelihood:
         )
         return head["log_l"], grad, head
 
+    def last_sites(self):
+        """Per-event sites of the LAST evaluation (analysis.py:260-264): ``logBFs``, ``log_nEffs``,
+        ``variance_log_BFs`` [E] and ``variance_log_detection_efficiency``, read back from the device."""
+        seg = self.model.last_sites()
+        return {"logBFs": seg[1:, 0].copy(), "log_nEffs": seg[1:, 1].copy(), "variance_log_BFs": seg[1:, 2].copy(), "variance_log_detection_efficiency": float(seg[0, 2])}
+
     def info(self):
         return self.model.info()
 
@@ -66,6 +81,10 @@ class LikelihoodResult:
             "variance_log_likelihood": head["variance"],
             "passed_cuts": bool(head["passed"]),
         }
+        # per-event sites of analysis.py:260-264 (read back from the device results of this evaluation)
+        for k in ("logBFs", "log_nEffs", "variance_log_BFs", "variance_log_detection_efficiency"):
+            if k in head:
+                self.sites[k] = head[k]
         if surveyed_hypervolume is not None:
             self.sites["surveyed_hypervolume"] = float(surveyed_hypervolume) / 1.0e9 * Tobs
         self._lowered = lowered
@@ -73,8 +92,13 @@ class LikelihoodResult:
         self.rate = None
 
     def grad(self, param):
-        """Gradient of log_l with respect to a parameter OBJECT that was passed to the model calls."""
-        return self.grad_flat[self._lowered.slots_for(param)]
+        """Gradient of log_l with respect to a parameter OBJECT that was passed to the model calls
+        (the total derivative: summed over every argument position the object was passed to)."""
+        sl = self._lowered.all_slots_for(param)
+        g = self.grad_flat[sl[0]]
+        for extra in sl[1:]:
+            g = g + self.grad_flat[extra]
+        return g
 
 
 def hierarchical_likelihood(
@@ -107,7 +131,11 @@ def hierarchical_likelihood(
     on lazy weights.  ``log=True`` takes lazy LOG-weights (``log_prob`` terms combined with ``+`` and
     ``- jnp.log(prior)``, analysis.py:401-421); the fused path always works in log space, so both forms
     lower to the same device model.  The categorical sub-population branch (:246-254) and posterior-predictive
-    resampling (:321-355) are outside the fused hot path and raise NotImplementedError."""
+    resampling (:321-355, with it ``param_names`` / ``pedata`` / ``injdata`` / ``m2min`` / ``m1min`` / ``mmax``)
+    are outside the fused hot path and raise NotImplementedError.  ``reconstruct_rate`` (:265-268): NumPyro
+    draws ``unscaled_rate ~ Gamma(Nobs)`` from the trace's key; here it is drawn from
+    ``numpy.random.default_rng(rngkey)`` (``rngkey``: an int seed or ``None``) when a surveyed hypervolume is
+    given, and returned -- as in the reference -- as the function's ``rate`` (``LikelihoodResult.rate``)."""
     if max_variance_cut and (marginalize_selection or min_neff_cut):
         raise ValueError(
             "max_variance_cut is True which requires marginalize_selection and min_neff_cut to be False but got "
@@ -117,22 +145,43 @@ def hierarchical_likelihood(
         raise ValueError("log=True expects log-weights (built from log_prob with + / -), log=False expects weights (built with * and /)")
     if categorical or marginal_qs:
         raise NotImplementedError("the categorical sub-population branch is not part of the fused path")
+    if posterior_predictive_check:
+        raise NotImplementedError("posterior-predictive resampling (analysis.py:321-355) is not part of the fused path: draw from the per-sample weights on the host")
     keys, pattern = lowering._structure(pe_weights, inj_weights)
     cache_key = (keys, pattern, float(total_inj), bool(marginalize_selection), int(device))
     eng = _ENGINES.get(cache_key)
     if eng is None:
+        shape_key = (tuple(k[0] if isinstance(k[0], str) else k[1] for k in keys), pattern)
+        _BUILDS[shape_key] += 1
+        if _BUILDS[shape_key] == 4:
+            warnings.warn("hierarchical_likelihood built a new device plan for the same model shape 4 times: a model object or sample array is "
+                          "re-created on every call (construct the models once, outside the sampled function)", RuntimeWarning, stacklevel=2)
         eng = PopulationLikelihood.from_weights(pe_weights, inj_weights, total_inj, device=device, need_neff_grad=bool(marginalize_selection))
         _ENGINES[cache_key] = eng
+        while len(_ENGINES) > _MAX_ENGINES:
+            _, old = _ENGINES.popitem(last=False)
+            old.model.close()
+            old.catalog.close()
         lowered = eng.lowered
     else:
+        _ENGINES.move_to_end(cache_key)
         # same static structure, new hyper-parameter objects: rebuild only the slot map
-        lowered = lowering.Lowered(eng.spec, eng.lowered.pe_cols, eng.lowered.inj_cols, eng.lowered.param_layout, _slot_map(pe_weights))
+        lowered = lowering.Lowered(eng.spec, eng.lowered.pe_cols, eng.lowered.inj_cols, eng.lowered.param_layout, lowering.object_slot_map(pe_weights))
     lam = lowering.flatten_params(pe_weights, eng.n_params)
     log_l, grad, head = eng.loglike(lam, Nobs=Nobs, marginalize_selection=marginalize_selection, min_neff_cut=min_neff_cut, max_variance_cut=max_variance_cut)
+    head = dict(head)
+    head.update(eng.last_sites())
     # O(P) host glue: chain rule through parameter maps; per-sample constants kept off the device
     grad = lowering.pull_back(pe_weights, grad)
     log_l, grad, head = apply_host_norm(log_l, grad, head, *lowering.host_log_norm(pe_weights, eng.n_params), n_events=eng.n_events, Nobs=Nobs)
-    return LikelihoodResult(log_l, grad, head, lowered, pe_weights, surveyed_hypervolume, Tobs, Nobs)
+    res = LikelihoodResult(log_l, grad, head, lowered, pe_weights, surveyed_hypervolume, Tobs, Nobs)
+    if reconstruct_rate and surveyed_hypervolume is not None:
+        # analysis.py:265-268
+        total_vt = float(surveyed_hypervolume) / 1.0e9 * Tobs
+        unscaled = float(np.random.default_rng(rngkey).gamma(Nobs))
+        res.sites["unscaled_rate"] = unscaled
+        res.rate = res.sites["rate"] = unscaled / float(np.exp(head["log_mu"])) / total_vt
+    return res
 
 
 def apply_host_norm(log_l, grad, head, logZ, dlogZ, n_events, Nobs):
@@ -145,20 +194,12 @@ def apply_host_norm(log_l, grad, head, logZ, dlogZ, n_events, Nobs):
     head = dict(head)
     head["log_mu"] = head["log_mu"] - logZ
     head["sum_logBF"] = head["sum_logBF"] - n_events * logZ
+    if "logBFs" in head:
+        head["logBFs"] = head["logBFs"] - logZ
     if head["passed"]:
         log_l = log_l + (Nobs - n_events) * logZ
         grad = grad + (Nobs - n_events) * dlogZ
     return log_l, grad, head
-
-
-def _slot_map(pe_w):
-    slot_of, off = {}, 0
-    for t in pe_w.terms:
-        for p, k in zip(t.params, t.param_keys):
-            if k not in slot_of:
-                slot_of[k] = off
-                off += p.size
-    return slot_of
 
 
 def clear_cache():

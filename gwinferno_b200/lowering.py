@@ -54,12 +54,21 @@ class Lowered:
         self.pe_cols = pe_cols  # name -> (E, S) float64
         self.inj_cols = inj_cols  # name -> (I,) float64
         self.param_layout = param_layout  # list of (slot, size) in order of first appearance
-        self.slot_of = slot_of  # id(parameter object of the lowering call) -> first Lambda slot
+        # id(parameter object of the lowering call) -> Lambda offsets of every argument position it was
+        # passed to (arrays shared by IID models: one; a scalar object passed twice: two)
+        self.slot_of = slot_of
+
+    def all_slots_for(self, obj):
+        """Every Lambda index range a parameter object of the model calls occupies."""
+        n = int(np.size(obj))
+        return [slice(off, off + n) for off in self.slot_of[id(obj)]]
 
     def slots_for(self, obj):
         """Lambda index range of a parameter object that was passed to the model calls."""
-        off = self.slot_of[id(obj)]
-        return slice(off, off + int(np.size(obj)))
+        sl = self.all_slots_for(obj)
+        if len(sl) != 1:
+            raise ValueError("this scalar object was passed to several argument positions (each has its own Lambda slot): use all_slots_for() / LikelihoodResult.grad()")
+        return sl[0]
 
 
 def _structure(pe_w, inj_w):
@@ -75,6 +84,21 @@ def _structure(pe_w, inj_w):
             pattern.append((seen[k], p.size))
     keys = tuple(t.key for t in pe_w.terms) + tuple(t.key for t in inj_w.terms)
     return keys, tuple(pattern)
+
+
+def object_slot_map(pe_w):
+    """``{id(parameter object): [Lambda offsets]}`` of one lowering call (the objects are alive in the
+    lazy terms for as long as the weights are)."""
+    key_off, obj_offs, off = {}, {}, 0
+    for t in pe_w.terms:
+        for p, k, o in zip(t.params, t.param_keys, t._orig):
+            if k not in key_off:
+                key_off[k] = off
+                off += p.size
+            lst = obj_offs.setdefault(id(o), [])
+            if key_off[k] not in lst:
+                lst.append(key_off[k])
+    return obj_offs
 
 
 def _param_blocks(pe_w):
@@ -195,4 +219,4 @@ def lower(pe_w, inj_w):
     shapes = {v.shape for v in inj_cols.values()}
     if len(shapes) != 1:
         raise ValueError(f"injection columns have inconsistent shapes: {shapes}")
-    return Lowered(spec, pe_cols, inj_cols, layout, slot_of)
+    return Lowered(spec, pe_cols, inj_cols, layout, object_slot_map(pe_w))

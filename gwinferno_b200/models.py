@@ -12,6 +12,10 @@ reference's weight assembly uses them (examples/simple_bspline_example.py:58-68)
 Nothing here evaluates a density on the CPU: there is no CPU fallback.
 """
 
+import collections
+import hashlib
+import itertools
+
 import numpy as np
 
 from . import spec as S
@@ -76,6 +80,68 @@ class LogXLogYBSpline(LogYBSpline):
     logx, logy, default_normalize, n_grid = True, True, True, 1500
 
 
+# ---- stable identities ---------------------------------------------------------------------------
+# The static plan (device-resident, expensive) is cached by WHICH model objects / sample arrays a
+# weight product is built from.  ``id()`` alone is not an identity: CPython re-uses the address of a
+# collected object, so a new model over a different catalog could hit the old plan.  Every keyed
+# object therefore gets a process-unique, never re-used uid: model objects carry it as an attribute,
+# arrays (which take no attributes) are looked up in a bounded registry that holds a strong
+# reference while the entry lives (an evicted array that shows up again simply gets a new uid: a
+# cache miss, never a wrong hit).
+_UID = itertools.count(1)
+_ARRAY_UIDS = collections.OrderedDict()  # id(array) -> (array, uid, fingerprint), LRU
+_ARRAY_BY_PRINT = {}  # fingerprint -> id(array) of the registered representative
+_ARRAY_UIDS_MAX = 256
+
+
+def _fingerprint(a):
+    """Cheap content fingerprint of an array (shape, dtype, <= 4096 strided elements)."""
+    flat = a.reshape(-1) if a.flags.c_contiguous else np.ravel(a)
+    n = flat.size
+    probe = flat[:: max(1, n // 4096)][:4096] if n else flat
+    return (a.shape, a.dtype.str, hashlib.blake2b(np.ascontiguousarray(probe).tobytes(), digest_size=16).digest())
+
+
+def _uid_of(obj):
+    """Process-unique identity of a keyed object.  Arrays: the SAME object, or an array with EQUAL
+    content (an array the user recomputes on every call, e.g. ``jnp.log(prior)`` or ``m1 * q`` inside
+    the model function, analysis.py:401-402), maps to the same uid; the content comparison only runs
+    on an identity miss and is exact (fingerprint first, then ``np.array_equal``)."""
+    if obj is None:
+        return 0
+    d = getattr(obj, "__dict__", None)
+    if d is not None:
+        u = d.get("_gwi_uid")
+        if u is None:
+            u = d["_gwi_uid"] = next(_UID)
+        return u
+    key = id(obj)
+    hit = _ARRAY_UIDS.get(key)
+    if hit is not None and hit[0] is obj:
+        _ARRAY_UIDS.move_to_end(key)
+        return hit[1]
+    fp = _fingerprint(obj) if isinstance(obj, np.ndarray) else None
+    if fp is not None:
+        rep = _ARRAY_UIDS.get(_ARRAY_BY_PRINT.get(fp))
+        if rep is not None and rep[2] == fp and np.array_equal(rep[0], obj, equal_nan=True):
+            return rep[1]  # equal content: the representative stays the registered one (nothing new is pinned)
+    u = next(_UID)
+    _ARRAY_UIDS[key] = (obj, u, fp)
+    if fp is not None:
+        _ARRAY_BY_PRINT[fp] = key
+    while len(_ARRAY_UIDS) > _ARRAY_UIDS_MAX:
+        k_old, (_, _, fp_old) = _ARRAY_UIDS.popitem(last=False)
+        if fp_old is not None and _ARRAY_BY_PRINT.get(fp_old) == k_old:
+            del _ARRAY_BY_PRINT[fp_old]
+    return u
+
+
+def _share():
+    """Token for a hyper-parameter that one model function hands to several of its terms on purpose
+    (``iid_*``: one Lambda slot, gradient = total derivative)."""
+    return ("shared", next(_UID))
+
+
 class _Column:
     """A (PE array, injection array) pair of one physical sample coordinate."""
 
@@ -88,7 +154,7 @@ class _LazyTerm:
     """One additive log-density term; ``params`` are the hyper-parameter VALUES of this call,
     ``build(slots, group_base)`` produces the static spec entries (terms, groups, cuts)."""
 
-    def __init__(self, key, columns, params, build, maps=None, host_norm=None):
+    def __init__(self, key, columns, params, build, maps=None, host_norm=None, param_keys=None):
         # ``maps``: {index in params: ParamMap} -- an O(P) host-side change of variables applied when
         # Lambda is assembled; gradients are pulled back through it (lowering.pull_back)
         self.maps = dict(maps or {})
@@ -98,10 +164,18 @@ class _LazyTerm:
         self.host_norm = host_norm
         self.key = key  # hashable identity of the STATIC part (model object id, dimension)
         self.columns = columns  # list[_Column]
-        # parameter OBJECTS passed by the caller: the same object given to two terms (IID models,
-        # separable.py:77-79) shares its Lambda slots, so gradients come back per object
+        # parameter OBJECTS passed by the caller.  An ARRAY given to two terms (IID models pass one
+        # coefficient vector to two dimensions, separable.py:77-79) shares its Lambda slots.  Scalars
+        # never share by identity -- equal Python floats are routinely the same object (literals,
+        # small ints, one variable passed twice) without meaning one parameter -- every scalar
+        # argument position is its own slot unless the calling model function shares it explicitly
+        # (``param_keys`` from ``_share()``); gradients come back per object as total derivatives
+        # (``LikelihoodResult.grad``).  Keys only need to be unique within one lowering call; the
+        # objects stay alive in ``_orig`` for that long.
         self._orig = list(params)
-        self.param_keys = [id(p) for p in self._orig]
+        if param_keys is None:
+            param_keys = [None] * len(self._orig)
+        self.param_keys = [k if k is not None else (("arr", id(p)) if np.ndim(p) >= 1 else ("pos", next(_UID))) for p, k in zip(self._orig, param_keys)]
         self.params = [np.atleast_1d(np.asarray(p, dtype=np.float64)) for p in params]
         self.build = build
 
@@ -112,6 +186,9 @@ class ParamMap:
 
     def __init__(self, fwd, vjp):
         self.fwd, self.vjp = fwd, vjp
+
+
+_EXP_CACHE = collections.OrderedDict()  # uid of a log-prior array -> exp of it (stable identity for the plan cache)
 
 
 class LazyWeight:
@@ -163,7 +240,13 @@ class LazyWeight:
         """``log_weight - jnp.log(prior)`` (analysis.py:401-402)."""
         if not self.log_domain or isinstance(other, LazyWeight):
             raise TypeError("only the log of the sampling prior can be subtracted, and only from a log-weight")
-        prior = np.exp(np.asarray(other, dtype=np.float64))
+        log_prior = np.asarray(other, dtype=np.float64)
+        u = _uid_of(log_prior)
+        prior = _EXP_CACHE.get(u)
+        if prior is None:
+            prior = _EXP_CACHE[u] = np.exp(log_prior)
+            while len(_EXP_CACHE) > 16:
+                _EXP_CACHE.popitem(last=False)
         w = weight_from_prior(prior, pe_samples=self.pe_samples)
         return LazyWeight(self.terms + w.terms, self._merge(w), log_domain=True)
 
@@ -179,7 +262,7 @@ def weight_from_prior(prior, pe_samples=None):
     def build(slots, group_base, cols):
         return [S.Term(S.TERM_STATIC, [cols[0]], feature=S.FEAT_NEG_LOG, name="1/prior")], [], []
 
-    return LazyWeight([_LazyTerm(("prior",), [col], [], build)], pe_samples)
+    return LazyWeight([_LazyTerm(("prior", _uid_of(prior)), [col], [], build)], pe_samples)
 
 
 def _is_pe(arr):
@@ -248,7 +331,7 @@ class Base1DBSplineModel:
 
         if np.shape(coefs) != (self.n_splines,):
             raise ValueError(f"expected {self.n_splines} coefficients, got shape {np.shape(coefs)}")
-        return LazyWeight([_LazyTerm((id(self), tag), [self.column], [coefs], build)], pe_samples)
+        return LazyWeight([_LazyTerm((_uid_of(self), tag), [self.column], [coefs], build)], pe_samples)
 
     def __call__(self, coefs, pe_samples=True):
         return self._lazy(coefs, pe_samples)
@@ -292,7 +375,7 @@ def _const_factor(value, column, pe_samples, tag):
     def build(slots, group_base, cols):
         return [S.Term(S.TERM_STATIC, [cols[0]], cst=[float(np.log(value))], feature=S.FEAT_CONST, name=f"const[{tag}]")], [], []
 
-    return LazyWeight([_LazyTerm(("const", tag, float(value), id(column)), [column], [], build)], pe_samples)
+    return LazyWeight([_LazyTerm(("const", tag, float(value), _uid_of(column)), [column], [], build)], pe_samples)
 
 
 class BSplineSymmetricChiEffective(Base1DBSplineModel):
@@ -379,11 +462,11 @@ class BSplineRedshift(Base1DBSplineModel):
         if np.shape(coefs) != (self.n_splines,):
             raise ValueError(f"expected {self.n_splines} coefficients, got shape {np.shape(coefs)}")
         if self._coef_map is None:
-            return LazyWeight([_LazyTerm((id(self), "bsz"), [self.column, self.dvdc_column], [coefs], build)], pe_samples)
+            return LazyWeight([_LazyTerm((_uid_of(self), "bsz"), [self.column, self.dvdc_column], [coefs], build)], pe_samples)
         # normalised basis: the exponent uses c' = c / (a.c) (device, through the ParamMap) while the
         # reference's normaliser uses the raw c (single.py:465-468): a per-sample constant, kept on the host
         return LazyWeight(
-            [_LazyTerm((id(self), "bsz-rescaled"), [self.column, self.dvdc_column], [coefs], build, maps={0: self._coef_map},
+            [_LazyTerm((_uid_of(self), "bsz-rescaled"), [self.column, self.dvdc_column], [coefs], build, maps={0: self._coef_map},
                        host_norm=self._host_norm)],
             pe_samples,
         )
@@ -483,7 +566,7 @@ def _pairing_term(m1col, m2col, beta, pe_samples, cut01):
         cuts = [S.Cut(S.CUT_RATIO_RANGE, [cols[0], cols[1]], 0.0, 1.0)] if cut01 else []
         return [t], [], cuts
 
-    return LazyWeight([_LazyTerm(("pairing", id(m1col), id(m2col), cut01), [m2col, m1col], [beta], build)], pe_samples)
+    return LazyWeight([_LazyTerm(("pairing", _uid_of(m1col), _uid_of(m2col), cut01), [m2col, m1col], [beta], build)], pe_samples)
 
 
 class BSplineIIDComponentMasses:
@@ -515,18 +598,22 @@ class BSplineIndependentComponentMasses:
 # Free functions of sample arrays, as in the reference; the sample set is inferred from the
 # dimensionality of the arrays (2-D = PE samples, 1-D = injections).
 # ================================================================================================
-_COLUMN_CACHE = {}
+_COLUMN_CACHE = collections.OrderedDict()  # uid of the caller's array -> _Column, LRU
+_COLUMN_CACHE_MAX = 64
 
 
 def _col_of(arr):
-    """One _Column per distinct sample array (identity-keyed so the static plan can be cached)."""
-    key = id(arr)
-    hit = _COLUMN_CACHE.get(key)
-    if hit is not None and hit[0] is arr:
-        return hit[1]
+    """One _Column per distinct sample array (keyed by its uid so the static plan can be cached)."""
+    key = _uid_of(arr)
+    col = _COLUMN_CACHE.get(key)
+    if col is not None:
+        _COLUMN_CACHE.move_to_end(key)
+        return col
     a = np.asarray(arr, dtype=np.float64)
     col = _Column(a if _is_pe(a) else None, None if _is_pe(a) else a)
-    _COLUMN_CACHE[key] = (arr, col)
+    _COLUMN_CACHE[key] = col
+    while len(_COLUMN_CACHE) > _COLUMN_CACHE_MAX:
+        _COLUMN_CACHE.popitem(last=False)
     return col
 
 
@@ -536,7 +623,7 @@ def _powerlaw_term(x, alpha, lo, hi, tag):
     def build(slots, group_base, cols):
         return [S.Term(S.TERM_POWERLAW, [cols[0]], slots=[slots[0]], cst=[float(lo), float(hi)], name=f"powerlaw[{cols[0]}]")], [], []
 
-    return LazyWeight([_LazyTerm(("pl", id(x), float(lo), float(hi), tag), [col], [alpha], build)], _is_pe(x))
+    return LazyWeight([_LazyTerm(("pl", _uid_of(x), float(lo), float(hi), tag), [col], [alpha], build)], _is_pe(x))
 
 
 def _powerlaw_ratio_term(q, m1, beta, mmin):
@@ -545,7 +632,7 @@ def _powerlaw_ratio_term(q, m1, beta, mmin):
     def build(slots, group_base, cols):
         return [S.Term(S.TERM_POWERLAW_RATIO, [cols[0], cols[1]], slots=[slots[0]], cst=[float(mmin)], name="powerlaw[q|m1]")], [], []
 
-    return LazyWeight([_LazyTerm(("plq", id(q), id(m1), float(mmin)), [cq, cm], [beta], build)], _is_pe(q))
+    return LazyWeight([_LazyTerm(("plq", _uid_of(q), _uid_of(m1), float(mmin)), [cq, cm], [beta], build)], _is_pe(q))
 
 
 def powerlaw_primary_ratio_pdf(m1, q, alpha, beta, mmin, mmax):
@@ -553,7 +640,7 @@ def powerlaw_primary_ratio_pdf(m1, q, alpha, beta, mmin, mmax):
     return _powerlaw_ratio_term(q, m1, beta, mmin) * _powerlaw_term(m1, alpha, mmin, mmax, "m1")
 
 
-def plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=None):
+def plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=None, _delta_key=None):
     """parametric.py:49-53; with ``delta`` the power-law part carries the low-mass window
     ``smooth(delta, m1, mmin)`` exactly as the reference evaluates it (distributions.py:16-21)."""
     col = _col_of(m1)
@@ -563,53 +650,56 @@ def plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=None):
         return [S.Term(S.TERM_PLPEAK, [cols[0]], slots=list(slots[: 5 if tapered else 4]), cst=[float(mmin), float(mmax)], name="plpeak[m1]")], [], []
 
     params = [alpha, mpp, sigpp, lam] + ([delta] if tapered else [])
-    return LazyWeight([_LazyTerm(("plpeak", id(m1), float(mmin), float(mmax), tapered), [col], params, build)], _is_pe(m1))
+    keys = [None] * 4 + ([_delta_key] if tapered else [])
+    return LazyWeight([_LazyTerm(("plpeak", _uid_of(m1), float(mmin), float(mmax), tapered), [col], params, build, param_keys=keys)], _is_pe(m1))
 
 
-def _smooth_term(delta, x, x2, xmin):
+def _smooth_term(delta, x, x2, xmin, _key=None):
     """``smooth(delta, x [* x2], xmin)`` (distributions.py:16-21) as a lazy factor."""
     cx = [_col_of(x)] + ([_col_of(x2)] if x2 is not None else [])
 
     def build(slots, group_base, cols):
         return [S.Term(S.TERM_SMOOTH, list(cols), slots=[slots[0]], cst=[float(xmin)], name="smooth")], [], []
 
-    return LazyWeight([_LazyTerm(("smooth", id(x), id(x2), float(xmin)), cx, [delta], build)], _is_pe(x))
+    return LazyWeight([_LazyTerm(("smooth", _uid_of(x), _uid_of(x2), float(xmin)), cx, [delta], build, param_keys=[_key])], _is_pe(x))
 
 
 def plpeak_primary_ratio_pdf(m1, q, alpha, beta, mmin, mmax, mpp, sigpp, lam, delta=None):
     """parametric.py:39-46."""
-    w = _powerlaw_ratio_term(q, m1, beta, mmin) * plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=delta)
+    dk = _share() if delta is not None else None  # ONE delta for both windows
+    w = _powerlaw_ratio_term(q, m1, beta, mmin) * plpeak_primary_pdf(m1, alpha, mmin, mmax, mpp, sigpp, lam, delta=delta, _delta_key=dk)
     if delta is not None:
-        w = w * _smooth_term(delta, q, m1, mmin)  # smooth(delta, q * m1, mmin)   (:46)
+        w = w * _smooth_term(delta, q, m1, mmin, _key=dk)  # smooth(delta, q * m1, mmin)   (:46)
     return w
 
 
-def beta_spin_magnitude(a, alpha, beta, amax=1):
+def beta_spin_magnitude(a, alpha, beta, amax=1, _keys=None):
     """parametric.py:63-64 -> distributions.py:146-162."""
     col = _col_of(a)
 
     def build(slots, group_base, cols):
         return [S.Term(S.TERM_BETA, [cols[0]], slots=list(slots[:2]), cst=[float(amax)], name=f"beta[{cols[0]}]")], [], []
 
-    return LazyWeight([_LazyTerm(("beta", id(a), float(amax)), [col], [alpha, beta], build)], _is_pe(a))
+    return LazyWeight([_LazyTerm(("beta", _uid_of(a), float(amax)), [col], [alpha, beta], build, param_keys=_keys)], _is_pe(a))
 
 
 def iid_spin_magnitude(a1, a2, alpha_mag, beta_mag, amax=1):
-    return beta_spin_magnitude(a1, alpha_mag, beta_mag, amax) * beta_spin_magnitude(a2, alpha_mag, beta_mag, amax)
+    keys = [_share(), _share()]  # identically distributed: both components read the same two slots
+    return beta_spin_magnitude(a1, alpha_mag, beta_mag, amax, _keys=keys) * beta_spin_magnitude(a2, alpha_mag, beta_mag, amax, _keys=keys)
 
 
 def independent_spin_magnitude_beta_dist(a1, a2, alpha_mag1, beta_mag1, alpha_mag2, beta_mag2, amax1=1, amax2=1):
     return beta_spin_magnitude(a1, alpha_mag1, beta_mag1, amax1) * beta_spin_magnitude(a2, alpha_mag2, beta_mag2, amax2)
 
 
-def mixture_isoalign_spin_tilt(ct, xi_tilt, sigma_tilt):
+def mixture_isoalign_spin_tilt(ct, xi_tilt, sigma_tilt, _keys=None):
     """parametric.py:84-86."""
     col = _col_of(ct)
 
     def build(slots, group_base, cols):
         return [S.Term(S.TERM_ISOALIGN, [cols[0]], slots=list(slots[:2]), name=f"isoalign[{cols[0]}]")], [], []
 
-    return LazyWeight([_LazyTerm(("isoalign", id(ct)), [col], [xi_tilt, sigma_tilt], build)], _is_pe(ct))
+    return LazyWeight([_LazyTerm(("isoalign", _uid_of(ct)), [col], [xi_tilt, sigma_tilt], build, param_keys=_keys)], _is_pe(ct))
 
 
 def default_spin_tilt(ct1, ct2, xi_tilt, sigma_tilt):
@@ -619,11 +709,12 @@ def default_spin_tilt(ct1, ct2, xi_tilt, sigma_tilt):
     def build(slots, group_base, cols):
         return [S.Term(S.TERM_ISOALIGN_PAIR, [cols[0], cols[1]], slots=list(slots[:2]), name=f"isoalign2[{cols[0]},{cols[1]}]")], [], []
 
-    return LazyWeight([_LazyTerm(("isoalign2", id(ct1), id(ct2)), [c1, c2], [xi_tilt, sigma_tilt], build)], _is_pe(ct1))
+    return LazyWeight([_LazyTerm(("isoalign2", _uid_of(ct1), _uid_of(ct2)), [c1, c2], [xi_tilt, sigma_tilt], build)], _is_pe(ct1))
 
 
 def iid_spin_tilt(ct1, ct2, xi_tilt, sigma_tilt):
-    return mixture_isoalign_spin_tilt(ct1, xi_tilt, sigma_tilt) * mixture_isoalign_spin_tilt(ct2, xi_tilt, sigma_tilt)
+    keys = [_share(), _share()]
+    return mixture_isoalign_spin_tilt(ct1, xi_tilt, sigma_tilt, _keys=keys) * mixture_isoalign_spin_tilt(ct2, xi_tilt, sigma_tilt, _keys=keys)
 
 
 def independent_spin_tilt(ct1, ct2, xi_tilt_1, xi_tilt_2, sigma_tilt1, sigma_tilt2):
@@ -697,7 +788,7 @@ class PowerlawRedshiftModel:
         def build(slots, group_base, cols):
             return model._terms(slots, group_base, cols)
 
-        return LazyWeight([_LazyTerm((id(self), "plz"), [self.column], [lamb], build)], pe_samples)
+        return LazyWeight([_LazyTerm((_uid_of(self), "plz"), [self.column], [lamb], build)], pe_samples)
 
     def log_prob(self, z, lamb):
         """parametric.py:129-136: the same density as ``__call__`` in the log domain (combine with
@@ -746,7 +837,7 @@ class PowerlawSplineRedshiftModel(PowerlawRedshiftModel):
 
         if np.shape(cs) != (self.n_splines,):
             raise ValueError(f"expected {self.n_splines} redshift coefficients, got shape {np.shape(cs)}")
-        return LazyWeight([_LazyTerm((id(self), "plsz"), [self.column], [lamb, cs], build)], pe_samples)
+        return LazyWeight([_LazyTerm((_uid_of(self), "plsz"), [self.column], [lamb, cs], build)], pe_samples)
 
     def normalization(self, lamb, cs):
         """Host-side ``Z(lamb, cs)`` (spline_perturbation.py:323-336): a 1000-point sum used for

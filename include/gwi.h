@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GWI_VERSION 2
+#define GWI_VERSION 3
 
 typedef enum {
   GWI_OK = 0,
@@ -234,6 +234,14 @@ typedef struct {
   int32_t active_switches;  /* tuning switches in effect: 1 fused epilogue, 2 CUDA-graph host call, 4 role-split stream kernel, 8 speculative shift */
 } gwi_model_info;
 int gwi_model_get_info(const gwi_model* m, gwi_model_info* info);
+
+/* Per-segment results of the LAST evaluation of this model (any of the calls above, chain 0), copied
+ * to HOST memory after synchronising with the stream that evaluation ran on: rows of 4 doubles
+ * {log mean weight, log N_eff, variance of the log mean, status}; row 0 = the injection set
+ * (log mu, log N_eff,inj, variance_log_detection_efficiency), rows 1..E = the events (`logBFs`,
+ * `log_nEffs`, `variance_log_BFs` sites of analysis.py:260-264).  Returns the number of doubles
+ * written (4 (E + 1)), or the number needed when dst == NULL, or a negative error. */
+int64_t gwi_model_last_sites(gwi_model* m, double* dst_host, int64_t cap_doubles);
 
 /* Log-sum-exp reference point.  By default spline-only models use an a-priori upper bound of the
  * per-sample log-weight per segment (single pass); if the bound is so loose for some Lambda that every

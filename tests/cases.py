@@ -15,6 +15,8 @@ GOLDEN_CASES = [
     "bspline_full",
     "bspline_full_margsel",
     "bspline_full_cutfail",
+    "bspline_full_maxvar",
+    "bspline_full_maxvar_fail",
     "bspline_iid",
     "bspline_indep_masses",
     "inference_test_bspline",
@@ -36,6 +38,8 @@ LIKE_KW = {
     "bspline_full": dict(marginalize_selection=False, min_neff_cut=True),
     "bspline_full_margsel": dict(marginalize_selection=True, min_neff_cut=True),
     "bspline_full_cutfail": dict(marginalize_selection=False, min_neff_cut=True),
+    "bspline_full_maxvar": dict(marginalize_selection=False, min_neff_cut=False, max_variance_cut=True),
+    "bspline_full_maxvar_fail": dict(marginalize_selection=False, min_neff_cut=False, max_variance_cut=True),
     "bspline_iid": dict(min_neff_cut=True),
     "bspline_indep_masses": dict(min_neff_cut=False),
     "inference_test_bspline": dict(marginalize_selection=False, min_neff_cut=False),

@@ -115,7 +115,7 @@ def _save(name, pe, inj, const, params, names, base, jac, meta):
 
 
 # ----------------------------------------------------------------------------------------------
-def case_bspline_full():
+def case_bspline_full(maxvar_only=False):
     """cfg-2/3 model (examples/simple_bspline_example.py): B-spline m1+q, independent spin
     magnitudes and tilts, power-law x spline redshift.  Default spline counts 50/30/16/16/20."""
     E, S, I = 8, 250, 6000
@@ -149,6 +149,16 @@ def case_bspline_full():
         return w
 
     vt = lambda p: rz.normalization(p["lamb"], p["z_cs"])  # noqa: E731
+    # max_variance_cut=True (analysis.py:309-317; needs marginalize_selection = min_neff_cut = False):
+    # one parameter point below the variance threshold of 1, one (the sharp population) above it
+    like_kw = dict(marginalize_selection=False, min_neff_cut=False, max_variance_cut=True)
+    for nm, pp in (("bspline_full_maxvar", params), ("bspline_full_maxvar_fail", sharp)):
+        base, jac = _complex_step(weights, pe, inj, const, pp, names, vt, like_kw)
+        var_l = const["nObs"] ** 2 * float(np.real(base["var_inj"])) + float(np.sum(np.real(base["var"])))
+        print(f"   ({nm}) variance_log_likelihood = {var_l:.4f}")
+        _save(nm, pe, inj, const, pp, names, base, jac, dict(model="bspline_full", mmin=mmin, mmax=mmax, max_variance_cut=1, **{f"n_{k}": v for k, v in ns.items()}))
+    if maxvar_only:
+        return
     like_kw = dict(marginalize_selection=False, min_neff_cut=True)
     base, jac = _complex_step(weights, pe, inj, const, params, names, vt, like_kw)
     _save("bspline_full", pe, inj, const, params, names, base, jac, dict(model="bspline_full", mmin=mmin, mmax=mmax, **{f"n_{k}": v for k, v in ns.items()}))
@@ -438,6 +448,7 @@ def case_bspline_symchieff():
 
 CASES = dict(
     bspline_full=case_bspline_full,
+    bspline_full_maxvar=lambda: case_bspline_full(maxvar_only=True),
     bspline_iid=case_bspline_iid,
     bspline_indep_masses=case_bspline_indep_masses,
     inference_test_bspline=case_inference_test_bspline,
