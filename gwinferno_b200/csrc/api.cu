@@ -20,8 +20,9 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 typedef void (*stream_fn)(const ModelDev*);
 stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, bool maxonly);
-stream_fn pick_stream_split_kernel(int ns, int ndeep, int nlin, bool g2);  // experiment builds only (else nullptr)
-size_t stream_split_extra_smem(int npairs);
+stream_fn pick_stream_cta_kernel(int ns, int ndeep, int nlin);  // CTA-cooperative kernel (stream_cta.cuh)
+stream_fn pick_stream_cta_max_kernel();
+unsigned stream_cta_smem_bytes(int nw, int ncol, int rows_total, int deep_entries);
 void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st, int use_learned_shift);
 void launch_segmax_learn(const ModelDev* Md, int n_seg, int nc, cudaStream_t st);
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux);
@@ -31,7 +32,6 @@ void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaS
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st);
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st);
-void launch_epilogue(const ModelDev* Md, int n_tasks0, int rec_doubles, int mode, double* rec, const gwi_like_opts& o, double* out, int nc, cudaStream_t st);
 
 }  // namespace gwi
 
@@ -68,10 +68,7 @@ struct gwi_model {
   std::vector<std::pair<ReduceTask*, int>> level_tasks;  // device task arrays (static, shared by all chains)
   int n_chain_alloc = 1;                                  // descriptors / scratch sets allocated (chain batch)
   bool force_exact_shift = false;                         // gwi_model_set_exact_shift
-  // GWI_FUSED_EPILOGUE=1 (tuning switch, default off until measured on the GPU): reduction tree,
-  // per-segment finish, partial record and single-rank combine in ONE launch (epilogue_kernel)
-  bool fused_epilogue = false;
-  // GWI_GRAPH=1 (tuning switch, default off until measured on the GPU): gwi_loglike_host replays ONE
+  // gwi_loglike_host replays ONE (GWI_GRAPH=0 switches it off)
   // captured CUDA graph (H2D copy of Lambda, every kernel of the evaluation with its aux-stream fork /
   // join, D2H copy of the result) instead of issuing ~10 stream operations per call
   bool use_graph = false;
@@ -79,17 +76,16 @@ struct gwi_model {
   gwi_like_opts graph_opts{};
   double* partial_batch = nullptr;                        // [n_chain_alloc][PR_HEADER + 3P]
   int stream_grid_x = 1;
+  bool cta = false;        // the CTA-cooperative stream kernel runs this model (plan.cta_mode)
+  int stream_block = 0;    // threads per block of the full pass
+  int max_grid_x = 1, max_block = 0;  // launch geometry of the max-only pass
   stream_fn k_full = nullptr, k_max = nullptr;
   size_t smem_full = 0, smem_max = 0;
-  // GWI_SPLIT=1 on a -DGWI_EXP_SPLIT=1 build: producer / consumer warp pairs (stream_split.cuh)
   // GWI_SPECULATIVE_SHIFT=1 on a -DGWI_EXP_TRACK_MAX=1 build (host call only, one chain): models that need
   // the exact per-segment maximum take it from the previous evaluation's full pass instead of a max-only pass
   bool spec_shift = false;      // switch
   bool spec_learned = false;    // shift_next holds maxima of an earlier evaluation
   bool spec_allowed_now = false;  // set by gwi_loglike_host around its first attempt
-  stream_fn k_split = nullptr;
-  size_t smem_split = 0;
-  int split_pairs = 0;
   int max_grid = 0;
   int launches_per_eval = 0;
   // scratch for the host-buffer call and single-rank likelihood
@@ -200,7 +196,7 @@ int64_t gwi_debug_plan_read(const gwi_plan* pp, int32_t what, void* dst, int64_t
   switch (what) {
     case 0:
       v = {p.n_columns, p.n_padded, (int64_t)p.chunks.size(), (int64_t)p.segments.size(), (int64_t)p.dims.size(), (int64_t)p.kops.size(),
-           p.rows_total, p.n_deep, (int64_t)p.n_gslots, p.rec_doubles};
+           p.rows_total, p.n_deep, (int64_t)p.n_gslots, p.rec_doubles, p.cta_mode ? p.cta_main_warps : 1};
       break;
     case 1:
       src = p.columns.data();
@@ -311,18 +307,6 @@ static int alloc_chain_scratch(gwi_model* m, ModelDev& H) {
   UPS(upload<double>(m, nullptr, (size_t)3 + 2 * P, &H.inj_raw));
   UPS(upload<double>(m, nullptr, (size_t)nseg, &H.shift_next));
   UPS(upload<double>(m, nullptr, (size_t)nseg, &H.spec_bad));
-  {
-    // arrival counters of the fused epilogue (zeroed here; the kernel leaves them zero)
-    int n_counters = 0;
-    for (int l = 0; l < 6; ++l) H.epi_level_off[l] = 0;
-    for (size_t l = 1; l < p.levels.size(); ++l) {
-      H.epi_level_off[l] = n_counters;
-      n_counters += (int)p.levels[l].size();
-    }
-    H.epi_seg_counter = n_counters++;
-    H.epi_pad = 0;
-    UPS(upload<int32_t>(m, nullptr, (size_t)n_counters, &H.epi_counters));
-  }
   H.n_levels = (int)p.levels.size();
   for (int l = 0; l < 6; ++l) {
     H.level_buf[l] = nullptr;
@@ -430,6 +414,8 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   H.g2 = p.g2 ? 1 : 0;
   H.n_chunks = (int)p.chunks.size();
   H.n_padded = p.n_padded;
+  H.cta_main_warps = p.cta_mode ? p.cta_main_warps : 0;
+  H.cta_pad = 0;
   H.total_inj = p.total_inj;
   H.two_pass = 0;
   H.liny_mask = 0;
@@ -560,8 +546,14 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   }
 
   // ---- kernels + shared memory ----
-  m->k_full = pick_stream_kernel(NS, p.n_deep, H.n_lin_fast, p.g2, param, false);
-  m->k_max = pick_stream_kernel(NS, p.n_deep, 0, p.g2, true, true);
+  m->cta = p.cta_mode;
+  if (m->cta) {
+    m->k_full = pick_stream_cta_kernel(NS, p.n_deep, H.n_lin_fast);
+    m->k_max = pick_stream_cta_max_kernel();
+  } else {
+    m->k_full = pick_stream_kernel(NS, p.n_deep, H.n_lin_fast, p.g2, param, false);
+    m->k_max = pick_stream_kernel(NS, p.n_deep, 0, p.g2, true, true);
+  }
   if (!m->k_full || !m->k_max) {
     set_error("no stream kernel instantiated for this (spline dims, deep dims) combination");
     gwi_model_destroy(m);
@@ -579,6 +571,19 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   }
   m->smem_full = (fixed + per_warp * wpb) * 8;
   m->smem_max = m->smem_full;
+  m->stream_block = wpb * 32;
+  m->max_block = wpb * 32;
+  if (m->cta) {
+    m->smem_full = stream_cta_smem_bytes(p.cta_main_warps, p.n_columns, p.rows_total, deep_entries);
+    m->smem_max = 0;
+    m->stream_block = (p.cta_main_warps + p.n_deep) * 32;
+    m->max_block = 256;
+    if (m->smem_full > (size_t)prop.sharedMemPerBlockOptin) {
+      set_error("internal: CTA-kernel geometry does not fit the device's shared memory");
+      gwi_model_destroy(m);
+      return GWI_ERR_UNSUPPORTED;
+    }
+  }
   if (cudaFuncSetAttribute((const void*)m->k_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_full) != cudaSuccess ||
       cudaFuncSetAttribute((const void*)m->k_max, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_max) != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(shared memory) failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -586,41 +591,28 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     return GWI_ERR_CUDA;
   }
   {
-    const char* e = std::getenv("GWI_FUSED_EPILOGUE");
-    m->fused_epilogue = e && e[0] == '1';
     const char* g = std::getenv("GWI_GRAPH");
-    m->use_graph = g && g[0] == '1';
+    m->use_graph = !(g && g[0] == '0');  // on by default (r02: +9 % e2e evals/s at config-2 size, bitwise-equal results)
 #if GWI_EXP_TRACK_MAX
     const char* sp = std::getenv("GWI_SPECULATIVE_SHIFT");
     m->spec_shift = sp && sp[0] == '1' && H.two_pass;
     if (m->spec_shift) m->use_graph = false;  // the launch sequence differs from call to call
 #endif
   }
-  {
-    const char* e = std::getenv("GWI_SPLIT");
-    if (e && e[0] == '1' && !param) {
-      m->k_split = pick_stream_split_kernel(NS, p.n_deep, H.n_lin_fast, p.g2);
-      // as many producer / consumer pairs as fit (the ring needs room next to the consumers' accumulators)
-      m->split_pairs = wpb;
-      while (m->split_pairs > 1 && (fixed + per_warp * m->split_pairs) * 8 + stream_split_extra_smem(m->split_pairs) > (size_t)prop.sharedMemPerBlockOptin) --m->split_pairs;
-      m->smem_split = (fixed + per_warp * m->split_pairs) * 8 + stream_split_extra_smem(m->split_pairs);
-      if (m->k_split && (m->smem_split > (size_t)prop.sharedMemPerBlockOptin ||
-                         cudaFuncSetAttribute((const void*)m->k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_split) != cudaSuccess))
-        m->k_split = nullptr;  // does not fit: keep the regular kernel
-    }
-  }
   m->stream_grid_x = std::max(1, std::min(p.grid_blocks, ((int)p.slice_begin.size() - 1 + p.warps_per_block - 1) / p.warps_per_block));
-  m->launches_per_eval = m->fused_epilogue ? 2 + (H.two_pass ? 2 : 0) + 1 + 1 : 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
+  m->max_grid_x = m->stream_grid_x;
+  if (m->cta) {
+    m->stream_grid_x = std::max(1, std::min(p.grid_blocks, (int)p.slice_begin.size() - 1));
+    m->max_grid_x = std::max(1, std::min(4 * p.grid_blocks, (int)p.chunks.size()));
+  }
+  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
   CUDA_TRY(cudaDeviceSynchronize());
   *out = m;
   return GWI_OK;
 }
 
-// launches prologue .. finish for `nc` chains on `st` (lam_dev: [nc][P]).  epi_mode (fused epilogue
-// only): 0 = per-segment results, 1 = + partial record into `rec`, 2 = + single-rank combine into `out`;
-// returns with *epi_done = true when the fused kernel has already produced what epi_mode asks for.
-static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st, bool exact_shift = false, int epi_mode = 0, double* rec = nullptr,
-                    const gwi_like_opts* opts = nullptr, double* out = nullptr, bool* epi_done = nullptr) {
+// launches prologue .. finish for `nc` chains on `st` (lam_dev: [nc][P])
+static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st, bool exact_shift = false) {
   const Plan& p = m->plan;
   const ModelDev& H = m->host;
   // fork: the grid normalisers (needed only by finish_kernel) overlap with the stream kernel
@@ -630,21 +622,16 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   cudaEventRecord(m->ev_join, m->aux_stream);
   const bool speculate = m->spec_shift && m->spec_allowed_now && m->spec_learned && nc == 1 && !exact_shift && !m->force_exact_shift;
   launch_prologue_tables(m->dev, lam_dev, H.n_groups, nc, st, speculate ? 1 : 0);
-  const dim3 grid(m->stream_grid_x, nc), block(p.warps_per_block * 32);
+  const dim3 grid(m->stream_grid_x, nc), block(m->stream_block);
   if (H.n_chunks > 0) {
     if ((H.two_pass && !speculate) || exact_shift || m->force_exact_shift) {
       // exact per-segment maximum first (always for models with non-linear terms; as a fallback when
       // the a-priori bound was so loose that every weight of a segment underflowed)
-      GWI_LAUNCH(m->k_max, grid, block, m->smem_max, st)(m->dev);
+      GWI_LAUNCH(m->k_max, dim3(m->max_grid_x, nc), dim3(m->max_block), m->smem_max, st)(m->dev);
       launch_segmax(m->dev, H.n_segments, nc, st);
     }
     if (m->timing) cudaEventRecord(m->ev0[m->n_timed % 64], st);
-    if (m->k_split) {
-      const dim3 block2(m->split_pairs * 64);  // a producer and a consumer warp per slice stream
-      GWI_LAUNCH(m->k_split, grid, block2, m->smem_split, st)(m->dev);
-    } else {
-      GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev);
-    }
+    GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev);
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
     if (m->spec_shift && nc == 1) {
       launch_segmax_learn(m->dev, H.n_segments, nc, st);  // next evaluation's shift; flags this one if its shift was off
@@ -652,15 +639,6 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
     }
   }
   const int n_levels = (int)m->level_tasks.size();
-  if (epi_done) *epi_done = false;
-  if (m->fused_epilogue) {
-    cudaStreamWaitEvent(st, m->ev_join, 0);  // join
-    gwi_like_opts none{};
-    launch_epilogue(m->dev, m->level_tasks[0].second, H.rec_doubles, epi_mode, rec, opts ? *opts : none, out, nc, st);
-    if (epi_done) *epi_done = true;
-    CUDA_TRY(cudaGetLastError());
-    return GWI_OK;
-  }
   for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, st);
   cudaStreamWaitEvent(st, m->ev_join, 0);  // join
   // the last reduction level (one task per segment) is fused into finish_kernel
@@ -696,10 +674,9 @@ int gwi_partial(gwi_model* m, const double* lambda_dev, double* record_dev, void
   }
   CUDA_TRY(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  bool done = false;
-  const int rc = run_eval(m, lambda_dev, 1, st, false, 1, record_dev, nullptr, nullptr, &done);
+  const int rc = run_eval(m, lambda_dev, 1, st);
   if (rc != GWI_OK) return rc;
-  if (!done) launch_partial(m->dev, record_dev, m->plan.n_params, 1, st);
+  launch_partial(m->dev, record_dev, m->plan.n_params, 1, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -728,23 +705,6 @@ int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opt
     set_error("null argument");
     return GWI_ERR_INVALID;
   }
-  if (m->fused_epilogue) {
-    // same argument checks as gwi_partial + gwi_combine, then ONE epilogue launch does both
-    if (!lambda_dev || !opts || !out_dev) {
-      set_error("null argument");
-      return GWI_ERR_INVALID;
-    }
-    if (opts->marginalize_selection && !m->plan.g2) {
-      set_error("marginalize_selection needs a model created with need_neff_grad");
-      return GWI_ERR_INVALID;
-    }
-    if (opts->max_variance_cut && (opts->marginalize_selection || opts->min_neff_cut)) {
-      set_error("max_variance_cut requires marginalize_selection and min_neff_cut to be off (analysis.py:237-244)");
-      return GWI_ERR_INVALID;
-    }
-    CUDA_TRY(cudaSetDevice(m->device));
-    return run_eval(m, lambda_dev, 1, (cudaStream_t)stream, false, 2, m->partial_dev, opts, out_dev, nullptr);
-  }
   int rc = gwi_partial(m, lambda_dev, m->partial_dev, stream);
   if (rc != GWI_OK) return rc;
   return gwi_combine(m, m->partial_dev, 1, opts, out_dev, stream);
@@ -770,13 +730,10 @@ int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, 
   cudaStream_t st = (cudaStream_t)stream;
   // ONE launch of every kernel covers all chains (chain = a grid coordinate): the whole machine works
   // on the batch instead of one small catalog at a time
-  bool done = false;
-  rc = run_eval(m, lambda_dev, n_chains, st, false, 2, m->partial_batch, opts, out_dev, &done);
+  rc = run_eval(m, lambda_dev, n_chains, st);
   if (rc != GWI_OK) return rc;
-  if (!done) {
-    launch_partial(m->dev, m->partial_batch, m->plan.n_params, n_chains, st);
-    launch_combine(m->dev, m->partial_batch, 1, *opts, out_dev, n_chains, st);
-  }
+  launch_partial(m->dev, m->partial_batch, m->plan.n_params, n_chains, st);
+  launch_combine(m->dev, m->partial_batch, 1, *opts, out_dev, n_chains, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -919,9 +876,9 @@ int gwi_model_get_info(const gwi_model* m, gwi_model_info* info) {
   info->n_linear = 0;
   for (auto& k : p.kops) (k.kind == KOP_LIN ? info->n_linear : info->n_param_terms)++;
   info->grid_blocks = p.grid_blocks;
-  info->block_threads = p.warps_per_block * 32;
+  info->block_threads = m->stream_block;
   info->kernel_launches_per_eval = m->launches_per_eval;
-  info->active_switches = (m->fused_epilogue ? 1 : 0) | (m->use_graph ? 2 : 0) | (m->k_split ? 4 : 0) | (m->spec_shift ? 8 : 0);
+  info->active_switches = 0 | (m->use_graph ? 2 : 0) | (m->cta ? 4 : 0) | (m->spec_shift ? 8 : 0);
   return GWI_OK;
 }
 

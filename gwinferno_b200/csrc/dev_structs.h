@@ -97,15 +97,11 @@ struct ModelDev {
   double* seg_J1;     // [n_segments * P]
   double* seg_Jn;     // [n_segments * P]
   double* inj_raw;    // [3 + 2P] {shift, S1, S2, G1raw[P], G2raw[P]}
-  // fused epilogue (epilogue_kernel): arrival counters, one per reduction task of the levels >= 1
-  // (level l starts at epi_level_off[l]) and one for the finished segments at [epi_seg_counter];
-  // zero between evaluations (the last arriver resets the counter it consumed)
-  int32_t* epi_counters;
-  int32_t epi_level_off[6];
-  int32_t epi_seg_counter, epi_pad;
   // speculative shift (GWI_EXP_TRACK_MAX): maxima learned from the last full pass; 1.0 where the shift used was too far off
   double* shift_next;  // [n_segments]
   double* spec_bad;    // [n_segments], zero unless a speculative evaluation has to be repeated
+  // CTA-cooperative stream kernel (stream_cta.cuh): main warps per CTA (0 = the one-role kernel's geometry)
+  int32_t cta_main_warps, cta_pad;
 };
 
 // partial (per-rank) likelihood record: 8 header doubles + 3P

@@ -17,6 +17,8 @@ constexpr int MAX_SOPS = 16;        // scalar (sample-independent) normaliser op
 constexpr int KC_STRIDE = 12;       // doubles of per-eval constants per kop
 constexpr int LANES = 32;
 constexpr int UNROLL = 2;           // samples per lane per load (16-byte vector loads)
+constexpr int CTA_STAGES = 3;       // stream_cta.cuh: staged 64-sample blocks per main warp (== CTA_NSTAGE)
+constexpr int CTA_WARPS_MAX = 12;   // stream_cta.cuh: main + deep warps per CTA (== CTA_MAX_WARPS)
 #ifndef GWI_DEEP_LANES
 #define GWI_DEEP_LANES 16
 #endif
@@ -24,9 +26,13 @@ constexpr int UNROLL = 2;           // samples per lane per load (16-byte vector
 // half the shared memory), 32 = fully lane-private (one phase)
 constexpr int DEEP_LANES = GWI_DEEP_LANES;
 
-// ---- packed spline word: bits 63..52 = piece index J, bits 51..0 = mantissa of (1 + u) --------
-constexpr uint64_t MANT_MASK = 0x000FFFFFFFFFFFFFull;
-constexpr uint64_t ONE_BITS = 0x3FF0000000000000ull;
+// ---- packed spline word: the fp64 value w = u - 1/2 (u in [0,1): offset inside the polynomial piece)
+// with its 6 least significant mantissa bits replaced by the piece index J.  The kernels use the word
+// AS the double w (no unpack arithmetic; the J bits perturb w by < 2^-46 |w|, i.e. the sample's
+// coordinate by < 1e-14 of a knot spacing, the same for the value and for the gradient) and take
+// J = low word & 63.
+constexpr uint64_t J_MASK = 63ull;
+static_assert(MAX_ROWS <= 64, "the piece index must fit the 6 low mantissa bits of the packed word");
 
 // per-sample operation executed by the stream kernel besides the spline dimensions
 enum KopKind : int32_t {
@@ -135,6 +141,10 @@ struct Plan {
   // launch geometry (fixed at plan time: the chunk -> warp assignment depends on it)
   int grid_blocks = 0, warps_per_block = 0;
   int chunk_steps = 0;
+  // CTA-cooperative geometry (stream_cta.cuh): a chunk is processed by ALL `cta_main_warps` main warps of one
+  // CTA (its padded range = cta_main_warps sub-chunks of steps x 32 samples) and owns cta_main_warps + 1 records
+  bool cta_mode = false;
+  int cta_main_warps = 0;
   double total_inj = 0.0;
   int64_t n_samples_pe = 0, n_samples_inj = 0, n_valid_pe = 0, n_valid_inj = 0;
 };

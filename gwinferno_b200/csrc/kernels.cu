@@ -698,82 +698,6 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
 }
 
 // =================================================================================================
-// fused epilogue: record reduction tree + per-segment finish + partial record (+ single-rank combine)
-// in ONE launch.  Block b starts with task b of reduction level 0; the block that delivers the LAST
-// input of a next-level task (arrival counter) goes on to execute that task, and so on up to the
-// segment's root, where it runs the per-segment finish; the block that finishes the last segment
-// writes the partial record and, for the single-rank likelihood, combines it.  Every task still sums
-// its inputs in the fixed order of the plan, so the results are bitwise those of the separate
-// reduce / finish / partial / combine kernels whichever block ends up doing the work.
-// mode: 0 = stop after the per-segment results, 1 = + partial record, 2 = + combine (R = 1).
-// =================================================================================================
-__global__ void __launch_bounds__(256) epilogue_kernel(const ModelDev* __restrict__ Mp, int mode, double* recd0, gwi_like_opts opts, double* out0) {
-  GWI_STAGED_DESC(M, Mp[blockIdx.y]);  // blockIdx.y = chain
-  extern __shared__ double srec[];
-  __shared__ int ticket_s;
-  const int rec = M.rec_doubles;
-  const int last_level = M.n_levels - 1;
-  int level = 0, t = blockIdx.x;
-  for (;;) {
-    const ReduceTask T = M.level_tasks[level][t];
-    const double* in = level == 0 ? M.records0 : M.level_buf[level - 1];
-    if (level == last_level) {
-      // root of segment T.out_slot: sum into shared memory, then the per-segment results
-      for (int i = threadIdx.x; i < rec; i += blockDim.x) {
-        double acc = 0.0;
-        for (int r = 0; r < T.in_count; ++r) acc += __ldcg(in + (size_t)(T.in_first + r) * rec + i);
-        srec[i] = acc;
-      }
-      __syncthreads();
-      finish_segment(M, T.out_slot, srec);
-      break;
-    }
-    double* out = M.level_buf[level];
-    for (int i = threadIdx.x; i < rec; i += blockDim.x) {
-      double acc = 0.0;
-      for (int r = 0; r < T.in_count; ++r) acc += __ldcg(in + (size_t)(T.in_first + r) * rec + i);
-      out[(size_t)T.out_slot * rec + i] = acc;
-    }
-    // publish, then count this input in at the consuming task
-    __threadfence();
-    __syncthreads();
-    const int parent_count = M.level_tasks[level + 1][T.parent].in_count;
-    int* counter = M.epi_counters + M.epi_level_off[level + 1] + T.parent;
-    if (threadIdx.x == 0) {
-      const int k = atomicAdd(counter, 1);
-      if (k == parent_count - 1) *counter = 0;  // last arriver: nobody else touches it in this evaluation
-      ticket_s = k;
-    }
-    __syncthreads();
-    const int k = ticket_s;
-    __syncthreads();  // ticket_s is rewritten on the next level
-    if (k != parent_count - 1) return;
-    __threadfence();
-    t = T.parent;
-    ++level;
-  }
-  if (mode == 0) return;
-  // ---- this block finished a segment: the last such block assembles the likelihood record ----
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int* counter = M.epi_counters + M.epi_seg_counter;
-    const int k = atomicAdd(counter, 1);
-    if (k == M.n_segments - 1) *counter = 0;
-    ticket_s = k;
-  }
-  __syncthreads();
-  if (ticket_s != M.n_segments - 1) return;
-  __threadfence();
-  const int P = M.n_params;
-  double* recd = recd0 + (size_t)blockIdx.y * (PR_HEADER + 3 * P);
-  partial_rows<true>(M, recd, threadIdx.x >> 5, blockDim.x >> 5);
-  if (mode == 1) return;
-  __syncthreads();  // the record written above is read by other threads of this block below
-  combine_records(M, recd, 1, opts, out0 + (size_t)blockIdx.y * (GWI_LIKE_HEADER + P));
-}
-
-// =================================================================================================
 // host-side launch helpers (called from api.cu)
 // =================================================================================================
 // tables + shifts (what the stream kernel needs) on `st`; the grid normalisers (only needed by
@@ -796,9 +720,6 @@ void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaS
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { GWI_LAUNCH(export_kernel, 64, 256, 0, st)(Md, out); }
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st) {
   GWI_LAUNCH(partial_kernel, dim3((n_params + 7) / 8, nc), 256, 0, st)(Md, rec);
-}
-void launch_epilogue(const ModelDev* Md, int n_tasks0, int rec_doubles, int mode, double* rec, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
-  GWI_LAUNCH(epilogue_kernel, dim3(n_tasks0, nc), 256, (size_t)rec_doubles * sizeof(double), st)(Md, mode, rec, o, out);
 }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
   GWI_LAUNCH(combine_kernel, nc, 256, 0, st)(Md, recs, R, o, out);

@@ -2,7 +2,7 @@
 // device-resident evaluation plan.  This replaces the reference's model construction
 // (gwinferno/models/bsplines/single.py:35-58 -- masks + dense Cox-de Boor design matrices,
 // gwinferno/interpolation.py:128-149) with, per sample and spline dimension, ONE 8-byte word
-// (piece index J | mantissa of 1+u) so that the kernel re-creates the 4 non-zero basis weights on
+// (w = u - 1/2 as fp64 with the piece index J in its 6 low mantissa bits) so that the kernel re-creates the 4 non-zero basis weights on
 // the fly.  Samples whose population density is identically zero (outside the model masks,
 // single.py:54-55,90-92; z > zmax, spline_perturbation.py:368-372; non-finite static weight) are
 // dropped here; the Monte-Carlo denominators keep the full sample counts.
@@ -163,10 +163,10 @@ inline bool spline_locate(const SplineGeom& g, double x, int& J, double& u) {
 }
 
 inline uint64_t pack_word(int J, double u) {
-  const double v = 1.0 + u;  // [1, 2): exponent bits are constant, the mantissa carries u exactly to 2^-52
+  const double w = u - 0.5;  // [-1/2, 1/2): the variable of the per-piece polynomials
   uint64_t b;
-  std::memcpy(&b, &v, 8);
-  return ((uint64_t)J << 52) | (b & MANT_MASK);
+  std::memcpy(&b, &w, 8);
+  return (b & ~J_MASK) | (uint64_t)J;
 }
 
 template <class F>
@@ -844,6 +844,27 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   wpb = std::max(1, std::min(wpb, 8));
   plan.warps_per_block = wpb;
   plan.grid_blocks = std::max(1, sm_count);
+  // CTA-cooperative geometry (stream_cta.cuh) for spline models with at most 2 linear terms and no N_eff
+  // gradient: main warps stage their blocks with bulk copies, one dedicated warp per deep dim accumulates
+  // that dim's moments for the whole CTA.  GWI_CTA_KERNEL=0 keeps the one-role kernel (tuning / bisection).
+  {
+    bool ok = !plan.g2 && plan.n_deep >= 1 && (int)plan.kops.size() == plan.n_lin && plan.n_lin <= 2;
+    for (const SplineDim& D : plan.dims) ok = ok && !D.liny;
+    if (const char* e = std::getenv("GWI_CTA_KERNEL")) ok = ok && !(e[0] == '0');
+    if (ok) {
+      const int64_t stage_bytes = (int64_t)(NS + (int)kop_feats.size() + 1) * 512 + 512;
+      const int64_t fixed = 3 * 8 * CTA_STAGES * CTA_WARPS_MAX + 16 + (int64_t)plan.rows_total * 32 + 256 + (int64_t)rows_deep * 1024;
+      int nw = (int)((226 * 1024 - fixed) / (CTA_STAGES * stage_bytes));
+      nw = std::min(nw, CTA_WARPS_MAX - plan.n_deep);
+      if (const char* e = std::getenv("GWI_TUNE_CTA_WARPS")) nw = std::min(nw, std::max(1, std::atoi(e)));
+      if (nw >= 2) {
+        plan.cta_mode = true;
+        plan.cta_main_warps = nw;
+      }
+    }
+  }
+  const int LW = plan.cta_mode ? plan.cta_main_warps : 1;  // warps that share a chunk
+  const int LPC = LANES * LW;                              // lane runs per chunk
   // GWI_TUNE_BATCH_HINT=n (tuning experiment, default 1): the model will be evaluated for ~n chains per
   // launch (gwi_loglike_batch), so the machine is filled by chains and ONE chain only needs W/n warps:
   // slices get n times longer (up to the cap), i.e. fewer record flushes and longer piece-sorted lane
@@ -851,17 +872,17 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   // the warp iterations with lanes on the piece-change path at n = 1.
   int batch_hint = 1;
   if (const char* e = std::getenv("GWI_TUNE_BATCH_HINT")) batch_hint = std::max(1, std::atoi(e));
-  const int W = std::max(plan.warps_per_block, plan.grid_blocks * plan.warps_per_block / batch_hint);
+  const int W = plan.cta_mode ? std::max(1, plan.grid_blocks / batch_hint) : std::max(plan.warps_per_block, plan.grid_blocks * plan.warps_per_block / batch_hint);
   // Balanced slicing: the piece-sorted sample stream of all segments (the events first, then the
   // injections) is cut into SLICES of L steps (32 samples per step); slice i belongs to warp i % W.
   // By default L = ceil(total steps / W): every warp gets exactly one slice, i.e. the same amount
   // of work.  A slice is split into CHUNKS at segment boundaries; the lanes of the warp own
   // contiguous sorted runs inside each chunk.  (desc.chunk_steps > 0 caps L: tests use it to force
   // many slices per warp.)
-  constexpr int Q = 2 * UNROLL;  // chunk steps are a multiple of the kernel's load pipeline depth
-  auto roundQ = [](int64_t v) { return (v + Q - 1) / Q * Q; };
+  const int Q = plan.cta_mode ? UNROLL : 2 * UNROLL;  // chunk steps are a multiple of the kernel's load pipeline depth
+  auto roundQ = [Q](int64_t v) { return (v + Q - 1) / Q * Q; };
   int64_t total_steps = 0;
-  for (int s = 0; s < n_seg; ++s) total_steps += roundQ((plan.segments[s].n_valid + LANES - 1) / LANES);
+  for (int s = 0; s < n_seg; ++s) total_steps += roundQ((plan.segments[s].n_valid + LPC - 1) / LPC);
   // Slices are pulled dynamically by the warps (stream.cuh), so they only need to be small enough
   // for a good tail (>= ~4 per warp when the problem allows) and large enough to amortise the
   // per-chunk record flush and the piece changes at every lane-run start: 64..768 steps
@@ -870,6 +891,14 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   const int64_t per_warp = (total_steps + W - 1) / W;
   int64_t L = roundQ(std::max<int64_t>(per_warp < 64 ? 32 : 64, std::min<int64_t>(768, per_warp / 4)));
   L = std::max<int64_t>(L, 8 * Q);
+  if (plan.cta_mode) {
+    // a slice is L steps of ALL main warps of a CTA: >= ~4 slices per CTA for the dynamic balance, but never
+    // fewer slices than CTAs on a small catalog
+    int64_t div = 4;
+    if (const char* e = std::getenv("GWI_TUNE_SLICE_DIV")) div = std::max(1, std::atoi(e));
+    L = roundQ(std::min<int64_t>(768, std::max<int64_t>(16, per_warp / div)));
+    if (L > per_warp) L = roundQ(std::max<int64_t>(Q, per_warp));
+  }
   if (desc.chunk_steps > 0) L = roundQ(desc.chunk_steps);  // explicit slice length (tests force tiny slices)
   plan.chunk_steps = (int)L;
   std::vector<int64_t> chunk_r0, chunk_nc;  // first sorted rank / valid samples of every chunk
@@ -903,7 +932,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
 
       // slice full -- or a new segment that does not fit into the rest of this slice: start it on a
       // fresh slice instead of fragmenting it (every chunk boundary costs a record flush)
-      if (L - fill < Q || (r0 == 0 && fill > 0 && roundQ((left + LANES - 1) / LANES) > L - fill)) {
+      if (L - fill < Q || (r0 == 0 && fill > 0 && roundQ((left + LPC - 1) / LPC) > L - fill)) {
         plan.slice_begin.push_back((int)plan.chunks.size());
         fill = 0;
         {
@@ -911,8 +940,8 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
           L = std::max<int64_t>(std::min<int64_t>(L_MIN, L_full), std::min<int64_t>(L_full, roundQ(remaining / (GUIDED_DIV * (int64_t)W))));
         }
       }
-      const int64_t steps = std::min<int64_t>(L - fill, roundQ((left + LANES - 1) / LANES));
-      const int64_t n_c = std::min<int64_t>(left, steps * LANES);
+      const int64_t steps = std::min<int64_t>(L - fill, roundQ((left + LPC - 1) / LPC));
+      const int64_t n_c = std::min<int64_t>(left, steps * LPC);
       Chunk c{};
       c.segment = s;
       c.steps = (int)steps;
@@ -920,7 +949,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       plan.chunks.push_back(c);
       chunk_r0.push_back(r0);
       chunk_nc.push_back(n_c);
-      pos += steps * LANES;
+      pos += steps * LPC;
       fill += steps;
       done_steps += steps;
       left -= n_c;
@@ -994,10 +1023,12 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
           st.fmin[k] = std::numeric_limits<double>::infinity();
           st.fmax[k] = -std::numeric_limits<double>::infinity();
         }
-        for (int lane = 0; lane < LANES; ++lane) {
+        for (int run = 0; run < LPC; ++run) {
+          const int lane = run % LANES;
+          const int64_t sub = C.first + (int64_t)(run / LANES) * C.steps * LANES;  // sub-chunk of warp run / 32
           for (int k = 0; k < C.steps; ++k) {
-            const int64_t r = (int64_t)lane * C.steps + k;
-            const int64_t p = C.first + (int64_t)(k / UNROLL) * (LANES * UNROLL) + lane * UNROLL + (k % UNROLL);
+            const int64_t r = (int64_t)run * C.steps + k;
+            const int64_t p = sub + (int64_t)(k / UNROLL) * (LANES * UNROLL) + lane * UNROLL + (k % UNROLL);
             if (r < n_c) {
               const int64_t j = r;  // row of the chunk-local sorted copy
               for (int d = 0; d < NS; ++d) {
@@ -1063,13 +1094,14 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   // ---- level-0 records: one per chunk (the chunks, hence the records, of a segment are
   //      consecutive); fixed-order tree reduction afterwards
   {
-    plan.n_records0 = n_chunks;
+    const int RPC = plan.cta_mode ? LW + 1 : 1;  // records per chunk (CTA mode: one per main warp + the deep warps')
+    plan.n_records0 = n_chunks * RPC;
     std::vector<int> cnt(n_seg, 0), first(n_seg, 0);
     for (int c = 0; c < n_chunks; ++c) {
-      plan.chunks[c].record_slot = c;
-      cnt[plan.chunks[c].segment]++;
+      plan.chunks[c].record_slot = c * RPC;
+      cnt[plan.chunks[c].segment] += RPC;
     }
-    for (int s = 0; s < n_seg; ++s) first[s] = plan.segments[s].first_chunk;  // chunks of a segment are consecutive
+    for (int s = 0; s < n_seg; ++s) first[s] = plan.segments[s].first_chunk * RPC;  // chunks (hence records) of a segment are consecutive
     // reduction tree, fan-in 64; the last level writes slot == segment
     constexpr int FAN = 64;
     for (;;) {

@@ -1,0 +1,5 @@
+// instantiation unit of the CTA-cooperative stream kernel for 3 spline dimension(s)
+#include "stream_cta.cuh"
+namespace gwi {
+stream_fn pick_stream_cta_ns3(int nd, int nlin) { return pick_stream_cta_for_ns<3>(nd, nlin); }
+}  // namespace gwi

@@ -1,5 +1,5 @@
 // dispatch to the per-dimension-count instantiation units
-#include "stream.cuh"
+#include "stream_cta.cuh"
 namespace gwi {
 stream_fn pick_stream_ns0(int nd, int nlin, bool g2, bool param, bool maxonly);
 stream_fn pick_stream_ns1(int nd, int nlin, bool g2, bool param, bool maxonly);
@@ -25,4 +25,29 @@ stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, b
   }
   return nullptr;
 }
+
+stream_fn pick_stream_cta_ns1(int nd, int nlin);
+stream_fn pick_stream_cta_ns2(int nd, int nlin);
+stream_fn pick_stream_cta_ns3(int nd, int nlin);
+stream_fn pick_stream_cta_ns4(int nd, int nlin);
+stream_fn pick_stream_cta_ns5(int nd, int nlin);
+stream_fn pick_stream_cta_ns6(int nd, int nlin);
+stream_fn pick_stream_cta_ns7(int nd, int nlin);
+stream_fn pick_stream_cta_ns8(int nd, int nlin);
+
+stream_fn pick_stream_cta_kernel(int ns, int ndeep, int nlin) {
+  switch (ns) {
+    case 1: return pick_stream_cta_ns1(ndeep, nlin);
+    case 2: return pick_stream_cta_ns2(ndeep, nlin);
+    case 3: return pick_stream_cta_ns3(ndeep, nlin);
+    case 4: return pick_stream_cta_ns4(ndeep, nlin);
+    case 5: return pick_stream_cta_ns5(ndeep, nlin);
+    case 6: return pick_stream_cta_ns6(ndeep, nlin);
+    case 7: return pick_stream_cta_ns7(ndeep, nlin);
+    case 8: return pick_stream_cta_ns8(ndeep, nlin);
+  }
+  return nullptr;
+}
+stream_fn pick_stream_cta_max_kernel() { return (stream_fn)stream_cta_max_kernel<0>; }
+unsigned stream_cta_smem_bytes(int nw, int ncol, int rows_total, int deep_entries) { return cta_layout(nw, ncol, rows_total, deep_entries).total; }
 }  // namespace gwi

@@ -323,9 +323,10 @@ typedef struct gwi_plan gwi_plan;
 int gwi_debug_plan_build(const gwi_catalog* cat, const gwi_model_desc* desc, int32_t n_workers, gwi_plan** out);
 void gwi_debug_plan_destroy(gwi_plan* p);
 /* what: 0 = dims {n_columns, n_padded, n_chunks, n_segments, n_spline, n_linear, rows_total, n_deep,
- *                 n_param_cols, rec_doubles}  (int64[10])
+ *                 n_param_cols, rec_doubles, warps sharing a chunk}  (int64[11])
  *       1 = stream words [n_padded/64][n_columns][64] (uint64 bit patterns; blocks of 64 samples)
- *       2 = chunk table   [n_chunks * 4] int64 {segment, first_sample, steps, record_slot}
+ *       2 = chunk table   [n_chunks * 4] int64 {segment, first_sample, steps, first record_slot}
+ *           (a chunk covers steps x 32 x (warps sharing a chunk) padded samples)
  *       3 = segment table [n_segments * 4] int64 {n_total, n_valid, first_chunk, n_chunks}
  *       4 = spline dim table [n_spline * 4] int64 {term index, rows (= n_splines-2), row offset, deep?}
  *       5 = non-spline op table [n_ops * 8] int64 {kind, column0, column1, slot0..slot3, bits of cst0}

@@ -16,8 +16,7 @@ from gwinferno_b200 import capi
 from oracle import popmodel
 from tests import cases
 
-MANT = np.uint64(0x000FFFFFFFFFFFFF)
-ONE = np.uint64(0x3FF0000000000000)
+JMASK = np.uint64(63)
 SPLINE_CASES = ["bspline_full", "bspline_iid", "bspline_indep_masses", "inference_test_bspline", "bspline_effspin", "bspline_symchieff"]
 
 
@@ -45,6 +44,7 @@ def test_struct_layouts_match_header_sizes():
 def _decode(case, plan):
     dims = plan.read(0)
     n_cols, n_pad, n_chunks, n_seg, ns, n_kops = (int(x) for x in dims[:6])
+    lw = int(dims[10])  # warps that share a chunk (CTA-cooperative geometry), 1 for the one-role kernel
     cols = np.ascontiguousarray(plan.read(1, dtype=np.uint64).reshape(n_pad // 64, n_cols, 64).transpose(1, 0, 2).reshape(n_cols, n_pad))
     chunks = plan.read(2).reshape(n_chunks, 4)
     segs = plan.read(3).reshape(n_seg, 4)
@@ -56,8 +56,8 @@ def _decode(case, plan):
     for d in range(ns):
         term = spec.terms[int(dimt[d, 0])]
         rows = int(dimt[d, 1])
-        J = (cols[d] >> np.uint64(52)).astype(np.int64)
-        u = ((cols[d] & MANT) | ONE).view(np.float64) - 1.0
+        J = (cols[d] & JMASK).astype(np.int64)
+        u = cols[d].view(np.float64) + 0.5  # the word is w = u - 1/2 (piece index in its 6 low mantissa bits)
         assert J.max() <= rows - 1
         real = J < rows - 1
         Jc = np.where(real, J, 0)
@@ -76,9 +76,9 @@ def _decode(case, plan):
         x += (Lam[s0] + off) * cols[c0].view(np.float64)
     seg_of = np.full(n_pad, -1)
     for seg, first, steps, _ in chunks:
-        seg_of[first : first + steps * 32] = seg
+        seg_of[first : first + steps * 32 * lw] = seg
     assert (seg_of >= 0).all()
-    return x, seg_of, segs, chunks, cols, dimt
+    return x, seg_of, segs, chunks, cols, dimt, lw
 
 
 @pytest.mark.parametrize("name", SPLINE_CASES)
@@ -86,7 +86,7 @@ def test_plan_reproduces_oracle(name):
     case = cases.load_case(name)
     cat = capi.Catalog(case.low.pe_cols, case.low.inj_cols, case.total_inj)
     plan = capi.HostPlan(cat, case.low.spec, chunk_steps=8)
-    x, seg_of, segs, chunks, cols, dimt = _decode(case, plan)
+    x, seg_of, segs, chunks, cols, dimt, lw = _decode(case, plan)
     ev = popmodel.evaluate(case.low.spec, case.low.pe_cols, case.low.inj_cols, case.total_inj, case.Lam, want_jac=False)
     sumZ = np.sum(ev["logZ"])
     E = case.Nobs
@@ -113,11 +113,11 @@ def test_plan_reproduces_oracle(name):
     ns = dimt.shape[0]
     key = np.zeros(cols.shape[1], dtype=np.int64)
     for d in range(ns):
-        key = key * 64 + (cols[d] >> np.uint64(52)).astype(np.int64)
+        key = key * 64 + (cols[d] & JMASK).astype(np.int64)
     valid = np.isfinite(cols[-1].view(np.float64))
     for seg, first, steps, _ in chunks[:50]:
-        blk = np.arange(first, first + steps * 32).reshape(steps // 2, 32, 2)  # [iter][lane][unroll]
-        lane_major = blk.transpose(1, 0, 2).reshape(32, steps)  # each lane's run in order
+        blk = np.arange(first, first + steps * 32 * lw).reshape(lw, steps // 2, 32, 2)  # [warp][iter][lane][unroll]
+        lane_major = blk.transpose(0, 2, 1, 3).reshape(32 * lw, steps)  # each lane's run in order
         kk = key[lane_major].reshape(-1)
         vv = valid[lane_major].reshape(-1)
         assert np.all(np.diff(kk[vv]) >= 0)
@@ -203,7 +203,7 @@ def test_plan_reproduces_oracle_on_random_small_models(seed):
     case.Lam = lowering.flatten_params(w(pe, True), case.low.spec.n_params)
     cat = capi.Catalog(case.low.pe_cols, case.low.inj_cols, const["total_inj"])
     plan = capi.HostPlan(cat, case.low.spec, chunk_steps=int(rng.choice([0, 4, 8, 32])))
-    x, seg_of, segs, chunks, cols, dimt = _decode(case, plan)
+    x, seg_of, segs, chunks, cols, dimt, _ = _decode(case, plan)
     ev = popmodel.evaluate(case.low.spec, case.low.pe_cols, case.low.inj_cols, const["total_inj"], case.Lam, want_jac=False)
     sumZ = np.sum(ev["logZ"])
     assert segs.shape[0] == E + 1
