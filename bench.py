@@ -36,6 +36,28 @@ UNIT = "evals/s"
 ALG_BYTES_PER_SAMPLE = 64  # 8 fp64 columns read once per evaluation
 
 
+def _config(name, family, E, S, I, n_params, chains, world, shard_by, l2_policy):
+    """The `config` object of BOTH arms (identical keys: the driver compares them)."""
+    from gwinferno_b200 import workloads
+
+    return {
+        "workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "model": family, "E": E, "S": S, "I": I,
+        "n_params": n_params, "samples_per_eval": E * S + I, "chains_per_step": chains,
+        "parallelism": ("single" if world == 1 else (f"shard{world}: injections by (m1, q) piece bucket, whole events round-robin, records exchanged through NVLink peer memory by libgwi"
+                                                     if shard_by == "bucket" else f"shard{world}: injections by index range")),
+        "l2_policy": l2_policy,
+        "neff_grad": False, "likelihood": "marginalize_selection=False, min_neff_cut=True (reference defaults)",
+    }
+
+
+def _l2_policy(name):
+    from gwinferno_b200 import workloads
+
+    _, _, E, S, I = workloads.WORKLOADS[name]
+    plan_gb = 72.0 * (E * S + I) / 1e9
+    return "inputs larger than L2 (plan ~%.2f GB in total)" % plan_gb if plan_gb > 0.26 else "inputs fit in L2; new Lambda every step, no flush"
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -132,7 +154,7 @@ def _cpu_arm(name, seconds_per_step, steps, warmup):
     t = float(np.sum(times[warmup:]))
     value = (steps / t) * n_sample / n_full
     return {
-        "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "value": value, "unit": UNIT, "cores": cores, "kind": "port", "n_params": int(low.spec.n_params),
         "sample": f"{n_ev} events x {S} samples + {n_inj} injections ({n_sample} of {n_full} samples), {1e3 * t / steps:.0f} ms per sampled step on {cores} threads, "
                   "extrapolated linearly in samples; plain-C port of the reference algorithm (oracle/c/gwi_oracle.c; the reference needs JAX, not installed)",
         "samples_per_s": n_sample * steps / t,
@@ -142,6 +164,63 @@ def _cpu_arm(name, seconds_per_step, steps, warmup):
 def cpu_baseline(name):
     """cpu_baseline object of the GPU arm's line: about 10 s of CPU work on rank 0."""
     return _cpu_arm(name, seconds_per_step=2.0, steps=4, warmup=1)[0]
+
+
+def parity_at_size(name, scale, lam, res, world):
+    """{rel_log_l, rel_grad}: GPU result `res` (header + gradient) vs oracle/c/gwi_oracle.c on the whole catalog."""
+    from gwinferno_b200 import capi, workloads
+    from oracle import c_oracle, popmodel
+
+    t0 = time.perf_counter()
+    pe, inj, const, z_range = workloads.shard_catalog(name, 0, 1, scale=scale, all_reduce_minmax=lambda lo, hi: (lo, hi))
+    weights, params_fn = workloads.build_model(const["family"], pe, inj, z_range=z_range)
+    low, _, _ = workloads.lower_workload(weights, params_fn, pe, inj)
+    cores = os.cpu_count() or 1
+    ev = c_oracle.evaluate(low.spec, low.pe_cols, low.inj_cols, const["total_inj"], lam, want_jac=True, want_neff_jac=False, n_threads=cores)
+    l_o, g_o, _ = popmodel.hierarchical_log_likelihood(ev, const["E"], min_neff_cut=True)
+    g = np.asarray(res[capi.GWI_LIKE_HEADER:])
+    return {"rel_log_l": float(abs(res[0] - l_o) / abs(l_o)), "rel_grad": float(np.max(np.abs(g - g_o)) / np.max(np.abs(g_o))), "log_l_oracle": float(l_o),
+            "tolerance": {"rel_log_l": 1e-10, "rel_grad": 1e-8}, "oracle": f"oracle/c/gwi_oracle.c, whole catalog, {cores} threads", "n_gpus": world,
+            "seconds": time.perf_counter() - t0}
+
+
+def nuts_block(device):
+    """The second half of BASELINE.json's metric: NUTS ESS/s on configs[1] (70 x 4000 + 5e5 injections, 164 free parameters),
+    the whole sampler loop in native code (csrc/nuts.cpp: multinomial NUTS, windowed adaptation, dense mass matrix -- NumPyro's
+    NUTS(dense_mass=True) in spirit) around gwi_loglike_host; priors of examples/simple_bspline_example.py.  The CPU row is the
+    same chain priced at the plain-C oracle's evaluation rate on this host (measured on a few evaluations, not run in full)."""
+    from gwinferno_b200 import nuts, pipeline, workloads
+    from gwinferno_b200.likelihood import PopulationLikelihood
+    from oracle import c_oracle
+
+    pe, inj, const, z_range = workloads.shard_catalog("cfg2", 0, 1)
+    weights, params_fn = workloads.build_model(const["family"], pe, inj, z_range=z_range)
+    low, lam0, p0 = workloads.lower_workload(weights, params_fn, pe, inj)
+    eng = PopulationLikelihood(low, const["total_inj"], device=device)
+    blocks = pipeline.bspline_prior_blocks(low.slots_for, p0)
+    dim = low.spec.n_params - 1
+    theta0 = 0.1 * np.random.default_rng(0).standard_normal(dim)
+    n_warm, n_samp, flags = 1000, 500, 7
+    t0 = time.perf_counter()
+    samples, info = nuts.nuts_native(eng, blocks, theta0, n_warm, n_samp, Nobs=const["E"], seed=0, max_depth=8, flags=flags)
+    wall = time.perf_counter() - t0
+    eng.model.close()
+    ess = np.array([nuts.effective_sample_size(samples[:, i]) for i in range(samples.shape[1])])
+    cores = os.cpu_count() or 1
+    c_oracle.evaluate(low.spec, low.pe_cols, low.inj_cols, const["total_inj"], lam0, want_jac=True, want_neff_jac=False, n_threads=cores)
+    t0 = time.perf_counter()
+    n_cpu = 5
+    for _ in range(n_cpu):
+        c_oracle.evaluate(low.spec, low.pe_cols, low.inj_cols, const["total_inj"], lam0, want_jac=True, want_neff_jac=False, n_threads=cores)
+    cpu_rate = n_cpu / (time.perf_counter() - t0)
+    gpu_rate = info["leapfrogs_sampling"] / info["sampling_seconds"]
+    return {"workload": "cfg2: BASELINE.json configs[1]", "dim": dim, "warmup": n_warm, "samples": n_samp, "max_tree_depth": 8,
+            "sampler": "csrc/nuts.cpp: multinomial NUTS + windowed adaptation + dense mass (flags 7), likelihood+gradient via gwi_loglike_host",
+            "ess_min": float(ess.min()), "ess_median": float(np.median(ess)), "ess_min_per_s": float(ess.min() / info["sampling_seconds"]),
+            "ess_median_per_s": float(np.median(ess) / info["sampling_seconds"]), "grad_evals_per_s": float(gpu_rate), "mean_accept": info["mean_accept"],
+            "step_size": info["step_size"], "wall_s": wall,
+            "cpu": {"grad_evals_per_s": float(cpu_rate), "cores": cores, "kind": "port (oracle/c/gwi_oracle.c), priced not run: the same chain at this evaluation rate",
+                    "ess_min_per_s": float(ess.min() / (info["leapfrogs_sampling"] / cpu_rate)), "ess_median_per_s": float(np.median(ess) / (info["leapfrogs_sampling"] / cpu_rate))}}
 
 
 def run_reference(args):
@@ -161,9 +240,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps * n_full / n_sample, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "model": family, "E": E, "S": S, "I": I,
-                   "samples_per_eval": n_full, "chains_per_step": 1, "parallelism": f"{base['cores']} host threads (CPU)",
-                   "neff_grad": False, "likelihood": "marginalize_selection=False, min_neff_cut=True (reference defaults)"},
+        "config": _config(name, family, E, S, I, base["n_params"], workloads.N_CHAINS.get(name, 1), args.gpus, "bucket", _l2_policy(name)),
+        "host": f"{base['cores']} host threads (CPU arm: no GPU in this line)",
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -226,11 +304,15 @@ def run_ours(args):
         out_chain = torch.zeros(chains * (capi.GWI_LIKE_HEADER + P), dtype=torch.float64, device="cuda")
     lam_dev = torch.from_numpy(lams).cuda()
     lam_pin = torch.from_numpy(lams).pin_memory()
-    nrec = mdl.partial_size()
-    rec = torch.zeros(nrec, dtype=torch.float64, device="cuda")
-    allrec = torch.zeros(world * nrec, dtype=torch.float64, device="cuda")
     out = torch.zeros(capi.GWI_LIKE_HEADER + P, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
+    if world > 1:
+        # the exchange belongs to libgwi (peer-memory pushes + flags inside its last kernel); torch.distributed only
+        # carries the 80-byte IPC handles once, here, and the barriers around the timed region
+        handles = [None] * world
+        dist.all_gather_object(handles, mdl.comm_local_handle(world))
+        mdl.comm_connect(handles, rank)
+        dist.barrier()
 
     def step(i, lam_ptr=None):
         ptr = lam_dev[i].data_ptr() if lam_ptr is None else lam_ptr
@@ -239,9 +321,7 @@ def run_ours(args):
         elif world == 1:
             mdl.loglike(ptr, out.data_ptr(), Nobs, stream=stream)
         else:
-            mdl.partial(ptr, rec.data_ptr(), stream=stream)
-            dist.all_gather_into_tensor(allrec, rec)
-            mdl.combine(allrec.data_ptr(), world, out.data_ptr(), Nobs, stream=stream)
+            mdl.loglike_sharded(ptr, out.data_ptr(), Nobs, stream=stream)
 
     def barrier():
         if world > 1:
@@ -296,6 +376,23 @@ def run_ours(args):
         t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t[0])
+    # ---- the same through the Python drop-in (hierarchical_likelihood on lazy weights), single GPU ----
+    e2e_python = None
+    if world == 1 and chains == 1:
+        from gwinferno_b200 import likelihood as L
+
+        pw, iw = weights(pe, True, params_fn(0)), weights(inj, False, params_fn(0))
+        keys, pattern = lowering._structure(pw, iw)
+        L._ENGINES[(keys, pattern, float(const["total_inj"]), False, int(local))] = eng  # this bench's resident plan, not a second one
+        n_py = min(args.steps, 20)
+        t0 = time.perf_counter()
+        for i in range(n_py):
+            p_i = params_fn(args.warmup + i)
+            r_py = L.hierarchical_likelihood(weights(pe, True, p_i), weights(inj, False, p_i), const["total_inj"], Nobs, 1.0)
+        t_py = time.perf_counter() - t0
+        e2e_python = {"value": n_py / t_py, "unit": UNIT, "steps": n_py, "api": "gwinferno_b200.likelihood.hierarchical_likelihood (model objects -> lazy weights -> one libgwi call; per-event sites read back)",
+                      "log_l": r_py.log_likelihood}
+        L._ENGINES.clear()  # the engine is closed by this function, not by the cache
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,17 +412,14 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": chains * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": f"{name}: BASELINE.json configs[{workloads.WORKLOADS[name][0]}]", "model": const["family"], "E": const["E"], "S": const["S"], "I": const["I"],
-            "n_params": P, "samples_per_eval": n_total, "chains_per_step": chains, "parallelism": (f"shard{world}: injections by (m1, q) piece bucket, whole events round-robin, one all-gather" if args.shard_by == "bucket" else f"shard{world}: injections by index range") if world > 1 else "single",
-            "l2_policy": "inputs larger than L2 (plan %.2f GB per GPU)" % (info["bytes_per_eval"] / 1e9) if info["bytes_per_eval"] > 2.6e8 else "inputs fit in L2; new Lambda every step, no flush",
-            "neff_grad": False, "likelihood": "marginalize_selection=False, min_neff_cut=True (reference defaults)",
-        },
+        "config": _config(name, const["family"], const["E"], const["S"], const["I"], P, chains, world, args.shard_by, _l2_policy(name)),
         "samples_per_s": n_total * chains * args.steps / (ms * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "stream_kernel", "kernel_ms": k_ms, "alg_bytes_per_launch": n_local * chains * ALG_BYTES_PER_SAMPLE,
                      "actual_bytes_per_launch": info["bytes_per_eval"], "kernel_share_of_step": k_ms / (ms / args.steps)},
-        "e2e": {"value": chains * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * P * chains, "d2h_bytes_per_step": 8 * (capi.GWI_LIKE_HEADER + P) * chains},
+        "e2e": {"value": chains * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * P * chains, "d2h_bytes_per_step": 8 * (capi.GWI_LIKE_HEADER + P) * chains,
+                "api": "gwi_loglike_host (C-ABI, host buffers: Lambda H2D, evaluation, log L + gradient D2H, synchronise)" if world == 1 and chains == 1 else "pinned Lambda H2D + libgwi device call + result D2H"},
+        "e2e_python": e2e_python,
         "gpu_launches": info["kernel_launches_per_eval"] * args.steps,  # a chain batch launches every kernel once
         "clocks": clocks,
         "result": {"log_l": float(res[0]), "passed": float(res[1]), "status": float(res[7])},
@@ -337,6 +431,12 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(name)
+    if not args.no_cpu_baseline and chains == 1:
+        # parity at the size that was timed: the last timed step's log L and gradient against the plain-C oracle on the
+        # WHOLE catalog (rank 0 regenerates it when the run is sharded), same Lambda
+        line["parity_at_size"] = parity_at_size(name, args.scale, lams[n_steps - 1], res, world)
+    if world == 1 and not args.no_cpu_baseline and not args.no_nuts:
+        line["nuts"] = nuts_block(local)
     emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -370,7 +470,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink S and I (testing only; the reported config then differs from BASELINE's)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline, parity_at_size, nuts): tuning runs")
+    ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS ESS/s block")
     ap.add_argument("--emulate-world", type=int, default=1, help="tuning aid: run rank 0's shard of a W-way partition on one GPU")
     ap.add_argument("--shard-by", default="bucket", choices=["bucket", "index"], help="multi-GPU partition of the found injections")
     ap.add_argument("--n-deep", type=int, default=-1, help="tuning experiment: spline dims with lane-private accumulators (-1 = auto)")

@@ -133,6 +133,11 @@ class gwi_model_info(C.Structure):
 
 # every symbol include/gwi.h declares (tests check that the library exports all of them)
 SYMBOLS = [
+    "gwi_comm_local_handle",
+    "gwi_comm_connect",
+    "gwi_loglike_sharded",
+    "gwi_sharded_push",
+    "gwi_sharded_combine",
     "gwi_model_last_sites",
     "gwi_catalog_create",
     "gwi_catalog_destroy",
@@ -197,6 +202,11 @@ def load_library(_allow_emulator=False):
     lib.gwi_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gwi_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
     lib.gwi_model_get_info.argtypes = [C.c_void_p, C.POINTER(gwi_model_info)]
+    lib.gwi_comm_local_handle.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.gwi_comm_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.gwi_loglike_sharded.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
+    lib.gwi_sharded_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gwi_sharded_combine.argtypes = [C.c_void_p, C.POINTER(gwi_like_opts), C.c_void_p, C.c_void_p]
     lib.gwi_model_last_sites.restype = C.c_int64
     lib.gwi_model_last_sites.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int64]
     lib.gwi_model_set_exact_shift.argtypes = [C.c_void_p, C.c_int32]
@@ -461,6 +471,29 @@ class Model:
         i = gwi_model_info()
         _check(load_library().gwi_model_get_info(self.handle, C.byref(i)))
         return {n: getattr(i, n) for n, _ in gwi_model_info._fields_ if n != "reserved"}
+
+    # -- library-owned multi-GPU exchange (include/gwi.h: gwi_comm_*) -------------------------
+    def comm_local_handle(self, n_ranks):
+        """This rank's exchange-buffer handle (80 bytes) to be all-gathered by any host-side means."""
+        buf = C.create_string_buffer(80)
+        _check(load_library().gwi_comm_local_handle(self.handle, int(n_ranks), buf))
+        return buf.raw
+
+    def comm_connect(self, handles, rank):
+        """``handles``: the 80-byte handles of ALL ranks in rank order.  Follow with a host barrier."""
+        blob = C.create_string_buffer(b"".join(handles), 80 * len(handles))
+        _check(load_library().gwi_comm_connect(self.handle, blob, int(rank), len(handles)))
+
+    def loglike_sharded(self, lam_ptr, out_ptr, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False, stream=None):
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        _check(load_library().gwi_loglike_sharded(self.handle, C.c_void_p(lam_ptr), C.byref(o), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def sharded_push(self, lam_ptr, stream=None):
+        _check(load_library().gwi_sharded_push(self.handle, C.c_void_p(lam_ptr), C.c_void_p(stream)))
+
+    def sharded_combine(self, out_ptr, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False, stream=None):
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        _check(load_library().gwi_sharded_combine(self.handle, C.byref(o), C.c_void_p(out_ptr), C.c_void_p(stream)))
 
     def last_sites(self):
         """``[E + 1, 4]`` {log mean weight, log N_eff, variance, status} of the last evaluation; row 0 = injections."""

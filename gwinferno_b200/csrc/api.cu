@@ -1,6 +1,7 @@
 // C-ABI entry points of libgwi.so (include/gwi.h): handle management, plan upload, and the
 // per-evaluation launch sequence.  No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -32,6 +33,7 @@ void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaS
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st);
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st);
+void launch_exchange(const ModelDev* Md, const double* rec_local, const CommDev& C, unsigned long long epoch, int mode, const gwi_like_opts& o, double* out, cudaStream_t st);
 
 }  // namespace gwi
 
@@ -98,6 +100,13 @@ struct gwi_model {
   cudaStream_t aux_stream = nullptr;  // grid normalisers run here, concurrently with the stream kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t bytes_per_eval = 0;
+  // library-owned multi-GPU exchange (gwi_comm_*): this rank's buffer {flags [2][R] | slots [2][R][stride]},
+  // the peers' buffers as opened here, and the number of sharded evaluations so far (the epoch)
+  void* comm_base = nullptr;
+  std::vector<void*> comm_opened;  // IPC mappings to close
+  CommDev comm{};
+  bool comm_connected = false;
+  unsigned long long comm_epoch = 0, comm_pushed = 0;
   // optional timing of the stream kernel (ring of event pairs)
   bool timing = false;
   std::vector<cudaEvent_t> ev0, ev1;
@@ -353,6 +362,9 @@ extern "C" {
 void gwi_model_destroy(gwi_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
+#ifndef GWI_HOST_EMULATION
+  for (void* p : m->comm_opened) cudaIpcCloseMemHandle(p);
+#endif
   for (void* p : m->allocs) cudaFree(p);
   if (m->lam_pinned) cudaFreeHost(m->lam_pinned);
   if (m->out_pinned) cudaFreeHost(m->out_pinned);
@@ -578,7 +590,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     m->smem_max = 0;
     m->stream_block = (p.cta_main_warps + p.n_deep) * 32;
     m->max_block = 256;
-    if (m->smem_full > (size_t)prop.sharedMemPerBlockOptin) {
+    if (m->smem_full == 0 || m->smem_full > (size_t)prop.sharedMemPerBlockOptin) {
       set_error("internal: CTA-kernel geometry does not fit the device's shared memory");
       gwi_model_destroy(m);
       return GWI_ERR_UNSUPPORTED;
@@ -708,6 +720,163 @@ int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opt
   int rc = gwi_partial(m, lambda_dev, m->partial_dev, stream);
   if (rc != GWI_OK) return rc;
   return gwi_combine(m, m->partial_dev, 1, opts, out_dev, stream);
+}
+
+// ---- library-owned multi-GPU exchange ------------------------------------------------------------------
+static size_t comm_flag_bytes(int R) { return ((size_t)2 * R * sizeof(unsigned long long) + 255) / 256 * 256; }
+
+int gwi_comm_local_handle(gwi_model* m, int32_t n_ranks, gwi_ipc_handle* out) {
+  if (!m || !out || n_ranks < 1 || n_ranks > MAX_RANKS) {
+    set_error("bad argument (1 <= n_ranks <= 16)");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  const size_t stride = (size_t)PR_HEADER + 3 * (size_t)m->plan.n_params;
+  if (m->comm_base && m->comm.n_ranks != n_ranks) {
+    set_error("the exchange buffer of this model was created for another number of ranks");
+    return GWI_ERR_INVALID;
+  }
+  if (!m->comm_base) {
+    const size_t bytes = comm_flag_bytes(n_ranks) + (size_t)2 * n_ranks * stride * sizeof(double);
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    m->allocs.push_back(p);
+    CUDA_TRY(cudaMemset(p, 0, bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    m->comm_base = p;
+    m->comm.n_ranks = n_ranks;
+  }
+  std::memset(out->bytes, 0, sizeof(out->bytes));
+#ifndef GWI_HOST_EMULATION
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, m->comm_base));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(out->bytes, &h, 64);
+#endif
+  const long long pid = (long long)getpid();
+  std::memcpy(out->bytes + 64, &pid, 8);
+  std::memcpy(out->bytes + 72, &m->comm_base, 8);
+  return GWI_OK;
+}
+
+int gwi_comm_connect(gwi_model* m, const gwi_ipc_handle* handles, int32_t rank, int32_t n_ranks) {
+  if (!m || !handles || n_ranks < 1 || n_ranks > MAX_RANKS || rank < 0 || rank >= n_ranks) {
+    set_error("bad argument");
+    return GWI_ERR_INVALID;
+  }
+  if (!m->comm_base || m->comm.n_ranks != n_ranks) {
+    set_error("call gwi_comm_local_handle(m, n_ranks, ...) first");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  const size_t fb = comm_flag_bytes(n_ranks);
+  for (int p = 0; p < n_ranks; ++p) {
+    void* base = nullptr;
+    long long pid = 0;
+    std::memcpy(&pid, handles[p].bytes + 64, 8);
+    if (p == rank) {
+      base = m->comm_base;
+    } else if (pid == (long long)getpid()) {
+      std::memcpy(&base, handles[p].bytes + 72, 8);  // same process: the pointer itself
+#ifndef GWI_HOST_EMULATION
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, base) == cudaSuccess && attr.device != m->device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          set_error(std::string("cudaDeviceEnablePeerAccess failed: ") + cudaGetErrorString(e));
+          return GWI_ERR_CUDA;
+        }
+        cudaGetLastError();
+      }
+#endif
+    } else {
+#ifndef GWI_HOST_EMULATION
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles[p].bytes, 64);
+      const cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        set_error(std::string("cudaIpcOpenMemHandle of rank ") + std::to_string(p) + " failed: " + cudaGetErrorString(e));
+        return GWI_ERR_CUDA;
+      }
+      m->comm_opened.push_back(base);
+#else
+      set_error("the host emulator has no inter-process exchange");
+      return GWI_ERR_UNSUPPORTED;
+#endif
+    }
+    m->comm.peer_flags[p] = reinterpret_cast<unsigned long long*>(base);
+    m->comm.peer_slots[p] = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(base) + fb);
+  }
+  m->comm.rank = rank;
+  m->comm_connected = true;
+  return GWI_OK;
+}
+
+static int sharded_checks(gwi_model* m, const gwi_like_opts* opts) {
+  if (!m->comm_connected) {
+    set_error("gwi_comm_connect has not been called on this model");
+    return GWI_ERR_INVALID;
+  }
+  if (opts) {
+    if (opts->marginalize_selection && !m->plan.g2) {
+      set_error("marginalize_selection needs a model created with need_neff_grad");
+      return GWI_ERR_INVALID;
+    }
+    if (opts->max_variance_cut && (opts->marginalize_selection || opts->min_neff_cut)) {
+      set_error("max_variance_cut requires marginalize_selection and min_neff_cut to be off (analysis.py:237-244)");
+      return GWI_ERR_INVALID;
+    }
+  }
+  return GWI_OK;
+}
+
+int gwi_loglike_sharded(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opts, double* out_dev, void* stream) {
+  if (!m || !lambda_dev || !opts || !out_dev) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  int rc = sharded_checks(m, opts);
+  if (rc != GWI_OK) return rc;
+  rc = gwi_partial(m, lambda_dev, m->partial_dev, stream);
+  if (rc != GWI_OK) return rc;
+  m->comm_pushed = ++m->comm_epoch;
+  launch_exchange(m->dev, m->partial_dev, m->comm, m->comm_epoch, 0, *opts, out_dev, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return GWI_OK;
+}
+
+int gwi_sharded_push(gwi_model* m, const double* lambda_dev, void* stream) {
+  if (!m || !lambda_dev) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  int rc = sharded_checks(m, nullptr);
+  if (rc != GWI_OK) return rc;
+  rc = gwi_partial(m, lambda_dev, m->partial_dev, stream);
+  if (rc != GWI_OK) return rc;
+  m->comm_pushed = ++m->comm_epoch;
+  gwi_like_opts none{};
+  launch_exchange(m->dev, m->partial_dev, m->comm, m->comm_epoch, 1, none, nullptr, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return GWI_OK;
+}
+
+int gwi_sharded_combine(gwi_model* m, const gwi_like_opts* opts, double* out_dev, void* stream) {
+  if (!m || !opts || !out_dev) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  const int rc = sharded_checks(m, opts);
+  if (rc != GWI_OK) return rc;
+  if (m->comm_pushed != m->comm_epoch || m->comm_epoch == 0) {
+    set_error("gwi_sharded_combine without a preceding gwi_sharded_push");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  m->comm_pushed = 0;
+  launch_exchange(m->dev, m->partial_dev, m->comm, m->comm_epoch, 2, *opts, out_dev, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return GWI_OK;
 }
 
 int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, const gwi_like_opts* opts, double* out_dev, void* stream) {

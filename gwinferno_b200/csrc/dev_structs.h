@@ -104,6 +104,15 @@ struct ModelDev {
   int32_t cta_main_warps, cta_pad;
 };
 
+// multi-GPU exchange (exchange_kernel): the exchange buffers of every rank as seen from this rank (peer
+// memory), passed to the kernel by value
+constexpr int MAX_RANKS = 16;
+struct CommDev {
+  double* peer_slots[MAX_RANKS];              // rank p's slots  [2 parities][n_ranks][PR_HEADER + 3P]
+  unsigned long long* peer_flags[MAX_RANKS];  // rank p's flags  [2 parities][n_ranks]: epoch of the record in the slot
+  int32_t rank, n_ranks;
+};
+
 // partial (per-rank) likelihood record: 8 header doubles + 3P
 enum { PR_SHIFT = 0, PR_S1 = 1, PR_S2 = 2, PR_SUM_LOGBF = 3, PR_MIN_LOGNEFF = 4, PR_SUM_VAR = 5, PR_N_EVENTS = 6, PR_STATUS = 7, PR_HEADER = 8 };
 

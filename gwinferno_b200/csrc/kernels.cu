@@ -601,9 +601,10 @@ __global__ void __launch_bounds__(256) partial_kernel(const ModelDev* __restrict
   partial_rows<false>(M, recd, blockIdx.x * wpb + warp, gridDim.x * wpb);
 }
 
-// rank-ordered merge of R partial records + the likelihood glue: all threads of one block.  (`recs`
-// is deliberately not __restrict__/const-qualified for the read-only cache: the fused epilogue calls
-// this on a record the same block has just written.)
+// rank-ordered merge of R partial records + the likelihood glue: all threads of one block.  CG: the
+// records were written by OTHER GPUs through peer memory while this kernel was running (exchange_kernel):
+// read them through L2.
+template <bool CG>
 __device__ void combine_records(const ModelDev& M, const double* recs, int R, const gwi_like_opts& opts, double* out) {
   const int P = M.n_params;
   const int stride = PR_HEADER + 3 * P;
@@ -612,19 +613,19 @@ __device__ void combine_records(const ModelDev& M, const double* recs, int R, co
   // injection sums of all ranks on a common shift
   double m = -INFINITY;
   for (int r = 0; r < R; ++r)
-    if (recs[(size_t)r * stride + PR_S1] > 0.0) m = fmax(m, recs[(size_t)r * stride + PR_SHIFT]);
+    if (ldd<CG>(&recs[(size_t)r * stride + PR_S1]) > 0.0) m = fmax(m, ldd<CG>(&recs[(size_t)r * stride + PR_SHIFT]));
   double S1 = 0.0, S2 = 0.0, sum_logBF = 0.0, min_ln = INFINITY, sum_var = 0.0, status = 0.0;
   for (int r = 0; r < R; ++r) {
     const double* q = recs + (size_t)r * stride;
-    if (q[PR_S1] > 0.0) {
-      const double f = exp(q[PR_SHIFT] - m);
-      S1 += q[PR_S1] * f;
-      S2 += q[PR_S2] * f * f;
+    if (ldd<CG>(&q[PR_S1]) > 0.0) {
+      const double f = exp(ldd<CG>(&q[PR_SHIFT]) - m);
+      S1 += ldd<CG>(&q[PR_S1]) * f;
+      S2 += ldd<CG>(&q[PR_S2]) * f * f;
     }
-    sum_logBF += q[PR_SUM_LOGBF];
-    min_ln = fmin(min_ln, q[PR_MIN_LOGNEFF]);
-    sum_var += q[PR_SUM_VAR];
-    status = fmax(status, q[PR_STATUS]);
+    sum_logBF += ldd<CG>(&q[PR_SUM_LOGBF]);
+    min_ln = fmin(min_ln, ldd<CG>(&q[PR_MIN_LOGNEFF]));
+    sum_var += ldd<CG>(&q[PR_SUM_VAR]);
+    status = fmax(status, ldd<CG>(&q[PR_STATUS]));
   }
   if (!(S1 > 0.0) || !(S1 < INFINITY)) status = 1.0;  // no injection weight survived on any rank
   double K = M.Ksum[0];
@@ -670,12 +671,12 @@ __device__ void combine_records(const ModelDev& M, const double* recs, int R, co
     double G1 = 0.0, G2s = 0.0, sumJ = 0.0;
     for (int r = 0; r < R; ++r) {
       const double* q = recs + (size_t)r * stride;
-      if (q[PR_S1] > 0.0) {
-        const double f = exp(q[PR_SHIFT] - m);
-        G1 += q[PR_HEADER + i] * f;
-        G2s += q[PR_HEADER + P + i] * f * f;
+      if (ldd<CG>(&q[PR_S1]) > 0.0) {
+        const double f = exp(ldd<CG>(&q[PR_SHIFT]) - m);
+        G1 += ldd<CG>(&q[PR_HEADER + i]) * f;
+        G2s += ldd<CG>(&q[PR_HEADER + P + i]) * f * f;
       }
-      sumJ += q[PR_HEADER + 2 * P + i];
+      sumJ += ldd<CG>(&q[PR_HEADER + 2 * P + i]);
     }
     double dK = M.Ksum[1 + i];
     for (int g = 0; g < M.n_groups; ++g) dK -= M.dlogZ[(size_t)g * P + i];
@@ -694,7 +695,79 @@ __global__ void __launch_bounds__(256) combine_kernel(const ModelDev* __restrict
   GWI_STAGED_DESC(M, Mp[blockIdx.x]);
   const int P = M.n_params;
   const int stride = PR_HEADER + 3 * P;
-  combine_records(M, recs0 + (size_t)blockIdx.x * R * stride, R, opts, out0 + (size_t)blockIdx.x * (GWI_LIKE_HEADER + P));
+  combine_records<false>(M, recs0 + (size_t)blockIdx.x * R * stride, R, opts, out0 + (size_t)blockIdx.x * (GWI_LIKE_HEADER + P));
+}
+
+// =================================================================================================
+// multi-GPU exchange owned by the library: every rank PUSHES its partial record into the exchange slots of
+// every rank (its own included) with plain stores through NVLink peer memory, publishes it with a
+// system-scope release of the slot's flag (the evaluation's epoch number), and the block that pushed into
+// the rank's OWN slots goes on to wait for the flags of all ranks and runs the rank-ordered combine -- one
+// launch, no collective library, no host in the loop.  Slots and flags are double-buffered by epoch parity:
+// a rank can only be one evaluation ahead of the slowest rank (its combine of epoch e needs everybody's
+// push of epoch e), so the slots of epoch e are never overwritten (epoch e + 2) while somebody still reads
+// them.  mode 0 = push + wait + combine, 1 = push only, 2 = wait + combine only (single-process tests).
+// =================================================================================================
+__device__ __forceinline__ void store_release_sys(unsigned long long* p, unsigned long long v) {
+#ifdef GWI_HOST_EMULATION
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long* p) {
+#ifdef GWI_HOST_EMULATION
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+
+__global__ void __launch_bounds__(256) exchange_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ rec_local, CommDev C, unsigned long long epoch, int mode,
+                                                       gwi_like_opts opts, double* __restrict__ out) {
+  const ModelDev& M = Mp[0];
+  const int P = M.n_params, stride = PR_HEADER + 3 * P, R = C.n_ranks;
+  const int par = (int)(epoch & 1ull);
+  const int b = blockIdx.x;  // the peer this block pushes to
+  if (mode != 2) {
+    double* dst = C.peer_slots[b] + (size_t)(par * R + C.rank) * stride;
+    for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[i] = rec_local[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) store_release_sys(C.peer_flags[b] + par * R + C.rank, epoch);
+  }
+  if (b != C.rank || mode == 1) return;
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < R) {
+    const unsigned long long* f = C.peer_flags[C.rank] + par * R + threadIdx.x;
+#ifdef GWI_HOST_EMULATION
+    if (load_acquire_sys(f) != epoch) timed_out = 1;  // the emulated launches are sequential: the pushes must have happened
+#else
+    const long long t0 = clock64();
+    while (load_acquire_sys(f) != epoch) {
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; report instead of hanging the GPU
+        timed_out = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+#endif
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (threadIdx.x == 0) {
+      out[GWI_LIKE_LOG_L] = -DBL_MAX;
+      out[GWI_LIKE_PASSED] = 0.0;
+      out[GWI_LIKE_STATUS] = 3.0;  // exchange timed out
+    }
+    return;
+  }
+  __threadfence_system();
+  combine_records<true>(M, C.peer_slots[C.rank] + (size_t)par * R * stride, R, opts, out);
 }
 
 // =================================================================================================
@@ -720,6 +793,9 @@ void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaS
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { GWI_LAUNCH(export_kernel, 64, 256, 0, st)(Md, out); }
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st) {
   GWI_LAUNCH(partial_kernel, dim3((n_params + 7) / 8, nc), 256, 0, st)(Md, rec);
+}
+void launch_exchange(const ModelDev* Md, const double* rec_local, const CommDev& C, unsigned long long epoch, int mode, const gwi_like_opts& o, double* out, cudaStream_t st) {
+  GWI_LAUNCH(exchange_kernel, C.n_ranks, 256, 0, st)(Md, rec_local, C, epoch, mode, o, out);
 }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
   GWI_LAUNCH(combine_kernel, nc, 256, 0, st)(Md, recs, R, o, out);

@@ -36,8 +36,8 @@ struct CtaLayout {
 };
 __host__ __device__ inline CtaLayout cta_layout(int nw, int ncol, int rows_total, int deep_entries) {
   CtaLayout L;
-  L.bars = 0;                                               // full / pready / free: 3 x nw x NSTAGE mbarriers
-  L.ctl = L.bars + 3u * (unsigned)nw * CTA_NSTAGE * 8u;     // 16 B: slice id broadcast
+  L.bars = 0;  // mbarriers: full[nw][NSTAGE] (one per staged block) | ready[NSTAGE] (count nw) | free[NSTAGE] (count n_deep)
+  L.ctl = (L.bars + ((unsigned)nw + 2u) * CTA_NSTAGE * 8u + 15u) & ~15u;  // 16 B: slice id broadcast (16-byte aligned: the tables follow)
   L.tables = L.ctl + 16u;
   L.blk_bytes = (unsigned)ncol * 512u;
   L.stage_bytes = L.blk_bytes + 512u;                       // + the 64 weights p of the block
@@ -55,6 +55,7 @@ __host__ __device__ inline CtaLayout cta_layout(int nw, int ncol, int rows_total
 // the threads of a block are fibers of ONE OS thread, so plain accesses + a yield in the wait loop do.
 typedef unsigned long long* mbar_t;
 __device__ inline mbar_t mbar_at(unsigned char* base, unsigned off) { return reinterpret_cast<unsigned long long*>(base + off); }
+__device__ inline mbar_t mbar_idx(mbar_t first, int i) { return first + i; }
 __device__ inline void mbar_init(mbar_t b, unsigned count) { *b = ((unsigned long long)count << 16) | count; }
 __device__ inline void mbar_fence_init() {}
 __device__ inline void mbar_arrive(mbar_t b) {
@@ -73,7 +74,7 @@ __device__ inline void mbar_wait(mbar_t b, unsigned parity) {
   unsigned long long spins = 0;
   while ((((*(volatile unsigned long long*)b) >> 32) & 1ull) == (unsigned long long)parity) {
     gwi_emu::warp_yield();
-    if (++spins == 4000000ull) {  // a protocol error in the emulated run: say where instead of hanging the test
+    if (++spins == 40000000ull) {  // a protocol error in the emulated run: say where instead of hanging the test
       extern thread_local double sm[];
       std::fprintf(stderr, "gwi_emu: mbarrier wait stuck: block %u thread %u barrier +%ld parity %u value %llx\n", blockIdx.x, threadIdx.x,
                    (long)((unsigned char*)b - (unsigned char*)sm), parity, *b);
@@ -86,6 +87,7 @@ __device__ inline void bulk_copy_g2s(void* dst, const void* src, unsigned bytes,
 typedef unsigned mbar_t;  // shared-window address
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ mbar_t mbar_at(unsigned char* base, unsigned off) { return smem_u32(base + off); }
+__device__ __forceinline__ mbar_t mbar_idx(mbar_t first, int i) { return first + 8u * (unsigned)i; }
 __device__ __forceinline__ void mbar_init(mbar_t b, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(mbar_t b) {
@@ -96,17 +98,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(mbar_t b, unsigned bytes) 
 }
 __device__ __forceinline__ bool mbar_try_wait(mbar_t b, unsigned parity) {
   unsigned ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+  // the hint lets the hardware SUSPEND the warp (no issue slots burnt) until the phase completes or ~the hint elapses
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b), "r"(parity), "r"(20000u) : "memory");
   return ok != 0u;
 }
+// all 32 lanes call this together (warp-uniform control flow: a lone lane spinning here while the others run ahead would
+// split the warp for the rest of the loop body -- measured: every main-loop instruction issued twice)
 __device__ __forceinline__ void mbar_wait(mbar_t b, unsigned parity) {
-  if (mbar_try_wait(b, parity)) return;
-  // a protocol error must end in a launch failure, not in a hung GPU: give up after ~4 s
-  const long long t0 = clock64();
-  unsigned spins = 0;
+  unsigned tries = 0;
   while (!mbar_try_wait(b, parity)) {
-    if ((++spins & 0xFFFu) == 0u && clock64() - t0 > 8000000000ll) __trap();
+    if (++tries > (1u << 22)) __trap();  // a protocol error must end in a launch failure, not in a hung GPU
   }
+  __syncwarp();
 }
 // one lane moves `bytes` (multiple of 16) from global to shared memory; completion is signalled on `bar`
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, mbar_t bar) {
@@ -164,9 +167,17 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
   const CtaLayout L = cta_layout(NW, ncol, rows_total, M.deep_entries);
   double* const tables = reinterpret_cast<double*>(smb + L.tables);
   volatile int* const ctl = reinterpret_cast<volatile int*>(smb + L.ctl);
-  auto bar_full = [&](int w, int s) { return mbar_at(smb, L.bars + (unsigned)((0 * NW + w) * CTA_NSTAGE + s) * 8u); };
-  auto bar_ready = [&](int w, int s) { return mbar_at(smb, L.bars + (unsigned)((1 * NW + w) * CTA_NSTAGE + s) * 8u); };
-  auto bar_free = [&](int w, int s) { return mbar_at(smb, L.bars + (unsigned)((2 * NW + w) * CTA_NSTAGE + s) * 8u); };
+  // Synchronisation (all mbarriers, phases = uses of a stage):
+  //   full[w][s]  the bulk copy of main warp w's block has landed in stage s            (waited by main warp w)
+  //   ready[s]    ALL main warps have published the weights of their block in stage s   (count NW; waited by the deep warps)
+  //   free[s]     ALL deep warps have read every block + weights of stage s             (count NDEEP; waited by the main warps
+  //               before they stage their next block there)
+  // so the main warps advance in lock-step within the ring depth and a deep warp synchronises ONCE per iteration for a
+  // burst of NW blocks (one wait per block made the deep warps the bottleneck: ~490 cycles per block, r02c3 profile).
+  const mbar_t bars0 = mbar_at(smb, L.bars);
+  auto bar_full = [&](int w, int s) { return mbar_idx(bars0, w * CTA_NSTAGE + s); };
+  auto bar_ready = [&](int s) { return mbar_idx(bars0, NW * CTA_NSTAGE + s); };
+  auto bar_free = [&](int s) { return mbar_idx(bars0, (NW + 1) * CTA_NSTAGE + s); };
   auto stage_ptr = [&](int w, int s) { return smb + L.stages + (unsigned)(w * CTA_NSTAGE + s) * L.stage_bytes; };
 
   for (int i = threadIdx.x; i < rows_total * 4; i += blockDim.x) tables[i] = M.tables[i];
@@ -175,12 +186,11 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
     for (int i = threadIdx.x; i < M.deep_entries * 32; i += blockDim.x) dz[i] = make_double2(0.0, 0.0);
   }
   if (threadIdx.x == 0) {
-    for (int w = 0; w < NW; ++w)
-      for (int s = 0; s < CTA_NSTAGE; ++s) {
-        mbar_init(bar_full(w, s), 1);
-        mbar_init(bar_ready(w, s), 1);
-        mbar_init(bar_free(w, s), NDEEP);
-      }
+    for (int s = 0; s < CTA_NSTAGE; ++s) {
+      for (int w = 0; w < NW; ++w) mbar_init(bar_full(w, s), 1);
+      mbar_init(bar_ready(s), NW);
+      mbar_init(bar_free(s), NDEEP);
+    }
     mbar_fence_init();
   }
   __syncthreads();
@@ -240,20 +250,19 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
         __syncwarp();  // the zeroing is ordered before every lane's reductions
         const uint64_t* const src = cols + ((size_t)(C.first >> 6) + (size_t)warp * iters) * blk_words;
         const unsigned g0 = ring_g;  // ring position of this chunk's first block
-        auto issue = [&](int t) {  // lane 0: stage block t of this sub-chunk
+        auto issue = [&](int t) {  // ALL lanes (uniform control flow); lane 0 stages block t of this sub-chunk
           const unsigned g = g0 + (unsigned)t;
           const unsigned s = g % CTA_NSTAGE, use = g / CTA_NSTAGE;
-          if (use > 0) mbar_wait(bar_free(warp, s), (use - 1u) & 1u);  // the deep warps are done with the previous block in this stage
-          const mbar_t fb = bar_full(warp, s);
-          mbar_arrive_expect_tx(fb, L.blk_bytes);
-          bulk_copy_g2s(stage_ptr(warp, s), src + (size_t)t * blk_words, L.blk_bytes, fb);
+          if (use > 0) mbar_wait(bar_free(s), (use - 1u) & 1u);  // the deep warps are done with the previous blocks in this stage
+          if (lane == 0) {
+            const mbar_t fb = bar_full(warp, s);
+            mbar_arrive_expect_tx(fb, L.blk_bytes);
+            bulk_copy_g2s(stage_ptr(warp, s), src + (size_t)t * blk_words, L.blk_bytes, fb);
+          }
         };
-        if (lane == 0) {
-          for (int t = 0; t < CTA_NSTAGE - 1 && t < iters; ++t) issue(t);
-        }
+        for (int t = 0; t < CTA_NSTAGE - 1 && t < iters; ++t) issue(t);
         for (int it = 0; it < iters; ++it) {
-          if (lane == 0 && it + CTA_NSTAGE - 1 < iters) issue(it + CTA_NSTAGE - 1);
-          __syncwarp();
+          if (it + CTA_NSTAGE - 1 < iters) issue(it + CTA_NSTAGE - 1);
           mbar_wait(bar_full(warp, ring_s), ring_ph);
           const unsigned char* const stg = stage_ptr(warp, ring_s);
           // ---- the two samples of this lane: words are w = u - 1/2 with J in the 6 low mantissa bits ----
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
           // ---- publish the weights for the deep warps ----
           *reinterpret_cast<double2*>(const_cast<unsigned char*>(stg) + L.blk_bytes + lane * 16) = make_double2(p0, p1);
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_ready(warp, ring_s));
+          if (lane == 0) mbar_arrive(bar_ready(ring_s));
           // ---- register-resident sums ----
           S1 += p0;
           S2 = fma(p0, p0, S2);
@@ -434,36 +443,42 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
         const Chunk C = M.chunks[c];
         const int iters = C.steps >> 1;
         for (int it = 0; it < iters; ++it) {
-          for (int w = 0; w < NW; ++w) {
-            mbar_wait(bar_ready(w, ring_s), ring_ph);
-            mbar_wait(bar_full(w, ring_s), ring_ph);  // (already complete: the async-proxy writes of the block are visible to this thread too)
-            const unsigned char* const stg = stage_ptr(w, ring_s);
+          mbar_wait(bar_ready(ring_s), ring_ph);  // every main warp has published the weights of its block in this stage
+          const unsigned char* stg = stage_ptr(0, ring_s);
+          for (int w = 0; w < NW; ++w, stg += CTA_NSTAGE * L.stage_bytes) {
             const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(stg + w_off);
             const double2 pp = *reinterpret_cast<const double2*>(stg + L.blk_bytes + lane * 16);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_free(w, ring_s));
+            if (w == NW - 1) {
+              __syncwarp();  // every lane has read the last block: the stage may be refilled
+              if (lane == 0) mbar_arrive(bar_free(ring_s));
+            }
+            // accumulators of both samples first (independent unless the pieces coincide)
+            const unsigned Ja = (unsigned)q.x & 63u, Jb = (unsigned)q.y & 63u;
+            double2* const ea = acc + (size_t)Ja * 64;
+            double2* const eb = acc + (size_t)Jb * 64;
+            double2 a0 = ea[0], a1 = ea[32], b0 = eb[0], b1 = eb[32];
             {
               const double wv = __longlong_as_double((long long)q.x), w2 = wv * wv, w3 = w2 * wv;
-              double2* e = acc + (size_t)((unsigned)q.x & 63u) * 64;
-              double2 v0 = e[0], v1 = e[32];
-              v0.x += pp.x;
-              v0.y = fma(pp.x, wv, v0.y);
-              v1.x = fma(pp.x, w2, v1.x);
-              v1.y = fma(pp.x, w3, v1.y);
-              e[0] = v0;
-              e[32] = v1;
+              a0.x += pp.x;
+              a0.y = fma(pp.x, wv, a0.y);
+              a1.x = fma(pp.x, w2, a1.x);
+              a1.y = fma(pp.x, w3, a1.y);
+            }
+            if (Ja == Jb) {  // same piece: the second sample continues from the first one's sums
+              b0 = a0;
+              b1 = a1;
             }
             {
               const double wv = __longlong_as_double((long long)q.y), w2 = wv * wv, w3 = w2 * wv;
-              double2* e = acc + (size_t)((unsigned)q.y & 63u) * 64;
-              double2 v0 = e[0], v1 = e[32];
-              v0.x += pp.y;
-              v0.y = fma(pp.y, wv, v0.y);
-              v1.x = fma(pp.y, w2, v1.x);
-              v1.y = fma(pp.y, w3, v1.y);
-              e[0] = v0;
-              e[32] = v1;
+              b0.x += pp.y;
+              b0.y = fma(pp.y, wv, b0.y);
+              b1.x = fma(pp.y, w2, b1.x);
+              b1.y = fma(pp.y, w3, b1.y);
             }
+            ea[0] = a0;
+            ea[32] = a1;
+            eb[0] = b0;  // (after the stores of sample a: if the pieces coincide these are the final values)
+            eb[32] = b1;
           }
           ++ring_g;
           if (++ring_s == CTA_NSTAGE) {

@@ -218,6 +218,32 @@ int64_t gwi_partial_size(const gwi_model* m);
 int gwi_partial(gwi_model* m, const double* lambda_dev, double* record_dev, void* stream);
 int gwi_combine(gwi_model* m, const double* records_dev, int32_t n_ranks, const gwi_like_opts* opts, double* out_dev, void* stream);
 
+/* ---- multi-GPU exchange owned by the library ----------------------------------------------
+ * ("no PyTorch in the loop".  The reference has no collective to cite: its only
+ * multi-device line is numpyro.set_host_device_count, examples/utils.py:62.)
+ * One process per GPU.  Every rank owns an exchange buffer in device memory; the ranks open each
+ * other's buffers as PEER memory once (CUDA IPC between processes, plain pointers inside one process),
+ * after which gwi_loglike_sharded needs no collective library and no host round trip: its last kernel
+ * pushes the rank's partial record into the slots of every rank over NVLink, publishes it with a
+ * system-scope release of a flag, waits for the flags of all ranks and runs the rank-ordered combine
+ * (identical results on every rank, bitwise equal to gwi_partial + all-gather + gwi_combine).
+ *   setup:  gwi_comm_local_handle on every rank -> exchange the 80-byte handles by ANY host-side means
+ *           (MPI, torch.distributed.all_gather_object, a file) -> gwi_comm_connect on every rank
+ *           -> a host barrier (nobody may push before everybody has connected).
+ * All ranks must then call gwi_loglike_sharded the same number of times (it is a collective). */
+typedef struct {
+  unsigned char bytes[80]; /* cudaIpcMemHandle_t [64] | process id [8] | device pointer [8] */
+} gwi_ipc_handle;
+int gwi_comm_local_handle(gwi_model* m, int32_t n_ranks, gwi_ipc_handle* out);
+int gwi_comm_connect(gwi_model* m, const gwi_ipc_handle* handles /* [n_ranks], rank order */, int32_t rank, int32_t n_ranks);
+/* Asynchronous on `stream`; out_dev as in gwi_loglike.  GWI_LIKE_STATUS = 3 if a peer's record did not
+ * arrive within ~10 s. */
+int gwi_loglike_sharded(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opts, double* out_dev, void* stream);
+/* The two halves of gwi_loglike_sharded, for callers that drive several ranks from ONE host thread
+ * (tests): push on every rank first, then combine on every rank. */
+int gwi_sharded_push(gwi_model* m, const double* lambda_dev, void* stream);
+int gwi_sharded_combine(gwi_model* m, const gwi_like_opts* opts, double* out_dev, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 typedef struct {
   int64_t n_samples_pe;     /* PE samples given (sum of event sizes) */

@@ -54,6 +54,7 @@ struct alignas(16) ulonglong2 {
   unsigned long long x, y;
 };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 
 extern thread_local uint3 threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
@@ -184,6 +185,7 @@ inline void gwi_named_barrier_sync(int id, int n_threads) { gwi_emu::named_barri
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __nanosleep(unsigned) { gwi_emu::warp_yield(); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src) {
