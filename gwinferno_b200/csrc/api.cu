@@ -24,7 +24,7 @@ stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, b
 stream_fn pick_stream_cta_kernel(int ns, int ndeep, int nlin);  // CTA-cooperative kernel (stream_cta.cuh)
 stream_fn pick_stream_cta_max_kernel();
 unsigned stream_cta_smem_bytes(int nw, int ncol, int rows_total, int deep_entries);
-void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st, int use_learned_shift);
+void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int n_seg, bool two_pass, int nc, cudaStream_t st, int use_learned_shift);
 void launch_segmax_learn(const ModelDev* Md, int n_seg, int nc, cudaStream_t st);
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux);
 void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st);
@@ -33,6 +33,8 @@ void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaS
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st);
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st);
+void launch_partial_tail(const ModelDev* Md, double* rec, int n_params, int tail, const gwi_like_opts& o, double* out, const CommDev& C, unsigned long long epoch, int nc,
+                         cudaStream_t st);
 void launch_exchange(const ModelDev* Md, const double* rec_local, const CommDev& C, unsigned long long epoch, int mode, const gwi_like_opts& o, double* out, cudaStream_t st);
 
 }  // namespace gwi
@@ -316,6 +318,7 @@ static int alloc_chain_scratch(gwi_model* m, ModelDev& H) {
   UPS(upload<double>(m, nullptr, (size_t)3 + 2 * P, &H.inj_raw));
   UPS(upload<double>(m, nullptr, (size_t)nseg, &H.shift_next));
   UPS(upload<double>(m, nullptr, (size_t)nseg, &H.spec_bad));
+  UPS(upload<int32_t>(m, nullptr, (size_t)1, &H.tail_counter));
   H.n_levels = (int)p.levels.size();
   for (int l = 0; l < 6; ++l) {
     H.level_buf[l] = nullptr;
@@ -617,7 +620,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     m->stream_grid_x = std::max(1, std::min(p.grid_blocks, (int)p.slice_begin.size() - 1));
     m->max_grid_x = std::max(1, std::min(4 * p.grid_blocks, (int)p.chunks.size()));
   }
-  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 2;
+  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 1;
   CUDA_TRY(cudaDeviceSynchronize());
   *out = m;
   return GWI_OK;
@@ -633,7 +636,7 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   launch_prologue_groups(m->dev, lam_dev, H.n_groups, m->max_grid, nc, m->aux_stream);
   cudaEventRecord(m->ev_join, m->aux_stream);
   const bool speculate = m->spec_shift && m->spec_allowed_now && m->spec_learned && nc == 1 && !exact_shift && !m->force_exact_shift;
-  launch_prologue_tables(m->dev, lam_dev, H.n_groups, nc, st, speculate ? 1 : 0);
+  launch_prologue_tables(m->dev, lam_dev, H.n_groups, H.n_segments, H.two_pass != 0, nc, st, speculate ? 1 : 0);
   const dim3 grid(m->stream_grid_x, nc), block(m->stream_block);
   if (H.n_chunks > 0) {
     if ((H.two_pass && !speculate) || exact_shift || m->force_exact_shift) {
@@ -717,9 +720,26 @@ int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opt
     set_error("null argument");
     return GWI_ERR_INVALID;
   }
-  int rc = gwi_partial(m, lambda_dev, m->partial_dev, stream);
+  if (!lambda_dev || !opts || !out_dev) {
+    set_error("null argument");
+    return GWI_ERR_INVALID;
+  }
+  if (opts->marginalize_selection && !m->plan.g2) {
+    set_error("marginalize_selection needs a model created with need_neff_grad");
+    return GWI_ERR_INVALID;
+  }
+  if (opts->max_variance_cut && (opts->marginalize_selection || opts->min_neff_cut)) {
+    set_error("max_variance_cut requires marginalize_selection and min_neff_cut to be off (analysis.py:237-244)");
+    return GWI_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rc = run_eval(m, lambda_dev, 1, st);
   if (rc != GWI_OK) return rc;
-  return gwi_combine(m, m->partial_dev, 1, opts, out_dev, stream);
+  // partial record + single-rank combine in one launch (the last block to finish its rows combines)
+  launch_partial_tail(m->dev, m->partial_dev, m->plan.n_params, 1, *opts, out_dev, m->comm, 0ull, 1, st);
+  CUDA_TRY(cudaGetLastError());
+  return GWI_OK;
 }
 
 // ---- library-owned multi-GPU exchange ------------------------------------------------------------------
@@ -837,10 +857,12 @@ int gwi_loglike_sharded(gwi_model* m, const double* lambda_dev, const gwi_like_o
   }
   int rc = sharded_checks(m, opts);
   if (rc != GWI_OK) return rc;
-  rc = gwi_partial(m, lambda_dev, m->partial_dev, stream);
+  CUDA_TRY(cudaSetDevice(m->device));
+  rc = run_eval(m, lambda_dev, 1, (cudaStream_t)stream);
   if (rc != GWI_OK) return rc;
   m->comm_pushed = ++m->comm_epoch;
-  launch_exchange(m->dev, m->partial_dev, m->comm, m->comm_epoch, 0, *opts, out_dev, (cudaStream_t)stream);
+  // partial record, push to every rank, wait for every rank, combine: one launch
+  launch_partial_tail(m->dev, m->partial_dev, m->plan.n_params, 2, *opts, out_dev, m->comm, m->comm_epoch, 1, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -901,8 +923,7 @@ int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, 
   // on the batch instead of one small catalog at a time
   rc = run_eval(m, lambda_dev, n_chains, st);
   if (rc != GWI_OK) return rc;
-  launch_partial(m->dev, m->partial_batch, m->plan.n_params, n_chains, st);
-  launch_combine(m->dev, m->partial_batch, 1, *opts, out_dev, n_chains, st);
+  launch_partial_tail(m->dev, m->partial_batch, m->plan.n_params, 1, *opts, out_dev, m->comm, 0ull, n_chains, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }

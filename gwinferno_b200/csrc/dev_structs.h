@@ -102,6 +102,7 @@ struct ModelDev {
   double* spec_bad;    // [n_segments], zero unless a speculative evaluation has to be repeated
   // CTA-cooperative stream kernel (stream_cta.cuh): main warps per CTA (0 = the one-role kernel's geometry)
   int32_t cta_main_warps, cta_pad;
+  int32_t* tail_counter;  // arrival counter of partial_tail_kernel (zero between evaluations)
 };
 
 // multi-GPU exchange (exchange_kernel): the exchange buffers of every rank as seen from this rank (peer

@@ -17,7 +17,7 @@ constexpr int MAX_SOPS = 16;        // scalar (sample-independent) normaliser op
 constexpr int KC_STRIDE = 12;       // doubles of per-eval constants per kop
 constexpr int LANES = 32;
 constexpr int UNROLL = 2;           // samples per lane per load (16-byte vector loads)
-constexpr int CTA_STAGES = 3;       // stream_cta.cuh: staged 64-sample blocks per main warp (== CTA_NSTAGE)
+constexpr int CTA_STAGES = 4;       // stream_cta.cuh: staged 64-sample blocks per main warp (== CTA_NSTAGE)
 constexpr int CTA_WARPS_MAX = 12;   // stream_cta.cuh: main + deep warps per CTA (== CTA_MAX_WARPS)
 #ifndef GWI_DEEP_LANES
 #define GWI_DEEP_LANES 16

@@ -255,7 +255,56 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     }
     return;
   }
-  // ---------------- tables, kop constants, scalar normalisers, shifts ----------------
+  // ---------------- per-segment shifts: blocks role > n_groups, 256 segments each ----------------
+  // (independent of the tables block: the per-piece bounds max(c_J..c_J+3) and the linear coefficients are
+  // recomputed from Lambda here, so that the ~300 segments of a catalog do not wait behind the serial table
+  // fill of ONE block -- the stream kernel starts after the slowest block of this launch)
+  if (role > M.n_groups) {
+    if (M.two_pass) return;
+    __shared__ double ub_s[MAX_SPLINE_DIMS * MAX_ROWS];
+    for (int r = tid; r < M.rows_total; r += nt) {
+      int d = 0;
+      while (d + 1 < M.n_dims && r >= M.dims[d + 1].row_off) ++d;
+      const DimDev& D = M.dims[d];
+      const int J = r - D.row_off;
+      double ub = 0.0;
+      if (J < D.rows - 1) {
+        const double* c = Lam + D.slot + J;
+        ub = fmax(fmax(c[0], c[1]), fmax(c[2], c[3]));
+      }
+      ub_s[r] = ub;
+    }
+    __syncthreads();
+    const int s = (role - M.n_groups - 1) * nt + tid;
+    if (s >= M.n_segments) return;
+    const SegDev& S = M.segs[s];
+    double sh = S.max_static;
+    unsigned long long occ_all[MAX_SPLINE_DIMS];
+#pragma unroll
+    for (int d = 0; d < MAX_SPLINE_DIMS; ++d) occ_all[d] = S.occ[d];  // independent loads, issued together
+#pragma unroll
+    for (int d = 0; d < MAX_SPLINE_DIMS; ++d) {
+      if (d >= M.n_dims) break;
+      const DimDev& D = M.dims[d];
+      double mx = -INFINITY;
+      unsigned long long occ = occ_all[d];
+      while (occ) {
+        const int J = __ffsll((long long)occ) - 1;
+        occ &= occ - 1;
+        mx = fmax(mx, ub_s[D.row_off + J]);
+      }
+      if (mx > -INFINITY) sh += mx;
+    }
+    for (int q = 0; q < M.n_kops; ++q) {
+      const KopDev& K = M.kops[q];
+      if (K.kind != KOP_LIN) continue;
+      const double th = Lam[K.slot[0]] + K.cst[0];
+      if (S.fmax[q] >= S.fmin[q]) sh += fmax(th * S.fmin[q], th * S.fmax[q]);
+    }
+    M.shift[s] = (sh == sh && sh > -INFINITY && sh < INFINITY) ? sh : 0.0;
+    return;
+  }
+  // ---------------- tables, kop constants, scalar normalisers ----------------
   if (tid == 0) {
     M.slice_counter[0] = 0;
     M.slice_counter[1] = 0;
@@ -337,40 +386,6 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     }
     M.Ksum[0] = K;
   }
-  if (!M.two_pass) {
-    // stage the per-piece bounds in shared memory (the per-segment loop below reads them ~100x)
-    __shared__ double ub_s[MAX_SPLINE_DIMS * MAX_ROWS];
-    __syncthreads();  // tables / piece_ub / kc written by this block are visible below
-    __threadfence_block();
-    for (int r = tid; r < M.rows_total; r += nt) ub_s[r] = M.piece_ub[r];
-    __syncthreads();
-    for (int s = tid; s < M.n_segments; s += nt) {
-      const SegDev& S = M.segs[s];
-      double sh = S.max_static;
-      unsigned long long occ_all[MAX_SPLINE_DIMS];
-#pragma unroll
-      for (int d = 0; d < MAX_SPLINE_DIMS; ++d) occ_all[d] = S.occ[d];  // independent loads, issued together
-#pragma unroll
-      for (int d = 0; d < MAX_SPLINE_DIMS; ++d) {
-        if (d >= M.n_dims) break;
-        const DimDev& D = M.dims[d];
-        double mx = -INFINITY;
-        unsigned long long occ = occ_all[d];
-        while (occ) {
-          const int J = __ffsll((long long)occ) - 1;
-          occ &= occ - 1;
-          mx = fmax(mx, ub_s[D.row_off + J]);
-        }
-        if (mx > -INFINITY) sh += mx;
-      }
-      for (int q = 0; q < M.n_kops; ++q) {
-        if (M.kops[q].kind != KOP_LIN) continue;
-        const double th = M.kc[q * KC_STRIDE];
-        if (S.fmax[q] >= S.fmin[q]) sh += fmax(th * S.fmin[q], th * S.fmax[q]);
-      }
-      M.shift[s] = (sh == sh && sh > -INFINITY && sh < INFINITY) ? sh : 0.0;
-    }
-  }
 }
 
 // =================================================================================================
@@ -384,9 +399,17 @@ __global__ void reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
   const ReduceTask T = M.level_tasks[level][blockIdx.x];
   const int i = blockIdx.y * blockDim.x + threadIdx.x;
   if (i >= rec) return;
-  double acc = 0.0;
-  for (int r = 0; r < T.in_count; ++r) acc += in[(size_t)(T.in_first + r) * rec + i];
-  out[(size_t)T.out_slot * rec + i] = acc;
+  // eight independent partial sums (inputs r, r+8, ...: eight loads in flight instead of a chain of <= 64 dependent
+  // load->add steps, which made this kernel latency-bound: 34 + 16 us for two levels), combined in a fixed order
+  const double* __restrict__ p = in + (size_t)T.in_first * rec + i;
+  double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  int r = 0;
+  for (; r + 8 <= T.in_count; r += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += p[(size_t)(r + k) * rec];
+  }
+  for (int k = 0; r + k < T.in_count; ++k) a[k] += p[(size_t)(r + k) * rec];
+  out[(size_t)T.out_slot * rec + i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
 __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict__ Mp) {
@@ -502,10 +525,18 @@ __global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict_
   extern __shared__ double srec[];
   {
     const ReduceTask T = tasks[s];
-    for (int i = threadIdx.x; i < M.rec_doubles; i += blockDim.x) {
-      double acc = 0.0;
-      for (int r = 0; r < T.in_count; ++r) acc += in[(size_t)(T.in_first + r) * M.rec_doubles + i];
-      srec[i] = acc;
+    const int rec = M.rec_doubles;
+    for (int i = threadIdx.x; i < rec; i += blockDim.x) {
+      // eight independent partial sums, fixed combination order (see reduce_kernel)
+      const double* __restrict__ p = in + (size_t)T.in_first * rec + i;
+      double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      int r = 0;
+      for (; r + 8 <= T.in_count; r += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += p[(size_t)(r + k) * rec];
+      }
+      for (int k = 0; r + k < T.in_count; ++k) a[k] += p[(size_t)(r + k) * rec];
+      srec[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
     __syncthreads();
   }
@@ -725,20 +756,18 @@ __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned lo
 #endif
 }
 
-__global__ void __launch_bounds__(256) exchange_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ rec_local, CommDev C, unsigned long long epoch, int mode,
-                                                       gwi_like_opts opts, double* __restrict__ out) {
-  const ModelDev& M = Mp[0];
-  const int P = M.n_params, stride = PR_HEADER + 3 * P, R = C.n_ranks;
-  const int par = (int)(epoch & 1ull);
-  const int b = blockIdx.x;  // the peer this block pushes to
-  if (mode != 2) {
-    double* dst = C.peer_slots[b] + (size_t)(par * R + C.rank) * stride;
-    for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[i] = rec_local[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) store_release_sys(C.peer_flags[b] + par * R + C.rank, epoch);
-  }
-  if (b != C.rank || mode == 1) return;
+// push this rank's record into peer `b`'s slots and publish it (all threads of the block)
+__device__ __forceinline__ void exchange_push(const CommDev& C, const double* rec_local, int stride, int par, unsigned long long epoch, int b) {
+  double* dst = C.peer_slots[b] + (size_t)(par * C.n_ranks + C.rank) * stride;
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[i] = rec_local[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) store_release_sys(C.peer_flags[b] + par * C.n_ranks + C.rank, epoch);
+}
+
+// wait for the records of all ranks in this rank's own slots, then the rank-ordered combine (all threads of the block)
+__device__ void exchange_wait_combine(const ModelDev& M, const CommDev& C, int stride, int par, unsigned long long epoch, const gwi_like_opts& opts, double* out) {
+  const int R = C.n_ranks;
   __shared__ int timed_out;
   if (threadIdx.x == 0) timed_out = 0;
   __syncthreads();
@@ -770,13 +799,62 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ModelDev* __restric
   combine_records<true>(M, C.peer_slots[C.rank] + (size_t)par * R * stride, R, opts, out);
 }
 
+__global__ void __launch_bounds__(256) exchange_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ rec_local, CommDev C, unsigned long long epoch, int mode,
+                                                       gwi_like_opts opts, double* __restrict__ out) {
+  const ModelDev& M = Mp[0];
+  const int stride = PR_HEADER + 3 * M.n_params;
+  const int par = (int)(epoch & 1ull);
+  const int b = blockIdx.x;  // the peer this block pushes to
+  if (mode != 2) exchange_push(C, rec_local, stride, par, epoch, b);
+  if (b != C.rank || mode == 1) return;
+  exchange_wait_combine(M, C, stride, par, epoch, opts, out);
+}
+
+// partial record + what follows it, in ONE launch: the blocks compute the rows of the rank's record; the block that
+// finishes last (arrival counter) goes on -- tail 1: single-rank combine; tail 2: push to every rank, wait, combine.
+// blockIdx.y = chain (tail 2: one chain).
+__global__ void __launch_bounds__(256) partial_tail_kernel(const ModelDev* __restrict__ Mp, double* recd0, int tail, gwi_like_opts opts, double* out0, CommDev C,
+                                                           unsigned long long epoch) {
+  const ModelDev& M = Mp[blockIdx.y];
+  const int P = M.n_params, stride = PR_HEADER + 3 * P;
+  double* recd = recd0 + (size_t)blockIdx.y * stride;
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  partial_rows<false>(M, recd, blockIdx.x * wpb + warp, gridDim.x * wpb);
+  __shared__ int last_s;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int k = atomicAdd(M.tail_counter, 1);
+    last_s = k == (int)gridDim.x - 1;
+    if (last_s) *M.tail_counter = 0;  // nobody else touches it in this evaluation
+  }
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  double* out = out0 + (size_t)blockIdx.y * (GWI_LIKE_HEADER + P);
+  if (tail == 1) {
+    combine_records<true>(M, recd, 1, opts, out);
+    return;
+  }
+  const int par = (int)(epoch & 1ull);
+  for (int b = 0; b < C.n_ranks; ++b) {
+    double* dst = C.peer_slots[b] + (size_t)(par * C.n_ranks + C.rank) * stride;
+    for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[i] = __ldcg(recd + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < C.n_ranks) store_release_sys(C.peer_flags[threadIdx.x] + par * C.n_ranks + C.rank, epoch);
+  exchange_wait_combine(M, C, stride, par, epoch, opts, out);
+}
+
 // =================================================================================================
 // host-side launch helpers (called from api.cu)
 // =================================================================================================
 // tables + shifts (what the stream kernel needs) on `st`; the grid normalisers (only needed by
 // finish_kernel) on `aux`, concurrently with the stream kernel.  `nc` = number of chains.
-void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int nc, cudaStream_t st, int use_learned_shift) {
-  GWI_LAUNCH(prologue_kernel, dim3(1, nc), 256, 0, st)(Md, lam, n_groups, use_learned_shift);
+void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int n_seg, bool two_pass, int nc, cudaStream_t st, int use_learned_shift) {
+  const int shift_blocks = two_pass ? 0 : (n_seg + 255) / 256;  // block 0: tables; blocks 1..: per-segment shifts
+  GWI_LAUNCH(prologue_kernel, dim3(1 + shift_blocks, nc), 256, 0, st)(Md, lam, n_groups, use_learned_shift);
 }
 void launch_segmax_learn(const ModelDev* Md, int n_seg, int nc, cudaStream_t st) { GWI_LAUNCH(segmax_learn_kernel, dim3(n_seg, nc), 256, 0, st)(Md); }
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux) {
@@ -796,6 +874,10 @@ void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaS
 }
 void launch_exchange(const ModelDev* Md, const double* rec_local, const CommDev& C, unsigned long long epoch, int mode, const gwi_like_opts& o, double* out, cudaStream_t st) {
   GWI_LAUNCH(exchange_kernel, C.n_ranks, 256, 0, st)(Md, rec_local, C, epoch, mode, o, out);
+}
+void launch_partial_tail(const ModelDev* Md, double* rec, int n_params, int tail, const gwi_like_opts& o, double* out, const CommDev& C, unsigned long long epoch, int nc,
+                         cudaStream_t st) {
+  GWI_LAUNCH(partial_tail_kernel, dim3((n_params + 7) / 8, nc), 256, 0, st)(Md, rec, tail, o, out, C, epoch);
 }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
   GWI_LAUNCH(combine_kernel, nc, 256, 0, st)(Md, recs, R, o, out);

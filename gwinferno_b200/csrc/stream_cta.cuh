@@ -27,7 +27,7 @@
 
 namespace gwi {
 
-constexpr int CTA_NSTAGE = 3;
+constexpr int CTA_NSTAGE = 4;
 constexpr int CTA_MAX_WARPS = 12;  // main + deep warps (launch bound 384 threads => 168 registers; 13 warps make ptxas fall back to 128 + spills)
 
 // shared-memory layout of the CTA kernel (bytes from the start of the dynamic shared memory)
@@ -262,7 +262,6 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
         };
         for (int t = 0; t < CTA_NSTAGE - 1 && t < iters; ++t) issue(t);
         for (int it = 0; it < iters; ++it) {
-          if (it + CTA_NSTAGE - 1 < iters) issue(it + CTA_NSTAGE - 1);
           mbar_wait(bar_full(warp, ring_s), ring_ph);
           const unsigned char* const stg = stage_ptr(warp, ring_s);
           // ---- the two samples of this lane: words are w = u - 1/2 with J in the 6 low mantissa bits ----
@@ -404,6 +403,10 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
             ring_s = 0;
             ring_ph ^= 1u;
           }
+          // stage the block NSTAGE - 1 iterations ahead into the stage of iteration it - 1: the deep warps have had this whole
+          // iteration to read that one (waiting for it at the TOP of the iteration put their burst on every iteration's
+          // critical path: r02c4 profile, 28 % of the samples in this wait); the copy still has NSTAGE - 2 iterations to land
+          if (it + CTA_NSTAGE - 1 < iters) issue(it + CTA_NSTAGE - 1);
         }
         // ---- this warp's record of the chunk ----
         __syncwarp();

@@ -56,3 +56,4 @@ unsigned stream_cta_smem_bytes(int nw, int ncol, int rows_total, int deep_entrie
   return L.total;
 }
 }  // namespace gwi
+static_assert(gwi::CTA_STAGES == gwi::CTA_NSTAGE && gwi::CTA_WARPS_MAX == gwi::CTA_MAX_WARPS, "plan.cpp sizes the CTA geometry with the kernel's constants");
