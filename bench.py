@@ -288,7 +288,8 @@ def run_ours(args):
     low, lam0, _ = workloads.lower_workload(weights, params_fn, pe, inj)
     P = low.spec.n_params
     t_gen = time.perf_counter() - t_setup
-    eng = PopulationLikelihood(low, const["total_inj"], device=local, need_neff_grad=False, chunk_steps=args.chunk_steps, n_deep=args.n_deep)
+    eng = PopulationLikelihood(low, const["total_inj"], device=local, need_neff_grad=False, chunk_steps=args.chunk_steps, n_deep=args.n_deep,
+                               batch_hint=workloads.N_CHAINS.get(name, 1))
     t_plan = time.perf_counter() - t_setup - t_gen
     info = eng.info()
     mdl = eng.model

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GWI_LIBRARY", os.path.join(_HERE, "libgwi.so"))  # override: tuning experiments only
 
-GWI_VERSION = 3  # include/gwi.h: GWI_VERSION (gwi_model_last_sites, library-owned exchange)
+GWI_VERSION = 4  # include/gwi.h: GWI_VERSION (gwi_model_desc.batch_hint, library-owned exchange)
 GWI_LIKE_HEADER = 8
 LIKE_FIELDS = ("log_l", "passed", "log_mu", "logNeff_inj", "min_logNeff", "sum_logBF", "variance", "status")
 PARTIAL_HEADER = 8
@@ -86,6 +86,8 @@ class gwi_model_desc(C.Structure):
         ("need_neff_grad", C.c_int32),
         ("chunk_steps", C.c_int32),
         ("n_deep", C.c_int32),
+        ("batch_hint", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -305,7 +307,7 @@ def synchronize():
 class _Desc:
     """Keeps the ctypes structures and every NumPy array they point to alive."""
 
-    def __init__(self, spec, col_index, need_neff_grad=False, chunk_steps=0, n_deep=-1):
+    def __init__(self, spec, col_index, need_neff_grad=False, chunk_steps=0, n_deep=-1, batch_hint=0):
         self.keep = []
         nt = len(spec.terms)
         self.terms = (gwi_term * max(1, nt))()
@@ -359,6 +361,8 @@ class _Desc:
         d.need_neff_grad = int(bool(need_neff_grad))
         d.chunk_steps = int(chunk_steps)
         d.n_deep = int(n_deep)
+        d.batch_hint = int(batch_hint)
+        d.reserved_ = 0
         self.desc = d
 
 
@@ -420,9 +424,9 @@ class Catalog:
 class HostPlan:
     """Test hook: the static plan built on the host (no CUDA needed)."""
 
-    def __init__(self, catalog, spec, need_neff_grad=False, chunk_steps=0, n_deep=-1, n_workers=0):
+    def __init__(self, catalog, spec, need_neff_grad=False, chunk_steps=0, n_deep=-1, n_workers=0, batch_hint=0):
         lib = load_library()
-        self._d = _Desc(spec, catalog.col_index, need_neff_grad, chunk_steps, n_deep)
+        self._d = _Desc(spec, catalog.col_index, need_neff_grad, chunk_steps, n_deep, batch_hint)
         h = C.c_void_p()
         _check(lib.gwi_debug_plan_build(catalog.handle, C.byref(self._d.desc), int(n_workers), C.byref(h)))
         self.handle = h
@@ -452,14 +456,14 @@ class HostPlan:
 class Model:
     """gwi_model: the device-resident evaluation plan of one (catalog, model description)."""
 
-    def __init__(self, catalog, spec, need_neff_grad=False, chunk_steps=0, n_deep=-1):
+    def __init__(self, catalog, spec, need_neff_grad=False, chunk_steps=0, n_deep=-1, batch_hint=0):
         lib = load_library()
         self.catalog = catalog
         self.n_params = int(spec.n_params)
         self.n_events = catalog.n_events
         self.n_groups = len(spec.groups)
         self.need_neff_grad = bool(need_neff_grad)
-        self._d = _Desc(spec, catalog.col_index, need_neff_grad, chunk_steps, n_deep)
+        self._d = _Desc(spec, catalog.col_index, need_neff_grad, chunk_steps, n_deep, batch_hint)
         h = C.c_void_p()
         _check(lib.gwi_model_create(catalog.handle, C.byref(self._d.desc), C.byref(h)))
         self.handle = h

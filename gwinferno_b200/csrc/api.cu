@@ -575,7 +575,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     return GWI_ERR_UNSUPPORTED;
   }
   const size_t per_warp = (size_t)p.rows_total * 4 * mom + (size_t)deep_entries * 2 * DEEP_LANES + (size_t)p.n_gslots * 32 * (1 + mom);  // deep: double2 x DEEP_LANES copies
-  const size_t fixed = (size_t)p.rows_total * 4 + (size_t)H.n_kops * KC_STRIDE + (size_t)H.n_kops * (sizeof(KopDev) / 8);
+  const size_t fixed = (size_t)p.rows_total * 4 + (size_t)(deep_entries / (2 * mom)) * 32 + (size_t)H.n_kops * KC_STRIDE + (size_t)H.n_kops * (sizeof(KopDev) / 8);
   static_assert(sizeof(KopDev) % 16 == 0, "KopDev copies must keep the shared layout 16-byte aligned");
   int wpb = p.warps_per_block;
   while (wpb > 1 && (fixed + per_warp * wpb) * 8 > (size_t)prop.sharedMemPerBlockOptin) --wpb;

@@ -839,7 +839,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     if (plan.dims[d].deep) rows_deep += plan.dims[d].rows;
   const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * DEEP_LANES * 8 +
                              (int64_t)plan.n_gslots * (1 + mom) * LANES * 8;
-  const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
+  const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)rows_deep * 256 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
   int wpb = (int)((220 * 1024 - cta_fixed) / std::max<int64_t>(1, warp_bytes));
   wpb = std::max(1, std::min(wpb, 8));
   plan.warps_per_block = wpb;
@@ -853,7 +853,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     if (const char* e = std::getenv("GWI_CTA_KERNEL")) ok = ok && !(e[0] == '0');
     if (ok) {
       const int64_t stage_bytes = (int64_t)(NS + (int)kop_feats.size() + 1) * 512 + 512;
-      const int64_t fixed = 3 * 8 * CTA_STAGES * CTA_WARPS_MAX + 16 + (int64_t)plan.rows_total * 32 + 256 + (int64_t)rows_deep * 1024;
+      const int64_t fixed = 3 * 8 * CTA_STAGES * CTA_WARPS_MAX + 16 + (int64_t)plan.rows_total * 32 + 256 + (int64_t)rows_deep * (1024 + 256);
       int nw = (int)((226 * 1024 - fixed) / (CTA_STAGES * stage_bytes));
       nw = std::min(nw, CTA_WARPS_MAX - plan.n_deep);
       if (const char* e = std::getenv("GWI_TUNE_CTA_WARPS")) nw = std::min(nw, std::max(1, std::atoi(e)));
@@ -870,7 +870,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   // slices get n times longer (up to the cap), i.e. fewer record flushes and longer piece-sorted lane
   // runs.  The emulator's path statistics for the config-2 catalog: 2 701 chunks of 8 steps and 88 % of
   // the warp iterations with lanes on the piece-change path at n = 1.
-  int batch_hint = 1;
+  int batch_hint = std::max(1, (int)desc.batch_hint);  // gwi_model_desc.batch_hint: chains per gwi_loglike_batch call
   if (const char* e = std::getenv("GWI_TUNE_BATCH_HINT")) batch_hint = std::max(1, std::atoi(e));
   const int W = plan.cta_mode ? std::max(1, plan.grid_blocks / batch_hint) : std::max(plan.warps_per_block, plan.grid_blocks * plan.warps_per_block / batch_hint);
   // Balanced slicing: the piece-sorted sample stream of all segments (the events first, then the

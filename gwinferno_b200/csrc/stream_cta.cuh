@@ -32,7 +32,7 @@ constexpr int CTA_MAX_WARPS = 12;  // main + deep warps (launch bound 384 thread
 
 // shared-memory layout of the CTA kernel (bytes from the start of the dynamic shared memory)
 struct CtaLayout {
-  unsigned bars, ctl, tables, stages, stage_bytes, blk_bytes, deep, total;
+  unsigned bars, ctl, tables, dtab, stages, stage_bytes, blk_bytes, deep, total;
 };
 __host__ __device__ inline CtaLayout cta_layout(int nw, int ncol, int rows_total, int deep_entries) {
   CtaLayout L;
@@ -41,7 +41,8 @@ __host__ __device__ inline CtaLayout cta_layout(int nw, int ncol, int rows_total
   L.tables = L.ctl + 16u;
   L.blk_bytes = (unsigned)ncol * 512u;
   L.stage_bytes = L.blk_bytes + 512u;                       // + the 64 weights p of the block
-  L.stages = (L.tables + (unsigned)rows_total * 32u + 127u) & ~127u;
+  L.dtab = L.tables + (unsigned)rows_total * 32u;  // deep-dim half-rows replicated 8x: [h][r][lane & 7] double2 (conflict-free LDS.128)
+  L.stages = (L.dtab + (unsigned)(deep_entries / 2) * 256u + 127u) & ~127u;
   L.deep = L.stages + (unsigned)nw * CTA_NSTAGE * L.stage_bytes;
   L.total = L.deep + (unsigned)deep_entries * 32u * 16u;    // double2 [entry][lane]
   return L;
@@ -181,6 +182,18 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
   auto stage_ptr = [&](int w, int s) { return smb + L.stages + (unsigned)(w * CTA_NSTAGE + s) * L.stage_bytes; };
 
   for (int i = threadIdx.x; i < rows_total * 4; i += blockDim.x) tables[i] = M.tables[i];
+  double2* const dtab = reinterpret_cast<double2*>(smb + L.dtab);
+  {
+    int dro = 0;
+    for (int d = NSH; d < NS; ++d) {
+      const int rows = M.dims[d].rows, ro = M.dims[d].row_off;
+      for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) {
+        const int h = i / (rows * 8), r = (i >> 3) % rows;  // [h][r][copy]
+        dtab[dro * 16 + i] = make_double2(M.tables[(ro + r) * 4 + 2 * h], M.tables[(ro + r) * 4 + 2 * h + 1]);
+      }
+      dro += rows;
+    }
+  }
   {
     double2* dz = reinterpret_cast<double2*>(smb + L.deep);
     for (int i = threadIdx.x; i < M.deep_entries * 32; i += blockDim.x) dz[i] = make_double2(0.0, 0.0);
@@ -205,11 +218,22 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
   int cur[NSHd];
   double cf[NSHd][4], m1[NSHd][4];
   const double* tab_d[NS];
+  const double2* dt01[NS];  // deep dims: conflict-free replicated half-rows (see CtaLayout::dtab)
+  int dt23_off[NS];
   int row_off[NS];
+  {
+    int dro = 0;
 #pragma unroll
-  for (int d = 0; d < NS; ++d) {
-    row_off[d] = M.dims[d].row_off;
-    tab_d[d] = tables + row_off[d] * 4;
+    for (int d = 0; d < NS; ++d) {
+      row_off[d] = M.dims[d].row_off;
+      tab_d[d] = tables + row_off[d] * 4;
+      dt01[d] = dtab + dro * 16 + (lane & 7);
+      dt23_off[d] = 0;
+      if (d >= NSH) {
+        dt23_off[d] = M.dims[d].rows * 8;
+        dro += M.dims[d].rows;
+      }
+    }
   }
 #pragma unroll
   for (int d = 0; d < NSH; ++d) {
@@ -313,8 +337,8 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
             if (d < NSH) {
               x0 += fma(fma(cf[d][3], w, cf[d][2]), w * w, fma(cf[d][1], w, cf[d][0]));
             } else {
-              const double2 a01 = *reinterpret_cast<const double2*>(tab_d[d] + J0[d] * 4);
-              const double2 a23 = *reinterpret_cast<const double2*>(tab_d[d] + J0[d] * 4 + 2);
+              const double2 a01 = dt01[d][J0[d] * 8];
+              const double2 a23 = dt01[d][dt23_off[d] + J0[d] * 8];
               x0 += fma(fma(a23.y, w, a23.x), w * w, fma(a01.y, w, a01.x));
             }
           }
@@ -344,8 +368,8 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
             if (d < NSH) {
               x1 += fma(fma(cf[d][3], w, cf[d][2]), w * w, fma(cf[d][1], w, cf[d][0]));
             } else {
-              const double2 a01 = *reinterpret_cast<const double2*>(tab_d[d] + J1[d] * 4);
-              const double2 a23 = *reinterpret_cast<const double2*>(tab_d[d] + J1[d] * 4 + 2);
+              const double2 a01 = dt01[d][J1[d] * 8];
+              const double2 a23 = dt01[d][dt23_off[d] + J1[d] * 8];
               x1 += fma(fma(a23.y, w, a23.x), w * w, fma(a01.y, w, a01.x));
             }
           }

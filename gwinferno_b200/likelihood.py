@@ -30,12 +30,12 @@ _BUILDS = collections.Counter()  # (term kinds, sharing pattern) -> plans built;
 class PopulationLikelihood:
     """Device-resident plan for one (catalog, population model) pair; evaluate for many Lambda."""
 
-    def __init__(self, lowered, total_inj, device=0, need_neff_grad=False, chunk_steps=0, n_deep=-1):
+    def __init__(self, lowered, total_inj, device=0, need_neff_grad=False, chunk_steps=0, n_deep=-1, batch_hint=0):
         self.lowered = lowered
         self.spec = lowered.spec
         self.n_params = lowered.spec.n_params
         self.catalog = capi.Catalog(lowered.pe_cols, lowered.inj_cols, total_inj, device=device)
-        self.model = capi.Model(self.catalog, lowered.spec, need_neff_grad=need_neff_grad, chunk_steps=chunk_steps, n_deep=n_deep)
+        self.model = capi.Model(self.catalog, lowered.spec, need_neff_grad=need_neff_grad, chunk_steps=chunk_steps, n_deep=n_deep, batch_hint=batch_hint)
         self.need_neff_grad = need_neff_grad
         self.n_events = self.catalog.n_events
 

@@ -31,7 +31,8 @@ class gwi_cut(C.Structure):
 
 class gwi_model_desc(C.Structure):
     _fields_ = [("n_terms", C.c_int32), ("terms", C.POINTER(gwi_term)), ("n_groups", C.c_int32), ("groups", C.POINTER(gwi_norm_group)), ("n_cuts", C.c_int32),
-                ("cuts", C.POINTER(gwi_cut)), ("n_params", C.c_int32), ("need_neff_grad", C.c_int32), ("chunk_steps", C.c_int32), ("n_deep", C.c_int32)]
+                ("cuts", C.POINTER(gwi_cut)), ("n_params", C.c_int32), ("need_neff_grad", C.c_int32), ("chunk_steps", C.c_int32), ("n_deep", C.c_int32),
+                ("batch_hint", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class gwi_catalog_desc(C.Structure):

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.load_library()
     for name in capi.SYMBOLS:
         assert hasattr(lib, name), name
-    assert lib.gwi_version() == capi.GWI_VERSION == 3
+    assert lib.gwi_version() == capi.GWI_VERSION == 4
     # header and binding agree on the symbol list
     import os, re
 
