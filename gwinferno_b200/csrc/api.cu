@@ -430,7 +430,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   H.n_chunks = (int)p.chunks.size();
   H.n_padded = p.n_padded;
   H.cta_main_warps = p.cta_mode ? p.cta_main_warps : 0;
-  H.cta_pad = 0;
+  H.cta_lead_doubles = 0;
   H.total_inj = p.total_inj;
   H.two_pass = 0;
   H.liny_mask = 0;
@@ -459,6 +459,13 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     X.inv_dxi = (double)(D.rows - 1) / (t.xi_hi - t.xi_lo);
   }
   H.deep_entries = deep_entries;
+  if (p.cta_mode) {
+    // what a main warp of the CTA-cooperative kernel writes of its record: {S1, S2}, the linear-term slots and the rows of
+    // the leading dims (the dims are in sort-key order, the deep ones last)
+    int lead_rows = 0;
+    for (int d = 0; d < NS - p.n_deep; ++d) lead_rows += p.dims[d].rows;
+    H.cta_lead_doubles = 2 + p.n_gslots + lead_rows * 4;
+  }
   for (int q = 0; q < H.n_kops; ++q) {
     const Kop& K = p.kops[q];
     KopDev& X = H.kops[q];

@@ -101,7 +101,7 @@ struct ModelDev {
   double* shift_next;  // [n_segments]
   double* spec_bad;    // [n_segments], zero unless a speculative evaluation has to be repeated
   // CTA-cooperative stream kernel (stream_cta.cuh): main warps per CTA (0 = the one-role kernel's geometry)
-  int32_t cta_main_warps, cta_pad;
+  int32_t cta_main_warps, cta_lead_doubles;  // cta_lead_doubles: header + linear slots + leading rows of a record (what a main warp writes)
   int32_t* tail_counter;  // arrival counter of partial_tail_kernel (zero between evaluations)
 };
 

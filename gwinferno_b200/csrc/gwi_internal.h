@@ -109,7 +109,7 @@ struct ReduceTask {
   int32_t out_slot;  // slot in the output buffer of this level
   int32_t in_first;  // first slot in the input buffer
   int32_t in_count;
-  int32_t parent;    // index (within the next level's task list) of the task that consumes out_slot; -1 on the last level
+  int32_t src;       // where the inputs are: -1 = the level-0 records of the stream kernel, l >= 0 = the output buffer of level l
 };
 
 // Host-side evaluation plan ("what the stream kernel reads")
@@ -137,7 +137,10 @@ struct Plan {
   // level-0 records and the reduction tree
   int rec_doubles = 0;
   int n_records0 = 0;
-  std::vector<std::vector<ReduceTask>> levels;  // levels.back() writes one record per segment (slot = segment)
+  // levels.back() has one task per segment (slot = segment; executed by finish_kernel); the earlier levels only hold
+  // tasks of the segments that still have more than one fan-in of inputs (a 10 000-sample event goes straight from its
+  // few records to the last level instead of being copied through every level)
+  std::vector<std::vector<ReduceTask>> levels;
   // launch geometry (fixed at plan time: the chunk -> warp assignment depends on it)
   int grid_blocks = 0, warps_per_block = 0;
   int chunk_steps = 0;

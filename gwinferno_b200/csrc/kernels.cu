@@ -391,25 +391,53 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
 // =================================================================================================
 // reductions
 // =================================================================================================
-__global__ void reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
-  const ModelDev& M = Mp[blockIdx.z];  // blockIdx.z = chain
+// element i of the sum of the task's input records.  Eight independent partial sums (inputs r, r+8, ...: eight loads
+// in flight instead of a chain of <= 64 dependent load->add steps, which made these kernels latency-bound), combined in
+// a fixed order.  Level-0 records of the CTA-cooperative stream kernel are sparse by construction -- the NW main-warp
+// records of a chunk hold the header + leading rows, the chunk's last record holds the deep rows, everything else is
+// zero for ever -- so only the records that can be non-zero at element i are read.
+__device__ __forceinline__ double reduce_element(const ModelDev& M, const ReduceTask& T, int i) {
   const int rec = M.rec_doubles;
-  const double* __restrict__ in = level == 0 ? M.records0 : M.level_buf[level - 1];
-  double* __restrict__ out = M.level_buf[level];
-  const ReduceTask T = M.level_tasks[level][blockIdx.x];
-  const int i = blockIdx.y * blockDim.x + threadIdx.x;
-  if (i >= rec) return;
-  // eight independent partial sums (inputs r, r+8, ...: eight loads in flight instead of a chain of <= 64 dependent
-  // load->add steps, which made this kernel latency-bound: 34 + 16 us for two levels), combined in a fixed order
+  const double* __restrict__ in = T.src < 0 ? M.records0 : M.level_buf[T.src];
   const double* __restrict__ p = in + (size_t)T.in_first * rec + i;
   double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  int r = 0;
-  for (; r + 8 <= T.in_count; r += 8) {
+  const int NW = M.cta_main_warps;
+  if (T.src < 0 && NW > 0) {
+    const int RPC = NW + 1;
+    if (i >= M.cta_lead_doubles) {  // deep rows: only the last record of every chunk
+      int k = 0;
+      for (int r = (NW + RPC - T.in_first % RPC) % RPC; r < T.in_count; r += RPC, k = (k + 1) & 7) a[k] += p[(size_t)r * rec];
+    } else {  // header + leading rows: the main-warp records
+      int ph = T.in_first % RPC, r = 0;
+      for (; r + 8 <= T.in_count; r += 8) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] += p[(size_t)(r + k) * rec];
+        for (int k = 0; k < 8; ++k) {
+          if (ph != NW) a[k] += p[(size_t)(r + k) * rec];
+          ph = ph == NW ? 0 : ph + 1;
+        }
+      }
+      for (int k = 0; r + k < T.in_count; ++k) {
+        if (ph != NW) a[k] += p[(size_t)(r + k) * rec];
+        ph = ph == NW ? 0 : ph + 1;
+      }
+    }
+  } else {
+    int r = 0;
+    for (; r + 8 <= T.in_count; r += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += p[(size_t)(r + k) * rec];
+    }
+    for (int k = 0; r + k < T.in_count; ++k) a[k] += p[(size_t)(r + k) * rec];
   }
-  for (int k = 0; r + k < T.in_count; ++k) a[k] += p[(size_t)(r + k) * rec];
-  out[(size_t)T.out_slot * rec + i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+__global__ void reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
+  const ModelDev& M = Mp[blockIdx.z];  // blockIdx.z = chain
+  const ReduceTask T = M.level_tasks[level][blockIdx.x];
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= M.rec_doubles) return;
+  M.level_buf[level][(size_t)T.out_slot * M.rec_doubles + i] = reduce_element(M, T, i);
 }
 
 __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict__ Mp) {
@@ -518,26 +546,13 @@ __device__ void finish_segment(const ModelDev& M, int s, const double* rec) {
 
 __global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp) {
   GWI_STAGED_DESC(M, Mp[blockIdx.y]);
-  const double* __restrict__ in = M.n_levels > 1 ? M.level_buf[M.n_levels - 2] : M.records0;
   const ReduceTask* __restrict__ tasks = M.level_tasks[M.n_levels - 1];
   const int s = blockIdx.x;
-  // last level of the record reduction (task s sums <= 64 records of segment s), fused in here
+  // last level of the record reduction (task s sums the <= 64 remaining inputs of segment s), fused in here
   extern __shared__ double srec[];
   {
     const ReduceTask T = tasks[s];
-    const int rec = M.rec_doubles;
-    for (int i = threadIdx.x; i < rec; i += blockDim.x) {
-      // eight independent partial sums, fixed combination order (see reduce_kernel)
-      const double* __restrict__ p = in + (size_t)T.in_first * rec + i;
-      double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      int r = 0;
-      for (; r + 8 <= T.in_count; r += 8) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a[k] += p[(size_t)(r + k) * rec];
-      }
-      for (int k = 0; r + k < T.in_count; ++k) a[k] += p[(size_t)(r + k) * rec];
-      srec[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-    }
+    for (int i = threadIdx.x; i < M.rec_doubles; i += blockDim.x) srec[i] = reduce_element(M, T, i);
     __syncthreads();
   }
   finish_segment(M, s, srec);

@@ -788,6 +788,11 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     // cost model (issue slots per sample): a register-resident dim pays the warp-wide spill path
     // whenever ANY of its 32 lanes changes piece (~60 slots incl. the shared-memory atomics); a
     // deep dim pays ~17 extra slots on every sample.  Deep dims must be a suffix of the sort order.
+    // r02 calibration (B200, unified pair path + RED spills + conflict-free deep tables; both kernels are bound by
+    // shared-memory wavefronts now): a deep dim costs ~22 slot-equivalents per sample; a register-resident dim costs ~12
+    // whenever any lane of the warp changes piece plus ~60 per changing lane.  cfg3: the 5th key (piece change every ~27
+    // samples) is better kept in registers (1.573 vs 1.726 ms), the 6th (every ~3 samples) is not.
+    const double COST_WARP = 12.0, COST_LANE = 60.0, COST_DEEP = 22.0;
     int want = desc.n_deep;
     int nd = 0;
     if (want < 0) {
@@ -796,15 +801,15 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         double cost = 0.0;
         for (int s = 0; s < n_seg; ++s) {
           const double n = (double)order[s].size();
-          for (int d = 0; d < NS - cand; ++d) cost += n * std::min(1.0, 32.0 * rate[s][d]) * 60.0;
-          cost += n * cand * 17.0;
+          for (int d = 0; d < NS - cand; ++d) cost += n * (std::min(1.0, 32.0 * rate[s][d]) * COST_WARP + rate[s][d] * COST_LANE);
+          cost += n * cand * COST_DEEP;
         }
         if (timing) {
           double ci = 0.0, cp = 0.0, np_ = 0.0;
           for (int s = 0; s < n_seg; ++s) {
             const double n = (double)order[s].size();
-            double c = cand * 17.0;
-            for (int d = 0; d < NS - cand; ++d) c += std::min(1.0, 32.0 * rate[s][d]) * 60.0;
+            double c = cand * COST_DEEP;
+            for (int d = 0; d < NS - cand; ++d) c += std::min(1.0, 32.0 * rate[s][d]) * COST_WARP + rate[s][d] * COST_LANE;
             if (s == 0) ci = c; else { cp += n * c; np_ += n; }
           }
           std::fprintf(stderr, "[gwi plan] n_deep=%d: modelled extra issue slots per sample: injections %.1f, events %.1f\n", cand, ci, np_ > 0 ? cp / np_ : 0.0);
@@ -840,7 +845,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * DEEP_LANES * 8 +
                              (int64_t)plan.n_gslots * (1 + mom) * LANES * 8;
   const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)rows_deep * 256 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
-  int wpb = (int)((220 * 1024 - cta_fixed) / std::max<int64_t>(1, warp_bytes));
+  int wpb = (int)((226 * 1024 - cta_fixed) / std::max<int64_t>(1, warp_bytes));  // 227 KB per CTA on sm_100; api.cu re-checks with the exact layout
   wpb = std::max(1, std::min(wpb, 8));
   plan.warps_per_block = wpb;
   plan.grid_blocks = std::max(1, sm_count);
@@ -1105,44 +1110,43 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       cnt[plan.chunks[c].segment] += RPC;
     }
     for (int s = 0; s < n_seg; ++s) first[s] = plan.segments[s].first_chunk * RPC;  // chunks (hence records) of a segment are consecutive
-    // reduction tree, fan-in 64; the last level writes slot == segment
+    // reduction tree, fan-in 64: per segment, levels are added only while it has more than one fan-in of inputs
     constexpr int FAN = 64;
+    std::vector<int> src(n_seg, -1);  // where the segment's current inputs are (-1 = level-0 records)
     for (;;) {
-      bool last = true;
+      bool any = false;
       for (int s = 0; s < n_seg; ++s)
-        if (cnt[s] > FAN) last = false;
+        if (cnt[s] > FAN) any = true;
+      if (!any) break;
+      const int lvl = (int)plan.levels.size();
       std::vector<ReduceTask> tasks;
-      std::vector<int> ncnt(n_seg), nfirst(n_seg);
-      int acc = 0;
       for (int s = 0; s < n_seg; ++s) {
-        const int nt = last ? 1 : std::max(1, (cnt[s] + FAN - 1) / FAN);
-        nfirst[s] = last ? s : acc;
-        ncnt[s] = nt;
+        if (cnt[s] <= FAN) continue;
+        const int nt = (cnt[s] + FAN - 1) / FAN;
+        const int out0 = (int)tasks.size();
         for (int t = 0; t < nt; ++t) {
           ReduceTask T{};
-          T.out_slot = nfirst[s] + t;
+          T.out_slot = out0 + t;
           T.in_first = first[s] + t * FAN;
-          T.in_count = std::max(0, std::min(FAN, cnt[s] - t * FAN));
+          T.in_count = std::min(FAN, cnt[s] - t * FAN);
+          T.src = src[s];
           tasks.push_back(T);
         }
-        acc += nt;
+        first[s] = out0;
+        cnt[s] = nt;
+        src[s] = lvl;
       }
       plan.levels.push_back(tasks);
-      cnt.swap(ncnt);
-      first.swap(nfirst);
-      if (last) break;
     }
-    // parent links (used by the fused epilogue, where the block that delivers the last input of a
-    // task goes on to execute it): the consumer of out_slot o is the next-level task whose input
-    // range contains o
-    for (size_t l = 0; l < plan.levels.size(); ++l) {
-      for (auto& T : plan.levels[l]) T.parent = -1;
-      if (l + 1 == plan.levels.size()) break;
-      const auto& up = plan.levels[l + 1];
-      std::vector<int32_t> owner(plan.levels[l].size(), -1);
-      for (size_t t = 0; t < up.size(); ++t)
-        for (int i = 0; i < up[t].in_count; ++i) owner[up[t].in_first + i] = (int32_t)t;
-      for (auto& T : plan.levels[l]) T.parent = owner[T.out_slot];
+    {
+      std::vector<ReduceTask> tasks(n_seg);
+      for (int s = 0; s < n_seg; ++s) {
+        tasks[s].out_slot = s;
+        tasks[s].in_first = first[s];
+        tasks[s].in_count = std::max(0, cnt[s]);
+        tasks[s].src = src[s];
+      }
+      plan.levels.push_back(tasks);
     }
   }
   return GWI_OK;

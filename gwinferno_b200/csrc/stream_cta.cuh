@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
     gl1[l] = 0.0;
   }
   const int st_off = M.col_static * 512 + lane * 16;
-  const int lead_doubles = 2 + n_gs + (NSH > 0 ? (M.dims[NSH > 0 ? NSH - 1 : 0].row_off + M.dims[NSH > 0 ? NSH - 1 : 0].rows) * 4 : 0);  // leading rows come first
+  const int lead_doubles = M.cta_lead_doubles;  // {S1, S2}, linear slots, leading rows (they come first in a record)
 
   for (;;) {
     if (threadIdx.x == 0) ctl[0] = atomicAdd(M.slice_counter, 1);
