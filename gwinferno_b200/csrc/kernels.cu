@@ -20,12 +20,12 @@
 
 #include "dev_structs.h"
 
-// GWI_EXP_STAGE_DESC (experiment switch, default 0): the small kernels read dozens of ModelDev fields,
+// GWI_EXP_STAGE_DESC (on since round 2; =0 restores direct reads): the small kernels read dozens of ModelDev fields,
 // each a dependent global load (the cold prologue takes 33 us under ncu, mostly load latency).  With
 // the switch a block first copies its chain's descriptor (~3 KB) into shared memory with coalesced
 // 8-byte loads and works from that copy.
 #ifndef GWI_EXP_STAGE_DESC
-#define GWI_EXP_STAGE_DESC 0
+#define GWI_EXP_STAGE_DESC 1
 #endif
 #if GWI_EXP_STAGE_DESC
 #define GWI_STAGED_DESC(M, src)                                                                              \
@@ -432,12 +432,40 @@ __device__ __forceinline__ double reduce_element(const ModelDev& M, const Reduce
   return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
-__global__ void reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
+// One block = one task x 32 record elements; the 8 warps split the task's <= 64 inputs (warp g takes inputs g, g+8, ...:
+// at most 8 independent loads per thread, ONE memory round trip) and the partial sums are combined through shared memory in
+// the same fixed order as reduce_element's.  (A thread per element walking all 64 inputs needed 8 dependent rounds: ~20 us per
+// level whatever the number of tasks.)
+__global__ void __launch_bounds__(256) reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
   const ModelDev& M = Mp[blockIdx.z];  // blockIdx.z = chain
   const ReduceTask T = M.level_tasks[level][blockIdx.x];
-  const int i = blockIdx.y * blockDim.x + threadIdx.x;
-  if (i >= M.rec_doubles) return;
-  M.level_buf[level][(size_t)T.out_slot * M.rec_doubles + i] = reduce_element(M, T, i);
+  const int rec = M.rec_doubles;
+  const int j = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.y * 32 + j;
+  __shared__ double part[8][33];
+  double acc = 0.0;
+  if (i < rec) {
+    const double* __restrict__ in = T.src < 0 ? M.records0 : M.level_buf[T.src];
+    const double* __restrict__ p = in + (size_t)T.in_first * rec + i;
+    const int NW = M.cta_main_warps;
+    const bool sparse = T.src < 0 && NW > 0;
+    const int RPC = NW + 1;
+    const bool want_deep = sparse && i >= M.cta_lead_doubles;
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = g + 8 * k;
+      bool use = r < T.in_count;
+      if (use && sparse) use = (((T.in_first + r) % RPC) == NW) == want_deep;
+      v[k] = use ? p[(size_t)r * rec] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k];
+  }
+  part[g][j] = acc;
+  __syncthreads();
+  if (g == 0 && i < rec)
+    M.level_buf[level][(size_t)T.out_slot * rec + i] = ((part[0][j] + part[1][j]) + (part[2][j] + part[3][j])) + ((part[4][j] + part[5][j]) + (part[6][j] + part[7][j]));
 }
 
 __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict__ Mp) {
@@ -629,9 +657,16 @@ __device__ __forceinline__ void partial_rows(const ModelDev& M, double* recd, in
   }
   // one warp per hyper-parameter: sum_e J_logBF[e][i]
   for (int i = gwarp; i < P; i += n_gwarps) {
-    double acc = 0.0;
-    for (int e = 1 + lane; e <= E; e += 32) acc += ldd<CG>(M.seg_J1 + (size_t)e * P + i);
-    acc = warp_sum(acc);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent chains (the loads of 128 events are in flight together)
+    int e = 1 + lane;
+    for (; e + 96 <= E; e += 128) {
+      a0 += ldd<CG>(M.seg_J1 + (size_t)e * P + i);
+      a1 += ldd<CG>(M.seg_J1 + (size_t)(e + 32) * P + i);
+      a2 += ldd<CG>(M.seg_J1 + (size_t)(e + 64) * P + i);
+      a3 += ldd<CG>(M.seg_J1 + (size_t)(e + 96) * P + i);
+    }
+    for (; e <= E; e += 32) a0 += ldd<CG>(M.seg_J1 + (size_t)e * P + i);
+    double acc = warp_sum((a0 + a1) + (a2 + a3));
     if (lane == 0) {
       recd[PR_HEADER + i] = ldd<CG>(M.inj_raw + 3 + i);
       recd[PR_HEADER + P + i] = ldd<CG>(M.inj_raw + 3 + P + i);
@@ -830,7 +865,7 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ModelDev* __restric
 // blockIdx.y = chain (tail 2: one chain).
 __global__ void __launch_bounds__(256) partial_tail_kernel(const ModelDev* __restrict__ Mp, double* recd0, int tail, gwi_like_opts opts, double* out0, CommDev C,
                                                            unsigned long long epoch) {
-  const ModelDev& M = Mp[blockIdx.y];
+  GWI_STAGED_DESC(M, Mp[blockIdx.y]);
   const int P = M.n_params, stride = PR_HEADER + 3 * P;
   double* recd = recd0 + (size_t)blockIdx.y * stride;
   const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -876,7 +911,7 @@ void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups,
   if (n_groups > 0) GWI_LAUNCH(prologue_kernel, dim3(n_groups, nc), 256, (size_t)max_grid * sizeof(double), aux)(Md, lam, 0, 0);
 }
 void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st) {
-  dim3 grid(n_tasks, (rec + 255) / 256, nc);
+  dim3 grid(n_tasks, (rec + 31) / 32, nc);
   GWI_LAUNCH(reduce_kernel, grid, 256, 0, st)(Md, level);
 }
 void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st) { GWI_LAUNCH(segmax_kernel, dim3(n_seg, nc), 256, 0, st)(Md); }

@@ -749,6 +749,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   plan.n_valid_inj = plan.segments[0].n_valid;
 
   tick("event keys + sorts");
+  bool want_cta = false;  // the CTA-cooperative stream kernel is the better one for this plan (decided below)
   // ---- deep dims: how often does each dim's piece index change along the sorted order? -------
   // Leading sort keys change rarely (register-resident moments, spilled on change); a dim whose
   // piece changes more than about once per 100 consecutive samples would make some lane of every
@@ -788,11 +789,25 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     // cost model (issue slots per sample): a register-resident dim pays the warp-wide spill path
     // whenever ANY of its 32 lanes changes piece (~60 slots incl. the shared-memory atomics); a
     // deep dim pays ~17 extra slots on every sample.  Deep dims must be a suffix of the sort order.
+    // Which stream kernel?  Measured on B200 (r02c7, kernel ms, one-role / CTA-cooperative): cfg3 1.03e8 samples 1.573 / 1.785,
+    // a 2-way shard (5.2e7) 0.835 / 0.929, cfg5 (2.2e7) 0.480 / 0.469, an 8-way shard (1.3e7) 0.270 / 0.261, cfg2 (7.8e5)
+    // 0.049 / 0.037, the 1024-chain batch 44.5k / 52.0k chain-evals/s: long piece-sorted lane runs favour the one-role
+    // kernel, everything else the CTA-cooperative one.  GWI_CTA_KERNEL=0 / 1 forces the choice.
+    {
+      int64_t n_valid_all = 0;
+      for (int s = 0; s < n_seg; ++s) n_valid_all += (int64_t)order[s].size();
+      want_cta = n_valid_all < 30000000 || desc.batch_hint > 1;
+      if (const char* e = std::getenv("GWI_CTA_KERNEL")) want_cta = e[0] != '0';
+      bool ok = !plan.g2 && (int)plan.kops.size() == plan.n_lin && plan.n_lin <= 2;
+      for (const SplineDim& D : plan.dims) ok = ok && !D.liny;
+      want_cta = want_cta && ok;
+    }
     // r02 calibration (B200, unified pair path + RED spills + conflict-free deep tables; both kernels are bound by
     // shared-memory wavefronts now): a deep dim costs ~22 slot-equivalents per sample; a register-resident dim costs ~12
     // whenever any lane of the warp changes piece plus ~60 per changing lane.  cfg3: the 5th key (piece change every ~27
     // samples) is better kept in registers (1.573 vs 1.726 ms), the 6th (every ~3 samples) is not.
-    const double COST_WARP = 12.0, COST_LANE = 60.0, COST_DEEP = 22.0;
+    // In the CTA-cooperative kernel the deep dims belong to dedicated warps: cheaper (cfg5 0.469 ms with 3 deep dims, 0.522 with 2).
+    const double COST_WARP = 12.0, COST_LANE = 60.0, COST_DEEP = want_cta ? 13.0 : 22.0;
     int want = desc.n_deep;
     int nd = 0;
     if (want < 0) {
@@ -853,9 +868,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   // gradient: main warps stage their blocks with bulk copies, one dedicated warp per deep dim accumulates
   // that dim's moments for the whole CTA.  GWI_CTA_KERNEL=0 keeps the one-role kernel (tuning / bisection).
   {
-    bool ok = !plan.g2 && plan.n_deep >= 1 && (int)plan.kops.size() == plan.n_lin && plan.n_lin <= 2;
-    for (const SplineDim& D : plan.dims) ok = ok && !D.liny;
-    if (const char* e = std::getenv("GWI_CTA_KERNEL")) ok = ok && !(e[0] == '0');
+    const bool ok = want_cta && plan.n_deep >= 1;
     if (ok) {
       const int64_t stage_bytes = (int64_t)(NS + (int)kop_feats.size() + 1) * 512 + 512;
       const int64_t fixed = 3 * 8 * CTA_STAGES * CTA_WARPS_MAX + 16 + (int64_t)plan.rows_total * 32 + 256 + (int64_t)rows_deep * (1024 + 256);
