@@ -102,6 +102,13 @@ struct gwi_model {
   cudaStream_t aux_stream = nullptr;  // grid normalisers run here, concurrently with the stream kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t bytes_per_eval = 0;
+  // GWI_PHASE_TIMING=1 (diagnostic): CUDA events between the kernels of every single-chain evaluation; the mean device
+  // time of each phase is printed to stderr when the model is destroyed (this serialises consecutive evaluations)
+  bool phase_timing = false;
+  cudaEvent_t ph_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double ph_sum[5] = {0, 0, 0, 0, 0};
+  int64_t ph_n = 0;
+  bool ph_pending = false;
   // library-owned multi-GPU exchange (gwi_comm_*): this rank's buffer {flags [2][R] | slots [2][R][stride]},
   // the peers' buffers as opened here, and the number of sharded evaluations so far (the epoch)
   void* comm_base = nullptr;
@@ -114,6 +121,21 @@ struct gwi_model {
   std::vector<cudaEvent_t> ev0, ev1;
   int64_t n_timed = 0;
 };
+
+static void phase_mark(gwi_model* m, int i, cudaStream_t st) {
+  if (m->phase_timing) cudaEventRecord(m->ph_ev[i], st);
+}
+static void phase_collect(gwi_model* m) {
+  if (!m->phase_timing || !m->ph_pending) return;
+  cudaEventSynchronize(m->ph_ev[5]);
+  for (int i = 0; i < 5; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, m->ph_ev[i], m->ph_ev[i + 1]);
+    m->ph_sum[i] += ms;
+  }
+  ++m->ph_n;
+  m->ph_pending = false;
+}
 
 #define CUDA_TRY(expr)                                                                                 \
   do {                                                                                                 \
@@ -365,6 +387,14 @@ extern "C" {
 void gwi_model_destroy(gwi_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
+  if (m->phase_timing) {
+    phase_collect(m);
+    if (m->ph_n > 0)
+      std::fprintf(stderr, "[gwi phases] %lld evaluations, mean device ms: prologue %.4f | stream %.4f | reduce %.4f | finish (+ join) %.4f | partial + combine %.4f\n",
+                   (long long)m->ph_n, m->ph_sum[0] / m->ph_n, m->ph_sum[1] / m->ph_n, m->ph_sum[2] / m->ph_n, m->ph_sum[3] / m->ph_n, m->ph_sum[4] / m->ph_n);
+    for (auto e : m->ph_ev)
+      if (e) cudaEventDestroy(e);
+  }
 #ifndef GWI_HOST_EMULATION
   for (void* p : m->comm_opened) cudaIpcCloseMemHandle(p);
 #endif
@@ -613,8 +643,13 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     return GWI_ERR_CUDA;
   }
   {
+    if (const char* pt = std::getenv("GWI_PHASE_TIMING")) {
+      m->phase_timing = pt[0] == '1';
+      if (m->phase_timing)
+        for (auto& e : m->ph_ev) cudaEventCreate(&e);
+    }
     const char* g = std::getenv("GWI_GRAPH");
-    m->use_graph = !(g && g[0] == '0');  // on by default (r02: +9 % e2e evals/s at config-2 size, bitwise-equal results)
+    m->use_graph = !(g && g[0] == '0') && !m->phase_timing;  // on by default (r02: +9 % e2e evals/s at config-2 size, bitwise-equal results)
 #if GWI_EXP_TRACK_MAX
     const char* sp = std::getenv("GWI_SPECULATIVE_SHIFT");
     m->spec_shift = sp && sp[0] == '1' && H.two_pass;
@@ -637,6 +672,8 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
 static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st, bool exact_shift = false) {
   const Plan& p = m->plan;
   const ModelDev& H = m->host;
+  phase_collect(m);
+  phase_mark(m, 0, st);
   // fork: the grid normalisers (needed only by finish_kernel) overlap with the stream kernel
   cudaEventRecord(m->ev_fork, st);
   cudaStreamWaitEvent(m->aux_stream, m->ev_fork, 0);
@@ -644,6 +681,7 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   cudaEventRecord(m->ev_join, m->aux_stream);
   const bool speculate = m->spec_shift && m->spec_allowed_now && m->spec_learned && nc == 1 && !exact_shift && !m->force_exact_shift;
   launch_prologue_tables(m->dev, lam_dev, H.n_groups, H.n_segments, H.two_pass != 0, nc, st, speculate ? 1 : 0);
+  phase_mark(m, 1, st);
   const dim3 grid(m->stream_grid_x, nc), block(m->stream_block);
   if (H.n_chunks > 0) {
     if ((H.two_pass && !speculate) || exact_shift || m->force_exact_shift) {
@@ -660,11 +698,14 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
       m->spec_learned = true;
     }
   }
+  phase_mark(m, 2, st);
   const int n_levels = (int)m->level_tasks.size();
   for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, st);
+  phase_mark(m, 3, st);
   cudaStreamWaitEvent(st, m->ev_join, 0);  // join
   // the last reduction level (one task per segment) is fused into finish_kernel
   launch_finish(m->dev, H.n_segments, H.rec_doubles, nc, st);
+  phase_mark(m, 4, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -745,6 +786,8 @@ int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opt
   if (rc != GWI_OK) return rc;
   // partial record + single-rank combine in one launch (the last block to finish its rows combines)
   launch_partial_tail(m->dev, m->partial_dev, m->plan.n_params, 1, *opts, out_dev, m->comm, 0ull, 1, st);
+  phase_mark(m, 5, st);
+  m->ph_pending = m->phase_timing;
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }

@@ -467,7 +467,7 @@ struct Sampler {
     double eps = find_reasonable_eps(theta, u, grad);
     double mu = std::log(10.0 * eps);
     const double gamma = 0.05, t0 = 10.0, kappa = 0.75;
-    double eps_bar = 1.0, Hbar = 0.0;
+    double eps_bar = o.n_warmup > 0 ? 1.0 : eps, Hbar = 0.0;  // no warm-up: sample with the step size the search found
     std::vector<Vec> warm;
     const bool multinomial = (o.flags & GWI_NUTS_MULTINOMIAL) != 0, windowed = (o.flags & GWI_NUTS_WINDOWED_ADAPT) != 0;
     want_dense = (o.flags & GWI_NUTS_DENSE_MASS) != 0;
@@ -570,7 +570,8 @@ struct Sampler {
           mu = std::log(10.0 * eps);
           eps_bar = 1.0;
           Hbar = 0.0;
-          if (windowed) adapt_origin = m + 1;
+          adapt_origin = m + 1;  // the dual averaging restarts with the new metric (otherwise eta = mm^-0.75 is already ~0.01 and
+                                 // the reset eps_bar = 1 is never averaged away: step size biased towards 1)
         }
       } else {
         std::memcpy(samples + (size_t)(m - o.n_warmup) * dim, theta.data(), sizeof(double) * dim);

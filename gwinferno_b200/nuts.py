@@ -159,9 +159,10 @@ def nuts(U, theta0, n_warmup, n_samples, rng, target_accept=0.8, max_depth=8):
             j += 1
         acc = a / max(na, 1)
         if m < n_warmup:
-            Hbar = (1.0 - 1.0 / (m + 1 + t0)) * Hbar + (target_accept - acc) / (m + 1 + t0)
-            eps = np.exp(mu - np.sqrt(m + 1) / gamma * Hbar)
-            eta = (m + 1) ** (-kappa)
+            mm = m + 1 - adapt_origin  # the dual averaging restarts after the mass-matrix update
+            Hbar = (1.0 - 1.0 / (mm + t0)) * Hbar + (target_accept - acc) / (mm + t0)
+            eps = np.exp(mu - np.sqrt(mm) / gamma * Hbar)
+            eta = mm ** (-kappa)
             eps_bar = np.exp(eta * np.log(eps) + (1.0 - eta) * np.log(eps_bar))
             warm.append(theta.copy())
             # one mass-matrix update in the middle of warm-up (diagonal, regularised sample variance)
@@ -174,6 +175,7 @@ def nuts(U, theta0, n_warmup, n_samples, rng, target_accept=0.8, max_depth=8):
                 eps = _find_reasonable_eps(U, theta, u, grad, inv_mass, rng)
                 mu = np.log(10.0 * eps)
                 eps_bar, Hbar = 1.0, 0.0
+                adapt_origin = m + 1
         else:
             samples[m - n_warmup] = theta
             accept_stat.append(acc)
