@@ -19,7 +19,7 @@ namespace gwi {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
-typedef void (*stream_fn)(const ModelDev*, const double*, int);
+typedef void (*stream_fn)(const ModelDev*);
 stream_fn pick_stream_kernel(int ns, int ndeep, int nlin, bool g2, bool param, bool maxonly);
 stream_fn pick_stream_cta_kernel(int ns, int ndeep, int nlin);  // CTA-cooperative kernel (stream_cta.cuh)
 stream_fn pick_stream_cta_max_kernel();
@@ -81,7 +81,6 @@ struct gwi_model {
   double* partial_batch = nullptr;                        // [n_chain_alloc][PR_HEADER + 3P]
   int stream_grid_x = 1;
   bool cta = false;        // the CTA-cooperative stream kernel runs this model (plan.cta_mode)
-  bool inline_ok = false;  // spline-only model: the stream kernel computes tables + shifts itself (SF_INLINE_PROLOGUE)
   int stream_block = 0;    // threads per block of the full pass
   int max_grid_x = 1, max_block = 0;  // launch geometry of the max-only pass
   stream_fn k_full = nullptr, k_max = nullptr;
@@ -613,8 +612,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     return GWI_ERR_UNSUPPORTED;
   }
   const size_t per_warp = (size_t)p.rows_total * 4 * mom + (size_t)deep_entries * 2 * DEEP_LANES + (size_t)p.n_gslots * 32 * (1 + mom);  // deep: double2 x DEEP_LANES copies
-  const size_t fixed = (size_t)p.rows_total * 4 + (size_t)(deep_entries / (2 * mom)) * 32 + (size_t)((p.rows_total + 1) & ~1) + (size_t)H.n_kops * KC_STRIDE +
-                       (size_t)H.n_kops * (sizeof(KopDev) / 8);
+  const size_t fixed = (size_t)p.rows_total * 4 + (size_t)(deep_entries / (2 * mom)) * 32 + (size_t)H.n_kops * KC_STRIDE + (size_t)H.n_kops * (sizeof(KopDev) / 8);
   static_assert(sizeof(KopDev) % 16 == 0, "KopDev copies must keep the shared layout 16-byte aligned");
   int wpb = p.warps_per_block;
   while (wpb > 1 && (fixed + per_warp * wpb) * 8 > (size_t)prop.sharedMemPerBlockOptin) --wpb;
@@ -625,7 +623,6 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   }
   m->smem_full = (fixed + per_warp * wpb) * 8;
   m->smem_max = m->smem_full;
-  m->inline_ok = !param && !H.two_pass && !(std::getenv("GWI_INLINE_PROLOGUE") && std::getenv("GWI_INLINE_PROLOGUE")[0] == '0');
   m->stream_block = wpb * 32;
   m->max_block = wpb * 32;
   if (m->cta) {
@@ -681,25 +678,20 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   cudaEventRecord(m->ev_fork, st);
   cudaStreamWaitEvent(m->aux_stream, m->ev_fork, 0);
   launch_prologue_groups(m->dev, lam_dev, H.n_groups, m->max_grid, nc, m->aux_stream);
-  const bool speculate = m->spec_shift && m->spec_allowed_now && m->spec_learned && nc == 1 && !exact_shift && !m->force_exact_shift;
-  // spline-only models: the stream kernel derives its tables and shifts from Lambda itself, so the prologue (whose other
-  // outputs -- scalar normalisers, linear coefficients, the global copy of the tables -- only finish_kernel and the exact-shift
-  // fallback read) runs on the auxiliary stream, off the critical path
-  const bool inline_prologue = m->inline_ok && !exact_shift && !m->force_exact_shift;
-  if (inline_prologue) launch_prologue_tables(m->dev, lam_dev, H.n_groups, H.n_segments, true, nc, m->aux_stream, 0);
   cudaEventRecord(m->ev_join, m->aux_stream);
-  if (!inline_prologue) launch_prologue_tables(m->dev, lam_dev, H.n_groups, H.n_segments, H.two_pass != 0, nc, st, speculate ? 1 : 0);
+  const bool speculate = m->spec_shift && m->spec_allowed_now && m->spec_learned && nc == 1 && !exact_shift && !m->force_exact_shift;
+  launch_prologue_tables(m->dev, lam_dev, H.n_groups, H.n_segments, H.two_pass != 0, nc, st, speculate ? 1 : 0);
   phase_mark(m, 1, st);
   const dim3 grid(m->stream_grid_x, nc), block(m->stream_block);
   if (H.n_chunks > 0) {
     if ((H.two_pass && !speculate) || exact_shift || m->force_exact_shift) {
       // exact per-segment maximum first (always for models with non-linear terms; as a fallback when
       // the a-priori bound was so loose that every weight of a segment underflowed)
-      GWI_LAUNCH(m->k_max, dim3(m->max_grid_x, nc), dim3(m->max_block), m->smem_max, st)(m->dev, lam_dev, 0);
+      GWI_LAUNCH(m->k_max, dim3(m->max_grid_x, nc), dim3(m->max_block), m->smem_max, st)(m->dev);
       launch_segmax(m->dev, H.n_segments, nc, st);
     }
     if (m->timing) cudaEventRecord(m->ev0[m->n_timed % 64], st);
-    GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev, lam_dev, inline_prologue ? (int)SF_INLINE_PROLOGUE : 0);
+    GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev);
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
     if (m->spec_shift && nc == 1) {
       launch_segmax_learn(m->dev, H.n_segments, nc, st);  // next evaluation's shift; flags this one if its shift was off

@@ -114,25 +114,6 @@ struct CommDev {
   int32_t rank, n_ranks;
 };
 
-// Stream-kernel flags (third kernel argument).  SF_INLINE_PROLOGUE: the model is spline-only (B-spline terms + linear terms,
-// a-priori shift bound), so the kernel derives the per-piece polynomials and the per-segment log-sum-exp shifts from Lambda
-// ITSELF instead of waiting for prologue_kernel: one dependent launch (~20-27 us measured in situ) leaves the critical path;
-// the prologue then runs on the auxiliary stream, next to the grid normalisers, for the pieces only finish_kernel needs.
-enum { SF_INLINE_PROLOGUE = 1 };
-
-#if defined(__CUDACC__) || defined(GWI_HOST_EMULATION)
-// the 4 coefficients (in w = u - 1/2) of polynomial piece J of a cubic B-spline with coefficients c[J..J+3], and the piece's
-// upper bound max(c[J..J+3]) (convex-hull property); same arithmetic as prologue_kernel
-__device__ __forceinline__ void piece_poly(const double* __restrict__ c, double (&a)[4], double& ub) {
-  const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
-  ub = fmax(fmax(c0, c1), fmax(c2, c3));
-  a[0] = c0 * (1.0 / 48.0) + c1 * (23.0 / 48.0) + c2 * (23.0 / 48.0) + c3 * (1.0 / 48.0);
-  a[1] = c0 * (-1.0 / 8.0) + c1 * (-5.0 / 8.0) + c2 * (5.0 / 8.0) + c3 * (1.0 / 8.0);
-  a[2] = c0 * (1.0 / 4.0) + c1 * (-1.0 / 4.0) + c2 * (-1.0 / 4.0) + c3 * (1.0 / 4.0);
-  a[3] = c0 * (-1.0 / 6.0) + c1 * (1.0 / 2.0) + c2 * (-1.0 / 2.0) + c3 * (1.0 / 6.0);
-}
-#endif
-
 // partial (per-rank) likelihood record: 8 header doubles + 3P
 enum { PR_SHIFT = 0, PR_S1 = 1, PR_S2 = 2, PR_SUM_LOGBF = 3, PR_MIN_LOGNEFF = 4, PR_SUM_VAR = 5, PR_N_EVENTS = 6, PR_STATUS = 7, PR_HEADER = 8 };
 

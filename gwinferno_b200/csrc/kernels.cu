@@ -305,8 +305,10 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     return;
   }
   // ---------------- tables, kop constants, scalar normalisers ----------------
-  // (the slice counters of the stream kernels are reset by finish_kernel at the END of every evaluation: this kernel may run
-  // on the auxiliary stream, concurrently with the stream kernel)
+  if (tid == 0) {
+    M.slice_counter[0] = 0;
+    M.slice_counter[1] = 0;
+  }
   if (use_learned_shift)  // speculative shift: the maxima of the previous evaluation's full pass
     for (int sg = tid; sg < M.n_segments; sg += nt) M.shift[sg] = M.shift_next[sg];
   for (int r = tid; r < M.rows_total; r += nt) {
@@ -580,10 +582,6 @@ __global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict_
     const ReduceTask T = tasks[s];
     for (int i = threadIdx.x; i < M.rec_doubles; i += blockDim.x) srec[i] = reduce_element(M, T, i);
     __syncthreads();
-  }
-  if (s == 0 && threadIdx.x == 0) {  // the stream kernels of this evaluation are done: re-arm their dynamic slice scheduling
-    M.slice_counter[0] = 0;
-    M.slice_counter[1] = 0;
   }
   finish_segment(M, s, srec);
 }

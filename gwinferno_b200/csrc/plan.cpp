@@ -859,7 +859,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     if (plan.dims[d].deep) rows_deep += plan.dims[d].rows;
   const int64_t warp_bytes = (int64_t)plan.rows_total * 4 * mom * 8 + (int64_t)rows_deep * 4 * mom * DEEP_LANES * 8 +
                              (int64_t)plan.n_gslots * (1 + mom) * LANES * 8;
-  const int64_t cta_fixed = (int64_t)plan.rows_total * 5 * 8 + 16 + (int64_t)rows_deep * 256 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
+  const int64_t cta_fixed = (int64_t)plan.rows_total * 4 * 8 + (int64_t)rows_deep * 256 + (int64_t)plan.kops.size() * (KC_STRIDE * 8 + 80) + 1024;
   int wpb = (int)((226 * 1024 - cta_fixed) / std::max<int64_t>(1, warp_bytes));  // 227 KB per CTA on sm_100; api.cu re-checks with the exact layout
   wpb = std::max(1, std::min(wpb, 8));
   plan.warps_per_block = wpb;

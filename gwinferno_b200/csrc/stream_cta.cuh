@@ -32,7 +32,7 @@ constexpr int CTA_MAX_WARPS = 12;  // main + deep warps (launch bound 384 thread
 
 // shared-memory layout of the CTA kernel (bytes from the start of the dynamic shared memory)
 struct CtaLayout {
-  unsigned bars, ctl, tables, dtab, ub, stages, stage_bytes, blk_bytes, deep, total;
+  unsigned bars, ctl, tables, dtab, stages, stage_bytes, blk_bytes, deep, total;
 };
 __host__ __device__ inline CtaLayout cta_layout(int nw, int ncol, int rows_total, int deep_entries) {
   CtaLayout L;
@@ -42,8 +42,7 @@ __host__ __device__ inline CtaLayout cta_layout(int nw, int ncol, int rows_total
   L.blk_bytes = (unsigned)ncol * 512u;
   L.stage_bytes = L.blk_bytes + 512u;                       // + the 64 weights p of the block
   L.dtab = L.tables + (unsigned)rows_total * 32u;  // deep-dim half-rows replicated 8x: [h][r][lane & 7] double2 (conflict-free LDS.128)
-  L.ub = L.dtab + (unsigned)(deep_entries / 2) * 256u;    // per-piece upper bounds (inline prologue)
-  L.stages = (L.ub + (unsigned)rows_total * 8u + 127u) & ~127u;
+  L.stages = (L.dtab + (unsigned)(deep_entries / 2) * 256u + 127u) & ~127u;
   L.deep = L.stages + (unsigned)nw * CTA_NSTAGE * L.stage_bytes;
   L.total = L.deep + (unsigned)deep_entries * 32u * 16u;    // double2 [entry][lane]
   return L;
@@ -156,10 +155,8 @@ __device__ __forceinline__ void flush_moments_red(double* recM, int row, int lan
 }
 
 template <int NS, int NDEEP, int NLIN>
-__global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ lam0, int flags) {
+__global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const ModelDev* __restrict__ Mp) {
   const ModelDev& M = Mp[blockIdx.y];  // blockIdx.y = chain
-  const double* __restrict__ Lam = lam0 + (size_t)blockIdx.y * M.n_params;
-  const bool inl = (flags & SF_INLINE_PROLOGUE) != 0;  // tables and shifts straight from Lambda (dev_structs.h)
   constexpr int NSH = NS - NDEEP;
   constexpr int NSHd = NSH > 0 ? NSH : 1;
   constexpr int NLd = NLIN > 0 ? NLIN : 1;
@@ -184,22 +181,7 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
   auto bar_free = [&](int s) { return mbar_idx(bars0, (NW + 1) * CTA_NSTAGE + s); };
   auto stage_ptr = [&](int w, int s) { return smb + L.stages + (unsigned)(w * CTA_NSTAGE + s) * L.stage_bytes; };
 
-  double* const ub_s = reinterpret_cast<double*>(smb + L.ub);
-  if (inl) {
-    for (int r = threadIdx.x; r < rows_total; r += blockDim.x) {
-      int d = 0;
-      while (d + 1 < NS && r >= M.dims[d + 1].row_off) ++d;
-      const int J = r - M.dims[d].row_off;
-      double a[4] = {0.0, 0.0, 0.0, 0.0}, ub = 0.0;
-      if (J < M.dims[d].rows - 1) piece_poly(Lam + M.dims[d].slot + J, a, ub);
-#pragma unroll
-      for (int n = 0; n < 4; ++n) tables[r * 4 + n] = a[n];
-      ub_s[r] = ub;
-    }
-  } else {
-    for (int i = threadIdx.x; i < rows_total * 4; i += blockDim.x) tables[i] = M.tables[i];
-  }
-  __syncthreads();
+  for (int i = threadIdx.x; i < rows_total * 4; i += blockDim.x) tables[i] = M.tables[i];
   double2* const dtab = reinterpret_cast<double2*>(smb + L.dtab);
   {
     int dro = 0;
@@ -207,7 +189,7 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
       const int rows = M.dims[d].rows, ro = M.dims[d].row_off;
       for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) {
         const int h = i / (rows * 8), r = (i >> 3) % rows;  // [h][r][copy]
-        dtab[dro * 16 + i] = make_double2(tables[(ro + r) * 4 + 2 * h], tables[(ro + r) * 4 + 2 * h + 1]);
+        dtab[dro * 16 + i] = make_double2(M.tables[(ro + r) * 4 + 2 * h], M.tables[(ro + r) * 4 + 2 * h + 1]);
       }
       dro += rows;
     }
@@ -266,16 +248,11 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
   int lin_off[NLd];
 #pragma unroll
   for (int l = 0; l < NLIN; ++l) {
-    theta[l] = inl ? Lam[M.kops[l].slot[0]] + M.kops[l].cst[0] : M.kc[l * KC_STRIDE];
+    theta[l] = M.kc[l * KC_STRIDE];
     lin_off[l] = M.kops[l].col0 * 512 + lane * 16;
     gl1[l] = 0.0;
   }
   const int st_off = M.col_static * 512 + lane * 16;
-  int shift_seg = -1;
-  double shift_val = 0.0;
-  int rows_of[NS];
-#pragma unroll
-  for (int d = 0; d < NS; ++d) rows_of[d] = M.dims[d].rows;
   const int lead_doubles = M.cta_lead_doubles;  // {S1, S2}, linear slots, leading rows (they come first in a record)
 
   for (;;) {
@@ -289,27 +266,7 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
       // ================================ main warp ================================
       for (int c = c_begin; c < c_end; ++c) {
         const Chunk C = M.chunks[c];
-        if (inl && C.segment != shift_seg) {
-          // a-priori bound of x over the segment (as prologue_kernel); lanes split the pieces, fixed-order warp maximum
-          const SegDev& S = M.segs[C.segment];
-          double sh = S.max_static;
-#pragma unroll
-          for (int d = 0; d < NS; ++d) {
-            const unsigned long long occ = S.occ[d];
-            double mx = -INFINITY;
-            for (int J = lane; J < rows_of[d]; J += 32)
-              if ((occ >> J) & 1ull) mx = fmax(mx, ub_s[row_off[d] + J]);
-            mx = wmax(mx);
-            if (mx > -INFINITY) sh += mx;
-          }
-#pragma unroll
-          for (int l = 0; l < NLIN; ++l)
-            if (S.fmax[l] >= S.fmin[l]) sh += fmax(theta[l] * S.fmin[l], theta[l] * S.fmax[l]);
-          shift_val = (sh == sh && sh > -INFINITY && sh < INFINITY) ? sh : 0.0;
-          shift_seg = C.segment;
-          if (warp == 0 && lane == 0) M.shift[C.segment] = shift_val;  // for finish_kernel
-        }
-        const double shift = inl ? shift_val : M.shift[C.segment];
+        const double shift = M.shift[C.segment];
         const int iters = C.steps >> 1;
         double* const rec = M.records0 + (size_t)(C.record_slot + warp) * M.rec_doubles;
         double* const recM = rec + 2 + n_gs;
@@ -586,7 +543,7 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
 // forward-only pass for the exact per-segment maximum of x (fallback when the a-priori shift bound of a
 // spline model was too loose): one block per chunk, plain loads.
 template <int DUMMY>
-__global__ void __launch_bounds__(256) stream_cta_max_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__, int) {
+__global__ void __launch_bounds__(256) stream_cta_max_kernel(const ModelDev* __restrict__ Mp) {
   const ModelDev& M = Mp[blockIdx.y];
   __shared__ double red[8];
   const int ncol = M.n_columns, NS = M.n_dims, nlin = M.n_lin_fast;
