@@ -200,7 +200,7 @@ def nuts_block(device):
     blocks = pipeline.bspline_prior_blocks(low.slots_for, p0)
     dim = low.spec.n_params - 1
     theta0 = 0.1 * np.random.default_rng(0).standard_normal(dim)
-    n_warm, n_samp, flags = 1000, 500, 7
+    n_warm, n_samp, flags = 1000, 800, 7
     t0 = time.perf_counter()
     samples, info = nuts.nuts_native(eng, blocks, theta0, n_warm, n_samp, Nobs=const["E"], seed=0, max_depth=8, flags=flags)
     wall = time.perf_counter() - t0
@@ -337,12 +337,28 @@ def run_ours(args):
     mdl.set_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
-    for i in range(args.warmup, n_steps):
-        step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    if args.flush_l2:
+        # cold numbers for the L2-resident configurations: a 512 MB write between steps evicts the plan
+        # from the 126 MB L2; only the steps themselves are timed (one event pair per step)
+        scrub = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        pairs = []
+        for i in range(args.warmup, n_steps):
+            scrub.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step(i)
+            b.record()
+            pairs.append((a, b))
+        barrier()
+        ms = float(sum(a.elapsed_time(b) for a, b in pairs))
+        del scrub
+    else:
+        e0.record()
+        for i in range(args.warmup, n_steps):
+            step(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
     kt = mdl.stream_times_ms(min(64, args.steps))
     mdl.set_timing(False)
     res = (out_chain[: capi.GWI_LIKE_HEADER + P] if chains > 1 else out).cpu().numpy()
@@ -413,7 +429,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": chains * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _config(name, const["family"], const["E"], const["S"], const["I"], P, chains, world, args.shard_by, _l2_policy(name)),
+        "config": _config(name, const["family"], const["E"], const["S"], const["I"], P, chains, world, args.shard_by,
+                          "L2 flushed between steps (512 MB write; one CUDA-event pair per step)" if args.flush_l2 else _l2_policy(name)),
         "samples_per_s": n_total * chains * args.steps / (ms * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "stream_kernel", "kernel_ms": k_ms, "alg_bytes_per_launch": n_local * chains * ALG_BYTES_PER_SAMPLE,
@@ -473,6 +490,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink S and I (testing only; the reported config then differs from BASELINE's)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline, parity_at_size, nuts): tuning runs")
     ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS ESS/s block")
+    ap.add_argument("--flush-l2", action="store_true", help="cold numbers: evict L2 between steps (for the L2-resident configurations)")
     ap.add_argument("--emulate-world", type=int, default=1, help="tuning aid: run rank 0's shard of a W-way partition on one GPU")
     ap.add_argument("--shard-by", default="bucket", choices=["bucket", "index"], help="multi-GPU partition of the found injections")
     ap.add_argument("--n-deep", type=int, default=-1, help="tuning experiment: spline dims with lane-private accumulators (-1 = auto)")

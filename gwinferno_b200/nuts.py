@@ -99,7 +99,8 @@ def nuts(U, theta0, n_warmup, n_samples, rng, target_accept=0.8, max_depth=8):
     u, grad = U(theta)
     eps = _find_reasonable_eps(U, theta, u, grad, inv_mass, rng)
     mu, gamma, t0, kappa = np.log(10.0 * eps), 0.05, 10.0, 0.75
-    eps_bar, Hbar = 1.0, 0.0
+    eps_bar, Hbar = (1.0 if n_warmup > 0 else eps), 0.0  # no warm-up: sample with the step size the search found
+    adapt_origin = 0  # the dual averaging restarts after the mass-matrix update
     samples = np.zeros((n_samples, dim))
     warm = []
     n_leapfrog = 0
