@@ -691,7 +691,7 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
       launch_segmax(m->dev, H.n_segments, nc, st);
     }
     if (m->timing) cudaEventRecord(m->ev0[m->n_timed % 64], st);
-    GWI_LAUNCH(m->k_full, grid, block, m->smem_full, st)(m->dev);
+    GWI_LAUNCH_PDL(m->k_full, grid, block, m->smem_full, st)(m->dev);
     if (m->timing) cudaEventRecord(m->ev1[m->n_timed++ % 64], st);
     if (m->spec_shift && nc == 1) {
       launch_segmax_learn(m->dev, H.n_segments, nc, st);  // next evaluation's shift; flags this one if its shift was off
@@ -1004,23 +1004,24 @@ int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opt
       const int rc_cap = gwi_loglike(m, m->lam_dev, opts, m->out_dev, m->own_stream);
       cudaMemcpyAsync(m->out_pinned, m->out_dev, sizeof(double) * (GWI_LIKE_HEADER + P), cudaMemcpyDeviceToHost, m->own_stream);
       const cudaError_t e_end = cudaStreamEndCapture(m->own_stream, &graph);  // always ends the capture, also after an error
-      if (rc_cap != GWI_OK) {
-        if (graph) cudaGraphDestroy(graph);
-        return rc_cap;
+      bool graph_ok = rc_cap == GWI_OK && e_end == cudaSuccess && graph != nullptr;  // (a genuine argument error shows again on the eager path)
+      if (graph_ok) {
+        const cudaError_t e_inst = cudaGraphInstantiate(&m->graph_exec, graph, 0);
+        graph_ok = e_inst == cudaSuccess;
+        if (!graph_ok) m->graph_exec = nullptr;
       }
-      if (e_end != cudaSuccess || !graph) {
-        set_error(std::string("stream capture of the evaluation failed: ") + cudaGetErrorString(e_end));
-        return GWI_ERR_CUDA;
+      if (graph) cudaGraphDestroy(graph);
+      if (!graph_ok) {
+        // this driver cannot capture the launch sequence (e.g. programmatic dependent launches inside a capture): eager launches
+        // from now on -- same results, a few microseconds more host latency per call
+        cudaGetLastError();
+        m->use_graph = false;
+      } else {
+        m->graph_opts = *opts;
       }
-      const cudaError_t e_inst = cudaGraphInstantiate(&m->graph_exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (e_inst != cudaSuccess) {
-        m->graph_exec = nullptr;
-        set_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(e_inst));
-        return GWI_ERR_CUDA;
-      }
-      m->graph_opts = *opts;
     }
+  }
+  if (m->use_graph && m->graph_exec && opts && !m->timing && !m->force_exact_shift) {
     CUDA_TRY(cudaGraphLaunch(m->graph_exec, m->own_stream));
   } else {
     CUDA_TRY(cudaMemcpyAsync(m->lam_dev, m->lam_pinned, sizeof(double) * P, cudaMemcpyHostToDevice, m->own_stream));

@@ -1,6 +1,7 @@
 // Device-visible, trivially copyable mirrors of the plan (passed to kernels by value / pointer).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 
 #include "gwi_internal.h"
 
@@ -9,8 +10,53 @@
 // compiles these same kernel sources with g++; it is never part of libgwi.so).
 #ifdef GWI_HOST_EMULATION
 #define GWI_LAUNCH(kernel, grid, block, smem, stream) GWI_EMU_LAUNCH(kernel, grid, block, smem, stream)
+#define GWI_LAUNCH_PDL(kernel, grid, block, smem, stream) GWI_EMU_LAUNCH(kernel, grid, block, smem, stream)
+#define GWI_PDL_WAIT() ((void)0)
+#define GWI_PDL_TRIGGER() ((void)0)
 #else
 #define GWI_LAUNCH(kernel, grid, block, smem, stream) kernel<<<(grid), (block), (smem), (stream)>>>
+// Programmatic dependent launch: the kernels of one evaluation form a chain of small dependent launches (~8 us each in
+// situ, mostly launch latency + ramp + dependent loads).  A kernel launched with the programmatic-serialisation attribute may
+// be SCHEDULED as soon as every block of its predecessor has executed GWI_PDL_TRIGGER(); it runs its preamble (descriptor
+// staging, task lookup, shared-memory initialisation -- static data only) and blocks in GWI_PDL_WAIT() until the predecessor
+// grid has completed and its writes are visible.  GWI_PDL=0 launches everything with plain stream order (A/B measurement).
+namespace gwi {
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("GWI_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <class... KArgs>
+struct PdlLauncher {
+  void (*kernel)(KArgs...);
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t stream;
+  template <class... A>
+  void operator()(A... args) const {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  }
+};
+template <class... KArgs>
+PdlLauncher<KArgs...> make_pdl_launcher(void (*k)(KArgs...), dim3 g, dim3 b, size_t s, cudaStream_t st) {
+  return PdlLauncher<KArgs...>{k, g, b, s, st};
+}
+}  // namespace gwi
+#define GWI_LAUNCH_PDL(kernel, grid, block, smem, stream) gwi::make_pdl_launcher((kernel), dim3(grid), dim3(block), (size_t)(smem), (stream))
+#define GWI_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define GWI_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #endif
 
 // GWI_EXP_TRACK_MAX (experiment switch, default 0; run-time side: GWI_SPECULATIVE_SHIFT=1): the full pass of

@@ -131,6 +131,7 @@ __device__ void powerlaw_lognorm(double alpha, double lo, double hi, double& log
 // prologue
 // =================================================================================================
 __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restrict__ Mp, const double* __restrict__ Lam0, int role_off, int use_learned_shift) {
+  GWI_PDL_TRIGGER();  // the stream kernel may be scheduled (it waits for this grid before it reads the tables)
   GWI_STAGED_DESC(M, Mp[blockIdx.y]);  // blockIdx.y = chain
   const double* __restrict__ Lam = Lam0 + (size_t)blockIdx.y * M.n_params;
   extern __shared__ double sm[];
@@ -437,10 +438,12 @@ __device__ __forceinline__ double reduce_element(const ModelDev& M, const Reduce
 // the same fixed order as reduce_element's.  (A thread per element walking all 64 inputs needed 8 dependent rounds: ~20 us per
 // level whatever the number of tasks.)
 __global__ void __launch_bounds__(256) reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
+  GWI_PDL_TRIGGER();
   const ModelDev& M = Mp[blockIdx.z];  // blockIdx.z = chain
-  const ReduceTask T = M.level_tasks[level][blockIdx.x];
+  const ReduceTask T = M.level_tasks[level][blockIdx.x];  // (static data: read before the dependency wait)
   const int rec = M.rec_doubles;
   const int j = threadIdx.x & 31, g = threadIdx.x >> 5;
+  GWI_PDL_WAIT();  // the producer of the input records has completed
   const int i = blockIdx.y * 32 + j;
   __shared__ double part[8][33];
   double acc = 0.0;
@@ -573,13 +576,15 @@ __device__ void finish_segment(const ModelDev& M, int s, const double* rec) {
 }
 
 __global__ void __launch_bounds__(256) finish_kernel(const ModelDev* __restrict__ Mp) {
+  GWI_PDL_TRIGGER();
   GWI_STAGED_DESC(M, Mp[blockIdx.y]);
   const ReduceTask* __restrict__ tasks = M.level_tasks[M.n_levels - 1];
   const int s = blockIdx.x;
+  const ReduceTask T = tasks[s];  // (static data: read before the dependency wait)
+  GWI_PDL_WAIT();
   // last level of the record reduction (task s sums the <= 64 remaining inputs of segment s), fused in here
   extern __shared__ double srec[];
   {
-    const ReduceTask T = tasks[s];
     for (int i = threadIdx.x; i < M.rec_doubles; i += blockDim.x) srec[i] = reduce_element(M, T, i);
     __syncthreads();
   }
@@ -865,9 +870,11 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ModelDev* __restric
 // blockIdx.y = chain (tail 2: one chain).
 __global__ void __launch_bounds__(256) partial_tail_kernel(const ModelDev* __restrict__ Mp, double* recd0, int tail, gwi_like_opts opts, double* out0, CommDev C,
                                                            unsigned long long epoch) {
+  GWI_PDL_TRIGGER();
   GWI_STAGED_DESC(M, Mp[blockIdx.y]);
   const int P = M.n_params, stride = PR_HEADER + 3 * P;
   double* recd = recd0 + (size_t)blockIdx.y * stride;
+  GWI_PDL_WAIT();  // finish_kernel has completed
   const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   partial_rows<false>(M, recd, blockIdx.x * wpb + warp, gridDim.x * wpb);
   __shared__ int last_s;
@@ -912,11 +919,11 @@ void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups,
 }
 void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st) {
   dim3 grid(n_tasks, (rec + 31) / 32, nc);
-  GWI_LAUNCH(reduce_kernel, grid, 256, 0, st)(Md, level);
+  GWI_LAUNCH_PDL(reduce_kernel, grid, 256, 0, st)(Md, level);
 }
 void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st) { GWI_LAUNCH(segmax_kernel, dim3(n_seg, nc), 256, 0, st)(Md); }
 void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaStream_t st) {
-  GWI_LAUNCH(finish_kernel, dim3(n_seg, nc), 256, (size_t)rec_doubles * sizeof(double), st)(Md);
+  GWI_LAUNCH_PDL(finish_kernel, dim3(n_seg, nc), 256, (size_t)rec_doubles * sizeof(double), st)(Md);
 }
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st) { GWI_LAUNCH(export_kernel, 64, 256, 0, st)(Md, out); }
 void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaStream_t st) {
@@ -927,7 +934,7 @@ void launch_exchange(const ModelDev* Md, const double* rec_local, const CommDev&
 }
 void launch_partial_tail(const ModelDev* Md, double* rec, int n_params, int tail, const gwi_like_opts& o, double* out, const CommDev& C, unsigned long long epoch, int nc,
                          cudaStream_t st) {
-  GWI_LAUNCH(partial_tail_kernel, dim3((n_params + 7) / 8, nc), 256, 0, st)(Md, rec, tail, o, out, C, epoch);
+  GWI_LAUNCH_PDL(partial_tail_kernel, dim3((n_params + 7) / 8, nc), 256, 0, st)(Md, rec, tail, o, out, C, epoch);
 }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
   GWI_LAUNCH(combine_kernel, nc, 256, 0, st)(Md, recs, R, o, out);

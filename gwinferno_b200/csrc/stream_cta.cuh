@@ -156,6 +156,7 @@ __device__ __forceinline__ void flush_moments_red(double* recM, int row, int lan
 
 template <int NS, int NDEEP, int NLIN>
 __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const ModelDev* __restrict__ Mp) {
+  GWI_PDL_TRIGGER();  // the record reduction may be scheduled behind this grid (it waits for it to complete)
   const ModelDev& M = Mp[blockIdx.y];  // blockIdx.y = chain
   constexpr int NSH = NS - NDEEP;
   constexpr int NSHd = NSH > 0 ? NSH : 1;
@@ -181,6 +182,21 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
   auto bar_free = [&](int s) { return mbar_idx(bars0, (NW + 1) * CTA_NSTAGE + s); };
   auto stage_ptr = [&](int w, int s) { return smb + L.stages + (unsigned)(w * CTA_NSTAGE + s) * L.stage_bytes; };
 
+  {
+    double2* dz = reinterpret_cast<double2*>(smb + L.deep);
+    for (int i = threadIdx.x; i < M.deep_entries * 32; i += blockDim.x) dz[i] = make_double2(0.0, 0.0);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CTA_NSTAGE; ++s) {
+      for (int w = 0; w < NW; ++w) mbar_init(bar_full(w, s), 1);
+      mbar_init(bar_ready(s), NW);
+      mbar_init(bar_free(s), NDEEP);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  // ---- everything above touches static data only; now wait for prologue_kernel's tables / shifts / counters ----
+  GWI_PDL_WAIT();  // prologue_kernel (tables, shifts, slice counters) has completed
   for (int i = threadIdx.x; i < rows_total * 4; i += blockDim.x) tables[i] = M.tables[i];
   double2* const dtab = reinterpret_cast<double2*>(smb + L.dtab);
   {
@@ -193,18 +209,6 @@ __global__ void __launch_bounds__(CTA_MAX_WARPS * 32, 1) stream_cta_kernel(const
       }
       dro += rows;
     }
-  }
-  {
-    double2* dz = reinterpret_cast<double2*>(smb + L.deep);
-    for (int i = threadIdx.x; i < M.deep_entries * 32; i += blockDim.x) dz[i] = make_double2(0.0, 0.0);
-  }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < CTA_NSTAGE; ++s) {
-      for (int w = 0; w < NW; ++w) mbar_init(bar_full(w, s), 1);
-      mbar_init(bar_ready(s), NW);
-      mbar_init(bar_free(s), NDEEP);
-    }
-    mbar_fence_init();
   }
   __syncthreads();
 
