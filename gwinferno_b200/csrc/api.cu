@@ -35,8 +35,6 @@ void launch_partial(const ModelDev* Md, double* rec, int n_params, int nc, cudaS
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st);
 void launch_partial_tail(const ModelDev* Md, double* rec, int n_params, int tail, const gwi_like_opts& o, double* out, const CommDev& C, unsigned long long epoch, int nc,
                          cudaStream_t st);
-bool launch_tail_coop(const ModelDev* Md, int n_seg, int rec_doubles, double* rec, int tail, const gwi_like_opts& o, double* out, const CommDev& C, unsigned long long epoch,
-                      int sm_count, cudaStream_t st);
 void launch_exchange(const ModelDev* Md, const double* rec_local, const CommDev& C, unsigned long long epoch, int mode, const gwi_like_opts& o, double* out, cudaStream_t st);
 
 }  // namespace gwi
@@ -83,9 +81,6 @@ struct gwi_model {
   double* partial_batch = nullptr;                        // [n_chain_alloc][PR_HEADER + 3P]
   int stream_grid_x = 1;
   bool cta = false;        // the CTA-cooperative stream kernel runs this model (plan.cta_mode)
-  bool coop_tail = true;   // single-chain likelihood calls finish with ONE cooperative launch (tail_coop_kernel); GWI_COOP_TAIL=0 or a
-                           // refused cooperative launch fall back to reduce / finish / partial_tail kernels
-  int sm_count = 0;
   int stream_block = 0;    // threads per block of the full pass
   int max_grid_x = 1, max_block = 0;  // launch geometry of the max-only pass
   stream_fn k_full = nullptr, k_max = nullptr;
@@ -346,7 +341,6 @@ static int alloc_chain_scratch(gwi_model* m, ModelDev& H) {
   UPS(upload<double>(m, nullptr, (size_t)nseg, &H.shift_next));
   UPS(upload<double>(m, nullptr, (size_t)nseg, &H.spec_bad));
   UPS(upload<int32_t>(m, nullptr, (size_t)1, &H.tail_counter));
-  UPS(upload<unsigned long long>(m, nullptr, (size_t)2, &H.coop_state));
   H.n_levels = (int)p.levels.size();
   for (int l = 0; l < 6; ++l) {
     H.level_buf[l] = nullptr;
@@ -442,8 +436,6 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   gwi_model* m = new (std::nothrow) gwi_model();
   if (!m) return GWI_ERR_ALLOC;
   m->device = cat->view.device;
-  m->sm_count = prop.multiProcessorCount;
-  if (const char* e = std::getenv("GWI_COOP_TAIL")) m->coop_tail = e[0] != '0';
   int rc = build_plan_noexcept(cat->view, *desc, prop.multiProcessorCount, 0, m->plan);
   if (rc != GWI_OK) {
     delete m;
@@ -677,8 +669,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
 }
 
 // launches prologue .. finish for `nc` chains on `st` (lam_dev: [nc][P])
-// (skip_tail: stop after the stream kernel + the join with the auxiliary stream; the caller launches the cooperative tail)
-static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st, bool exact_shift = false, bool skip_tail = false) {
+static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st, bool exact_shift = false) {
   const Plan& p = m->plan;
   const ModelDev& H = m->host;
   phase_collect(m);
@@ -708,11 +699,6 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
     }
   }
   phase_mark(m, 2, st);
-  if (skip_tail) {
-    cudaStreamWaitEvent(st, m->ev_join, 0);  // join
-    CUDA_TRY(cudaGetLastError());
-    return GWI_OK;
-  }
   const int n_levels = (int)m->level_tasks.size();
   for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, st);
   phase_mark(m, 3, st);
@@ -720,16 +706,6 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   // the last reduction level (one task per segment) is fused into finish_kernel
   launch_finish(m->dev, H.n_segments, H.rec_doubles, nc, st);
   phase_mark(m, 4, st);
-  CUDA_TRY(cudaGetLastError());
-  return GWI_OK;
-}
-
-// reduction levels + finish as separate launches, after run_eval(..., skip_tail = true) (the join has been issued)
-static int run_tail_separate(gwi_model* m, int nc, cudaStream_t st) {
-  const ModelDev& H = m->host;
-  const int n_levels = (int)m->level_tasks.size();
-  for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, st);
-  launch_finish(m->dev, H.n_segments, H.rec_doubles, nc, st);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }
@@ -806,19 +782,10 @@ int gwi_loglike(gwi_model* m, const double* lambda_dev, const gwi_like_opts* opt
   }
   CUDA_TRY(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = run_eval(m, lambda_dev, 1, st, false, m->coop_tail);
+  const int rc = run_eval(m, lambda_dev, 1, st);
   if (rc != GWI_OK) return rc;
-  if (m->coop_tail && !launch_tail_coop(m->dev, m->host.n_segments, m->host.rec_doubles, m->partial_dev, 1, *opts, out_dev, m->comm, 0ull, m->sm_count, st)) {
-    m->coop_tail = false;  // refused (driver / capture / emulator): the separate kernels from now on
-    rc = run_tail_separate(m, 1, st);
-    if (rc != GWI_OK) return rc;
-  }
   // partial record + single-rank combine in one launch (the last block to finish its rows combines)
-  if (!m->coop_tail) launch_partial_tail(m->dev, m->partial_dev, m->plan.n_params, 1, *opts, out_dev, m->comm, 0ull, 1, st);
-  if (m->coop_tail) {
-    phase_mark(m, 3, st);
-    phase_mark(m, 4, st);
-  }
+  launch_partial_tail(m->dev, m->partial_dev, m->plan.n_params, 1, *opts, out_dev, m->comm, 0ull, 1, st);
   phase_mark(m, 5, st);
   m->ph_pending = m->phase_timing;
   CUDA_TRY(cudaGetLastError());
@@ -941,17 +908,11 @@ int gwi_loglike_sharded(gwi_model* m, const double* lambda_dev, const gwi_like_o
   int rc = sharded_checks(m, opts);
   if (rc != GWI_OK) return rc;
   CUDA_TRY(cudaSetDevice(m->device));
-  rc = run_eval(m, lambda_dev, 1, (cudaStream_t)stream, false, m->coop_tail);
+  rc = run_eval(m, lambda_dev, 1, (cudaStream_t)stream);
   if (rc != GWI_OK) return rc;
   m->comm_pushed = ++m->comm_epoch;
-  if (m->coop_tail && !launch_tail_coop(m->dev, m->host.n_segments, m->host.rec_doubles, m->partial_dev, 2, *opts, out_dev, m->comm, m->comm_epoch, m->sm_count,
-                                        (cudaStream_t)stream)) {
-    m->coop_tail = false;
-    rc = run_tail_separate(m, 1, (cudaStream_t)stream);
-    if (rc != GWI_OK) return rc;
-  }
   // partial record, push to every rank, wait for every rank, combine: one launch
-  if (!m->coop_tail) launch_partial_tail(m->dev, m->partial_dev, m->plan.n_params, 2, *opts, out_dev, m->comm, m->comm_epoch, 1, (cudaStream_t)stream);
+  launch_partial_tail(m->dev, m->partial_dev, m->plan.n_params, 2, *opts, out_dev, m->comm, m->comm_epoch, 1, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return GWI_OK;
 }

@@ -149,7 +149,6 @@ struct ModelDev {
   // CTA-cooperative stream kernel (stream_cta.cuh): main warps per CTA (0 = the one-role kernel's geometry)
   int32_t cta_main_warps, cta_lead_doubles;  // cta_lead_doubles: header + linear slots + leading rows of a record (what a main warp writes)
   int32_t* tail_counter;  // arrival counter of partial_tail_kernel (zero between evaluations)
-  unsigned long long* coop_state;  // tail_coop_kernel: [0] grid-barrier arrival counter (only grows), [1] launches completed
 };
 
 // multi-GPU exchange (exchange_kernel): the exchange buffers of every rank as seen from this rank (peer

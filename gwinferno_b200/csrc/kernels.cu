@@ -18,9 +18,6 @@
 #include <cfloat>
 #include <cmath>
 
-#include <algorithm>
-#include <cstdlib>
-
 #include "dev_structs.h"
 
 // GWI_EXP_STAGE_DESC (on since round 2; =0 restores direct reads): the small kernels read dozens of ModelDev fields,
@@ -400,12 +397,6 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
 // a fixed order.  Level-0 records of the CTA-cooperative stream kernel are sparse by construction -- the NW main-warp
 // records of a chunk hold the header + leading rows, the chunk's last record holds the deep rows, everything else is
 // zero for ever -- so only the records that can be non-zero at element i are read.
-template <bool CG>
-__device__ __forceinline__ double ldd(const double* p) {
-  return CG ? __ldcg(p) : *p;
-}
-
-template <bool CG = false>
 __device__ __forceinline__ double reduce_element(const ModelDev& M, const ReduceTask& T, int i) {
   const int rec = M.rec_doubles;
   const double* __restrict__ in = T.src < 0 ? M.records0 : M.level_buf[T.src];
@@ -416,18 +407,18 @@ __device__ __forceinline__ double reduce_element(const ModelDev& M, const Reduce
     const int RPC = NW + 1;
     if (i >= M.cta_lead_doubles) {  // deep rows: only the last record of every chunk
       int k = 0;
-      for (int r = (NW + RPC - T.in_first % RPC) % RPC; r < T.in_count; r += RPC, k = (k + 1) & 7) a[k] += ldd<CG>(p + (size_t)r * rec);
+      for (int r = (NW + RPC - T.in_first % RPC) % RPC; r < T.in_count; r += RPC, k = (k + 1) & 7) a[k] += p[(size_t)r * rec];
     } else {  // header + leading rows: the main-warp records
       int ph = T.in_first % RPC, r = 0;
       for (; r + 8 <= T.in_count; r += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (ph != NW) a[k] += ldd<CG>(p + (size_t)(r + k) * rec);
+          if (ph != NW) a[k] += p[(size_t)(r + k) * rec];
           ph = ph == NW ? 0 : ph + 1;
         }
       }
       for (int k = 0; r + k < T.in_count; ++k) {
-        if (ph != NW) a[k] += ldd<CG>(p + (size_t)(r + k) * rec);
+        if (ph != NW) a[k] += p[(size_t)(r + k) * rec];
         ph = ph == NW ? 0 : ph + 1;
       }
     }
@@ -435,9 +426,9 @@ __device__ __forceinline__ double reduce_element(const ModelDev& M, const Reduce
     int r = 0;
     for (; r + 8 <= T.in_count; r += 8) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] += ldd<CG>(p + (size_t)(r + k) * rec);
+      for (int k = 0; k < 8; ++k) a[k] += p[(size_t)(r + k) * rec];
     }
-    for (int k = 0; r + k < T.in_count; ++k) a[k] += ldd<CG>(p + (size_t)(r + k) * rec);
+    for (int k = 0; r + k < T.in_count; ++k) a[k] += p[(size_t)(r + k) * rec];
   }
   return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
@@ -446,12 +437,15 @@ __device__ __forceinline__ double reduce_element(const ModelDev& M, const Reduce
 // at most 8 independent loads per thread, ONE memory round trip) and the partial sums are combined through shared memory in
 // the same fixed order as reduce_element's.  (A thread per element walking all 64 inputs needed 8 dependent rounds: ~20 us per
 // level whatever the number of tasks.)
-// all 256 threads of a block: elements [tile*32, tile*32+32) of task T of `level`
-template <bool CG>
-__device__ __forceinline__ void reduce_tile(const ModelDev& M, const ReduceTask& T, int level, int tile, double (*part)[33]) {
+__global__ void __launch_bounds__(256) reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
+  GWI_PDL_TRIGGER();
+  const ModelDev& M = Mp[blockIdx.z];  // blockIdx.z = chain
+  const ReduceTask T = M.level_tasks[level][blockIdx.x];  // (static data: read before the dependency wait)
   const int rec = M.rec_doubles;
   const int j = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int i = tile * 32 + j;
+  GWI_PDL_WAIT();  // the producer of the input records has completed
+  const int i = blockIdx.y * 32 + j;
+  __shared__ double part[8][33];
   double acc = 0.0;
   if (i < rec) {
     const double* __restrict__ in = T.src < 0 ? M.records0 : M.level_buf[T.src];
@@ -466,7 +460,7 @@ __device__ __forceinline__ void reduce_tile(const ModelDev& M, const ReduceTask&
       const int r = g + 8 * k;
       bool use = r < T.in_count;
       if (use && sparse) use = (((T.in_first + r) % RPC) == NW) == want_deep;
-      v[k] = use ? ldd<CG>(p + (size_t)r * rec) : 0.0;
+      v[k] = use ? p[(size_t)r * rec] : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc += v[k];
@@ -475,15 +469,6 @@ __device__ __forceinline__ void reduce_tile(const ModelDev& M, const ReduceTask&
   __syncthreads();
   if (g == 0 && i < rec)
     M.level_buf[level][(size_t)T.out_slot * rec + i] = ((part[0][j] + part[1][j]) + (part[2][j] + part[3][j])) + ((part[4][j] + part[5][j]) + (part[6][j] + part[7][j]));
-}
-
-__global__ void __launch_bounds__(256) reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
-  GWI_PDL_TRIGGER();
-  const ModelDev& M = Mp[blockIdx.z];  // blockIdx.z = chain
-  const ReduceTask T = M.level_tasks[level][blockIdx.x];  // (static data: read before the dependency wait)
-  __shared__ double part[8][33];
-  GWI_PDL_WAIT();  // the producer of the input records has completed
-  reduce_tile<false>(M, T, level, blockIdx.y, part);
 }
 
 __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict__ Mp) {
@@ -634,6 +619,10 @@ __global__ void export_kernel(const ModelDev* __restrict__ Mp, gwi_outputs out) 
 // =================================================================================================
 // likelihood: per-rank partial record, then the rank-ordered combine (analysis.py:257-319)
 // =================================================================================================
+template <bool CG>
+__device__ __forceinline__ double ldd(const double* p) {
+  return CG ? __ldcg(p) : *p;
+}
 
 // The rank's partial record.  Warp `gwarp` of `n_gwarps` takes the hyper-parameters gwarp, gwarp +
 // n_gwarps, ...; warp 0 also writes the header.  CG: the per-segment results were written by other
@@ -915,83 +904,6 @@ __global__ void __launch_bounds__(256) partial_tail_kernel(const ModelDev* __res
   exchange_wait_combine(M, C, stride, par, epoch, opts, out);
 }
 
-// The whole tail of a single-chain evaluation in ONE cooperative launch: record reduction levels, per-segment finish, partial
-// rows, combine / exchange, separated by grid-wide barriers (an arrival counter in global memory; every block of the grid is
-// resident -- cooperative launch).  Four dependent launches of ~8-15 us each become ~2 us barriers.  Same arithmetic in the
-// same order as reduce_kernel / finish_kernel / partial_tail_kernel (bitwise-equal results).  GPU only: the host emulator
-// runs the blocks of a grid one after the other and keeps the separate kernels, as do chain batches (too many blocks).
-__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1ull);
-#ifndef GWI_HOST_EMULATION
-    while (load_acquire_sys(counter) < target) __nanosleep(32);
-#endif
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) tail_coop_kernel(const ModelDev* __restrict__ Mp, double* recd, int tail, gwi_like_opts opts, double* out, CommDev C,
-                                                        unsigned long long epoch) {
-  GWI_STAGED_DESC(M, Mp[0]);
-  extern __shared__ double srec[];
-  __shared__ double part[8][33];
-  const unsigned long long G = gridDim.x;
-  // barrier targets: the counter only grows; launches_done (device memory, updated by block 0 at the very end) tells which
-  // generation this launch is -- it cannot change before every block has passed the last barrier
-  unsigned long long* const counter = M.coop_state;
-  const unsigned long long n_bar = (unsigned long long)(M.n_levels - 1) + 2ull;
-  unsigned long long target = __ldcg(M.coop_state + 1) * n_bar * G;
-  const int n_tiles = (M.rec_doubles + 31) / 32;
-  for (int level = 0; level + 1 < M.n_levels; ++level) {
-    const int units = M.level_ntasks[level] * n_tiles;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const ReduceTask T = M.level_tasks[level][u / n_tiles];
-      reduce_tile<true>(M, T, level, u % n_tiles, part);
-      __syncthreads();  // `part` is reused
-    }
-    target += G;
-    grid_barrier(counter, target);
-  }
-  {
-    const ReduceTask* __restrict__ tasks = M.level_tasks[M.n_levels - 1];
-    for (int s = blockIdx.x; s < M.n_segments; s += gridDim.x) {
-      const ReduceTask T = tasks[s];
-      for (int i = threadIdx.x; i < M.rec_doubles; i += blockDim.x) srec[i] = reduce_element<true>(M, T, i);
-      __syncthreads();
-      if (s == 0 && threadIdx.x == 0) {
-        M.slice_counter[0] = 0;
-        M.slice_counter[1] = 0;
-      }
-      finish_segment(M, s, srec);
-      __syncthreads();  // `srec` is reused
-    }
-    target += G;
-    grid_barrier(counter, target);
-  }
-  partial_rows<true>(M, recd, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5));
-  target += G;
-  grid_barrier(counter, target);
-  if (blockIdx.x != 0) return;
-  if (threadIdx.x == 0) M.coop_state[1] = __ldcg(M.coop_state + 1) + 1ull;  // next launch's generation
-  const int P = M.n_params, stride = PR_HEADER + 3 * P;
-  if (tail == 1) {
-    combine_records<true>(M, recd, 1, opts, out);
-    return;
-  }
-  const int par = (int)(epoch & 1ull);
-  for (int b = 0; b < C.n_ranks; ++b) {
-    double* dst = C.peer_slots[b] + (size_t)(par * C.n_ranks + C.rank) * stride;
-    for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[i] = __ldcg(recd + i);
-  }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < C.n_ranks) store_release_sys(C.peer_flags[threadIdx.x] + par * C.n_ranks + C.rank, epoch);
-  exchange_wait_combine(M, C, stride, par, epoch, opts, out);
-}
-
 // =================================================================================================
 // host-side launch helpers (called from api.cu)
 // =================================================================================================
@@ -1023,32 +935,6 @@ void launch_exchange(const ModelDev* Md, const double* rec_local, const CommDev&
 void launch_partial_tail(const ModelDev* Md, double* rec, int n_params, int tail, const gwi_like_opts& o, double* out, const CommDev& C, unsigned long long epoch, int nc,
                          cudaStream_t st) {
   GWI_LAUNCH_PDL(partial_tail_kernel, dim3((n_params + 7) / 8, nc), 256, 0, st)(Md, rec, tail, o, out, C, epoch);
-}
-// returns false when the cooperative tail cannot be used (emulator, driver refusal): the caller launches the separate kernels
-bool launch_tail_coop(const ModelDev* Md, int n_seg, int rec_doubles, double* rec, int tail, const gwi_like_opts& o, double* out, const CommDev& C, unsigned long long epoch,
-                      int sm_count, cudaStream_t st) {
-#ifdef GWI_HOST_EMULATION
-  return false;
-#else
-  static int max_per_sm = -1;
-  const size_t smem = (size_t)rec_doubles * sizeof(double);
-  if (max_per_sm < 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, tail_coop_kernel, 256, smem) != cudaSuccess) max_per_sm = 0;
-    cudaGetLastError();
-  }
-  if (max_per_sm <= 0) return false;
-  int G = std::max(n_seg, 2 * sm_count);
-  G = std::min(G, max_per_sm * sm_count);
-  gwi_like_opts oo = o;
-  CommDev CC = C;
-  void* args[] = {(void*)&Md, (void*)&rec, (void*)&tail, (void*)&oo, (void*)&out, (void*)&CC, (void*)&epoch};
-  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)tail_coop_kernel, dim3(G), dim3(256), args, smem, st);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return true;
-#endif
 }
 void launch_combine(const ModelDev* Md, const double* recs, int R, const gwi_like_opts& o, double* out, int nc, cudaStream_t st) {
   GWI_LAUNCH(combine_kernel, nc, 256, 0, st)(Md, recs, R, o, out);
