@@ -287,12 +287,15 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     for (int d = 0; d < MAX_SPLINE_DIMS; ++d) {
       if (d >= M.n_dims) break;
       const DimDev& D = M.dims[d];
+      // all rows with a predicate (independent shared-memory loads, pipelined) instead of a find-first-set walk over the
+      // occupied pieces (a dependent chain of up to ~330 shared-memory round trips per segment)
       double mx = -INFINITY;
-      unsigned long long occ = occ_all[d];
-      while (occ) {
-        const int J = __ffsll((long long)occ) - 1;
-        occ &= occ - 1;
-        mx = fmax(mx, ub_s[D.row_off + J]);
+      const unsigned long long occ = occ_all[d];
+      const double* ub = ub_s + D.row_off;
+#pragma unroll 8
+      for (int J = 0; J < D.rows; ++J) {
+        const double v = ub[J];
+        if ((occ >> J) & 1ull) mx = fmax(mx, v);
       }
       if (mx > -INFINITY) sh += mx;
     }

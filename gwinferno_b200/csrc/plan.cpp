@@ -796,7 +796,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     {
       int64_t n_valid_all = 0;
       for (int s = 0; s < n_seg; ++s) n_valid_all += (int64_t)order[s].size();
-      want_cta = n_valid_all < 16000000 || desc.batch_hint > 1;  // crossover of the two linear fits t(N) measured on cfg3 shards: ~1.5e7 samples
+      want_cta = n_valid_all < 24000000 || desc.batch_hint > 1;  // between cfg5 (2.2e7: CTA 0.467 vs 0.481 ms) and a 4-way cfg3 shard (2.6e7: one-role by the linear fits)
       if (const char* e = std::getenv("GWI_CTA_KERNEL")) want_cta = e[0] != '0';
       bool ok = !plan.g2 && (int)plan.kops.size() == plan.n_lin && plan.n_lin <= 2;
       for (const SplineDim& D : plan.dims) ok = ok && !D.liny;
