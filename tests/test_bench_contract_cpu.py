@@ -23,6 +23,12 @@ def test_reference_arm_prints_one_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "samples" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # both arms describe the workload with the SAME config object (the driver compares them key by key)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    ours = bench._config("cfg2", "bspline", 70, 4000, 500000, cb["n_params"], 1, 1, "bucket", bench._l2_policy("cfg2"))
+    assert d["config"] == ours
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():
