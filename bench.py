@@ -362,7 +362,13 @@ def run_ours(args):
     kt = mdl.stream_times_ms(min(64, args.steps))
     mdl.set_timing(False)
     res = (out_chain[: capi.GWI_LIKE_HEADER + P] if chains > 1 else out).cpu().numpy()
+    per_rank = None
     if world > 1:
+        # per-rank spread (the exchange makes every rank wait for the slowest one): own timed loop, own stream kernel, own shard
+        mine = {"rank": rank, "ms_per_step": ms / args.steps, "kernel_ms": float(np.mean(kt)) if len(kt) else None,
+                "samples": int(info["n_samples_pe"] + info["n_samples_inj"])}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
@@ -442,6 +448,7 @@ def run_ours(args):
         "clocks": clocks,
         "result": {"log_l": float(res[0]), "passed": float(res[1]), "status": float(res[7])},
         "setup_s": {"generate": t_gen, "plan_build_and_upload": t_plan},
+        "per_rank": per_rank,
         "plan": {k: info[k] for k in ("n_valid_pe", "n_valid_inj", "n_padded", "n_chunks", "n_stream_columns", "n_spline_dims", "n_deep", "grid_blocks", "block_threads")},
         # tuning switches in effect (all default off: 0 / empty in the product configuration)
         "switches": {"active": info["active_switches"], "library": os.path.basename(capi.LIB_PATH),
