@@ -909,15 +909,54 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   const int64_t per_warp = (total_steps + W - 1) / W;
   int64_t L = roundQ(std::max<int64_t>(per_warp < 64 ? 32 : 64, std::min<int64_t>(768, per_warp / 4)));
   L = std::max<int64_t>(L, 8 * Q);
+  bool fixed_L = false;  // one slice per CTA: no guided shrink
   if (plan.cta_mode) {
     // a slice is L steps of ALL main warps of a CTA: >= ~4 slices per CTA for the dynamic balance, but never
     // fewer slices than CTAs on a small catalog
-    int64_t div = 4;
+    // r02 sweeps (B200, ms/step at div = 1 / 2 / 3 / 4): 8-way cfg3 shard 0.390 / 0.327 / 0.325 / 0.331, cfg5 - / 0.531 / 0.539 / 0.539
+    int64_t div = 2;
     if (const char* e = std::getenv("GWI_TUNE_SLICE_DIV")) div = std::max(1, std::atoi(e));
     L = roundQ(std::min<int64_t>(768, std::max<int64_t>(16, per_warp / div)));
     if (L > per_warp) L = roundQ(std::max<int64_t>(Q, per_warp));
+    // Small catalogs (a few blocks per warp: the kernel is latency, not throughput): every slice costs a counter round trip,
+    // a pipeline fill and a record flush, so give every CTA exactly ONE slice -- the shortest L whose slice count still fits
+    // the grid (cfg2, 70 events of 18 steps + 2232 injection steps on 148 CTAs: L = 30 -> 145 slices / 145 chunks instead of
+    // L = 16 -> 280 chunks, where every event was cut into a 16-step and a 2-step chunk).  GWI_TUNE_ONE_SLICE=0 disables.
+    bool one_slice = per_warp < 64;
+    if (const char* e = std::getenv("GWI_TUNE_ONE_SLICE")) one_slice = one_slice && e[0] != '0';
+    if (one_slice) {
+      auto n_slices_for = [&](int64_t Lt) {
+        int64_t slices = 1, fill_t = 0;
+        for (int si = 0; si < n_seg; ++si) {
+          const int sg = (si + 1) % n_seg;
+          int64_t left = plan.segments[sg].n_valid;
+          bool first = true;
+          while (left > 0) {
+            const int64_t want = roundQ((left + LPC - 1) / LPC);
+            if (Lt - fill_t < Q || (first && fill_t > 0 && want > Lt - fill_t)) {
+              ++slices;
+              fill_t = 0;
+            }
+            const int64_t steps = std::min<int64_t>(Lt - fill_t, want);
+            left -= std::min<int64_t>(left, steps * LPC);
+            fill_t += steps;
+            first = false;
+          }
+        }
+        return slices;
+      };
+      for (int64_t Lt = roundQ(std::max<int64_t>(Q, per_warp)); Lt <= 4 * per_warp + 4 * Q; Lt += Q)
+        if (n_slices_for(Lt) <= W) {
+          L = Lt;
+          fixed_L = true;
+          break;
+        }
+    }
   }
-  if (desc.chunk_steps > 0) L = roundQ(desc.chunk_steps);  // explicit slice length (tests force tiny slices)
+  if (desc.chunk_steps > 0) {  // explicit slice length (tests force tiny slices)
+    L = roundQ(desc.chunk_steps);
+    fixed_L = false;
+  }
   plan.chunk_steps = (int)L;
   std::vector<int64_t> chunk_r0, chunk_nc;  // first sorted rank / valid samples of every chunk
   plan.slice_begin.clear();
@@ -938,7 +977,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   // r02 measurements (B200): DIV 1 / LMIN 32 instead of 2 / 8 cut the chunks of an 8-way cfg3 shard from 10 044 to 5 764 and its
   // stream kernel from 0.427 to 0.372 ms, the full catalog from 15 167 to 8 477 chunks and 1.807 to 1.752 ms (fewer record
   // flushes and records to reduce; the tail stays short because the final slices are still small)
-  const int64_t L_MIN = roundQ(env_int("GWI_TUNE_LMIN", 32, Q, 1024));
+  const int64_t L_MIN = fixed_L ? L : roundQ(env_int("GWI_TUNE_LMIN", 32, Q, 1024));
   const int64_t GUIDED_DIV = env_int("GWI_TUNE_GUIDED_DIV", 1, 1, 16);  // slice = remaining / (DIV * W)
   int64_t done_steps = 0;
   int64_t pos = 0, fill = 0;
