@@ -184,7 +184,7 @@ def parity_at_size(name, scale, lam, res, world):
             "seconds": time.perf_counter() - t0}
 
 
-def nuts_block(device):
+def nuts_block(device, n_chains=8):
     """The second half of BASELINE.json's metric: NUTS ESS/s on configs[1] (70 x 4000 + 5e5 injections, 164 free parameters),
     the whole sampler loop in native code (csrc/nuts.cpp: multinomial NUTS, windowed adaptation, dense mass matrix -- NumPyro's
     NUTS(dense_mass=True) in spirit) around gwi_loglike_host; priors of examples/simple_bspline_example.py.  The CPU row is the
@@ -206,6 +206,26 @@ def nuts_block(device):
     wall = time.perf_counter() - t0
     eng.model.close()
     ess = np.array([nuts.effective_sample_size(samples[:, i]) for i in range(samples.shape[1])])
+    # the same sampler, K chains advanced together: one batched evaluation (gwi_loglike_batch_host) per round of leapfrog
+    # steps -- the reference's MCMC(chain_method="vectorized") on one GPU.  ESS = sum of the per-chain ESS.
+    chains_obj = None
+    if n_chains > 1:
+        engK = PopulationLikelihood(low, const["total_inj"], device=device, batch_hint=n_chains)
+        th0 = 0.1 * np.random.default_rng(1).standard_normal((n_chains, dim))
+        t0 = time.perf_counter()
+        sK, infK = nuts.nuts_native_chains(engK, blocks, th0, n_warm, n_samp, Nobs=const["E"], seed=100, max_depth=8, flags=flags)
+        wallK = time.perf_counter() - t0
+        engK.model.close()
+        essK = np.array([sum(nuts.effective_sample_size(sK[c, :, i]) for c in range(n_chains)) for i in range(dim)])
+        rhat = np.array([nuts.split_rhat(sK[:, :, i]) for i in range(dim)])
+        t_samp = max(i["sampling_seconds"] for i in infK)
+        chains_obj = {"n_chains": n_chains, "warmup": n_warm, "samples_per_chain": n_samp,
+                      "driver": "gwi_nuts_sample_posterior_chains: one host thread per chain, one gwi_loglike_batch_host call per round of leapfrog steps (model built with batch_hint = n_chains)",
+                      "ess_min": float(essK.min()), "ess_median": float(np.median(essK)), "ess_min_per_s": float(essK.min() / t_samp),
+                      "ess_median_per_s": float(np.median(essK) / t_samp), "ess_min_per_wall_s": float(essK.min() / wallK),
+                      "grad_evals_per_s": float(sum(i["leapfrogs_sampling"] for i in infK) / t_samp), "split_rhat_max": float(np.nanmax(rhat)),
+                      "mean_accept": float(np.mean([i["mean_accept"] for i in infK])), "step_size": [float(i["step_size"]) for i in infK],
+                      "sampling_seconds": float(t_samp), "wall_s": wallK}
     cores = os.cpu_count() or 1
     c_oracle.evaluate(low.spec, low.pe_cols, low.inj_cols, const["total_inj"], lam0, want_jac=True, want_neff_jac=False, n_threads=cores)
     t0 = time.perf_counter()
@@ -218,7 +238,7 @@ def nuts_block(device):
             "sampler": "csrc/nuts.cpp: multinomial NUTS + windowed adaptation + dense mass (flags 7), likelihood+gradient via gwi_loglike_host",
             "ess_min": float(ess.min()), "ess_median": float(np.median(ess)), "ess_min_per_s": float(ess.min() / info["sampling_seconds"]),
             "ess_median_per_s": float(np.median(ess) / info["sampling_seconds"]), "grad_evals_per_s": float(gpu_rate), "mean_accept": info["mean_accept"],
-            "step_size": info["step_size"], "wall_s": wall,
+            "step_size": info["step_size"], "wall_s": wall, "chains": chains_obj,
             "cpu": {"grad_evals_per_s": float(cpu_rate), "cores": cores, "kind": "port (oracle/c/gwi_oracle.c), priced not run: the same chain at this evaluation rate",
                     "ess_min_per_s": float(ess.min() / (info["leapfrogs_sampling"] / cpu_rate)), "ess_median_per_s": float(np.median(ess) / (info["leapfrogs_sampling"] / cpu_rate))}}
 
@@ -461,7 +481,7 @@ def run_ours(args):
         # WHOLE catalog (rank 0 regenerates it when the run is sharded), same Lambda
         line["parity_at_size"] = parity_at_size(name, args.scale, lams[n_steps - 1], res, world)
     if world == 1 and not args.no_cpu_baseline and not args.no_nuts:
-        line["nuts"] = nuts_block(local)
+        line["nuts"] = nuts_block(local, args.nuts_chains)
     emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -497,6 +517,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink S and I (testing only; the reported config then differs from BASELINE's)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline, parity_at_size, nuts): tuning runs")
     ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS ESS/s block")
+    ap.add_argument("--nuts-chains", type=int, default=8, help="chains of the multi-chain NUTS run (advanced together, batched evaluations); 1 = skip it")
     ap.add_argument("--flush-l2", action="store_true", help="cold numbers: evict L2 between steps (for the L2-resident configurations)")
     ap.add_argument("--emulate-world", type=int, default=1, help="tuning aid: run rank 0's shard of a W-way partition on one GPU")
     ap.add_argument("--shard-by", default="bucket", choices=["bucket", "index"], help="multi-GPU partition of the found injections")

@@ -149,6 +149,7 @@ SYMBOLS = [
     "gwi_loglike",
     "gwi_loglike_host",
     "gwi_loglike_batch",
+    "gwi_loglike_batch_host",
     "gwi_partial_size",
     "gwi_partial",
     "gwi_combine",
@@ -167,6 +168,7 @@ SYMBOLS = [
     "gwi_posterior_dim",
     "gwi_posterior_potential",
     "gwi_nuts_sample_posterior",
+    "gwi_nuts_sample_posterior_chains",
 ]
 
 _lib = None
@@ -225,6 +227,8 @@ def load_library(_allow_emulator=False):
     lib.gwi_posterior_potential.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.gwi_posterior_potential.restype = C.c_double
     lib.gwi_nuts_sample_posterior.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(gwi_nuts_opts), C.POINTER(C.c_double), C.POINTER(gwi_nuts_info)]
+    lib.gwi_nuts_sample_posterior_chains.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(gwi_nuts_opts), C.POINTER(C.c_double), C.POINTER(gwi_nuts_info)]
+    lib.gwi_loglike_batch_host.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.POINTER(gwi_like_opts), C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -604,6 +608,18 @@ class Model:
         out_d.free()
         return out[:, 0].copy(), out[:, GWI_LIKE_HEADER:].copy(), out[:, :GWI_LIKE_HEADER].copy()
 
+    def loglike_batch_host(self, lams, Nobs, marginalize_selection=False, min_neff_cut=True, max_variance_cut=False):
+        """gwi_loglike_batch_host over ``lams[n_chains, P]``: one call, host buffers in and out (graph-replayed per batch
+        size).  Returns ``(log_l[n], grad[n, P], header[n, GWI_LIKE_HEADER])``."""
+        lams = np.ascontiguousarray(lams, dtype=np.float64)
+        n, P = lams.shape
+        if P != self.n_params:
+            raise ValueError(f"expected {self.n_params} hyper-parameters per chain, got {P}")
+        out = np.empty((n, GWI_LIKE_HEADER + P), dtype=np.float64)
+        o = gwi_like_opts(int(Nobs), int(marginalize_selection), int(min_neff_cut), int(max_variance_cut))
+        _check(load_library().gwi_loglike_batch_host(self.handle, _dptr(lams), n, C.byref(o), _dptr(out)))
+        return out[:, 0].copy(), out[:, GWI_LIKE_HEADER:].copy(), out[:, :GWI_LIKE_HEADER].copy()
+
     def close(self):
         if getattr(self, "handle", None):
             self._owner.gwi_model_destroy(self.handle)
@@ -682,6 +698,19 @@ class Posterior:
         o = _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept, flags)
         _check(self._owner.gwi_nuts_sample_posterior(self.handle, _dptr(theta0), C.byref(o), _dptr(samples), C.byref(info)))
         return samples, _nuts_info(info)
+
+    def sample_chains(self, theta0, n_warmup, n_samples, seed=0, target_accept=0.8, max_depth=8, flags=0):
+        """``theta0[n_chains, dim]`` -> ``(samples[n_chains, n_samples, dim], [info per chain])``: the chains advance together,
+        one batched likelihood call per round of leapfrog steps (gwi_nuts_sample_posterior_chains; chain c = ``sample`` with
+        ``seed + c``).  Build the model with ``batch_hint = n_chains``."""
+        theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
+        assert theta0.ndim == 2 and theta0.shape[1] == self.dim
+        K = theta0.shape[0]
+        samples = np.empty((K, int(n_samples), self.dim), dtype=np.float64)
+        infos = (gwi_nuts_info * K)()
+        o = _nuts_opts(n_warmup, n_samples, max_depth, seed, target_accept, flags)
+        _check(self._owner.gwi_nuts_sample_posterior_chains(self.handle, K, _dptr(theta0), C.byref(o), _dptr(samples), infos))
+        return samples, [_nuts_info(infos[c]) for c in range(K)]
 
     def close(self):
         if getattr(self, "handle", None):

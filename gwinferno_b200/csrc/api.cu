@@ -10,6 +10,7 @@
 #include <exception>
 #include <new>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "dev_structs.h"
@@ -98,6 +99,14 @@ struct gwi_model {
   double* partial_dev = nullptr;
   double* lam_pinned = nullptr;
   double* out_pinned = nullptr;
+  // gwi_loglike_batch_host: staging for `batch_cap` chains and one captured graph per batch size in use
+  int batch_cap = 0;
+  double* lam_pinned_b = nullptr;
+  double* out_pinned_b = nullptr;
+  double* lam_dev_b = nullptr;
+  double* out_dev_b = nullptr;
+  std::map<int, cudaGraphExec_t> batch_graphs;
+  gwi_like_opts batch_graph_opts{};
   cudaStream_t own_stream = nullptr;
   cudaStream_t aux_stream = nullptr;  // grid normalisers run here, concurrently with the stream kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -401,6 +410,10 @@ void gwi_model_destroy(gwi_model* m) {
   for (void* p : m->allocs) cudaFree(p);
   if (m->lam_pinned) cudaFreeHost(m->lam_pinned);
   if (m->out_pinned) cudaFreeHost(m->out_pinned);
+  if (m->lam_pinned_b) cudaFreeHost(m->lam_pinned_b);
+  if (m->out_pinned_b) cudaFreeHost(m->out_pinned_b);
+  for (auto& g : m->batch_graphs)
+    if (g.second) cudaGraphExecDestroy(g.second);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -1048,6 +1061,96 @@ int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opt
     return GWI_ERR_RANGE;
   }
   return GWI_OK;
+}
+
+int gwi_loglike_batch_host(gwi_model* m, const double* lambda_host, int32_t n_chains, const gwi_like_opts* opts, double* out_host) {
+  if (!m || !lambda_host || !out_host || !opts || n_chains < 1 || n_chains > 65535) {
+    set_error("bad argument (1 <= n_chains <= 65535)");
+    return GWI_ERR_INVALID;
+  }
+  const int P = m->plan.n_params;
+  const size_t row_out = (size_t)GWI_LIKE_HEADER + P;
+  if (n_chains == 1) return gwi_loglike_host(m, lambda_host, opts, out_host);
+  CUDA_TRY(cudaSetDevice(m->device));
+  if (n_chains > m->batch_cap) {
+    // staging grows to the largest batch seen (the old, smaller device buffers stay in m->allocs until destroy)
+    for (auto& g : m->batch_graphs)
+      if (g.second) cudaGraphExecDestroy(g.second);
+    m->batch_graphs.clear();
+    if (m->lam_pinned_b) cudaFreeHost(m->lam_pinned_b);
+    if (m->out_pinned_b) cudaFreeHost(m->out_pinned_b);
+    m->lam_pinned_b = m->out_pinned_b = nullptr;
+    m->batch_cap = 0;
+    if (cudaMallocHost((void**)&m->lam_pinned_b, sizeof(double) * P * n_chains) != cudaSuccess ||
+        cudaMallocHost((void**)&m->out_pinned_b, sizeof(double) * row_out * n_chains) != cudaSuccess) {
+      set_error("cudaMallocHost failed");
+      return GWI_ERR_ALLOC;
+    }
+    int rc = upload<double>(m, nullptr, (size_t)P * n_chains, &m->lam_dev_b);
+    if (rc != GWI_OK) return rc;
+    rc = upload<double>(m, nullptr, row_out * n_chains, &m->out_dev_b);
+    if (rc != GWI_OK) return rc;
+    m->batch_cap = n_chains;
+  }
+  {
+    const int rc = ensure_chains(m, n_chains);  // (outside any capture: it allocates)
+    if (rc != GWI_OK) return rc;
+  }
+  std::memcpy(m->lam_pinned_b, lambda_host, sizeof(double) * P * n_chains);
+  const bool want_graph = m->use_graph && !m->timing && !m->force_exact_shift;
+  if (want_graph && !m->batch_graphs.empty() && std::memcmp(&m->batch_graph_opts, opts, sizeof(gwi_like_opts)) != 0) {
+    for (auto& g : m->batch_graphs)
+      if (g.second) cudaGraphExecDestroy(g.second);
+    m->batch_graphs.clear();
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (want_graph) {
+    auto it = m->batch_graphs.find(n_chains);
+    if (it != m->batch_graphs.end()) {
+      exec = it->second;
+    } else if (m->batch_graphs.size() < 64) {
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(m->own_stream, cudaStreamCaptureModeThreadLocal));
+      cudaMemcpyAsync(m->lam_dev_b, m->lam_pinned_b, sizeof(double) * P * n_chains, cudaMemcpyHostToDevice, m->own_stream);
+      const int rc_cap = gwi_loglike_batch(m, m->lam_dev_b, n_chains, opts, m->out_dev_b, m->own_stream);
+      cudaMemcpyAsync(m->out_pinned_b, m->out_dev_b, sizeof(double) * row_out * n_chains, cudaMemcpyDeviceToHost, m->own_stream);
+      const cudaError_t e_end = cudaStreamEndCapture(m->own_stream, &graph);
+      bool ok = rc_cap == GWI_OK && e_end == cudaSuccess && graph != nullptr;
+      if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok) {
+        cudaGetLastError();
+        exec = nullptr;
+        m->use_graph = false;  // eager launches from now on (same results)
+      } else {
+        m->batch_graphs[n_chains] = exec;
+        m->batch_graph_opts = *opts;
+      }
+    }
+  }
+  if (exec) {
+    CUDA_TRY(cudaGraphLaunch(exec, m->own_stream));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(m->lam_dev_b, m->lam_pinned_b, sizeof(double) * P * n_chains, cudaMemcpyHostToDevice, m->own_stream));
+    const int rc = gwi_loglike_batch(m, m->lam_dev_b, n_chains, opts, m->out_dev_b, m->own_stream);
+    if (rc != GWI_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(m->out_pinned_b, m->out_dev_b, sizeof(double) * row_out * n_chains, cudaMemcpyDeviceToHost, m->own_stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(m->own_stream));
+  std::memcpy(out_host, m->out_pinned_b, sizeof(double) * row_out * n_chains);
+  // a chain whose a-priori shift bound was too loose (status != 0) is repeated alone: the single-chain call falls back to
+  // the exact per-segment maximum; GWI_ERR_RANGE only if that fails too (the chain's row then keeps its non-zero status)
+  int rc_all = GWI_OK;
+  for (int c = 0; c < n_chains; ++c) {
+    double* row = out_host + (size_t)c * row_out;
+    if (row[GWI_LIKE_STATUS] == 0.0) continue;
+    const int rc = gwi_loglike_host(m, lambda_host + (size_t)c * P, opts, row);
+    if (rc == GWI_ERR_RANGE)
+      rc_all = GWI_ERR_RANGE;
+    else if (rc != GWI_OK)
+      return rc;
+  }
+  return rc_all;
 }
 
 int gwi_model_set_exact_shift(gwi_model* m, int32_t on) {

@@ -287,32 +287,24 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     for (int d = 0; d < MAX_SPLINE_DIMS; ++d) {
       if (d >= M.n_dims) break;
       const DimDev& D = M.dims[d];
-      // Maximum of the piece bounds over the OCCUPIED pieces.  Narrow segments (single events: a handful of pieces) walk the
-      // set bits four at a time -- the bit extraction is ALU-only, the four shared-memory loads are independent; wide ones
-      // (the injection set: most pieces) read ALL rows with a predicate, unrolled.  Measured prologue (eager, us): one-at-a-
-      // time walk cfg3 27.5 / cfg2 21.1, all rows 47.8 / 18.1, four at a time 29.1 / 21.5.
+      // Maximum of the piece bounds over the OCCUPIED pieces: walk the set bits four at a time -- the bit extraction is
+      // ALU-only, the four shared-memory loads are independent.  Measured prologue (eager, us, cfg3 / cfg2): one-at-a-time
+      // walk 27.5 / 21.1, ALL rows with a predicate 47.8 / 18.1, four at a time 29.1 / 21.5, width-adaptive mix 74.2 / 21.6
+      // (divergence inside the injection segment's warp).
       double mx = -INFINITY;
       unsigned long long occ = occ_all[d];
       const double* ub = ub_s + D.row_off;
-      if (2 * __popcll(occ) > D.rows) {
-#pragma unroll 8
-        for (int J = 0; J < D.rows; ++J) {
-          const double v = ub[J];
-          if ((occ >> J) & 1ull) mx = fmax(mx, v);
-        }
-      } else {
-        while (occ) {
-          const int J0 = __ffsll((long long)occ) - 1;
-          occ &= occ - 1;
-          const int J1 = occ ? __ffsll((long long)occ) - 1 : J0;
-          occ &= occ - 1;
-          const int J2 = occ ? __ffsll((long long)occ) - 1 : J0;
-          occ &= occ - 1;
-          const int J3 = occ ? __ffsll((long long)occ) - 1 : J0;
-          occ &= occ - 1;
-          const double v0 = ub[J0], v1 = ub[J1], v2 = ub[J2], v3 = ub[J3];
-          mx = fmax(fmax(mx, fmax(v0, v1)), fmax(v2, v3));
-        }
+      while (occ) {
+        const int J0 = __ffsll((long long)occ) - 1;
+        occ &= occ - 1;
+        const int J1 = occ ? __ffsll((long long)occ) - 1 : J0;
+        occ &= occ - 1;
+        const int J2 = occ ? __ffsll((long long)occ) - 1 : J0;
+        occ &= occ - 1;
+        const int J3 = occ ? __ffsll((long long)occ) - 1 : J0;
+        occ &= occ - 1;
+        const double v0 = ub[J0], v1 = ub[J1], v2 = ub[J2], v3 = ub[J3];
+        mx = fmax(fmax(mx, fmax(v0, v1)), fmax(v2, v3));
       }
       if (mx > -INFINITY) sh += mx;
     }

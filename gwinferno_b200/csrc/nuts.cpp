@@ -15,6 +15,7 @@
 // diagonal mass matrix estimated once in the middle of warm-up -- the same as gwinferno_b200/nuts.py
 // (the NumPy implementation, kept as the readable specification and cross-check).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -22,6 +23,8 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <system_error>
+#include <thread>
 #include <vector>
 
 #include "gwi_internal.h"
@@ -690,40 +693,51 @@ void gwi_posterior_destroy(gwi_posterior* p) { delete p; }
 
 int gwi_posterior_dim(const gwi_posterior* p) { return p ? p->dim : (int)GWI_ERR_INVALID; }
 
-// matches gwi_potential_fn (ctx = the gwi_posterior); +inf where the likelihood's cuts fail (the
-// reference's nan_to_num(-inf) sentinel, analysis.py:272-277) or the evaluation reports an error
-double gwi_posterior_potential(void* ctx, const double* theta, double* grad) {
-  gwi_posterior* p = static_cast<gwi_posterior*>(ctx);
+// theta -> Lambda: the free slots, everything else 0
+static void posterior_fill_lambda(const gwi_posterior* p, const double* theta, double* lam) {
+  std::fill(lam, lam + p->n_params, 0.0);
+  for (int i = 0; i < p->dim; ++i) lam[p->free_slot[i]] = theta[i];
+}
+
+// (Lambda, likelihood row) -> potential and its gradient in theta; `gp`: n_params doubles of scratch
+static double posterior_finish(const gwi_posterior* p, const double* lam, const double* out, double* gp, double* grad) {
   const double inf = std::numeric_limits<double>::infinity();
-  std::fill(p->lam.begin(), p->lam.end(), 0.0);
-  for (int i = 0; i < p->dim; ++i) p->lam[p->free_slot[i]] = theta[i];
-  ++p->n_evals;
-  const int rc = gwi_loglike_host(p->model, p->lam.data(), &p->opts, p->out.data());
   for (int i = 0; i < p->dim; ++i) grad[i] = 0.0;
-  if (rc != GWI_OK) {
-    if (rc != GWI_ERR_RANGE) p->last_rc = rc;
-    return inf;
-  }
-  const double log_l = p->out[GWI_LIKE_LOG_L];
+  const double log_l = out[GWI_LIKE_LOG_L];
   if (!std::isfinite(log_l) || log_l < -1e300) return inf;
   double lp = 0.0;
-  std::fill(p->gp.begin(), p->gp.end(), 0.0);
+  std::fill(gp, gp + p->n_params, 0.0);
   for (const auto& B : p->blocks) {
-    const double* c = p->lam.data() + B.first;
+    const double* c = lam + B.first;
     const int n = B.count;
     for (int i = 0; i < n; ++i) {
       double qc = 0.0;
       const double* row = B.Q.data() + (size_t)i * n;
       for (int j = 0; j < n; ++j) qc += row[j] * c[j];
       lp -= 0.5 * c[i] * qc;
-      p->gp[B.first + i] -= qc;
+      gp[B.first + i] -= qc;
     }
   }
   for (int i = 0; i < p->dim; ++i) {
     const int s = p->free_slot[i];
-    grad[i] = -(p->out[GWI_LIKE_HEADER + s] + p->gp[s]);
+    grad[i] = -(out[GWI_LIKE_HEADER + s] + gp[s]);
   }
   return -(log_l + lp);
+}
+
+// matches gwi_potential_fn (ctx = the gwi_posterior); +inf where the likelihood's cuts fail (the
+// reference's nan_to_num(-inf) sentinel, analysis.py:272-277) or the evaluation reports an error
+double gwi_posterior_potential(void* ctx, const double* theta, double* grad) {
+  gwi_posterior* p = static_cast<gwi_posterior*>(ctx);
+  posterior_fill_lambda(p, theta, p->lam.data());
+  ++p->n_evals;
+  const int rc = gwi_loglike_host(p->model, p->lam.data(), &p->opts, p->out.data());
+  if (rc != GWI_OK) {
+    for (int i = 0; i < p->dim; ++i) grad[i] = 0.0;
+    if (rc != GWI_ERR_RANGE) p->last_rc = rc;
+    return std::numeric_limits<double>::infinity();
+  }
+  return posterior_finish(p, p->lam.data(), p->out.data(), p->gp.data(), grad);
 }
 
 int gwi_nuts_sample_posterior(gwi_posterior* p, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info) {
@@ -737,6 +751,141 @@ int gwi_nuts_sample_posterior(gwi_posterior* p, const double* theta0, const gwi_
   if (info) info->n_evals = p->n_evals - before;
   if (rc != GWI_OK) return rc;
   return p->last_rc;  // a CUDA / argument error inside an evaluation surfaces here
+}
+
+// ---- several chains advanced together (one batched likelihood call per round of leapfrog steps) ----
+namespace {
+enum : int { CH_RUNNING = 0, CH_PENDING = 1, CH_READY = 2, CH_ENDED = 3 };
+struct ChainShared {
+  gwi_posterior* p = nullptr;
+  int K = 0;
+  size_t row_out = 0;
+  std::vector<double> lam, out;     // [K][P], [K][row_out]: one row per chain
+  std::vector<std::atomic<int>> state;
+  std::vector<int> rc_eval;         // result code of the chain's last evaluation (written before CH_READY)
+  std::atomic<int> fatal{GWI_OK};   // a CUDA / argument error: no more evaluations, every potential is +inf from then on
+  explicit ChainShared(int k) : K(k), state(k), rc_eval(k, GWI_OK) {
+    for (auto& s : state) s.store(CH_RUNNING);
+  }
+};
+struct ChainCtx {
+  ChainShared* sh;
+  int c;
+  std::vector<double> gp;
+  int64_t n_evals = 0;
+};
+double chain_potential(void* ctx, const double* theta, double* grad) {
+  ChainCtx* x = static_cast<ChainCtx*>(ctx);
+  ChainShared& S = *x->sh;
+  const gwi_posterior* p = S.p;
+  const double inf = std::numeric_limits<double>::infinity();
+  double* lam = S.lam.data() + (size_t)x->c * p->n_params;
+  posterior_fill_lambda(p, theta, lam);
+  ++x->n_evals;
+  if (S.fatal.load(std::memory_order_acquire) != GWI_OK) {
+    for (int i = 0; i < p->dim; ++i) grad[i] = 0.0;
+    return inf;
+  }
+  S.state[x->c].store(CH_PENDING, std::memory_order_release);
+  for (unsigned spin = 0; S.state[x->c].load(std::memory_order_acquire) != CH_READY; ++spin)
+    if (spin > 64) std::this_thread::yield();
+  S.state[x->c].store(CH_RUNNING, std::memory_order_relaxed);
+  if (S.rc_eval[x->c] != GWI_OK) {
+    for (int i = 0; i < p->dim; ++i) grad[i] = 0.0;
+    return inf;
+  }
+  return posterior_finish(p, lam, S.out.data() + (size_t)x->c * S.row_out, x->gp.data(), grad);
+}
+}  // namespace
+
+int gwi_nuts_sample_posterior_chains(gwi_posterior* p, int32_t n_chains, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info) {
+  if (!p || !theta0 || !opts || n_chains < 1 || n_chains > 4096 || (!samples && opts->n_samples > 0) || opts->n_warmup < 0 || opts->n_samples < 0 ||
+      opts->max_depth < 1 || opts->max_depth > 20 || !(opts->target_accept > 0.0 && opts->target_accept < 1.0)) {
+    set_error("gwi_nuts_sample_posterior_chains: bad argument");
+    return GWI_ERR_INVALID;
+  }
+  try {
+    const int K = n_chains, P = p->n_params, dim = p->dim;
+    ChainShared S(K);
+    S.p = p;
+    S.row_out = (size_t)GWI_LIKE_HEADER + P;
+    S.lam.assign((size_t)K * P, 0.0);
+    S.out.assign((size_t)K * S.row_out, 0.0);
+    std::vector<ChainCtx> ctx(K);
+    std::vector<int> rc_chain(K, GWI_OK);
+    std::vector<gwi_nuts_info> inf(K);
+    std::vector<std::thread> threads;
+    threads.reserve(K);
+    for (int c = 0; c < K; ++c) {
+      ctx[c].sh = &S;
+      ctx[c].c = c;
+      ctx[c].gp.assign(P, 0.0);
+      threads.emplace_back([&, c]() {
+        try {
+          gwi_nuts_opts o = *opts;
+          o.seed = opts->seed + c;
+          Sampler smp(chain_potential, &ctx[c], dim, (uint64_t)o.seed);
+          rc_chain[c] = smp.run(theta0 + (size_t)c * dim, o, samples ? samples + (size_t)c * o.n_samples * dim : nullptr, &inf[c]);
+        } catch (...) {
+          rc_chain[c] = GWI_ERR_ALLOC;
+        }
+        S.state[c].store(CH_ENDED, std::memory_order_release);
+      });
+    }
+    // coordinator: whenever every chain that is still running stands at a gradient, evaluate those Lambda rows in one call
+    std::vector<double> lam_b((size_t)K * P), out_b((size_t)K * S.row_out);
+    std::vector<int> who;
+    who.reserve(K);
+    for (unsigned spin = 0;; ++spin) {
+      int ended = 0, pending = 0;
+      for (int c = 0; c < K; ++c) {
+        const int st = S.state[c].load(std::memory_order_acquire);
+        ended += st == CH_ENDED;
+        pending += st == CH_PENDING;
+      }
+      if (ended == K) break;
+      if (pending == 0 || pending + ended < K) {
+        if (spin > 64) std::this_thread::yield();
+        continue;
+      }
+      spin = 0;
+      who.clear();
+      for (int c = 0; c < K; ++c)
+        if (S.state[c].load(std::memory_order_acquire) == CH_PENDING) who.push_back(c);
+      const int n = (int)who.size();
+      for (int i = 0; i < n; ++i) std::memcpy(lam_b.data() + (size_t)i * P, S.lam.data() + (size_t)who[i] * P, sizeof(double) * P);
+      const int rc = gwi_loglike_batch_host(p->model, lam_b.data(), n, &p->opts, out_b.data());
+      p->n_evals += n;
+      if (rc != GWI_OK && rc != GWI_ERR_RANGE) S.fatal.store(rc, std::memory_order_release);
+      for (int i = 0; i < n; ++i) {
+        const int c = who[i];
+        const double* row = out_b.data() + (size_t)i * S.row_out;
+        std::memcpy(S.out.data() + (size_t)c * S.row_out, row, sizeof(double) * S.row_out);
+        S.rc_eval[c] = (rc != GWI_OK && rc != GWI_ERR_RANGE) ? rc : (row[GWI_LIKE_STATUS] != 0.0 ? (int)GWI_ERR_RANGE : (int)GWI_OK);
+        S.state[c].store(CH_READY, std::memory_order_release);
+      }
+    }
+    for (auto& t : threads) t.join();
+    for (int c = 0; c < K; ++c) {
+      if (info) {
+        info[c] = inf[c];
+        info[c].n_evals = ctx[c].n_evals;
+      }
+    }
+    if (S.fatal.load() != GWI_OK) return S.fatal.load();  // (gwi_last_error holds the failing call's message: it ran on this thread)
+    for (int c = 0; c < K; ++c)
+      if (rc_chain[c] != GWI_OK) {
+        set_error("NUTS chain " + std::to_string(c) + ": the potential is not finite at the starting point, or out of memory");
+        return rc_chain[c];
+      }
+    return GWI_OK;
+  } catch (const std::bad_alloc&) {
+    set_error("out of host memory in the sampler");
+    return GWI_ERR_ALLOC;
+  } catch (const std::system_error&) {
+    set_error("could not start the chain threads");
+    return GWI_ERR_ALLOC;
+  }
 }
 
 }  // extern "C"

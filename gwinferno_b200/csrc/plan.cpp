@@ -789,14 +789,16 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     // cost model (issue slots per sample): a register-resident dim pays the warp-wide spill path
     // whenever ANY of its 32 lanes changes piece (~60 slots incl. the shared-memory atomics); a
     // deep dim pays ~17 extra slots on every sample.  Deep dims must be a suffix of the sort order.
-    // Which stream kernel?  Measured on B200 (r02c7, kernel ms, one-role / CTA-cooperative): cfg3 1.03e8 samples 1.573 / 1.785,
-    // a 2-way shard (5.2e7) 0.835 / 0.929, cfg5 (2.2e7) 0.480 / 0.469, an 8-way shard (1.3e7) 0.270 / 0.261, cfg2 (7.8e5)
-    // 0.049 / 0.037, the 1024-chain batch 44.5k / 52.0k chain-evals/s: long piece-sorted lane runs favour the one-role
-    // kernel, everything else the CTA-cooperative one.  GWI_CTA_KERNEL=0 / 1 forces the choice.
+    // Which stream kernel?  Measured on B200 after the one-role kernel's chunk flush became fire-and-forget reductions (r02c17 /
+    // r02c18, stream-kernel ms, one-role / CTA-cooperative): cfg3 1.03e8 samples 1.52 / 1.79, 4-way shard (2.6e7) 0.420 / 0.471,
+    // cfg5 (2.2e7) 0.434 / 0.462, 8-way shard (1.3e7) 0.237 / 0.256, 16-way (6.4e6) 0.142 / 0.148, 32-way (3.2e6) 0.085 / 0.094,
+    // 64-way (1.6e6) 0.062 / 0.052, cfg2 (7.8e5) 0.043 / 0.035, the 1024-chain batch 45.8k / 50.6k chain-evals/s: the
+    // CTA-cooperative kernel (no per-warp accumulators to set up and flush, one slice per CTA) wins on SMALL catalogs and
+    // on chain batches, the one-role kernel everywhere else.  GWI_CTA_KERNEL=0 / 1 forces the choice.
     {
       int64_t n_valid_all = 0;
       for (int s = 0; s < n_seg; ++s) n_valid_all += (int64_t)order[s].size();
-      want_cta = n_valid_all < 24000000 || desc.batch_hint > 1;  // between cfg5 (2.2e7: CTA 0.467 vs 0.481 ms) and a 4-way cfg3 shard (2.6e7: one-role by the linear fits)
+      want_cta = n_valid_all < 2400000 || desc.batch_hint > 1;
       if (const char* e = std::getenv("GWI_CTA_KERNEL")) want_cta = e[0] != '0';
       bool ok = !plan.g2 && (int)plan.kops.size() == plan.n_lin && plan.n_lin <= 2;
       for (const SplineDim& D : plan.dims) ok = ok && !D.liny;

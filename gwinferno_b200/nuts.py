@@ -201,6 +201,32 @@ def nuts_native(engine, blocks, theta0, n_warmup, n_samples, Nobs=None, seed=0, 
         post.close()
 
 
+def nuts_native_chains(engine, blocks, theta0, n_warmup, n_samples, Nobs=None, seed=0, target_accept=0.8, max_depth=8, flags=0, **like_kw):
+    """``theta0[n_chains, dim]``: that many independent chains of :func:`nuts_native`, advanced together -- whenever all
+    chains stand at a leapfrog step their Lambda vectors are evaluated in ONE batched GPU call (gwi_loglike_batch_host),
+    the reference's ``MCMC(..., chain_method="vectorized")`` on one GPU.  Chain ``c`` draws what :func:`nuts_native`
+    draws with ``seed + c``.  Create ``engine`` with ``batch_hint = n_chains``.  Returns
+    ``(samples[n_chains, n_samples, dim], [info per chain])``."""
+    post = capi.Posterior(engine.model, blocks, engine.n_events if Nobs is None else Nobs, **like_kw)
+    try:
+        return post.sample_chains(theta0, n_warmup, n_samples, seed=seed, target_accept=target_accept, max_depth=max_depth, flags=flags)
+    finally:
+        post.close()
+
+
+def split_rhat(chains):
+    """Split-R-hat of ``chains[n_chains, n_samples]`` (Gelman et al. 2013): every chain cut in halves, between- over
+    within-half variance.  ~1 when the chains sample the same distribution."""
+    x = np.asarray(chains, dtype=np.float64)
+    n = x.shape[1] // 2
+    if n < 2:
+        return float("nan")
+    h = np.concatenate([x[:, :n], x[:, n : 2 * n]], axis=0)
+    w = h.var(axis=1, ddof=1).mean()
+    b = n * h.mean(axis=1).var(ddof=1)
+    return float(np.sqrt(((n - 1) / n * w + b / n) / w)) if w > 0 else float("nan")
+
+
 def effective_sample_size(x):
     """ESS of a 1-D chain (Geyer's initial positive sequence on the FFT autocorrelation)."""
     x = np.asarray(x, dtype=np.float64)

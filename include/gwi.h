@@ -214,6 +214,14 @@ int gwi_loglike_batch(gwi_model* m, const double* lambda_dev, int32_t n_chains, 
  * synchronises (this is the end-to-end call timed as `e2e` by bench.py). */
 int gwi_loglike_host(gwi_model* m, const double* lambda_host, const gwi_like_opts* opts, double* out_host);
 
+/* gwi_loglike_batch with HOST buffers (lambda_host [n_chains][P], out_host [n_chains][GWI_LIKE_HEADER + P]): one
+ * host->device copy, one batched evaluation, one copy back, synchronised; replayed as a CUDA graph per batch size.
+ * A chain whose a-priori shift bound underflowed is repeated alone with the exact bound, as gwi_loglike_host does;
+ * GWI_ERR_RANGE if that fails too (that chain's row keeps a non-zero GWI_LIKE_STATUS, the other rows are valid).
+ * This is what the multi-chain sampler below calls once per round of leapfrog steps (the reference's
+ * numpyro MCMC(chain_method="vectorized"), pipeline/analysis.py's chains, on one GPU). */
+int gwi_loglike_batch_host(gwi_model* m, const double* lambda_host, int32_t n_chains, const gwi_like_opts* opts, double* out_host);
+
 /* ---- multi-GPU: injections sharded by index range, whole events sharded across ranks ------
  * Each rank evaluates its shard into a packed partial record (gwi_partial_size doubles, device
  * memory, asynchronous); the caller all-gathers the records of all ranks (NCCL over NVLink) into
@@ -345,6 +353,15 @@ void gwi_posterior_destroy(gwi_posterior* p);
 int gwi_posterior_dim(const gwi_posterior* p);
 double gwi_posterior_potential(void* posterior, const double* theta, double* grad);
 int gwi_nuts_sample_posterior(gwi_posterior* p, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info);
+
+/* n_chains independent NUTS chains of the same posterior, advanced TOGETHER: every chain runs the sampler above (own
+ * adaptation, own random stream: seed = opts->seed + chain) on its own host thread; whenever all running chains stand at a
+ * leapfrog step their Lambda vectors go to the GPU in ONE gwi_loglike_batch_host call, so a small catalog that cannot
+ * fill the GPU for one chain fills it with the batch (create the model with batch_hint = n_chains).  A chain that ends its
+ * transition early starts the next one at once -- chains are not synchronised per transition, only per gradient.
+ * theta0 [n_chains][dim], samples [n_chains][n_samples][dim], info [n_chains].  Chain c draws exactly what
+ * gwi_nuts_sample_posterior draws with seed opts->seed + c (the batched evaluation is bitwise the single one). */
+int gwi_nuts_sample_posterior_chains(gwi_posterior* p, int32_t n_chains, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info);
 
 const char* gwi_last_error(void);
 int gwi_version(void);
