@@ -154,6 +154,7 @@ SYMBOLS = [
     "gwi_partial",
     "gwi_combine",
     "gwi_model_get_info",
+    "gwi_model_batch_hint",
     "gwi_model_set_exact_shift",
     "gwi_model_set_timing",
     "gwi_model_stream_times",

@@ -1153,6 +1153,8 @@ int gwi_loglike_batch_host(gwi_model* m, const double* lambda_host, int32_t n_ch
   return rc_all;
 }
 
+int gwi_model_batch_hint(const gwi_model* m) { return m ? std::max(1, m->plan.batch_hint) : (int)GWI_ERR_INVALID; }
+
 int gwi_model_set_exact_shift(gwi_model* m, int32_t on) {
   if (!m) return GWI_ERR_INVALID;
   m->force_exact_shift = on != 0;

@@ -147,6 +147,7 @@ struct Plan {
   // CTA-cooperative geometry (stream_cta.cuh): a chunk is processed by ALL `cta_main_warps` main warps of one
   // CTA (its padded range = cta_main_warps sub-chunks of steps x 32 samples) and owns cta_main_warps + 1 records
   bool cta_mode = false;
+  int batch_hint = 1;  // chains per launch the geometry was laid out for (gwi_model_desc.batch_hint)
   int cta_main_warps = 0;
   double total_inj = 0.0;
   int64_t n_samples_pe = 0, n_samples_inj = 0, n_valid_pe = 0, n_valid_inj = 0;

@@ -763,8 +763,10 @@ struct ChainShared {
   std::vector<double> lam, out;     // [K][P], [K][row_out]: one row per chain
   std::vector<std::atomic<int>> state;
   std::vector<int> rc_eval;         // result code of the chain's last evaluation (written before CH_READY)
+  std::vector<uint64_t> ticket;     // arrival order of the pending requests (written before CH_PENDING)
+  std::atomic<uint64_t> next_ticket{0};
   std::atomic<int> fatal{GWI_OK};   // a CUDA / argument error: no more evaluations, every potential is +inf from then on
-  explicit ChainShared(int k) : K(k), state(k), rc_eval(k, GWI_OK) {
+  explicit ChainShared(int k) : K(k), state(k), rc_eval(k, GWI_OK), ticket(k, 0) {
     for (auto& s : state) s.store(CH_RUNNING);
   }
 };
@@ -786,6 +788,7 @@ double chain_potential(void* ctx, const double* theta, double* grad) {
     for (int i = 0; i < p->dim; ++i) grad[i] = 0.0;
     return inf;
   }
+  S.ticket[x->c] = S.next_ticket.fetch_add(1, std::memory_order_relaxed);
   S.state[x->c].store(CH_PENDING, std::memory_order_release);
   for (unsigned spin = 0; S.state[x->c].load(std::memory_order_acquire) != CH_READY; ++spin)
     if (spin > 64) std::this_thread::yield();
@@ -832,7 +835,12 @@ int gwi_nuts_sample_posterior_chains(gwi_posterior* p, int32_t n_chains, const d
         S.state[c].store(CH_ENDED, std::memory_order_release);
       });
     }
-    // coordinator: whenever every chain that is still running stands at a gradient, evaluate those Lambda rows in one call
+    // coordinator: a batch goes to the GPU as soon as `width` chains (or all that are still running) stand at a gradient,
+    // oldest request first.  width = the chain count the model's plan was laid out for (gwi_model_desc.batch_hint): with
+    // batch_hint = n_chains every round evaluates all chains together; with batch_hint = n_chains / 2 the chains fall into
+    // two alternating groups -- one computes its leapfrog arithmetic on the host while the other is being evaluated -- and
+    // the GPU never waits for the host (measured on B200, cfg2, 16 chains: see DESIGN.md section 5b).
+    const int width = std::max(1, std::min<int>(K, gwi_model_batch_hint(p->model)));
     std::vector<double> lam_b((size_t)K * P), out_b((size_t)K * S.row_out);
     std::vector<int> who;
     who.reserve(K);
@@ -844,7 +852,7 @@ int gwi_nuts_sample_posterior_chains(gwi_posterior* p, int32_t n_chains, const d
         pending += st == CH_PENDING;
       }
       if (ended == K) break;
-      if (pending == 0 || pending + ended < K) {
+      if (pending == 0 || pending < std::min(width, K - ended)) {
         if (spin > 64) std::this_thread::yield();
         continue;
       }
@@ -852,6 +860,8 @@ int gwi_nuts_sample_posterior_chains(gwi_posterior* p, int32_t n_chains, const d
       who.clear();
       for (int c = 0; c < K; ++c)
         if (S.state[c].load(std::memory_order_acquire) == CH_PENDING) who.push_back(c);
+      std::sort(who.begin(), who.end(), [&](int a, int b) { return S.ticket[a] < S.ticket[b]; });
+      if ((int)who.size() > width) who.resize(width);
       const int n = (int)who.size();
       for (int i = 0; i < n; ++i) std::memcpy(lam_b.data() + (size_t)i * P, S.lam.data() + (size_t)who[i] * P, sizeof(double) * P);
       const int rc = gwi_loglike_batch_host(p->model, lam_b.data(), n, &p->opts, out_b.data());

@@ -892,6 +892,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   // the warp iterations with lanes on the piece-change path at n = 1.
   int batch_hint = std::max(1, (int)desc.batch_hint);  // gwi_model_desc.batch_hint: chains per gwi_loglike_batch call
   if (const char* e = std::getenv("GWI_TUNE_BATCH_HINT")) batch_hint = std::max(1, std::atoi(e));
+  plan.batch_hint = batch_hint;
   const int W = plan.cta_mode ? std::max(1, plan.grid_blocks / batch_hint) : std::max(plan.warps_per_block, plan.grid_blocks * plan.warps_per_block / batch_hint);
   // Balanced slicing: the piece-sorted sample stream of all segments (the events first, then the
   // injections) is cut into SLICES of L steps (32 samples per step); slice i belongs to warp i % W.

@@ -273,6 +273,8 @@ typedef struct {
   int32_t active_switches;  /* tuning switches in effect: 1 fused epilogue, 2 CUDA-graph host call, 4 role-split stream kernel, 8 speculative shift */
 } gwi_model_info;
 int gwi_model_get_info(const gwi_model* m, gwi_model_info* info);
+/* chains per call the model's launch geometry was laid out for (gwi_model_desc.batch_hint, at least 1) */
+int gwi_model_batch_hint(const gwi_model* m);
 
 /* Per-segment results of the LAST evaluation of this model (any of the calls above, chain 0), copied
  * to HOST memory after synchronising with the stream that evaluation ran on: rows of 4 doubles
@@ -357,8 +359,11 @@ int gwi_nuts_sample_posterior(gwi_posterior* p, const double* theta0, const gwi_
 /* n_chains independent NUTS chains of the same posterior, advanced TOGETHER: every chain runs the sampler above (own
  * adaptation, own random stream: seed = opts->seed + chain) on its own host thread; whenever all running chains stand at a
  * leapfrog step their Lambda vectors go to the GPU in ONE gwi_loglike_batch_host call, so a small catalog that cannot
- * fill the GPU for one chain fills it with the batch (create the model with batch_hint = n_chains).  A chain that ends its
- * transition early starts the next one at once -- chains are not synchronised per transition, only per gradient.
+ * fill the GPU for one chain fills it with the batch.  A chain that ends its transition early starts the next one at once
+ * -- chains are not synchronised per transition, only per gradient.  A batch is launched as soon as batch_hint chains
+ * (gwi_model_desc.batch_hint of the model; or all that are still running) wait for a gradient, oldest request first:
+ * batch_hint = n_chains evaluates all chains together; batch_hint = n_chains / 2 lets the chains fall into two alternating
+ * groups, one doing its host arithmetic while the other is on the GPU, which keeps the GPU busy (the faster choice).
  * theta0 [n_chains][dim], samples [n_chains][n_samples][dim], info [n_chains].  Chain c draws exactly what
  * gwi_nuts_sample_posterior draws with seed opts->seed + c (the batched evaluation is bitwise the single one). */
 int gwi_nuts_sample_posterior_chains(gwi_posterior* p, int32_t n_chains, const double* theta0, const gwi_nuts_opts* opts, double* samples, gwi_nuts_info* info);
