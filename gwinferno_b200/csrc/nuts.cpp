@@ -108,11 +108,21 @@ struct Sampler {
       for (int i = 0; i < dim; ++i) v[i] = inv_mass[i] * r[i];
       return;
     }
+    // four independent partial sums per row: one running sum is a serial chain of `dim` dependent additions (the compiler
+    // may not re-associate them), ~4 cycles each -- at dim = 164 that was the sampler's largest host cost per leapfrog step
+    const double* rp = r.data();
     for (int i = 0; i < dim; ++i) {
       const double* row = cov.data() + (size_t)i * dim;
-      double a = 0.0;
-      for (int j = 0; j < dim; ++j) a += row[j] * r[j];
-      v[i] = a;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int j = 0;
+      for (; j + 4 <= dim; j += 4) {
+        a0 += row[j] * rp[j];
+        a1 += row[j + 1] * rp[j + 1];
+        a2 += row[j + 2] * rp[j + 2];
+        a3 += row[j + 3] * rp[j + 3];
+      }
+      for (; j < dim; ++j) a0 += row[j] * rp[j];
+      v[i] = (a0 + a1) + (a2 + a3);
     }
   }
   double kinetic(const Vec& r) const {
@@ -279,12 +289,20 @@ struct Sampler {
       S.z.u = leapfrog(S.z.theta, S.z.r, S.z.grad, sign * S.eps);
       ++S.n_leapfrog;
       ++n_leapfrog;
-      const double h = finite_or_inf(S.z.u + kinetic(S.z.r));
+      // M^-1 r once: it is both the U-turn criterion's "sharp" vector and, dotted with r, twice the kinetic energy
+      sharp(S.z.r, sharp_beg);
+      double kin = 0.0;
+      if (dense) {
+        for (int i = 0; i < dim; ++i) kin += S.z.r[i] * sharp_beg[i];
+        kin *= 0.5;
+      } else {
+        kin = kinetic(S.z.r);
+      }
+      const double h = finite_or_inf(S.z.u + kin);
       if (h - S.H0 > 1000.0) S.divergent = true;
       log_sum_weight = log_add_exp(log_sum_weight, S.H0 - h);
       S.sum_metro += S.H0 - h > 0.0 ? 1.0 : std::exp(S.H0 - h);
       z_propose = S.z;
-      sharp(S.z.r, sharp_beg);
       sharp_end = sharp_beg;
       for (int i = 0; i < dim; ++i) rho[i] += S.z.r[i];
       p_beg = S.z.r;
