@@ -161,6 +161,7 @@ struct CatalogView {
   int64_t n_inj = 0;
   double total_inj = 0.0;
   int device = 0;
+  bool on_device = false;  // the column pointers are device pointers (gwi_catalog_desc.columns_on_device)
 };
 
 // record layout helpers --------------------------------------------------------------------------

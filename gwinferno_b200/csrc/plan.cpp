@@ -22,46 +22,31 @@
 #include <thread>
 
 #include "gwi_internal.h"
+#include "plan_sample.h"
 
 namespace gwi {
 
 // ---------------------------------------------------------------------------------------------
 // cosmology: flat LCDM, Planck15-LVK constants (gwinferno/cosmology.py:19-22), comoving-distance
-// table by sequential trapezoid on z = arange(0, 10, 1e-3) (cosmology.py:48-77), dVc/dz with Dc
-// linearly interpolated (cosmology.py:95-120).
+// table by sequential trapezoid on z = arange(0, 10, 1e-3) (cosmology.py:48-77); dVc/dz with Dc
+// linearly interpolated (cosmology.py:95-120) is in plan_sample.h (host + device).
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct Cosmo {
   static constexpr double C_SI = 299792458.0;
   static constexpr double Ho = 67.90 / 1e-3;
-  static constexpr double Om = 0.3065;
-  static constexpr double Ol = 1.0 - 0.3065;
-  static constexpr double DZ = 1e-3;
   double c_over_Ho;
-  std::vector<double> z, Dc;
-  double dDcdz(double zz) const {
-    const double opz = 1.0 + zz;
-    return c_over_Ho / std::sqrt(Ol + Om * opz * opz * opz);
-  }
+  std::vector<double> Dc;
   Cosmo() {
     c_over_Ho = C_SI / Ho;
-    const int n = (int)std::ceil(10.0 / DZ);
-    z.resize(n);
+    const int n = (int)std::ceil(10.0 / COSMO_DZ);
     Dc.resize(n);
-    for (int i = 0; i < n; ++i) z[i] = i * DZ;  // numpy arange(0, 10, 1e-3): start + i*step
+    const CosmoView v{nullptr, n, c_over_Ho};
     Dc[0] = 0.0;
-    for (int i = 0; i + 1 < n; ++i) Dc[i + 1] = Dc[i] + 0.5 * (dDcdz(z[i]) + dDcdz(z[i] + DZ)) * DZ;
-  }
-  double interp_Dc(double zz) const {
-    if (!(zz >= 0.0)) return std::numeric_limits<double>::quiet_NaN();
-    const int n = (int)z.size();
-    if (zz >= z[n - 1]) return std::numeric_limits<double>::quiet_NaN();  // beyond the table (z < 10)
-    int i = (int)(zz / DZ);
-    if (i > n - 2) i = n - 2;
-    while (i > 0 && z[i] > zz) --i;
-    while (i < n - 2 && z[i + 1] <= zz) ++i;
-    const double f = (zz - z[i]) / (z[i + 1] - z[i]);
-    return Dc[i] + f * (Dc[i + 1] - Dc[i]);
+    for (int i = 0; i + 1 < n; ++i) {
+      const double zi = i * COSMO_DZ;  // numpy arange(0, 10, 1e-3): start + i*step
+      Dc[i + 1] = Dc[i] + 0.5 * (cosmo_dDcdz(v, zi) + cosmo_dDcdz(v, zi + COSMO_DZ)) * COSMO_DZ;
+    }
   }
 };
 const Cosmo& cosmo() {
@@ -70,104 +55,15 @@ const Cosmo& cosmo() {
 }
 }  // namespace
 
-double log_dvcdz(double z) {
+CosmoView cosmo_view_host() {
   const Cosmo& c = cosmo();
-  const double Dc = c.interp_Dc(z);
-  return std::log(4.0 * M_PI * Dc * Dc * c.dDcdz(z));
+  return CosmoView{c.Dc.data(), (int)c.Dc.size(), c.c_over_Ho};
 }
+
+double log_dvcdz(double z) { return cosmo_log_dvcdz(cosmo_view_host(), z); }
 
 // ---------------------------------------------------------------------------------------------
 namespace {
-
-enum FeatKind : int { F_LOG1P = 1, F_LOG = 2, F_LOG_RATIO = 3, F_LOG_DVDZ = 4, F_NEG_LOG = 5, F_RAW = 6, F_LOG_C_OVER = 7, F_LOG_S_MINUS = 8, F_NEG_LOG1P = 9, F_CONST = 10, F_MINUS_C = 11, F_PROD_MINUS_C = 12 };
-struct Feat {
-  int kind;
-  int col[2];
-  double cst;
-};
-
-inline double eval_feat(const Feat& f, const double* const* cols, int64_t j) {
-  const double a = cols[f.col[0]][j];
-  switch (f.kind) {
-    case F_LOG1P: return std::log(1.0 + a);
-    case F_LOG: return std::log(a);
-    case F_LOG_RATIO: return std::log(a / cols[f.col[1]][j]);
-    case F_LOG_DVDZ: return log_dvcdz(a);
-    case F_NEG_LOG: return -std::log(a);
-    case F_NEG_LOG1P: return -std::log(1.0 + a);
-    case F_CONST: return f.cst;
-    case F_MINUS_C: return a - f.cst;
-    case F_PROD_MINUS_C: return a * cols[f.col[1]][j] - f.cst;
-    case F_RAW: return a;
-    case F_LOG_C_OVER: return std::log(f.cst / a);
-    case F_LOG_S_MINUS: return std::log(f.cst - a);
-  }
-  return std::numeric_limits<double>::quiet_NaN();
-}
-
-struct RangeCut {
-  int kind;  // 1 range, 2 ratio range, 3 open range (lo < x < hi), 4 q >= c/m1 && q <= 1 && c/m1 < 1
-  int col[2];
-  double lo, hi;
-};
-
-inline bool pass_cut(const RangeCut& c, const double* const* cols, int64_t j) {
-  const double a = cols[c.col[0]][j];
-  switch (c.kind) {
-    case 1: return a >= c.lo && a <= c.hi;
-    case 2: {
-      const double r = a / cols[c.col[1]][j];
-      return r >= c.lo && r <= c.hi;
-    }
-    case 3: return a > c.lo && a < c.hi;
-    case 4: {
-      const double lo = c.lo / cols[c.col[1]][j];
-      return a >= lo && a <= 1.0 && lo < 1.0;
-    }
-  }
-  return false;
-}
-
-struct SplineGeom {
-  int col;
-  bool logx;
-  int outside;
-  double x_lo, x_hi, xi_lo, xi_hi, inv_dxi;
-  int rows;
-};
-
-// piece index and local coordinate u in [0,1) of one sample; returns false if the sample must be
-// dropped (GWI_OUTSIDE_DROP and outside the mask)
-inline bool spline_locate(const SplineGeom& g, double x, int& J, double& u) {
-  const bool inside = (x >= g.x_lo) && (x <= g.x_hi);
-  if (!inside) {
-    if (g.outside == GWI_OUTSIDE_DROP) return false;
-    J = g.rows - 1;  // dummy all-zero piece: bases are 0 outside the range (interpolation.py:175)
-    u = 0.0;
-    return x == x;  // NaN coordinate => drop
-  }
-  double xi = g.logx ? std::log(x) : x;
-  if (xi < g.xi_lo) xi = g.xi_lo;
-  if (xi > g.xi_hi) xi = g.xi_hi;
-  const double t = (xi - g.xi_lo) * g.inv_dxi;
-  int j = (int)std::floor(t);
-  if (j < 0) j = 0;
-  if (j > g.rows - 2) j = g.rows - 2;
-  double uu = t - (double)j;
-  if (uu < 0.0) uu = 0.0;
-  const double top = 1.0 - 0x1p-52;  // 1 + top = 2 - 2^-52 is the largest double below 2
-  if (uu > top) uu = top;
-  J = j;
-  u = uu;
-  return true;
-}
-
-inline uint64_t pack_word(int J, double u) {
-  const double w = u - 0.5;  // [-1/2, 1/2): the variable of the per-piece polynomials
-  uint64_t b;
-  std::memcpy(&b, &w, 8);
-  return (b & ~J_MASK) | (uint64_t)J;
-}
 
 template <class F>
 void parallel_for(int64_t n, int n_workers, F&& fn, int64_t min_n = 4096) {
@@ -245,32 +141,32 @@ void radix_sort_pairs(std::vector<uint64_t>& keys, std::vector<uint32_t>& idx, i
 
 }  // namespace
 
-// ---------------------------------------------------------------------------------------------
-int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count, int n_workers, Plan& plan) {
+namespace {
+// GWI_PLAN_TIMING=1: print the wall time of every build phase to stderr
+struct PlanTimer {
+  bool on = std::getenv("GWI_PLAN_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  void tick(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[gwi plan] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - last).count());
+    last = now;
+  }
+};
+}  // namespace
+
+// stage 1 (host, O(model)): terms -> spline dims / per-sample operations / cuts / grids; sort-key layout
+int plan_classify(int n_cat_columns, const gwi_model_desc& desc, Plan& plan, PlanInputs& in) {
   if (desc.n_terms <= 0 || !desc.terms || desc.n_params <= 0) {
     set_error("model description needs at least one term and one parameter");
     return GWI_ERR_INVALID;
   }
-  if (n_workers <= 0) n_workers = (int)std::max(1u, std::thread::hardware_concurrency());
-  n_workers = std::min(n_workers, 64);
   plan = Plan();
   plan.n_params = desc.n_params;
   plan.n_terms = desc.n_terms;
   plan.g2 = desc.need_neff_grad != 0;
-  plan.total_inj = cat.total_inj;
-
-  auto col_ok = [&](int c) { return c >= 0 && c < cat.n_columns; };
+  auto col_ok = [&](int c) { return c >= 0 && c < n_cat_columns; };
   auto slot_ok = [&](int s, int n) { return s >= 0 && s + n <= desc.n_params; };
-
-  // GWI_PLAN_TIMING=1: print the wall time of every build phase to stderr
-  const bool timing = std::getenv("GWI_PLAN_TIMING") != nullptr;
-  auto t_last = std::chrono::steady_clock::now();
-  auto tick = [&](const char* what) {
-    if (!timing) return;
-    const auto now = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[gwi plan] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
-    t_last = now;
-  };
   // ---- norm groups --------------------------------------------------------------------------
   for (int g = 0; g < desc.n_groups; ++g) {
     const gwi_norm_group& G = desc.groups[g];
@@ -295,11 +191,12 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   };
 
   // ---- classify terms -----------------------------------------------------------------------
-  std::vector<SplineGeom> geom;  // parallel to plan.dims (before ordering)
-  std::vector<Feat> kop_feats;   // feature columns of the kops, in stream-column order
-  std::vector<Feat> static_feats;
-  std::vector<RangeCut> cuts;
-  std::vector<int> used_cols;
+  in = PlanInputs();
+  std::vector<SplineGeom>& geom = in.geom;  // parallel to plan.dims (before ordering)
+  std::vector<Feat>& kop_feats = in.kop_feats;
+  std::vector<Feat>& static_feats = in.static_feats;
+  std::vector<RangeCut>& cuts = in.cuts;
+  std::vector<int>& used_cols = in.used_cols;
   auto use_col = [&](int c) {
     if (std::find(used_cols.begin(), used_cols.end(), c) == used_cols.end()) used_cols.push_back(c);
   };
@@ -630,59 +527,40 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   }
   plan.rec_doubles = rec_size(plan.n_gslots, plan.g2, plan.rows_total);
 
-  tick("terms, grids");
-  // ---- pass 1: validity + sort key per sample -----------------------------------------------
-  const int E = cat.n_events;
-  const int64_t n_pe = E > 0 ? cat.pe_offsets[E] : 0;
-  const int64_t n_inj = cat.n_inj;
-  plan.n_samples_pe = n_pe;
-  plan.n_samples_inj = n_inj;
-  if (n_pe + n_inj >= (int64_t)0xFFFFFFF0u) {
-    set_error("more than 2^32 samples per process are not supported");
-    return GWI_ERR_UNSUPPORTED;
-  }
-  int key_bits = 0;
-  std::vector<int> key_shift(NS);
   {
     int sh = 0;
     for (int d = NS - 1; d >= 0; --d) {
-      key_shift[d] = sh;
+      in.key_shift[d] = sh;
       sh += 6;
     }
-    key_bits = sh;
+    in.key_bits = sh;
   }
-  constexpr uint64_t INVALID = ~0ull;
-  auto sample_key = [&](const double* const* cols, int64_t j) -> uint64_t {
-    for (int c : used_cols) {
-      const double v = cols[c][j];
-      if (!(v == v)) return INVALID;
-    }
-    for (const RangeCut& c : cuts)
-      if (!pass_cut(c, cols, j)) return INVALID;
-    uint64_t key = 0;
-    for (int d = 0; d < NS; ++d) {
-      int J;
-      double u;
-      if (!spline_locate(geom[d], cols[geom[d].col][j], J, u)) return INVALID;
-      key |= (uint64_t)J << key_shift[d];
-    }
-    double st = 0.0;
-    for (const Feat& f : static_feats) st += eval_feat(f, cols, j);
-    if (!std::isfinite(st)) return INVALID;
-    for (const Feat& f : kop_feats)
-      if (!std::isfinite(eval_feat(f, cols, j))) return INVALID;
-    return key;
-  };
+  return GWI_OK;
+}
 
-  // segments: 0 = injections, 1..E = events
+namespace {
+// stage 2, host form: validity + sort key per sample, order-preserving compaction, stable LSD radix sort per segment;
+// piece-change rates along the sorted order (sampled)
+void plan_order_host(const CatalogView& cat, const PlanInputs& in, int n_workers, Plan& plan, std::vector<std::vector<uint32_t>>& order,
+                     std::vector<std::vector<double>>& rate, PlanTimer& tm) {
+  const int NS = (int)plan.dims.size();
+  const std::vector<SplineGeom>& geom = in.geom;
+  const CosmoView cv = cosmo_view_host();
+  const int E = cat.n_events;
+  const int64_t n_inj = cat.n_inj;
+  const int key_bits = in.key_bits;
+  constexpr uint64_t INVALID = PLAN_KEY_INVALID;
+  auto sample_key_ = [&](const double* const* cols, int64_t j) -> uint64_t {
+    return sample_key(cols, j, in.used_cols.data(), (int)in.used_cols.size(), in.cuts.data(), (int)in.cuts.size(), geom.data(), in.key_shift, NS, in.static_feats.data(),
+                      (int)in.static_feats.size(), in.kop_feats.data(), (int)in.kop_feats.size(), cv);
+  };
   const int n_seg = E + 1;
-  plan.segments.assign(n_seg, Segment{});
-  std::vector<std::vector<uint32_t>> order(n_seg);  // sorted valid sample indices per segment
+  order.assign(n_seg, {});
   {
     // injections
     std::vector<uint64_t> keys(n_inj);
     parallel_for(n_inj, n_workers, [&](int64_t a, int64_t b, int) {
-      for (int64_t j = a; j < b; ++j) keys[j] = sample_key(cat.inj_columns.data(), j);
+      for (int64_t j = a; j < b; ++j) keys[j] = sample_key_(cat.inj_columns.data(), j);
     });
     // compaction of the valid samples, order-preserving: per-block counts, scan, per-block copy
     std::vector<uint64_t> vk;
@@ -714,9 +592,9 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     }
     keys.clear();
     keys.shrink_to_fit();
-    tick("injection keys + compaction");
+    tm.tick("injection keys + compaction");
     radix_sort_pairs(vk, vi, key_bits, n_workers);
-    tick("injection sort");
+    tm.tick("injection sort");
     plan.segments[0].n_total = n_inj;
     plan.segments[0].n_valid = (int64_t)vi.size();
   }
@@ -730,7 +608,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
         std::vector<uint64_t> vk;
         std::vector<uint32_t>& vi = order[e + 1];
         for (int64_t j = a; j < b; ++j) {
-          const uint64_t k = sample_key(cat.pe_columns.data(), j);
+          const uint64_t k = sample_key_(cat.pe_columns.data(), j);
           if (k != INVALID) {
             vk.push_back(k);
             vi.push_back((uint32_t)j);
@@ -748,16 +626,10 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   for (int s = 1; s < n_seg; ++s) plan.n_valid_pe += plan.segments[s].n_valid;
   plan.n_valid_inj = plan.segments[0].n_valid;
 
-  tick("event keys + sorts");
-  bool want_cta = false;  // the CTA-cooperative stream kernel is the better one for this plan (decided below)
-  // ---- deep dims: how often does each dim's piece index change along the sorted order? -------
-  // Leading sort keys change rarely (register-resident moments, spilled on change); a dim whose
-  // piece changes more than about once per 100 consecutive samples would make some lane of every
-  // warp take the spill path on nearly every sample, so it (and every later key) gets
-  // lane-pair-private shared-memory accumulators instead ("deep").
+  tm.tick("event keys + sorts");
   {
     // per segment: fraction of consecutive sorted samples whose piece index differs, per dim
-    std::vector<std::vector<double>> rate(n_seg, std::vector<double>(NS, 0.0));
+    rate.assign(n_seg, std::vector<double>(NS, 0.0));
     std::atomic<int> next_seg{0};
     auto rate_work = [&]() {
       for (;;) {
@@ -786,6 +658,23 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       for (int w = 0; w < std::min(n_workers, n_seg); ++w) th.emplace_back(rate_work);
       for (auto& t : th) t.join();
     }
+  }
+}
+}  // namespace
+
+// stage 3 (host, O(segments + chunks)): deep dims from the piece-change rates, kernel choice, launch geometry, slices and chunks.
+// Needs only plan.segments[s].n_valid and the rates.
+int plan_geometry(const gwi_model_desc& desc, int sm_count, const PlanInputs& in, const std::vector<std::vector<double>>& rate, Plan& plan,
+                  std::vector<int64_t>& chunk_r0, std::vector<int64_t>& chunk_nc) {
+  PlanTimer tm;
+  const bool timing = tm.on;
+  const int NS = (int)plan.dims.size();
+  const int n_seg = (int)plan.segments.size();
+  const std::vector<Feat>& kop_feats = in.kop_feats;
+  chunk_r0.clear();
+  chunk_nc.clear();
+  bool want_cta = false;  // the CTA-cooperative stream kernel is the better one for this plan (decided below)
+  {
     // cost model (issue slots per sample): a register-resident dim pays the warp-wide spill path
     // whenever ANY of its 32 lanes changes piece (~60 slots incl. the shared-memory atomics); a
     // deep dim pays ~17 extra slots on every sample.  Deep dims must be a suffix of the sort order.
@@ -797,7 +686,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     // on chain batches, the one-role kernel everywhere else.  GWI_CTA_KERNEL=0 / 1 forces the choice.
     {
       int64_t n_valid_all = 0;
-      for (int s = 0; s < n_seg; ++s) n_valid_all += (int64_t)order[s].size();
+      for (int s = 0; s < n_seg; ++s) n_valid_all += plan.segments[s].n_valid;
       want_cta = n_valid_all < 2400000 || desc.batch_hint > 1;
       if (const char* e = std::getenv("GWI_CTA_KERNEL")) want_cta = e[0] != '0';
       bool ok = !plan.g2 && (int)plan.kops.size() == plan.n_lin && plan.n_lin <= 2;
@@ -817,14 +706,14 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       for (int cand = 0; cand <= std::min(NS, 4); ++cand) {
         double cost = 0.0;
         for (int s = 0; s < n_seg; ++s) {
-          const double n = (double)order[s].size();
+          const double n = (double)plan.segments[s].n_valid;
           for (int d = 0; d < NS - cand; ++d) cost += n * (std::min(1.0, 32.0 * rate[s][d]) * COST_WARP + rate[s][d] * COST_LANE);
           cost += n * cand * COST_DEEP;
         }
         if (timing) {
           double ci = 0.0, cp = 0.0, np_ = 0.0;
           for (int s = 0; s < n_seg; ++s) {
-            const double n = (double)order[s].size();
+            const double n = (double)plan.segments[s].n_valid;
             double c = cand * COST_DEEP;
             for (int d = 0; d < NS - cand; ++d) c += std::min(1.0, 32.0 * rate[s][d]) * COST_WARP + rate[s][d] * COST_LANE;
             if (s == 0) ci = c; else { cp += n * c; np_ += n; }
@@ -851,8 +740,6 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     plan.n_deep = nd;
     for (int d = 0; d < NS; ++d) plan.dims[d].deep = d >= NS - nd;
   }
-
-  tick("piece-change rates");
   // ---- launch geometry + chunking -----------------------------------------------------------
   // shared memory per warp: shallow accumulators + deep lane-private arrays + generic slots
   const int mom = plan.g2 ? 2 : 1;
@@ -961,7 +848,6 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     fixed_L = false;
   }
   plan.chunk_steps = (int)L;
-  std::vector<int64_t> chunk_r0, chunk_nc;  // first sorted rank / valid samples of every chunk
   plan.slice_begin.clear();
   plan.slice_begin.push_back(0);
   // Guided scheduling: the warps pull slices in order, so the slices shrink towards the end of
@@ -1027,9 +913,25 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
   }
   plan.slice_begin.push_back((int)plan.chunks.size());
   plan.n_padded = pos;
-  const int n_chunks = (int)plan.chunks.size();
 
-  tick("slicing");
+  return GWI_OK;
+}
+
+namespace {
+// stage 4, host form: gather the sorted samples chunk by chunk and write the stream columns + per-segment statistics
+int plan_fill_host(const CatalogView& cat, const PlanInputs& in, const std::vector<std::vector<uint32_t>>& order, const std::vector<int64_t>& chunk_r0,
+                   const std::vector<int64_t>& chunk_nc, int n_workers, Plan& plan, PlanTimer& tm) {
+  const bool timing = tm.on;
+  const int NS = (int)plan.dims.size();
+  const int NK = (int)in.kop_feats.size();
+  const int n_chunks = (int)plan.chunks.size();
+  const std::vector<SplineGeom>& geom = in.geom;
+  const std::vector<Feat>& kop_feats = in.kop_feats;
+  const std::vector<Feat>& static_feats = in.static_feats;
+  const std::vector<int>& used_cols = in.used_cols;
+  const CosmoView cv = cosmo_view_host();
+  const int LW = plan.cta_mode ? plan.cta_main_warps : 1;
+  const int LPC = LANES * LW;
   // ---- pass 2: fill the stream columns ------------------------------------------------------
   try {
     plan.columns.assign((size_t)plan.n_columns * (size_t)std::max<int64_t>(1, plan.n_padded), 0ull);
@@ -1102,11 +1004,11 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
                 st.occ[d] |= 1ull << J;
               }
               for (int f = 0; f < NK; ++f) {
-                const double v = eval_feat(kop_feats[f], cols, j);
+                const double v = eval_feat(kop_feats[f], cols, j, cv);
                 std::memcpy(&plan.columns[col_index(NS + f, p)], &v, 8);
               }
               double sw = 0.0;
-              for (const Feat& f : static_feats) sw += eval_feat(f, cols, j);
+              for (const Feat& f : static_feats) sw += eval_feat(f, cols, j, cv);
               std::memcpy(&plan.columns[col_index(plan.col_static, p)], &sw, 8);
               st.max_static = std::max(st.max_static, sw);
               for (size_t q = 0; q < plan.kops.size(); ++q)
@@ -1127,7 +1029,7 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
                 plan.columns[col_index(d, p)] = pack_word(J, u);
               }
               for (int f = 0; f < NK; ++f) {
-                const double v = eval_feat(kop_feats[f], cols, j);
+                const double v = eval_feat(kop_feats[f], cols, j, cv);
                 std::memcpy(&plan.columns[col_index(NS + f, p)], &v, 8);
               }
               std::memcpy(&plan.columns[col_index(plan.col_static, p)], &NEG_INF, 8);
@@ -1152,8 +1054,17 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
     }
   }
 
-  tick("column fill");
+  tm.tick("column fill");
   if (timing) std::fprintf(stderr, "[gwi plan]   of which gather (thread-seconds) %8.3f s over %d workers\n", gather_seconds.load() * 1e-6, n_workers);
+  return GWI_OK;
+}
+}  // namespace
+
+// stage 5 (host): level-0 records and the fixed-order reduction tree
+void plan_tree(Plan& plan) {
+  const int n_chunks = (int)plan.chunks.size();
+  const int n_seg = (int)plan.segments.size();
+  const int LW = plan.cta_mode ? plan.cta_main_warps : 1;
   // ---- level-0 records: one per chunk (the chunks, hence the records, of a segment are
   //      consecutive); fixed-order tree reduction afterwards
   {
@@ -1204,6 +1115,49 @@ int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count,
       plan.levels.push_back(tasks);
     }
   }
+}
+
+// segments: 0 = injections, 1..E = events
+int plan_begin_segments(const CatalogView& cat, Plan& plan) {
+  const int E = cat.n_events;
+  const int64_t n_pe = E > 0 ? cat.pe_offsets[E] : 0;
+  plan.total_inj = cat.total_inj;
+  plan.n_samples_pe = n_pe;
+  plan.n_samples_inj = cat.n_inj;
+  if (n_pe + cat.n_inj >= (int64_t)0xFFFFFFF0u) {
+    set_error("more than 2^32 samples per process are not supported");
+    return GWI_ERR_UNSUPPORTED;
+  }
+  plan.segments.assign(E + 1, Segment{});
+  return GWI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int build_plan(const CatalogView& cat, const gwi_model_desc& desc, int sm_count, int n_workers, Plan& plan) {
+  if (cat.on_device) {
+    set_error("the host plan builder cannot read device-resident catalog columns");
+    return GWI_ERR_INVALID;
+  }
+  if (n_workers <= 0) n_workers = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_workers = std::min(n_workers, 64);
+  PlanTimer tm;
+  PlanInputs in;
+  int rc = plan_classify(cat.n_columns, desc, plan, in);
+  if (rc != GWI_OK) return rc;
+  rc = plan_begin_segments(cat, plan);
+  if (rc != GWI_OK) return rc;
+  tm.tick("terms, grids");
+  std::vector<std::vector<uint32_t>> order;  // sorted valid sample indices per segment
+  std::vector<std::vector<double>> rate;
+  plan_order_host(cat, in, n_workers, plan, order, rate, tm);
+  tm.tick("piece-change rates");
+  std::vector<int64_t> chunk_r0, chunk_nc;  // first sorted rank / valid samples of every chunk
+  rc = plan_geometry(desc, sm_count, in, rate, plan, chunk_r0, chunk_nc);
+  if (rc != GWI_OK) return rc;
+  tm.tick("slicing");
+  rc = plan_fill_host(cat, in, order, chunk_r0, chunk_nc, n_workers, plan, tm);
+  if (rc != GWI_OK) return rc;
+  plan_tree(plan);
   return GWI_OK;
 }
 
