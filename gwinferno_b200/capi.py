@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GWI_LIBRARY", os.path.join(_HERE, "libgwi.so"))  # override: tuning experiments only
 
-GWI_VERSION = 4  # include/gwi.h: GWI_VERSION (gwi_model_desc.batch_hint, library-owned exchange)
+GWI_VERSION = 5  # include/gwi.h: GWI_VERSION (device-resident catalogs, device plan builder, plan timings in gwi_model_info)
 GWI_LIKE_HEADER = 8
 LIKE_FIELDS = ("log_l", "passed", "log_mu", "logNeff_inj", "min_logNeff", "sum_logBF", "variance", "status")
 PARTIAL_HEADER = 8
@@ -101,6 +101,7 @@ class gwi_catalog_desc(C.Structure):
         ("inj_columns", C.POINTER(C.POINTER(C.c_double))),
         ("total_inj", C.c_double),
         ("device", C.c_int32),
+        ("columns_on_device", C.c_int32),
     ]
 
 
@@ -130,6 +131,9 @@ class gwi_model_info(C.Structure):
         ("block_threads", C.c_int32),
         ("kernel_launches_per_eval", C.c_int32),
         ("active_switches", C.c_int32),
+        ("plan_on_device", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("plan_seconds", C.c_double * 5),
     ]
 
 
@@ -163,6 +167,7 @@ SYMBOLS = [
     "gwi_debug_plan_build",
     "gwi_debug_plan_destroy",
     "gwi_debug_plan_read",
+    "gwi_debug_model_read",
     "gwi_nuts_sample",
     "gwi_posterior_create",
     "gwi_posterior_destroy",
@@ -194,6 +199,8 @@ def load_library(_allow_emulator=False):
     lib.gwi_partial_size.argtypes = [C.c_void_p]
     lib.gwi_debug_plan_read.restype = C.c_int64
     lib.gwi_debug_plan_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    lib.gwi_debug_model_read.restype = C.c_int64
+    lib.gwi_debug_model_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     lib.gwi_catalog_create.argtypes = [C.POINTER(gwi_catalog_desc), C.POINTER(C.c_void_p)]
     lib.gwi_catalog_destroy.argtypes = [C.c_void_p]
     lib.gwi_catalog_destroy.restype = None
@@ -375,7 +382,10 @@ class Catalog:
     """gwi_catalog over NumPy columns.  PE columns: dict name -> (E, S) array (or a ragged list of
     per-event 1-D arrays); injection columns: dict name -> (I,) array."""
 
-    def __init__(self, pe_cols, inj_cols, total_inj, device=0):
+    def __init__(self, pe_cols, inj_cols, total_inj, device=0, on_device=False):
+        """on_device=True: the columns are copied into device memory HERE (once) and the catalog hands the library device
+        pointers (gwi_catalog_desc.columns_on_device) -- the situation of a caller whose sample arrays already live on the
+        GPU (jax / torch arrays): gwi_model_create then builds the plan without any host <-> device traffic."""
         lib = load_library()
         self.names = list(pe_cols.keys())
         if list(inj_cols.keys()) != self.names:
@@ -396,8 +406,24 @@ class Catalog:
         self.n_inj = int(self.inj[0].size)
         self.total_inj = float(total_inj)
         ncol = len(self.names)
-        self._pe_ptrs = (C.POINTER(C.c_double) * ncol)(*[_dptr(a) for a in self.pe])
-        self._inj_ptrs = (C.POINTER(C.c_double) * ncol)(*[_dptr(a) for a in self.inj])
+        self.on_device = bool(on_device)
+        if self.on_device:
+            self._dev = []
+            ptrs = []
+            for cols in (self.pe, self.inj):
+                row = []
+                for a in cols:
+                    b = DeviceBuffer(a.size, device)
+                    if a.size:
+                        b.upload(a)
+                    self._dev.append(b)
+                    row.append(C.cast(C.c_void_p(b.ptr), C.POINTER(C.c_double)))
+                ptrs.append(row)
+            self._pe_ptrs = (C.POINTER(C.c_double) * ncol)(*ptrs[0])
+            self._inj_ptrs = (C.POINTER(C.c_double) * ncol)(*ptrs[1])
+        else:
+            self._pe_ptrs = (C.POINTER(C.c_double) * ncol)(*[_dptr(a) for a in self.pe])
+            self._inj_ptrs = (C.POINTER(C.c_double) * ncol)(*[_dptr(a) for a in self.inj])
         d = gwi_catalog_desc()
         d.n_columns = ncol
         d.n_events = self.n_events
@@ -407,6 +433,7 @@ class Catalog:
         d.inj_columns = self._inj_ptrs
         d.total_inj = self.total_inj
         d.device = int(device)
+        d.columns_on_device = 1 if self.on_device else 0
         self.device = int(device)
         self._desc = d
         h = C.c_void_p()
@@ -479,7 +506,19 @@ class Model:
     def info(self):
         i = gwi_model_info()
         _check(load_library().gwi_model_get_info(self.handle, C.byref(i)))
-        return {n: getattr(i, n) for n, _ in gwi_model_info._fields_ if n != "reserved"}
+        d = {n: getattr(i, n) for n, _ in gwi_model_info._fields_ if not n.startswith("reserved")}
+        d["plan_seconds"] = dict(zip(("total", "columns_upload", "keys_sort_bounds", "geometry_host", "fill"), [float(x) for x in i.plan_seconds]))
+        return d
+
+    def read_plan(self, what, dtype=np.int64):
+        """Test hook (gwi_debug_model_read): the plan of the live model; what = 1 copies the stream columns back from the device."""
+        lib = load_library()
+        n = lib.gwi_debug_model_read(self.handle, what, None, 0)
+        if n < 0:
+            raise GwiError(n, "gwi_debug_model_read")
+        out = np.empty(n, dtype=dtype)
+        lib.gwi_debug_model_read(self.handle, what, out.ctypes.data, n)
+        return out
 
     # -- library-owned multi-GPU exchange (include/gwi.h: gwi_comm_*) -------------------------
     def comm_local_handle(self, n_ranks):

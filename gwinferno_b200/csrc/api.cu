@@ -4,6 +4,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,6 +15,7 @@
 #include <vector>
 
 #include "dev_structs.h"
+#include "plan_sample.h"
 
 namespace gwi {
 
@@ -52,6 +54,18 @@ static int build_plan_noexcept(const CatalogView& cat, const gwi_model_desc& des
     return GWI_ERR_ALLOC;
   } catch (const std::exception& e) {
     set_error(std::string("plan builder failed: ") + e.what());
+    return GWI_ERR_INVALID;
+  }
+}
+
+static int build_plan_device_noexcept(const CatalogView& cat, const gwi_model_desc& desc, int sm_count, Plan& plan, uint64_t** d_cols, double* secs) {
+  try {
+    return build_plan_device(cat, desc, sm_count, plan, d_cols, secs);
+  } catch (const std::bad_alloc&) {
+    set_error("out of host memory building the plan");
+    return GWI_ERR_ALLOC;
+  } catch (const std::exception& e) {
+    set_error(std::string("device plan builder failed: ") + e.what());
     return GWI_ERR_INVALID;
   }
 }
@@ -111,6 +125,8 @@ struct gwi_model {
   cudaStream_t aux_stream = nullptr;  // grid normalisers run here, concurrently with the stream kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t bytes_per_eval = 0;
+  bool plan_on_device = false;  // built by plan_device.cu
+  double plan_seconds[5] = {0, 0, 0, 0, 0};
   // GWI_PHASE_TIMING=1 (diagnostic): CUDA events between the kernels of every single-chain evaluation; the mean device
   // time of each phase is printed to stderr when the model is destroyed (this serialises consecutive evaluations)
   bool phase_timing = false;
@@ -185,6 +201,7 @@ int gwi_catalog_create(const gwi_catalog_desc* d, gwi_catalog** out) {
   c->view.n_inj = d->n_inj;
   c->view.total_inj = d->total_inj;
   c->view.device = d->device;
+  c->view.on_device = d->columns_on_device != 0;
   c->view.pe_offsets.assign(1, 0);
   if (d->n_events > 0) {
     c->view.pe_offsets.assign(d->pe_offsets, d->pe_offsets + d->n_events + 1);
@@ -229,9 +246,28 @@ int gwi_debug_plan_build(const gwi_catalog* cat, const gwi_model_desc* desc, int
 }
 void gwi_debug_plan_destroy(gwi_plan* p) { delete p; }
 
+static int64_t plan_read(const Plan& p, int32_t what, void* dst, int64_t cap);
 int64_t gwi_debug_plan_read(const gwi_plan* pp, int32_t what, void* dst, int64_t cap) {
   if (!pp) return GWI_ERR_INVALID;
-  const Plan& p = pp->plan;
+  return plan_read(pp->plan, what, dst, cap);
+}
+int64_t gwi_debug_model_read(const gwi_model* m, int32_t what, void* dst, int64_t cap) {
+  if (!m) return GWI_ERR_INVALID;
+  if (what == 1) {
+    const int64_t n = (int64_t)m->plan.n_columns * m->plan.n_padded;
+    if (dst) {
+      if (cap < n) return GWI_ERR_INVALID;
+      if (n > 0 && cudaMemcpy(dst, m->host.columns, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("cudaMemcpy of the plan columns failed");
+        return GWI_ERR_CUDA;
+      }
+    }
+    return n;
+  }
+  return plan_read(m->plan, what, dst, cap);
+}
+
+static int64_t plan_read(const Plan& p, int32_t what, void* dst, int64_t cap) {
   std::vector<int64_t> v;
   const void* src = nullptr;
   int64_t n = 0;
@@ -449,11 +485,36 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   gwi_model* m = new (std::nothrow) gwi_model();
   if (!m) return GWI_ERR_ALLOC;
   m->device = cat->view.device;
-  int rc = build_plan_noexcept(cat->view, *desc, prop.multiProcessorCount, 0, m->plan);
+  // the plan is built on the GPU (plan_device.cu) unless GWI_PLAN_DEVICE=0 asks for the host builder; the host warp
+  // emulator of the CPU test suite defaults to the host builder (GWI_PLAN_DEVICE=1 runs the device builder's kernels there)
+#ifdef GWI_HOST_EMULATION
+  bool dev_build = false;
+#else
+  bool dev_build = true;
+#endif
+  if (const char* e = std::getenv("GWI_PLAN_DEVICE")) dev_build = e[0] != '0';
+  if (cat->view.on_device) dev_build = true;
+  const auto t_plan0 = std::chrono::steady_clock::now();
+  uint64_t* d_cols_built = nullptr;
+  int rc = GWI_OK;
+  if (dev_build) {
+    rc = build_plan_device_noexcept(cat->view, *desc, prop.multiProcessorCount, m->plan, &d_cols_built, m->plan_seconds + 1);
+    if (rc == PLAN_DEVICE_FALLBACK) {
+      if (cat->view.on_device) {
+        set_error("model too large for the device plan builder's tables and the catalog columns are device-resident");
+        rc = GWI_ERR_UNSUPPORTED;
+      } else {
+        dev_build = false;
+      }
+    }
+  }
+  if (!dev_build) rc = build_plan_noexcept(cat->view, *desc, prop.multiProcessorCount, 0, m->plan);
   if (rc != GWI_OK) {
     delete m;
     return rc;
   }
+  m->plan_on_device = dev_build;
+  if (d_cols_built) m->allocs.push_back(d_cols_built);
   Plan& p = m->plan;
   ModelDev& H = m->host;
   const int P = p.n_params, NS = (int)p.dims.size(), nseg = (int)p.segments.size();
@@ -562,10 +623,12 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     }                       \
   } while (0)
 
-  uint64_t* d_cols;
-  UP(upload(m, p.columns.data(), p.columns.size(), &d_cols));
+  uint64_t* d_cols = d_cols_built;
+  if (!d_cols) {
+    UP(upload(m, p.columns.data(), p.columns.size(), &d_cols));
+    std::vector<uint64_t>().swap(p.columns);  // host copy no longer needed
+  }
   m->bytes_per_eval = (int64_t)p.n_columns * p.n_padded * 8;
-  std::vector<uint64_t>().swap(p.columns);  // host copy no longer needed
   H.columns = d_cols;
   Chunk* d_chunks;
   UP(upload(m, p.chunks.data(), p.chunks.size(), &d_chunks));
@@ -677,6 +740,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
   }
   m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 1;
   CUDA_TRY(cudaDeviceSynchronize());
+  m->plan_seconds[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_plan0).count();
   *out = m;
   return GWI_OK;
 }
@@ -1225,6 +1289,8 @@ int gwi_model_get_info(const gwi_model* m, gwi_model_info* info) {
   info->block_threads = m->stream_block;
   info->kernel_launches_per_eval = m->launches_per_eval;
   info->active_switches = 0 | (m->use_graph ? 2 : 0) | (m->cta ? 4 : 0) | (m->spec_shift ? 8 : 0);
+  info->plan_on_device = m->plan_on_device ? 1 : 0;
+  for (int i = 0; i < 5; ++i) info->plan_seconds[i] = m->plan_seconds[i];
   return GWI_OK;
 }
 

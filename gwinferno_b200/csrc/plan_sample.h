@@ -24,6 +24,12 @@ GWI_HD inline double plan_nan() {
   memcpy(&d, &b, 8);
   return d;
 }
+GWI_HD inline double plan_inf() {
+  const uint64_t b = 0x7ff0000000000000ull;
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+}
 GWI_HD inline bool plan_finite(double x) { return ::fabs(x) <= 1.7976931348623157e308; }  // false for NaN
 
 // ---- cosmology: flat LCDM, Planck15-LVK constants (gwinferno/cosmology.py:19-22); the comoving-distance table
@@ -195,5 +201,8 @@ int plan_geometry(const gwi_model_desc& desc, int sm_count, const PlanInputs& in
 void plan_tree(Plan& plan);
 int plan_begin_segments(const CatalogView& cat, Plan& plan);
 CosmoView cosmo_view_host();
+// plan_device.cu: the order and fill stages as kernels on the catalog's GPU; *d_columns_out = the plan's device array
+constexpr int PLAN_DEVICE_FALLBACK = 1;  // the model exceeds the device builder's fixed tables: use the host builder
+int build_plan_device(const CatalogView& cat, const gwi_model_desc& desc, int sm_count, Plan& plan, uint64_t** d_columns_out, double* stats_seconds);
 
 }  // namespace gwi

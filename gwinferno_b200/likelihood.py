@@ -30,11 +30,13 @@ _BUILDS = collections.Counter()  # (term kinds, sharing pattern) -> plans built;
 class PopulationLikelihood:
     """Device-resident plan for one (catalog, population model) pair; evaluate for many Lambda."""
 
-    def __init__(self, lowered, total_inj, device=0, need_neff_grad=False, chunk_steps=0, n_deep=-1, batch_hint=0):
+    def __init__(self, lowered, total_inj, device=0, need_neff_grad=False, chunk_steps=0, n_deep=-1, batch_hint=0, catalog_on_device=False):
         self.lowered = lowered
         self.spec = lowered.spec
         self.n_params = lowered.spec.n_params
-        self.catalog = capi.Catalog(lowered.pe_cols, lowered.inj_cols, total_inj, device=device)
+        # catalog_on_device=True: the sample columns are placed in device memory first and the plan is built from there
+        # (capi.Catalog(on_device=True)): the setting of a caller whose arrays already live on the GPU
+        self.catalog = capi.Catalog(lowered.pe_cols, lowered.inj_cols, total_inj, device=device, on_device=catalog_on_device)
         self.model = capi.Model(self.catalog, lowered.spec, need_neff_grad=need_neff_grad, chunk_steps=chunk_steps, n_deep=n_deep, batch_hint=batch_hint)
         self.need_neff_grad = need_neff_grad
         self.n_events = self.catalog.n_events

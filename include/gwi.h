@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GWI_VERSION 4
+#define GWI_VERSION 5
 
 typedef enum {
   GWI_OK = 0,
@@ -140,23 +140,29 @@ typedef struct {
   int32_t n_columns;
   int32_t n_events;
   const int64_t* pe_offsets;       /* n_events+1 : event i owns samples [off[i], off[i+1]) of each PE column */
-  const double* const* pe_columns; /* n_columns host pointers */
+  const double* const* pe_columns; /* n_columns pointers (host memory, or device memory with columns_on_device) */
   int64_t n_inj;                   /* found injections held by THIS process (its shard) */
   const double* const* inj_columns;
   double total_inj;                /* total generated injections of the WHOLE injection set (analysis.py:91) */
   int32_t device;                  /* CUDA device ordinal */
+  int32_t columns_on_device;       /* 1: pe_columns[k] / inj_columns[k] point to DEVICE memory of `device` (e.g. the buffers of
+                                      jax / torch arrays that hold the samples already); pe_offsets stays a host array */
 } gwi_catalog_desc;
 
 typedef struct gwi_catalog gwi_catalog;
 typedef struct gwi_model gwi_model;
 
-/* The catalog BORROWS the host column pointers: they must stay valid until the last
+/* The catalog BORROWS the column pointers: they must stay valid until the last
  * gwi_model_create() on it has returned.  Nothing is uploaded here. */
 int gwi_catalog_create(const gwi_catalog_desc* desc, gwi_catalog** out);
 void gwi_catalog_destroy(gwi_catalog* cat);
 
 /* Builds the static evaluation plan (masks, spline interval/offset words, static log-weights,
- * interval-sorted work chunks) on the host and uploads it to the catalog's device. */
+ * interval-sorted work chunks) -- what the reference's model constructors do with dense design matrices
+ * (gwinferno/models/bsplines/single.py:54-57, interpolation.py:128-149, cosmology.py:95-120).
+ * By default ON THE GPU (csrc/plan_device.cu: key kernel, radix sort, fill kernel writing the plan straight
+ * into device memory; host columns are uploaded through pinned staging buffers, device-resident columns are
+ * used in place); GWI_PLAN_DEVICE=0 selects the multi-threaded host builder + upload (same plan). */
 int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** out);
 void gwi_model_destroy(gwi_model* m);
 
@@ -271,6 +277,10 @@ typedef struct {
   int32_t grid_blocks, block_threads;
   int32_t kernel_launches_per_eval; /* kernels launched by one gwi_loglike call */
   int32_t active_switches;  /* tuning switches in effect: 1 fused epilogue, 2 CUDA-graph host call, 4 role-split stream kernel, 8 speculative shift */
+  int32_t plan_on_device;   /* 1: the plan was built by the device builder */
+  int32_t reserved_;
+  double plan_seconds[5];   /* wall time of gwi_model_create: total | raw-column upload (device builder) | keys + sort + bounds |
+                               host geometry | fill.  Host builder: total only. */
 } gwi_model_info;
 int gwi_model_get_info(const gwi_model* m, gwi_model_info* info);
 /* chains per call the model's launch geometry was laid out for (gwi_model_desc.batch_hint, at least 1) */
@@ -385,6 +395,9 @@ void gwi_debug_plan_destroy(gwi_plan* p);
  *       5 = non-spline op table [n_ops * 8] int64 {kind, column0, column1, slot0..slot3, bits of cst0}
  * Returns the number of 8-byte items written (or needed when dst == NULL). */
 int64_t gwi_debug_plan_read(const gwi_plan* p, int32_t what, void* dst, int64_t cap_items);
+/* The same reader on a live model (what = 0, 2, 3, 4, 5 as above; what = 1 copies the plan's stream columns back
+ * from device memory): lets the tests compare the device-built plan with the host-built one. */
+int64_t gwi_debug_model_read(const gwi_model* m, int32_t what, void* dst, int64_t cap_items);
 
 #ifdef __cplusplus
 }

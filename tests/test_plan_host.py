@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.load_library()
     for name in capi.SYMBOLS:
         assert hasattr(lib, name), name
-    assert lib.gwi_version() == capi.GWI_VERSION == 4
+    assert lib.gwi_version() == capi.GWI_VERSION == 5
     # header and binding agree on the symbol list
     import os, re
 
@@ -38,7 +38,8 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(capi.gwi_term) == 4 * 4 + 2 * 4 + 6 * 4 + 4 * 8 + 2 * 4 + 4 * 8 + 8
     assert C.sizeof(capi.gwi_cut) == 4 + 8 + 4 + 16 or C.sizeof(capi.gwi_cut) == 32
     assert C.sizeof(capi.gwi_like_opts) == 16
-    assert C.sizeof(capi.gwi_model_info) == 6 * 8 + 10 * 4
+    assert C.sizeof(capi.gwi_model_info) == 6 * 8 + 10 * 4 + 2 * 4 + 5 * 8
+    assert C.sizeof(capi.gwi_catalog_desc) == 56
 
 
 def _decode(case, plan):
