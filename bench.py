@@ -469,12 +469,12 @@ def run_ours(args):
         "gpu_launches": info["kernel_launches_per_eval"] * args.steps,  # a chain batch launches every kernel once
         "clocks": clocks,
         "result": {"log_l": float(res[0]), "passed": float(res[1]), "status": float(res[7])},
-        "setup_s": {"generate": t_gen, "plan_build_and_upload": t_plan},
+        "setup_s": {"generate": t_gen, "plan_build_and_upload": t_plan, "plan_on_device": info["plan_on_device"], "gwi_model_create": info["plan_seconds"]},
         "per_rank": per_rank,
         "plan": {k: info[k] for k in ("n_valid_pe", "n_valid_inj", "n_padded", "n_chunks", "n_stream_columns", "n_spline_dims", "n_deep", "grid_blocks", "block_threads")},
         # tuning switches in effect (all default off: 0 / empty in the product configuration)
         "switches": {"active": info["active_switches"], "library": os.path.basename(capi.LIB_PATH),
-                     "env": {k: v for k, v in os.environ.items() if k.startswith(("GWI_TUNE_", "GWI_EXP_", "GWI_FUSED", "GWI_GRAPH", "GWI_SPLIT"))}},
+                     "env": {k: v for k, v in os.environ.items() if k.startswith(("GWI_TUNE_", "GWI_EXP_", "GWI_FUSED", "GWI_GRAPH", "GWI_SPLIT", "GWI_PLAN"))}},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(name)

@@ -270,7 +270,7 @@ struct DevBuf {  // frees what the build allocated unless released
 
 // Host columns -> device through pinned staging buffers filled by worker threads (a pageable cudaMemcpy stages through ONE
 // driver thread: ~6 GB/s; several memcpy threads + asynchronous copies run at the PCIe rate)
-bool upload_columns(const std::vector<std::pair<const double*, double*>>& jobs_src_dst, const std::vector<int64_t>& counts) {
+bool upload_columns(const std::vector<std::pair<const double*, double*>>& jobs_src_dst, const std::vector<int64_t>& counts, int device) {
   constexpr size_t STAGE = (size_t)32 << 20;  // bytes per staging buffer
   struct Piece {
     const char* src;
@@ -305,7 +305,8 @@ bool upload_columns(const std::vector<std::pair<const double*, double*>>& jobs_s
     void* stage[2] = {nullptr, nullptr};
     cudaStream_t st = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    if (cudaMallocHost(&stage[0], STAGE) != cudaSuccess || cudaMallocHost(&stage[1], STAGE) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaSetDevice(device) != cudaSuccess ||  // (the current device is per thread)
+        cudaMallocHost(&stage[0], STAGE) != cudaSuccess || cudaMallocHost(&stage[1], STAGE) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess) {
       ok = false;
     } else {
@@ -458,7 +459,7 @@ int build_plan_device(const CatalogView& cat, const gwi_model_desc& desc, int sm
         counts.push_back(n_inj);
       }
     }
-    if (!upload_columns(jobs, counts)) {
+    if (!upload_columns(jobs, counts, cat.device)) {
       set_error(std::string("device plan build: upload of the catalog columns failed: ") + cudaGetErrorString(cudaGetLastError()));
       return GWI_ERR_CUDA;
     }

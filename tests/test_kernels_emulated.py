@@ -23,6 +23,7 @@ from tests import test_gpu_parity as G
 golden = G.golden
 medium = G.medium
 cfg2 = G.cfg2
+ppd_ref = G.ppd_ref
 for _name in dir(G):
     if _name.startswith("test_"):
         globals()[_name] = getattr(G, _name)
