@@ -40,6 +40,9 @@ class gwi_term(C.Structure):
         ("xi_lo", C.c_double),
         ("xi_hi", C.c_double),
         ("grid", C.POINTER(C.c_double)),
+        ("knots", C.POINTER(C.c_double)),
+        ("n_knots", C.c_int32),
+        ("order", C.c_int32),
     ]
 
 
@@ -351,6 +354,10 @@ class _Desc:
                     raise ValueError(f"term {t.name}: grid length does not match its norm group")
                 self.keep.append(g)
                 ct.grid = _dptr(g)
+            if getattr(t, "knots", None) is not None:  # explicit knot vector / order (interpolation.py:72-106)
+                kn = np.ascontiguousarray(t.knots, dtype=np.float64)
+                self.keep.append(kn)
+                ct.knots, ct.n_knots, ct.order = _dptr(kn), kn.size, int(t.order)
         ng = len(spec.groups)
         self.groups = (gwi_norm_group * max(1, ng))()
         for i, g in enumerate(spec.groups):

@@ -559,6 +559,10 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
       H.liny_mask |= 1 << d;
       H.two_pass = 1;  // no a-priori bound through the log of the spline: exact max first
     }
+    X.basis_off = D.basis_off;
+    X.first_off = D.first_off;
+    X.floor_off = D.floor_off;
+    X.pad_ = 0;
     X.xi_lo = t.xi_lo;
     X.inv_dxi = (double)(D.rows - 1) / (t.xi_hi - t.xi_lo);
   }

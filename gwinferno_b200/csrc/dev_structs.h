@@ -77,6 +77,8 @@ struct DimDev {
   int32_t deep, deep_off;  // deep_off: first double2 entry of this dim in the lane-private deep block
   int32_t norm_group, grid_off;
   int32_t grid_aux, liny;  // derived grid taps (see SplineDim::grid_aux); liny: SplineDim::liny
+  int32_t basis_off, first_off;  // SplineDim::basis_off / first_off (-1: uniform cubic pieces)
+  int32_t floor_off, pad_;
   double xi_lo, inv_dxi;
 };
 

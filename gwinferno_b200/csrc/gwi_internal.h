@@ -81,6 +81,10 @@ struct SplineDim {
   int32_t grid_aux;  // offset of the derived per-grid-point taps: W[4G], J[G], then lo[n], hi[n] per basis
   int32_t outside;
   int32_t liny;      // GWI_TERM_SPLINE_LINEAR: the spline is the density (log-weight = log of the cubic)
+  // explicit knot vector / order (gwi_term.knots): per-piece tables in the grid pool, -1 = default uniform cubic pieces
+  int32_t basis_off;  // [rows-1][4][4]: basis first[J]+k on piece J = sum_n basis[J][k][n] w^n
+  int32_t first_off;  // [rows-1]: first coefficient a piece uses (stored as doubles)
+  int32_t floor_off;  // [rows-1]: 0 where the piece's bases do not sum to one (spline <= max(max c, 0)), else -inf
 };
 
 struct NormGroup {

@@ -332,10 +332,24 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     double a[4] = {0.0, 0.0, 0.0, 0.0};
     double ub = 0.0;
     if (J < D.rows - 1) {
-      const double* c = Lam + D.slot + J;
-      ub = fmax(fmax(c[0], c[1]), fmax(c[2], c[3]));
+      if (D.basis_off < 0) {  // default uniform cubic pieces
+        const double* c = Lam + D.slot + J;
+        ub = fmax(fmax(c[0], c[1]), fmax(c[2], c[3]));
 #pragma unroll
-      for (int n = 0; n < 4; ++n) a[n] = c[0] * BETA[0][n] + c[1] * BETA[1][n] + c[2] * BETA[2][n] + c[3] * BETA[3][n];
+        for (int n = 0; n < 4; ++n) a[n] = c[0] * BETA[0][n] + c[1] * BETA[1][n] + c[2] * BETA[2][n] + c[3] * BETA[3][n];
+      } else {  // explicit knot vector / order: per-piece basis polynomials, only the coefficients the piece uses count
+        const double* Bm = M.grid_pool + D.basis_off + J * 16;
+        const double* c = Lam + D.slot + (int)M.grid_pool[D.first_off + J];
+        ub = M.grid_pool[D.floor_off + J];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double* b = Bm + k * 4;
+          if (b[0] != 0.0 || b[1] != 0.0 || b[2] != 0.0 || b[3] != 0.0) ub = fmax(ub, c[k]);
+#pragma unroll
+          for (int n = 0; n < 4; ++n) a[n] += c[k] * b[n];
+        }
+        if (ub == -INFINITY) ub = 0.0;  // a piece without any basis: the spline is 0 there
+      }
     }
 #pragma unroll
     for (int n = 0; n < 4; ++n) M.tables[r * 4 + n] = a[n];
@@ -556,6 +570,20 @@ __device__ void finish_segment(const ModelDev& M, int s, const double* rec) {
       const DimDev& D = M.dims[d];
       const int k = i - D.slot;
       if (k < 0 || k >= D.n_splines) continue;
+      if (D.basis_off >= 0) {  // explicit knot vector: every piece whose 4 coefficients include k
+        for (int J = 0; J < D.rows - 1; ++J) {
+          const int kk = k - (int)M.grid_pool[D.first_off + J];
+          if (kk < 0 || kk > 3) continue;
+          const double* b = M.grid_pool + D.basis_off + J * 16 + kk * 4;
+          const double* m1 = M1 + (D.row_off + J) * 4;
+          G1 += b[0] * m1[0] + b[1] * m1[1] + b[2] * m1[2] + b[3] * m1[3];
+          if (g2) {
+            const double* m2 = M2 + (D.row_off + J) * 4;
+            G2s += b[0] * m2[0] + b[1] * m2[1] + b[2] * m2[2] + b[3] * m2[3];
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const int J = k - kk;

@@ -11,6 +11,7 @@
 // piece indices so that consecutive samples of one GPU lane share polynomial pieces: the kernel
 // keeps the per-piece gradient moments in registers and only spills when a piece index changes.
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -155,6 +156,79 @@ struct PlanTimer {
 };
 }  // namespace
 
+namespace {
+// Per-piece polynomial form of the canonical B-spline basis of an explicit knot vector, restating the reference's
+// Cox-de Boor recursion (gwinferno/interpolation.py:128-149: M-spline recursion with half-open order-1 indicators and the
+// "support shorter than 1e-6 => zero" guard at every level; :268-278: rescaled by (t[i+k]-t[i])/k to canonical
+// B-splines) with polynomials in w = u - 1/2 instead of numbers, u = (x - t[m]) / (t[m+1] - t[m]) on the knot span m.
+// Pieces = the spans that meet [x0, x1] (bases are zeroed outside the range, interpolation.py:175), clipped to it; a span
+// that STARTS at x1 is kept as a piece that only x1 itself falls into (half-open spans).  Where no span covers part of
+// the range the piece has no basis (the spline is 0 there).
+using Poly = std::array<double, 4>;
+struct SpanPoly {
+  const double* t;
+  int m, n_knots;
+  double xa, xb;  // x(w) = xa + xb w on span m
+  Poly M(int i, int kk) const {
+    Poly z{0.0, 0.0, 0.0, 0.0};
+    if (i < 0 || i + kk > n_knots - 1) return z;
+    if (t[i + kk] - t[i] < 1e-6) return z;  // interpolation.py:141
+    if (kk == 1) {
+      if (i == m) z[0] = 1.0 / (t[i + 1] - t[i]);  // :143-146 (on span m only the indicator of [t_m, t_m+1) is 1)
+      return z;
+    }
+    const Poly a = M(i, kk - 1), b = M(i + 1, kk - 1);
+    // (x - t_i) a + (t_{i+kk} - x) b   (:148)
+    const double a0 = xa - t[i], b0 = t[i + kk] - xa;
+    Poly v{0.0, 0.0, 0.0, 0.0};
+    for (int n = 0; n < 4; ++n) {
+      v[n] += a0 * a[n] + b0 * b[n];
+      if (n + 1 < 4) v[n + 1] += xb * a[n] - xb * b[n];
+    }
+    const double f = (double)kk / ((double)(kk - 1) * (t[i + kk] - t[i]));  // :149
+    for (int n = 0; n < 4; ++n) v[n] *= f;
+    return v;
+  }
+};
+
+int build_piece_table(const double* t, int n_knots, int order, int N, double x0, double x1, PieceTable& T) {
+  const double NEG_INF = -std::numeric_limits<double>::infinity();
+  auto add_piece = [&](double lo, double origin, double inv_h, int first, const double* basis16, double floor_) {
+    T.lo.push_back(lo);
+    T.origin.push_back(origin);
+    T.inv_h.push_back(inv_h);
+    T.first.push_back(first);
+    T.floor_.push_back(floor_);
+    for (int i = 0; i < 16; ++i) T.basis.push_back(basis16 ? basis16[i] : 0.0);
+  };
+  for (int m = 0; m + 1 < n_knots; ++m)
+    if (!(t[m + 1] >= t[m])) return GWI_ERR_INVALID;  // must be non-decreasing (NaN fails too)
+  if (t[0] > x0) add_piece(x0, x0, 1.0, 0, nullptr, 0.0);  // below the first knot: every basis is 0
+  for (int m = 0; m + 1 < n_knots; ++m) {
+    const double h = t[m + 1] - t[m];
+    if (!(h > 0.0) || !(t[m + 1] > x0) || !(t[m] <= x1)) continue;
+    SpanPoly sp{t, m, n_knots, t[m] + 0.5 * h, h};
+    const int first = std::max(0, std::min(m - order + 1, N - 4));
+    double B[16] = {0};
+    double sum[4] = {0, 0, 0, 0};
+    for (int i = std::max(0, m - order + 1); i <= std::min(N - 1, m); ++i) {
+      Poly Mi = sp.M(i, order);
+      const double scale = (t[i + order] - t[i]) / (double)order;  // :278
+      for (int n = 0; n < 4; ++n) {
+        B[(i - first) * 4 + n] = scale * Mi[n];
+        sum[n] += scale * Mi[n];
+      }
+    }
+    const bool unity = std::fabs(sum[0] - 1.0) < 1e-9 && std::fabs(sum[1]) < 1e-9 && std::fabs(sum[2]) < 1e-9 && std::fabs(sum[3]) < 1e-9;
+    add_piece(std::max(t[m], x0), t[m], 1.0 / h, first, B, unity ? NEG_INF : 0.0);
+  }
+  if (t[n_knots - 1] <= x1) add_piece(t[n_knots - 1], t[n_knots - 1], 1.0, 0, nullptr, 0.0);  // at / beyond the last knot: 0
+  if (T.n() == 0 || T.n() > MAX_ROWS - 1) return GWI_ERR_UNSUPPORTED;
+  return GWI_OK;
+}
+
+}  // namespace
+
 // stage 1 (host, O(model)): terms -> spline dims / per-sample operations / cuts / grids; sort-key layout
 int plan_classify(int n_cat_columns, const gwi_model_desc& desc, Plan& plan, PlanInputs& in) {
   if (desc.n_terms <= 0 || !desc.terms || desc.n_params <= 0) {
@@ -236,7 +310,8 @@ int plan_classify(int n_cat_columns, const gwi_model_desc& desc, Plan& plan, Pla
           set_error("term " + std::to_string(ti) + ": a spline density must drop the samples outside its range");
           return GWI_ERR_INVALID;
         }
-        if (t.n_splines < 4 || t.n_splines - 2 > MAX_ROWS || !slot_ok(t.slot[0], t.n_splines) || !(t.xi_hi > t.xi_lo)) {
+        const bool general = t.knots != nullptr;
+        if (t.n_splines < 4 || (!general && t.n_splines - 2 > MAX_ROWS) || !slot_ok(t.slot[0], t.n_splines) || !(t.xi_hi > t.xi_lo)) {
           set_error("term " + std::to_string(ti) + ": bad spline description");
           return GWI_ERR_INVALID;
         }
@@ -244,10 +319,33 @@ int plan_classify(int n_cat_columns, const gwi_model_desc& desc, Plan& plan, Pla
           set_error("too many spline dimensions");
           return GWI_ERR_UNSUPPORTED;
         }
+        std::shared_ptr<PieceTable> table;
+        if (general) {
+          if (t.order < 1 || t.order > 4 || t.n_knots != t.n_splines + t.order) {
+            set_error("term " + std::to_string(ti) + ": an explicit knot vector needs order 1..4 (degree <= 3) and n_knots == n_splines + order");
+            return t.order > 4 ? GWI_ERR_UNSUPPORTED : GWI_ERR_INVALID;
+          }
+          table = std::make_shared<PieceTable>();
+          const int rc = build_piece_table(t.knots, t.n_knots, t.order, t.n_splines, t.xi_lo, t.xi_hi, *table);
+          if (rc != GWI_OK) {
+            set_error("term " + std::to_string(ti) + (rc == GWI_ERR_UNSUPPORTED ? ": more than 61 polynomial pieces inside the range" : ": the knot vector must be non-decreasing"));
+            return rc;
+          }
+          in.piece_tables.push_back(table);
+        }
         SplineDim d{};
         d.term = ti;
         d.n_splines = t.n_splines;
-        d.rows = t.n_splines - 2;
+        d.rows = general ? table->n() + 1 : t.n_splines - 2;
+        d.basis_off = d.first_off = d.floor_off = -1;
+        if (general) {
+          d.basis_off = (int)plan.grid_pool.size();
+          plan.grid_pool.insert(plan.grid_pool.end(), table->basis.begin(), table->basis.end());
+          d.first_off = (int)plan.grid_pool.size();
+          for (int f : table->first) plan.grid_pool.push_back((double)f);
+          d.floor_off = (int)plan.grid_pool.size();
+          plan.grid_pool.insert(plan.grid_pool.end(), table->floor_.begin(), table->floor_.end());
+        }
         d.slot = t.slot[0];
         d.norm_group = t.norm_group;
         d.outside = t.outside;
@@ -264,6 +362,12 @@ int plan_classify(int n_cat_columns, const gwi_model_desc& desc, Plan& plan, Pla
         g.xi_hi = t.xi_hi;
         g.rows = d.rows;
         g.inv_dxi = (double)(d.rows - 1) / (t.xi_hi - t.xi_lo);
+        if (general) {
+          g.n_pieces = table->n();
+          g.piece_lo = table->lo.data();
+          g.piece_origin = table->origin.data();
+          g.piece_inv_h = table->inv_h.data();
+        }
         geom.push_back(g);
         break;
       }
@@ -485,14 +589,33 @@ int plan_classify(int n_cat_columns, const gwi_model_desc& desc, Plan& plan, Pla
         aux[(size_t)4 * G + i] = -1.0;
         continue;
       }
-      const double t = (xi - geom[d].xi_lo) * geom[d].inv_dxi;
-      int J = (int)std::floor(t);
-      J = std::max(0, std::min(J, D.rows - 2));
-      const double u = t - (double)J, omu = 1.0 - u;
-      aux[(size_t)4 * i + 0] = omu * omu * omu * (1.0 / 6.0);
-      aux[(size_t)4 * i + 1] = (3.0 * u * u * u - 6.0 * u * u + 4.0) * (1.0 / 6.0);
-      aux[(size_t)4 * i + 2] = (-3.0 * u * u * u + 3.0 * u * u + 3.0 * u + 1.0) * (1.0 / 6.0);
-      aux[(size_t)4 * i + 3] = u * u * u * (1.0 / 6.0);
+      int J;
+      if (geom[d].n_pieces > 0) {
+        // explicit knot vector: the piece of the (clamped) grid coordinate, its 4 tap weights from the per-piece
+        // polynomials, and the FIRST coefficient of the piece in the J field
+        const SplineGeom& g = geom[d];
+        const double xc = std::min(std::max(xi, g.xi_lo), g.xi_hi);
+        int lo = 0, hi = g.n_pieces - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (g.piece_lo[mid] <= xc) lo = mid; else hi = mid - 1;
+        }
+        double u = (xc - g.piece_origin[lo]) * g.piece_inv_h[lo];
+        u = std::min(std::max(u, 0.0), 1.0);
+        const double* b16 = plan.grid_pool.data() + D.basis_off + (size_t)lo * 16;
+        const double w = u - 0.5;
+        for (int k = 0; k < 4; ++k) aux[(size_t)4 * i + k] = ((b16[k * 4 + 3] * w + b16[k * 4 + 2]) * w + b16[k * 4 + 1]) * w + b16[k * 4 + 0];
+        J = (int)plan.grid_pool[D.first_off + lo];
+      } else {
+        const double t = (xi - geom[d].xi_lo) * geom[d].inv_dxi;
+        J = (int)std::floor(t);
+        J = std::max(0, std::min(J, D.rows - 2));
+        const double u = t - (double)J, omu = 1.0 - u;
+        aux[(size_t)4 * i + 0] = omu * omu * omu * (1.0 / 6.0);
+        aux[(size_t)4 * i + 1] = (3.0 * u * u * u - 6.0 * u * u + 4.0) * (1.0 / 6.0);
+        aux[(size_t)4 * i + 2] = (-3.0 * u * u * u + 3.0 * u * u + 3.0 * u + 1.0) * (1.0 / 6.0);
+        aux[(size_t)4 * i + 3] = u * u * u * (1.0 / 6.0);
+      }
       aux[(size_t)4 * G + i] = (double)J;
       Jg[i] = J;
       if (J < lastJ) monotone = false;

@@ -404,6 +404,17 @@ int build_plan_device(const CatalogView& cat, const gwi_model_desc& desc, int sm
     A.geom[d] = in.geom[d];
     A.geom[d].col = cc(in.geom[d].col);
     A.key_shift[d] = in.key_shift[d];
+    if (in.geom[d].n_pieces > 0) {  // explicit knot vector: the piece tables go to device memory
+      const int np = in.geom[d].n_pieces;
+      double* dp;
+      PD_ALLOC(dp, 3 * (size_t)np);
+      PD_CUDA(cudaMemcpy(dp, in.geom[d].piece_lo, sizeof(double) * np, cudaMemcpyHostToDevice));
+      PD_CUDA(cudaMemcpy(dp + np, in.geom[d].piece_origin, sizeof(double) * np, cudaMemcpyHostToDevice));
+      PD_CUDA(cudaMemcpy(dp + 2 * np, in.geom[d].piece_inv_h, sizeof(double) * np, cudaMemcpyHostToDevice));
+      A.geom[d].piece_lo = dp;
+      A.geom[d].piece_origin = dp + np;
+      A.geom[d].piece_inv_h = dp + 2 * np;
+    }
   }
   auto copy_feats = [&](const std::vector<Feat>& src, Feat* dst) {
     for (size_t i = 0; i < src.size(); ++i) {

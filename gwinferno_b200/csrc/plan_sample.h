@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "gwi_internal.h"
@@ -122,6 +123,14 @@ struct SplineGeom {
   int outside;
   int rows;
   double x_lo, x_hi, xi_lo, xi_hi, inv_dxi;
+  // explicit knot vector (gwi_term.knots): piece J covers [piece_lo[J], piece_lo[J+1]) of the spline coordinate and its
+  // local coordinate is u = (xi - piece_origin[J]) * piece_inv_h[J] (origin and width of the knot SPAN the piece lies in).
+  // n_pieces == 0: the default uniform pieces.  Host pointers in the host builder, device pointers in the device builder.
+  int n_pieces;
+  int pad_;
+  const double* piece_lo;
+  const double* piece_origin;
+  const double* piece_inv_h;
 };
 
 // piece index and local coordinate u in [0,1) of one sample; returns false if the sample must be
@@ -137,13 +146,27 @@ GWI_HD inline bool spline_locate(const SplineGeom& g, double x, int& J, double& 
   double xi = g.logx ? ::log(x) : x;
   if (xi < g.xi_lo) xi = g.xi_lo;
   if (xi > g.xi_hi) xi = g.xi_hi;
-  const double t = (xi - g.xi_lo) * g.inv_dxi;
-  int j = (int)::floor(t);
-  if (j < 0) j = 0;
-  if (j > g.rows - 2) j = g.rows - 2;
-  double uu = t - (double)j;
-  if (uu < 0.0) uu = 0.0;
   const double top = 1.0 - 0x1p-52;  // 1 + top = 2 - 2^-52 is the largest double below 2
+  int j;
+  double uu;
+  if (g.n_pieces > 0) {
+    // half-open spans as in the reference's order-1 indicator (interpolation.py:143-146): the last piece whose
+    // lower edge is <= xi
+    int lo = 0, hi = g.n_pieces - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (g.piece_lo[mid] <= xi) lo = mid; else hi = mid - 1;
+    }
+    j = lo;
+    uu = (xi - g.piece_origin[j]) * g.piece_inv_h[j];
+  } else {
+    const double t = (xi - g.xi_lo) * g.inv_dxi;
+    j = (int)::floor(t);
+    if (j < 0) j = 0;
+    if (j > g.rows - 2) j = g.rows - 2;
+    uu = t - (double)j;
+  }
+  if (uu < 0.0) uu = 0.0;
   if (uu > top) uu = top;
   J = j;
   u = uu;
@@ -159,7 +182,18 @@ GWI_HD inline uint64_t pack_word(int J, double u) {
 
 // ---- what both builders derive from the model description (plan_classify) -------------------------
 constexpr uint64_t PLAN_KEY_INVALID = ~0ull;
+// per-piece tables of a spline term with an explicit knot vector (plan.cpp: build_piece_table)
+struct PieceTable {
+  std::vector<double> lo, inv_h;  // [n]: lower edge of the piece; origin / inverse width of its knot span
+  std::vector<double> origin;     // [n]: origin of the local coordinate (the span's lower knot)
+  std::vector<double> floor_;     // [n]: 0 where the bases do not sum to one on the piece, else -inf
+  std::vector<int> first;         // [n]: first coefficient used
+  std::vector<double> basis;      // [n][4][4]
+  int n() const { return (int)lo.size(); }
+};
+
 struct PlanInputs {
+  std::vector<std::shared_ptr<PieceTable>> piece_tables;  // keeps SplineGeom::piece_* alive
   std::vector<SplineGeom> geom;  // parallel to plan.dims (sort-key order)
   std::vector<Feat> kop_feats;   // feature columns of the kops, in stream-column order
   std::vector<Feat> static_feats;

@@ -277,10 +277,8 @@ class Base1DBSplineModel:
     basis description; ``__call__(coefs, pe_samples)`` returns a :class:`LazyWeight`."""
 
     def __init__(self, n_splines, xx, xx_inj, xrange=(0.0, 1.0), degree=3, basis=BSpline, **kwargs):
-        if degree != 3:
-            raise NotImplementedError("only cubic B-splines (degree=3) are implemented on the CUDA path")
-        if kwargs.get("knots") is not None or kwargs.get("interior_knots") is not None:
-            raise NotImplementedError("non-uniform knot vectors are not implemented on the CUDA path")
+        if not 0 <= int(degree) <= 3:
+            raise NotImplementedError("B-spline degrees 0..3 are implemented on the CUDA path (4 coefficients per polynomial piece)")
         self.n_splines = int(n_splines)
         self.xmin, self.xmax = float(xrange[0]), float(xrange[1])
         self.degree = degree
@@ -296,6 +294,28 @@ class Base1DBSplineModel:
             self.xi_range = (self.xmin, self.xmax)
             grid = np.linspace(self.xmin, self.xmax, basis.n_grid)  # interpolation.py:378
             grid_xi = grid
+        # explicit knot vector / order: built exactly as BasisSpline.__init__ does (interpolation.py:94-106; the log-x
+        # bases take the logarithm of user-given knots first, :335-338,425-428).  ``interior_knots`` only sets the COUNT of
+        # knots and the spacing of the extension (:99-101) -- the reference lays a uniform vector over the extended range.
+        self.knots, self.order = None, int(degree) + 1
+        knots, interior = kwargs.get("knots"), kwargs.get("interior_knots")
+        if int(degree) != 3 or knots is not None or interior is not None:
+            k = self.order
+            knots = None if knots is None else np.asarray(knots, dtype=np.float64)
+            interior = None if interior is None else np.asarray(interior, dtype=np.float64)
+            if basis.logx:
+                knots = None if knots is None else np.log(knots)
+                interior = None if interior is None else np.log(interior)
+            if knots is None:
+                if interior is None:
+                    interior = np.linspace(self.xi_range[0], self.xi_range[1], self.n_splines - k + 2)
+                dx = interior[1] - interior[0]
+                knots = np.linspace(self.xi_range[0] - dx * (k - 1), self.xi_range[1] + dx * (k - 1), len(interior) + (k - 1) * 2)
+            if len(knots) != self.n_splines + k:
+                raise AssertionError("len(knots) must be n_splines + degree + 1 (interpolation.py:106)")
+            if self.n_splines < 4:
+                raise NotImplementedError("the CUDA path needs at least 4 basis functions per spline")
+            self.knots = np.ascontiguousarray(knots, dtype=np.float64)
         self.grid = grid
         inside = (grid_xi >= self.xi_range[0]) & (grid_xi <= self.xi_range[1])
         with np.errstate(divide="ignore"):
@@ -327,6 +347,7 @@ class Base1DBSplineModel:
                 name=f"spline[{cols[0]}]",
             )
             term.xi_range = model.xi_range
+            term.knots, term.order = model.knots, model.order
             return [term], groups, []
 
         if np.shape(coefs) != (self.n_splines,):
@@ -412,6 +433,8 @@ class BSplineRedshift(Base1DBSplineModel):
             raise NotImplementedError("only the LogXBSpline basis is implemented for BSplineRedshift")
         xrange = kwargs.pop("xrange", (1e-4, zmax))
         super().__init__(n_splines, z, z_inj, xrange=xrange, basis=basis, **kwargs)
+        if self.knots is not None:
+            raise NotImplementedError("BSplineRedshift with an explicit knot vector / degree != 3 is not implemented (its host-side normaliser map assumes the default knots)")
         self._coef_map = None
         if self.normalize:
             from .lowering import host_spline_design  # tiny, grid-only helper

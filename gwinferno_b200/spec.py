@@ -67,6 +67,10 @@ class Term:
     # grids (one entry per grid point of ``norm_group``)
     grid_xi: Optional[np.ndarray] = None  # SPLINE: spline coordinate at the grid points
     grid_feat: Optional[np.ndarray] = None  # LINEAR: feature value at the grid points
+    # SPLINE: explicit knot vector in spline-coordinate units (len n_splines + order) and order = degree + 1, the
+    # reference's knots= / interior_knots= / k= (interpolation.py:72-106); None = default uniform cubic knots
+    knots: Optional[np.ndarray] = None
+    order: int = 4
     name: str = ""
 
 

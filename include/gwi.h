@@ -104,6 +104,16 @@ typedef struct {
   const double* grid;  /* member of a norm group: per grid point, SPLINE: xi (NaN = outside the
                           basis range => contributes 0), LINEAR: feature value.  Host pointer,
                           n_grid doubles, copied during gwi_model_create. */
+  /* SPLINE, optional: an explicit knot vector and order -- the reference's `knots=` / `interior_knots=` /
+   * `k=` arguments (gwinferno/interpolation.py:72-106; Base1DBSplineModel(degree=), single.py:42-53).
+   * knots == NULL: the default uniform knots of a cubic basis on [xi_lo, xi_hi] (interpolation.py:98-106).
+   * Otherwise n_knots == n_splines + order doubles in spline-coordinate units (host pointer, copied), order in
+   * 1..4 (degree 0..3); the canonical B-spline basis of that knot vector is evaluated per polynomial piece
+   * exactly as the reference's Cox-de Boor recursion does (half-open spans, spans / supports shorter than
+   * 1e-6 contribute nothing, interpolation.py:128-149,268-278). */
+  const double* knots;
+  int32_t n_knots;
+  int32_t order;
 } gwi_term;
 
 typedef struct {

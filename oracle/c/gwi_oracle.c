@@ -128,8 +128,32 @@ static double feature(const gwi_term* t, const double* const* cols, int64_t j) {
   }
   return NAN;
 }
-/* first tap index and the 4 tap weights of the uniform cubic basis at spline coordinate xi (clamped) */
+/* M-spline basis i of order k at x on an explicit knot vector: the reference's recursion, number for number
+ * (gwinferno/interpolation.py:128-149: support shorter than 1e-6 => 0; order 1 = half-open indicator / width) */
+static double mspline(const double* t, int i, int k, double x) {
+  if (t[i + k] - t[i] < 1e-6) return 0.0;
+  if (k == 1) return (x >= t[i] && x < t[i + 1]) ? 1.0 / (t[i + 1] - t[i]) : 0.0;
+  const double v = (x - t[i]) * mspline(t, i, k - 1, x) + (t[i + k] - x) * mspline(t, i + 1, k - 1, x);
+  return (v * k) / ((k - 1) * (t[i + k] - t[i]));
+}
+/* first tap index and the 4 tap weights of the basis at spline coordinate xi (clamped to the range):
+ * explicit knot vector (gwi_term.knots; canonical B-splines = M-splines x (t[i+k]-t[i])/k, interpolation.py:278),
+ * else the closed form of the default uniform cubic basis */
 static int spline_taps(const gwi_term* t, double xi, double w[4]) {
+  if (t->knots) {
+    const double* kn = t->knots;
+    const int k = t->order, N = t->n_splines;
+    if (xi < t->xi_lo) xi = t->xi_lo;
+    if (xi > t->xi_hi) xi = t->xi_hi;
+    int m = -1; /* last knot <= xi */
+    for (int q = 0; q < t->n_knots; ++q)
+      if (kn[q] <= xi) m = q;
+    int j = m - k + 1;
+    if (j > N - 4) j = N - 4;
+    if (j < 0) j = 0;
+    for (int q = 0; q < 4; ++q) w[q] = (kn[j + q + k] - kn[j + q]) / k * mspline(kn, j + q, k, xi);
+    return j;
+  }
   const int n_int = t->n_splines - 2;
   const double dx = (t->xi_hi - t->xi_lo) / (n_int - 1);
   if (xi < t->xi_lo) xi = t->xi_lo;

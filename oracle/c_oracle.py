@@ -18,7 +18,7 @@ _dp = C.POINTER(C.c_double)
 class gwi_term(C.Structure):
     _fields_ = [("kind", C.c_int32), ("feature", C.c_int32), ("outside", C.c_int32), ("logx", C.c_int32), ("col", C.c_int32 * 2), ("slot", C.c_int32 * 6),
                 ("cst", C.c_double * 4), ("n_splines", C.c_int32), ("norm_group", C.c_int32), ("x_lo", C.c_double), ("x_hi", C.c_double),
-                ("xi_lo", C.c_double), ("xi_hi", C.c_double), ("grid", _dp)]
+                ("xi_lo", C.c_double), ("xi_hi", C.c_double), ("grid", _dp), ("knots", _dp), ("n_knots", C.c_int32), ("order", C.c_int32)]
 
 
 class gwi_norm_group(C.Structure):
@@ -89,6 +89,10 @@ class _Marshalled:
                 g = np.ascontiguousarray(grid, dtype=np.float64)
                 self.keep.append(g)
                 ct.grid = _ptr(g)
+            if getattr(t, "knots", None) is not None:
+                kn = np.ascontiguousarray(t.knots, dtype=np.float64)
+                self.keep.append(kn)
+                ct.knots, ct.n_knots, ct.order = _ptr(kn), kn.size, int(t.order)
         ng = len(spec.groups)
         self.groups = (gwi_norm_group * max(1, ng))()
         for i, g in enumerate(spec.groups):

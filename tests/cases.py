@@ -29,6 +29,9 @@ GOLDEN_CASES = [
     "default_spin",
     "mixed_bspline_m1",
     "mixed_plpeak_m1",
+    "bspline_knots",
+    "bspline_knots_margsel",
+    "bspline_knots_density",
 ]
 # Cases whose model carries host-side glue (a parameter map / a host normaliser, lowering.pull_back and
 # lowering.host_log_norm): the DEVICE model is an ordinary one, so they are checked on the CPU with the
@@ -53,7 +56,35 @@ LIKE_KW = {
     "mixed_bspline_m1": dict(min_neff_cut=False),
     "mixed_plpeak_m1": dict(min_neff_cut=False),
     "bspline_redshift_default": dict(min_neff_cut=False),
+    "bspline_knots": dict(min_neff_cut=False),
+    "bspline_knots_margsel": dict(marginalize_selection=True, min_neff_cut=False),
+    "bspline_knots_density": dict(min_neff_cut=False),
 }
+
+
+# knot vectors / degrees of the "bspline_knots" case; tests/cases.py rebuilds the mirror models from the same numbers
+def knots_case_kwargs(mmin=3.0, mmax=100.0):
+    n_m1, n_q, n_a1, n_a2, n_t = 13, 9, 8, 7, 10
+    # (a) explicit NON-UNIFORM knot vector for the mass (given in x units: the log-x bases take its logarithm,
+    #     interpolation.py:425-428): clamped cubic knots, denser at low mass
+    inner = mmin * (mmax / mmin) ** (np.linspace(0.0, 1.0, n_m1 - 2) ** 1.6)
+    m_knots = np.concatenate([[mmin * 0.7, mmin * 0.8, mmin * 0.9], inner, [mmax * 1.1, mmax * 1.2, mmax * 1.3]])
+    # (b) quadratic basis on default knots for q; (c) `interior_knots=` for a_1 (only their count and first spacing
+    #     matter, interpolation.py:99-101: the basis does NOT sum to one near the upper end); (d) linear basis for a_2;
+    # (e) a cubic vector with a repeated knot for the tilts (C^1 only there)
+    a1_interior = np.array([0.0, 0.08, 0.2, 0.45, 0.7, 1.0])
+    t_knots = np.concatenate([[-1.6, -1.4, -1.2], [-1.0, -0.5, 0.0, 0.0, 0.4, 0.8, 1.0], [1.2, 1.4, 1.6, 1.8]])
+    return dict(
+        ns=dict(m1=n_m1, q=n_q, a1=n_a1, a2=n_a2, t=n_t, z=6),
+        kwargs_m=dict(knots=m_knots), kwargs_q=dict(degree=2), kwargs_a1=dict(interior_knots=a1_interior), kwargs_a2=dict(degree=1), kwargs_t=dict(knots=t_knots),
+    )
+
+
+def knots_density_kwargs(mmin=3.0, mmax=100.0):
+    """Knots of the "bspline_knots_density" case: a non-uniform cubic vector for the LogXBSpline mass density (in x units),
+    a quadratic chi_eff density on default knots."""
+    inner = mmin * (mmax / mmin) ** (np.linspace(0.0, 1.0, 9) ** 0.7)
+    return dict(kwargs_m=dict(knots=np.concatenate([[2.0, 2.3, 2.6], inner, [120.0, 140.0, 160.0]])), kwargs_e=dict(degree=2))
 
 
 class Case:
@@ -179,6 +210,34 @@ def build_weight_fn(model, pe, inj, meta):
     if model == "bspline_symchieff":
         mm = M.BSplineMass(int(meta["n_m1"]), pe["mass_1"], inj["mass_1"], mmin=mmin, mmax=mmax, basis=M.LogXBSpline)
         me = M.BSplineSymmetricChiEffective(int(meta["n_e"]), pe["chi_eff"], inj["chi_eff"], normalize=True)
+        mp = M.BSplineChiPrecess(int(meta["n_p"]), pe["chi_p"], inj["chi_p"], basis=M.LogYBSpline)
+        mz = M.PowerlawSplineRedshiftModel(int(meta["n_z"]), pe["redshift"], inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            w = mm(p["mass_cs"], pe_samples=pe_samples) * me(p["chieff_cs"], pe_samples=pe_samples) * mp(p["chip_cs"], pe_samples=pe_samples)
+            return w * mz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(p["lamb"], p["z_cs"]))
+    if model == "bspline_knots":
+        K = knots_case_kwargs(mmin, mmax)
+        ns = K["ns"]
+        mm = M.BSplinePrimaryBSplineRatio(
+            ns["m1"], ns["q"], pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax,
+            kwargs_m={"basis": M.LogXLogYBSpline, **K["kwargs_m"]}, kwargs_q={"basis": M.LogYBSpline, **K["kwargs_q"]},
+        )
+        ma = M.BSplineIndependentSpinMagnitudes(ns["a1"], ns["a2"], pe["a_1"], pe["a_2"], inj["a_1"], inj["a_2"], kwargs1=K["kwargs_a1"], kwargs2=K["kwargs_a2"], normalize=True)
+        mt = M.BSplineIIDSpinTilts(ns["t"], pe["cos_tilt_1"], pe["cos_tilt_2"], inj["cos_tilt_1"], inj["cos_tilt_2"], normalize=True, **K["kwargs_t"])
+        mz = M.PowerlawSplineRedshiftModel(ns["z"], pe["redshift"], inj["redshift"])
+
+        def weights(d, pe_samples, p):
+            w = mm(p["mass_cs"], p["q_cs"], pe_samples=pe_samples) * ma(p["a1_cs"], p["a2_cs"], pe_samples=pe_samples)
+            return w * mt(p["tilt_cs"], pe_samples=pe_samples) * mz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+
+        return weights, (lambda p: mz.normalization(p["lamb"], p["z_cs"]))
+    if model == "bspline_knots_density":
+        K = knots_density_kwargs(mmin, mmax)
+        mm = M.BSplineMass(int(meta["n_m1"]), pe["mass_1"], inj["mass_1"], mmin=mmin, mmax=mmax, basis=M.LogXBSpline, **K["kwargs_m"])
+        me = M.BSplineChiEffective(int(meta["n_e"]), pe["chi_eff"], inj["chi_eff"], normalize=True, **K["kwargs_e"])
         mp = M.BSplineChiPrecess(int(meta["n_p"]), pe["chi_p"], inj["chi_p"], basis=M.LogYBSpline)
         mz = M.PowerlawSplineRedshiftModel(int(meta["n_z"]), pe["redshift"], inj["redshift"])
 

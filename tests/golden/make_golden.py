@@ -446,6 +446,71 @@ def case_bspline_symchieff():
     _save("bspline_symchieff", pe, inj, const, params, names, base, jac, dict(model="bspline_symchieff", mmin=mmin, mmax=mmax, **{f"n_{k}": v for k, v in ns.items()}))
 
 
+from tests.cases import knots_case_kwargs, knots_density_kwargs  # noqa: E402  (the same numbers build the mirror models)
+
+
+def case_bspline_knots():
+    """Explicit knot vectors and degrees != 3 through every basis flavour (interpolation.py:72-106,128-149): the legal
+    API the named configs do not use."""
+    E, S, I = 7, 240, 5000
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=140)
+    mmin, mmax = 3.0, 100.0
+    K = knots_case_kwargs(mmin, mmax)
+    ns = K["ns"]
+    assert len(K["kwargs_t"]["knots"]) == ns["t"] + 4 and len(K["kwargs_m"]["knots"]) == ns["m1"] + 4
+    rm = SEP.BSplinePrimaryBSplineRatio(
+        ns["m1"], ns["q"], pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax,
+        kwargs_m={"basis": INT.LogXLogYBSpline, **K["kwargs_m"]}, kwargs_q={"basis": INT.LogYBSpline, **K["kwargs_q"]},
+    )
+    ra = SEP.BSplineIndependentSpinMagnitudes(ns["a1"], ns["a2"], pe["a_1"], pe["a_2"], inj["a_1"], inj["a_2"], kwargs1=K["kwargs_a1"], kwargs2=K["kwargs_a2"], normalize=True)
+    rt = SEP.BSplineIIDSpinTilts(ns["t"], pe["cos_tilt_1"], pe["cos_tilt_2"], inj["cos_tilt_1"], inj["cos_tilt_2"], normalize=True, **K["kwargs_t"])
+    rz = SPL.PowerlawSplineRedshiftModel(ns["z"], pe["redshift"], inj["redshift"])
+    rng = np.random.default_rng(140002)
+    params = dict(
+        mass_cs=0.4 * rng.standard_normal(ns["m1"]), q_cs=0.4 * rng.standard_normal(ns["q"]), a1_cs=0.4 * rng.standard_normal(ns["a1"]),
+        a2_cs=0.4 * rng.standard_normal(ns["a2"]), tilt_cs=0.4 * rng.standard_normal(ns["t"]), lamb=np.float64(2.4), z_cs=0.3 * rng.standard_normal(ns["z"]),
+    )
+    names = ["mass_cs", "q_cs", "a1_cs", "a2_cs", "tilt_cs", "lamb", "z_cs"]
+
+    def weights(d, pe_samples, p):
+        w = rm(p["mass_cs"], p["q_cs"], pe_samples=pe_samples) * ra(p["a1_cs"], p["a2_cs"], pe_samples=pe_samples)
+        return w * rt(p["tilt_cs"], pe_samples=pe_samples) * rz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+
+    vt = lambda p: rz.normalization(p["lamb"], p["z_cs"])  # noqa: E731
+    for name, kw in (("bspline_knots", dict(min_neff_cut=False)), ("bspline_knots_margsel", dict(marginalize_selection=True, min_neff_cut=False))):
+        base, jac = _complex_step(weights, pe, inj, const, params, names, vt, kw)
+        _save(name, pe, inj, const, params, names, base, jac, dict(model="bspline_knots", mmin=mmin, mmax=mmax, **{f"n_{k}": v for k, v in ns.items()}))
+
+
+def case_bspline_knots_density():
+    """Spline DENSITIES (BSpline / LogXBSpline bases: the spline is the pdf, interpolation.py:293-317) on explicit knots and
+    with degree 2: the linear normaliser (BSpline.norm, :280-291) over per-piece polynomials."""
+    E, S, I = 6, 200, 4000
+    pe, inj, const = synthetic.make_catalog(E, S, I, cfg=141)
+    _with_derived(pe, inj)
+    ns = dict(m1=11, e=8, p=7, z=6)
+    mmin, mmax = 3.0, 100.0
+    K = knots_density_kwargs(mmin, mmax)
+    rm = SGL.BSplineMass(ns["m1"], pe["mass_1"], inj["mass_1"], mmin=mmin, mmax=mmax, basis=INT.LogXBSpline, **K["kwargs_m"])
+    re_ = SGL.BSplineChiEffective(ns["e"], pe["chi_eff"], inj["chi_eff"], normalize=True, **K["kwargs_e"])
+    rp = SGL.BSplineChiPrecess(ns["p"], pe["chi_p"], inj["chi_p"], basis=INT.LogYBSpline)
+    rz = SPL.PowerlawSplineRedshiftModel(ns["z"], pe["redshift"], inj["redshift"])
+    rng = np.random.default_rng(141002)
+    params = dict(
+        mass_cs=np.exp(0.8 * rng.standard_normal(ns["m1"])), chieff_cs=np.exp(0.5 * rng.standard_normal(ns["e"])),
+        chip_cs=0.5 * rng.standard_normal(ns["p"]), lamb=np.float64(2.2), z_cs=0.3 * rng.standard_normal(ns["z"]),
+    )
+    names = ["mass_cs", "chieff_cs", "chip_cs", "lamb", "z_cs"]
+
+    def weights(d, pe_samples, p):
+        w = rm(p["mass_cs"], pe_samples=pe_samples) * re_(p["chieff_cs"], pe_samples=pe_samples) * rp(p["chip_cs"], pe_samples=pe_samples)
+        return w * rz(d["redshift"], p["lamb"], p["z_cs"]) / d["prior"]
+
+    vt = lambda p: rz.normalization(p["lamb"], p["z_cs"])  # noqa: E731
+    base, jac = _complex_step(weights, pe, inj, const, params, names, vt, dict(min_neff_cut=False))
+    _save("bspline_knots_density", pe, inj, const, params, names, base, jac, dict(model="bspline_knots_density", mmin=mmin, mmax=mmax, **{f"n_{k}": v for k, v in ns.items()}))
+
+
 CASES = dict(
     bspline_full=case_bspline_full,
     bspline_full_maxvar=lambda: case_bspline_full(maxvar_only=True),
@@ -460,6 +525,8 @@ CASES = dict(
     default_spin=case_default_spin,
     mixed_mass=case_mixed_mass,
     bspline_redshift_default=case_bspline_redshift_default,
+    bspline_knots=case_bspline_knots,
+    bspline_knots_density=case_bspline_knots_density,
 )
 
 if __name__ == "__main__":

@@ -71,9 +71,15 @@ def test_unsupported_reference_options_fail_loudly(cat):
     with pytest.raises(NotImplementedError):
         M.BSplineRedshift(8, pe["redshift"], inj["redshift"], pe["redshift"], inj["redshift"], basis=M.LogYBSpline)
     with pytest.raises(NotImplementedError):
-        M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], degree=2)
+        M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], degree=4)  # 5 coefficients per piece: not on the CUDA path
+    with pytest.raises(AssertionError):
+        M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], knots=np.linspace(0, 1, 11))  # interpolation.py:106
     with pytest.raises(NotImplementedError):
-        M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], knots=np.linspace(0, 1, 12))
+        M.BSplineRedshift(8, pe["redshift"], inj["redshift"], pe["redshift"], inj["redshift"], degree=2)
+    m = M.BSplineSpinMagnitude(8, pe["a_1"], inj["a_1"], degree=2)  # explicit knots / other degrees lower to a knot vector
+    assert m.order == 3 and len(m.knots) == 8 + 3
+    m = M.BSplineMass(9, pe["mass_1"], inj["mass_1"], mmin=3, mmax=100, knots=np.geomspace(2.0, 150.0, 13))
+    assert np.allclose(m.knots, np.log(np.geomspace(2.0, 150.0, 13)))  # log-x bases take the log of user knots (:425-428)
 
 
 def test_parametric_free_functions_lower_to_parametric_terms(cat):

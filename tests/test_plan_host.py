@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header_sizes():
     # sizes implied by include/gwi.h on LP64
-    assert C.sizeof(capi.gwi_term) == 4 * 4 + 2 * 4 + 6 * 4 + 4 * 8 + 2 * 4 + 4 * 8 + 8
+    assert C.sizeof(capi.gwi_term) == 4 * 4 + 2 * 4 + 6 * 4 + 4 * 8 + 2 * 4 + 4 * 8 + 8 + 8 + 2 * 4
     assert C.sizeof(capi.gwi_cut) == 4 + 8 + 4 + 16 or C.sizeof(capi.gwi_cut) == 32
     assert C.sizeof(capi.gwi_like_opts) == 16
     assert C.sizeof(capi.gwi_model_info) == 6 * 8 + 10 * 4 + 2 * 4 + 5 * 8
