@@ -279,6 +279,10 @@ def _cuda_check(rc, what):
         raise GwiError(-2, f"{what}: {cudart().cudaGetErrorString(rc).decode()}")
 
 
+def _is_device_array(a):
+    return not isinstance(a, np.ndarray) and hasattr(a, "__cuda_array_interface__")
+
+
 class DeviceBuffer:
     """fp64 device array (cudaMalloc) with host <-> device copies."""
 
@@ -316,6 +320,25 @@ class DeviceBuffer:
 
 def synchronize():
     _cuda_check(cudart().cudaDeviceSynchronize(), "cudaDeviceSynchronize")
+
+
+class DeviceArray:
+    """A float64 array in device memory exposing ``__cuda_array_interface__`` -- what a jax / torch / cupy array looks like
+    to this package (tests and the bench use it to hand device-resident sample columns to the model classes)."""
+
+    def __init__(self, a, device=0):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self.shape = tuple(a.shape)
+        self._buf = DeviceBuffer(a.size, device)
+        if a.size:
+            self._buf.upload(a.reshape(-1))
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "<f8", "data": (int(self._buf.ptr or 0), False), "version": 3, "strides": None}
+
+    def download(self):
+        return self._buf.download().reshape(self.shape)
 
 
 # ---- description marshalling -----------------------------------------------------------------
@@ -399,6 +422,13 @@ class Catalog:
             raise ValueError("PE and injection column names must match")
         self.col_index = {n: i for i, n in enumerate(self.names)}
         first = pe_cols[self.names[0]]
+        dev = [_is_device_array(v) for v in list(pe_cols.values()) + list(inj_cols.values())]
+        if any(dev):
+            # device-resident columns (jax / torch / cupy arrays, DeviceArray): borrowed as device pointers
+            if not all(dev):
+                raise ValueError("the sample columns of one catalog must be all host arrays or all device arrays")
+            self._init_from_device_arrays(lib, pe_cols, inj_cols, total_inj, device)
+            return
         if isinstance(first, np.ndarray) and first.ndim == 2:
             E, S_ = first.shape
             self.offsets = np.arange(E + 1, dtype=np.int64) * S_
@@ -447,6 +477,38 @@ class Catalog:
         _check(lib.gwi_catalog_create(C.byref(d), C.byref(h)))
         self.handle = h
         self._owner = lib  # a handle is destroyed by the library that created it
+
+    def _init_from_device_arrays(self, lib, pe_cols, inj_cols, total_inj, device):
+        def ptr(a, ndim):
+            ci = a.__cuda_array_interface__
+            if ci.get("typestr") != "<f8" or ci.get("strides") is not None or len(ci["shape"]) != ndim:
+                raise ValueError("device-resident sample arrays must be C-contiguous float64, (E, S) for PE samples and (I,) for injections")
+            return C.cast(C.c_void_p(int(ci["data"][0])), C.POINTER(C.c_double)), tuple(int(x) for x in ci["shape"])
+
+        pe = [ptr(pe_cols[n], 2) for n in self.names]
+        inj = [ptr(inj_cols[n], 1) for n in self.names]
+        if len({s for _, s in pe}) != 1 or len({s for _, s in inj}) != 1:
+            raise ValueError("inconsistent column shapes")
+        E, S_ = pe[0][1]
+        self._keep = (list(pe_cols.values()), list(inj_cols.values()))  # the arrays own the device memory
+        self.pe = self.inj = None
+        self.offsets = np.arange(E + 1, dtype=np.int64) * S_
+        self.n_events, self.n_inj, self.total_inj = int(E), int(inj[0][1][0]), float(total_inj)
+        ncol = len(self.names)
+        self.on_device = True
+        self._pe_ptrs = (C.POINTER(C.c_double) * ncol)(*[p for p, _ in pe])
+        self._inj_ptrs = (C.POINTER(C.c_double) * ncol)(*[p for p, _ in inj])
+        d = gwi_catalog_desc()
+        d.n_columns, d.n_events = ncol, self.n_events
+        d.pe_offsets = self.offsets.ctypes.data_as(C.POINTER(C.c_int64))
+        d.pe_columns, d.n_inj, d.inj_columns = self._pe_ptrs, self.n_inj, self._inj_ptrs
+        d.total_inj, d.device, d.columns_on_device = self.total_inj, int(device), 1
+        self.device = int(device)
+        self._desc = d
+        h = C.c_void_p()
+        _check(lib.gwi_catalog_create(C.byref(d), C.byref(h)))
+        self.handle = h
+        self._owner = lib
 
     def close(self):
         if getattr(self, "handle", None):

@@ -194,7 +194,7 @@ def lower(pe_w, inj_w):
         if key not in col_names:
             name = f"c{len(col_names)}"
             col_names[key] = name
-            if pe_arr.ndim != 2 or inj_arr.ndim != 1:
+            if len(pe_arr.shape) != 2 or len(inj_arr.shape) != 1:
                 raise ValueError("PE columns must be (E, S) arrays and injection columns (I,) arrays")
             pe_cols[name] = pe_arr
             inj_cols[name] = inj_arr
@@ -213,10 +213,10 @@ def lower(pe_w, inj_w):
             if not any(c.kind == o.kind and c.cols == o.cols and c.lo == o.lo and c.hi == o.hi for o in cuts):
                 cuts.append(c)
     spec = S.ModelSpec(terms, groups, cuts, n_params)
-    shapes = {v.shape for v in pe_cols.values()}
+    shapes = {tuple(v.shape) for v in pe_cols.values()}
     if len(shapes) != 1:
         raise ValueError(f"PE columns have inconsistent shapes: {shapes}")
-    shapes = {v.shape for v in inj_cols.values()}
+    shapes = {tuple(v.shape) for v in inj_cols.values()}
     if len(shapes) != 1:
         raise ValueError(f"injection columns have inconsistent shapes: {shapes}")
     return Lowered(spec, pe_cols, inj_cols, layout, object_slot_map(pe_w))

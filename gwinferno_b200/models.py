@@ -142,12 +142,28 @@ def _share():
     return ("shared", next(_UID))
 
 
+def is_device_array(a):
+    """Sample arrays may live in DEVICE memory: any object exposing ``__cuda_array_interface__`` (jax / torch / cupy arrays,
+    ``capi.DeviceArray``).  They flow through the model classes untouched and reach the library as device pointers
+    (``gwi_catalog_desc.columns_on_device``): the plan is then built on the GPU without a host round trip."""
+    return not isinstance(a, np.ndarray) and hasattr(a, "__cuda_array_interface__")
+
+
+def _as_samples(a):
+    if is_device_array(a):
+        ci = a.__cuda_array_interface__
+        if ci.get("typestr") != "<f8" or ci.get("strides") is not None:
+            raise ValueError("device-resident sample arrays must be C-contiguous float64")
+        return a
+    return np.asarray(a, dtype=np.float64)
+
+
 class _Column:
     """A (PE array, injection array) pair of one physical sample coordinate."""
 
     def __init__(self, pe, inj):
-        self.pe = None if pe is None else np.asarray(pe, dtype=np.float64)
-        self.inj = None if inj is None else np.asarray(inj, dtype=np.float64)
+        self.pe = None if pe is None else _as_samples(pe)
+        self.inj = None if inj is None else _as_samples(inj)
 
 
 class _LazyTerm:
@@ -224,7 +240,7 @@ class LazyWeight:
         if self.log_domain:
             raise TypeError("log-weights combine with + and -, not /")
         # division by the sampling-prior array (examples/simple_bspline_example.py:66)
-        arr = np.asarray(other, dtype=np.float64)
+        arr = _as_samples(other)
         return self * weight_from_prior(arr, pe_samples=self.pe_samples)
 
     def __add__(self, other):
@@ -254,9 +270,9 @@ class LazyWeight:
 def weight_from_prior(prior, pe_samples=None):
     """``1/prior`` as a lazy static term.  ``pe_samples`` is inferred from the dimensionality when
     omitted (2-D = PE samples, 1-D = injections; same convention as parametric.py:130)."""
-    prior = np.asarray(prior, dtype=np.float64)
+    prior = _as_samples(prior)
     if pe_samples is None:
-        pe_samples = prior.ndim == 2
+        pe_samples = len(prior.shape) == 2
     col = _Column(prior if pe_samples else None, None if pe_samples else prior)
 
     def build(slots, group_base, cols):
@@ -266,7 +282,7 @@ def weight_from_prior(prior, pe_samples=None):
 
 
 def _is_pe(arr):
-    return np.ndim(arr) == 2
+    return (len(arr.shape) if is_device_array(arr) else np.ndim(arr)) == 2
 
 
 # ================================================================================================
@@ -404,6 +420,8 @@ class BSplineSymmetricChiEffective(Base1DBSplineModel):
 
     def __init__(self, n_splines, chieff, chieff_inj, basis=BSpline, **kwargs):
         xrange = kwargs.pop("xrange", (0.0, 1.0))
+        if is_device_array(chieff) or is_device_array(chieff_inj):
+            raise NotImplementedError("device-resident arrays: pass |chi_eff| to BSplineChiEffective(xrange=(0, 1)) yourself (the abs() of single.py:262-263 is a host operation here)")
         super().__init__(n_splines, np.abs(chieff), np.abs(chieff_inj), basis=basis, xrange=xrange, **kwargs)
 
     def __call__(self, coefs, pe_samples=True):
@@ -452,6 +470,8 @@ class BSplineRedshift(Base1DBSplineModel):
             self._coef_map = ParamMap(fwd, vjp)
         self.dvdc_column = _Column(dVdc, dVdc_inj)
         if z_range is None:
+            if is_device_array(self.column.pe) or is_device_array(self.column.inj):
+                raise ValueError("device-resident redshift arrays: pass z_range=(zmin, zmax)")
             self.zmin = float(max(np.min(self.column.pe), np.min(self.column.inj)))  # single.py:445
             self.zmax = float(min(np.max(self.column.pe), np.max(self.column.inj)))  # :446
         else:  # a process holding a SHARD passes the whole catalog's range
@@ -632,7 +652,7 @@ def _col_of(arr):
     if col is not None:
         _COLUMN_CACHE.move_to_end(key)
         return col
-    a = np.asarray(arr, dtype=np.float64)
+    a = _as_samples(arr)
     col = _Column(a if _is_pe(a) else None, None if _is_pe(a) else a)
     _COLUMN_CACHE[key] = col
     while len(_COLUMN_CACHE) > _COLUMN_CACHE_MAX:
@@ -775,6 +795,8 @@ class PowerlawRedshiftModel:
         z_pe = self.column.pe
         z_inj = self.column.inj
         if z_range is None:
+            if is_device_array(z_pe) or is_device_array(z_inj):
+                raise ValueError("device-resident redshift arrays: pass z_range=(zmin, zmax) (the data-derived range of parametric.py:114-115 needs the values on the host)")
             self.zmin = float(max(np.min(z_pe), np.min(z_inj)))  # parametric.py:114
             self.zmax = float(min(np.max(z_pe), np.max(z_inj)))  # parametric.py:115
         else:
@@ -787,7 +809,7 @@ class PowerlawRedshiftModel:
         self._norm_cache = None
 
     def _which(self, z):
-        if z is self.column.pe or (_is_pe(z) and np.shape(z) == np.shape(self.column.pe)):
+        if z is self.column.pe or (_is_pe(z) and tuple(z.shape) == tuple(self.column.pe.shape)):
             return True
         return False
 
