@@ -127,6 +127,26 @@ __device__ void powerlaw_lognorm(double alpha, double lo, double hi, double& log
   dnorm = 1.0 / a1 - (ha * log(hi) - la * log(lo)) / den;
 }
 
+// Upper bound of the spline on polynomial piece J of dim D (convex-hull property: the bases are >= 0 and sum to <= 1):
+// the maximum of the coefficients the piece uses.  Default pieces: c[J..J+3]; explicit knot vector: the coefficients whose
+// basis polynomial on the piece is not identically zero, floored at 0 where the bases do not sum to one.
+__device__ __forceinline__ double piece_upper_bound(const ModelDev& M, const DimDev& D, int J, const double* __restrict__ Lam) {
+  if (J >= D.rows - 1) return 0.0;  // the dummy all-zero piece
+  if (D.basis_off < 0) {
+    const double* c = Lam + D.slot + J;
+    return fmax(fmax(c[0], c[1]), fmax(c[2], c[3]));
+  }
+  const double* Bm = M.grid_pool + D.basis_off + J * 16;
+  const double* c = Lam + D.slot + (int)M.grid_pool[D.first_off + J];
+  double ub = M.grid_pool[D.floor_off + J];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double* b = Bm + k * 4;
+    if (b[0] != 0.0 || b[1] != 0.0 || b[2] != 0.0 || b[3] != 0.0) ub = fmax(ub, c[k]);
+  }
+  return ub == -INFINITY ? 0.0 : ub;  // a piece without any basis: the spline is 0 there
+}
+
 // =================================================================================================
 // prologue
 // =================================================================================================
@@ -267,13 +287,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
       int d = 0;
       while (d + 1 < M.n_dims && r >= M.dims[d + 1].row_off) ++d;
       const DimDev& D = M.dims[d];
-      const int J = r - D.row_off;
-      double ub = 0.0;
-      if (J < D.rows - 1) {
-        const double* c = Lam + D.slot + J;
-        ub = fmax(fmax(c[0], c[1]), fmax(c[2], c[3]));
-      }
-      ub_s[r] = ub;
+      ub_s[r] = piece_upper_bound(M, D, r - D.row_off, Lam);
     }
     __syncthreads();
     const int s = (role - M.n_groups - 1) * nt + tid;
@@ -330,25 +344,19 @@ __global__ void __launch_bounds__(256) prologue_kernel(const ModelDev* __restric
     const DimDev& D = M.dims[d];
     const int J = r - D.row_off;
     double a[4] = {0.0, 0.0, 0.0, 0.0};
-    double ub = 0.0;
+    const double ub = piece_upper_bound(M, D, J, Lam);
     if (J < D.rows - 1) {
       if (D.basis_off < 0) {  // default uniform cubic pieces
         const double* c = Lam + D.slot + J;
-        ub = fmax(fmax(c[0], c[1]), fmax(c[2], c[3]));
 #pragma unroll
         for (int n = 0; n < 4; ++n) a[n] = c[0] * BETA[0][n] + c[1] * BETA[1][n] + c[2] * BETA[2][n] + c[3] * BETA[3][n];
-      } else {  // explicit knot vector / order: per-piece basis polynomials, only the coefficients the piece uses count
+      } else {  // explicit knot vector / order: per-piece basis polynomials
         const double* Bm = M.grid_pool + D.basis_off + J * 16;
         const double* c = Lam + D.slot + (int)M.grid_pool[D.first_off + J];
-        ub = M.grid_pool[D.floor_off + J];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double* b = Bm + k * 4;
-          if (b[0] != 0.0 || b[1] != 0.0 || b[2] != 0.0 || b[3] != 0.0) ub = fmax(ub, c[k]);
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int n = 0; n < 4; ++n) a[n] += c[k] * b[n];
-        }
-        if (ub == -INFINITY) ub = 0.0;  // a piece without any basis: the spline is 0 there
+          for (int n = 0; n < 4; ++n) a[n] += c[k] * Bm[k * 4 + n];
       }
     }
 #pragma unroll
