@@ -311,8 +311,8 @@ def run_ours(args):
     P = low.spec.n_params
     t_gen = time.perf_counter() - t_setup
     eng = PopulationLikelihood(low, const["total_inj"], device=local, need_neff_grad=False, chunk_steps=args.chunk_steps, n_deep=args.n_deep,
-                               batch_hint=workloads.N_CHAINS.get(name, 1))
-    t_plan = time.perf_counter() - t_setup - t_gen
+                               batch_hint=workloads.N_CHAINS.get(name, 1), catalog_on_device=args.catalog_on_device)
+    t_plan = time.perf_counter() - t_setup - t_gen  # (with --catalog-on-device this includes the up-front column upload; gwi_model_create alone is in setup_s)
     info = eng.info()
     mdl = eng.model
     Nobs = const["E"]
@@ -523,6 +523,8 @@ def main():
     ap.add_argument("--flush-l2", action="store_true", help="cold numbers: evict L2 between steps (for the L2-resident configurations)")
     ap.add_argument("--emulate-world", type=int, default=1, help="tuning aid: run rank 0's shard of a W-way partition on one GPU")
     ap.add_argument("--shard-by", default="bucket", choices=["bucket", "index"], help="multi-GPU partition of the found injections")
+    ap.add_argument("--catalog-on-device", action="store_true",
+                    help="place the sample columns in device memory before gwi_model_create (a caller whose arrays already live on the GPU): the plan build then moves nothing over PCIe")
     ap.add_argument("--n-deep", type=int, default=-1, help="tuning experiment: spline dims with lane-private accumulators (-1 = auto)")
     ap.add_argument("--chunk-steps", type=int, default=0, help="tuning experiment: samples per lane per chunk (0 = auto)")
     args = ap.parse_args()

@@ -39,6 +39,13 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 done
+# plan build on the device: the builder's own kernels (key, CUB radix sort passes, bounds, rates, fill) with their device times,
+# and gwi_model_create with a device-resident catalog (nothing crosses PCIe)
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"pd_|RadixSort" -c 40 --csv --log-file "$OUT/${TAG}_cfg3_plan_build_launches.csv" \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> "$OUT/${TAG}_ncu_plan_err.txt"
+GWI_PLAN_TIMING=1 python bench.py --steps 20 --no-cpu-baseline --catalog-on-device 2> "$OUT/${TAG}_plan_on_device_catalog_err.txt" | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg3 device-resident catalog: setup', d['setup_s'], 'log_l', d['result']['log_l'])" | tee "$OUT/${TAG}_plan_on_device_catalog.txt"
+grep "gwi plan" "$OUT/${TAG}_plan_on_device_catalog_err.txt" | tail -1 | tee -a "$OUT/${TAG}_plan_on_device_catalog.txt"
 # launch list of the default command (short run: ncu serialises and replays)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --log-file "$OUT/${TAG}_cfg3_launches.csv" \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2> "$OUT/${TAG}_ncu_launches_err.txt"
