@@ -171,6 +171,8 @@ SYMBOLS = [
     "gwi_debug_plan_destroy",
     "gwi_debug_plan_read",
     "gwi_debug_model_read",
+    "gwi_synth_injections",
+    "gwi_device_minmax",
     "gwi_nuts_sample",
     "gwi_posterior_create",
     "gwi_posterior_destroy",
@@ -202,6 +204,8 @@ def load_library(_allow_emulator=False):
     lib.gwi_partial_size.argtypes = [C.c_void_p]
     lib.gwi_debug_plan_read.restype = C.c_int64
     lib.gwi_debug_plan_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    lib.gwi_synth_injections.argtypes = [C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.gwi_device_minmax.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
     lib.gwi_debug_model_read.restype = C.c_int64
     lib.gwi_debug_model_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     lib.gwi_catalog_create.argtypes = [C.POINTER(gwi_catalog_desc), C.POINTER(C.c_void_p)]
@@ -333,12 +337,37 @@ class DeviceArray:
         if a.size:
             self._buf.upload(a.reshape(-1))
 
+    @classmethod
+    def empty(cls, shape, device=0):
+        self = cls.__new__(cls)
+        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
+        self._buf = DeviceBuffer(int(np.prod(self.shape)), device)
+        return self
+
     @property
     def __cuda_array_interface__(self):
         return {"shape": self.shape, "typestr": "<f8", "data": (int(self._buf.ptr or 0), False), "version": 3, "strides": None}
 
     def download(self):
         return self._buf.download().reshape(self.shape)
+
+    def minmax(self):
+        """(min, max) computed on the device (gwi_device_minmax), NaN entries ignored."""
+        out = (C.c_double * 2)()
+        _check(load_library().gwi_device_minmax(int(self._buf.device), C.c_void_p(self._buf.ptr), int(np.prod(self.shape)), out))
+        return float(out[0]), float(out[1])
+
+
+INJ_COLUMNS = ["mass_1", "mass_ratio", "mass_2", "a_1", "a_2", "cos_tilt_1", "cos_tilt_2", "redshift", "prior"]
+
+
+def synth_injections_device(seed, first, count, device=0):
+    """The synthetic found-injection set ``[first, first + count)`` generated on the device (gwi_synth_injections):
+    {column name: DeviceArray}.  Bit-identical to ``synthetic.make_injections_philox(seed, first, count)``."""
+    cols = {n: DeviceArray.empty((int(count),), device) for n in INJ_COLUMNS}
+    ptrs = (C.c_void_p * 9)(*[C.c_void_p(cols[n]._buf.ptr) for n in INJ_COLUMNS])
+    _check(load_library().gwi_synth_injections(int(device), int(seed), int(first), int(count), ptrs, None))
+    return cols
 
 
 # ---- description marshalling -----------------------------------------------------------------

@@ -506,6 +506,11 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
       } else {
         dev_build = false;
       }
+    } else if (rc == GWI_ERR_ALLOC && !cat->view.on_device) {
+      // the device builder holds the raw columns, the sort buffers AND the plan at its peak (~2.2x the plan): a shard that
+      // only just fits the GPU is built on the host instead (the plan alone is uploaded)
+      cudaGetLastError();
+      dev_build = false;
     }
   }
   if (!dev_build) rc = build_plan_noexcept(cat->view, *desc, prop.multiProcessorCount, 0, m->plan);

@@ -77,6 +77,38 @@ def make_injections(I, seed, start=0, stop=None):
     return dict(zip(INJ_COLS, out))
 
 
+# ---- the counter-based generator of libgwi's gwi_synth_injections (csrc/synth.cu), bit for bit ---------------------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 on arrays of 32-bit words held in uint64 (so that 32 x 32 -> 64-bit products are exact)."""
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85, np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0), p1 & MASK, (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1), p0 & MASK
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def make_injections_philox(seed, first, count):
+    """Injections ``[first, first + count)`` of the device generator (``gwi_synth_injections``): the same uniform draw over
+    the support as :func:`make_injections`, but every injection takes its seven uniforms from Philox blocks keyed by its own
+    GLOBAL index -- any range can be produced on any rank, on the device, without the rest."""
+    i = np.arange(first, first + count, dtype=np.uint64)
+    lo, hi = i & np.uint64(0xFFFFFFFF), i >> np.uint64(32)
+    u = []
+    for b in range(4):
+        x, y, z, w = philox4x32_10(lo, hi, np.full(count, b, dtype=np.uint64), np.zeros(count, dtype=np.uint64), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        for h, l in ((x, y), (z, w)):
+            u.append((((h << np.uint64(32)) | l) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0))
+    m1 = MMIN + (MMAX - MMIN) * u[0]
+    qlo = MMIN / m1
+    q = qlo + (1.0 - qlo) * u[1]
+    z = ZLO + (ZHI - ZLO) * u[6]
+    prior = 1.0 / (MMAX - MMIN) / (1.0 - qlo) / 4.0 / (ZHI - ZLO)
+    return dict(zip(INJ_COLS, [m1, q, m1 * q, u[2], u[3], -1.0 + 2.0 * u[4], -1.0 + 2.0 * u[5], z, prior]))
+
+
 def make_events(E, S, seed):
     rng = np.random.default_rng(seed)
     # fiducial population for the event centres

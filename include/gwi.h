@@ -391,6 +391,18 @@ int gwi_nuts_sample_posterior_chains(gwi_posterior* p, int32_t n_chains, const d
 const char* gwi_last_error(void);
 int gwi_version(void);
 
+/* ---- device-side helpers for device-resident catalogs ----------------------------------------
+ * The synthetic found-injection set of the benchmarks (uniform over the support, `prior` = the density of the
+ * draw) generated on the device: counter-based (Philox4x32-10 keyed by `seed`, counter = global injection index),
+ * so a rank generates exactly its index range [first, first + count) and nothing crosses PCIe.
+ * columns_dev[9]: device pointers to `count` doubles each -- mass_1, mass_ratio, mass_2, a_1, a_2, cos_tilt_1,
+ * cos_tilt_2, redshift, prior.  Asynchronous on `stream`.  (The reference has no counterpart: its injections are
+ * read from files, gwinferno/preprocess/selection.py; gwinferno_b200/synthetic.py holds the bit-exact NumPy twin.) */
+int gwi_synth_injections(int32_t device, uint64_t seed, int64_t first, int64_t count, double* const* columns_dev, void* stream);
+/* min / max of a device array, NaN entries ignored (the data-derived redshift range of parametric.py:114-115 for
+ * device-resident columns); out_host[2].  Synchronous. */
+int gwi_device_minmax(int32_t device, const double* x_dev, int64_t n, double* out_host);
+
 /* ---- test hooks (host-only, no CUDA needed): build the plan and read it back -------------- */
 typedef struct gwi_plan gwi_plan;
 int gwi_debug_plan_build(const gwi_catalog* cat, const gwi_model_desc* desc, int32_t n_workers, gwi_plan** out);
