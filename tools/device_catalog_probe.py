@@ -30,7 +30,15 @@ def main():
     cfg = int(args.workload[3:])
     S, I = max(8, int(round(S * args.scale))), max(64, int(round(I * args.scale)))
     capi.load_library()
-    capi.DeviceArray(np.zeros(1))  # CUDA context
+    # warm-up: CUDA context, module load of libgwi's kernels (a tiny model through the same calls), so that the times below are
+    # the work itself and not the process start-up
+    wpe, winj, wconst = synthetic.make_catalog(4, 64, 2000, cfg=9)
+    wd_pe, wd_inj = {k: capi.DeviceArray(v) for k, v in wpe.items()}, capi.synth_injections_device(1, 0, 2000)
+    ww, wp = workloads.build_model(family, wd_pe, wd_inj, z_range=(0.01, 1.5))
+    wlow, wlam, _ = workloads.lower_workload(ww, wp, wd_pe, wd_inj)
+    weng = PopulationLikelihood(wlow, 8000.0)
+    weng.loglike(wlam, Nobs=4)
+    weng.model.close()
     t = {}
     t0 = time.perf_counter()
     pe = synthetic.make_events(E, S, 1000 * cfg + 0)
