@@ -318,6 +318,22 @@ static int64_t plan_read(const Plan& p, int32_t what, void* dst, int64_t cap) {
         v.push_back(bits);
       }
       break;
+    case 6:  // per-segment statistics behind the a-priori shift: max static weight, occupied pieces, LIN feature ranges (bit patterns)
+      for (auto& sg : p.segments) {
+        int64_t bits;
+        std::memcpy(&bits, &sg.max_static, 8);
+        v.push_back(bits);
+        for (int d = 0; d < MAX_SPLINE_DIMS; ++d) v.push_back((int64_t)sg.occ[d]);
+        for (int q = 0; q < MAX_KOPS; ++q) {
+          std::memcpy(&bits, &sg.fmin[q], 8);
+          v.push_back(bits);
+        }
+        for (int q = 0; q < MAX_KOPS; ++q) {
+          std::memcpy(&bits, &sg.fmax[q], 8);
+          v.push_back(bits);
+        }
+      }
+      break;
     default:
       return GWI_ERR_INVALID;
   }

@@ -415,6 +415,8 @@ void gwi_debug_plan_destroy(gwi_plan* p);
  *       3 = segment table [n_segments * 4] int64 {n_total, n_valid, first_chunk, n_chunks}
  *       4 = spline dim table [n_spline * 4] int64 {term index, rows (= n_splines-2), row offset, deep?}
  *       5 = non-spline op table [n_ops * 8] int64 {kind, column0, column1, slot0..slot3, bits of cst0}
+ *       6 = per-segment statistics behind the a-priori shift [n_segments * 41] int64 {bits of max static weight,
+ *           occupied pieces[8], bits of LIN feature min[16], max[16]}
  * Returns the number of 8-byte items written (or needed when dst == NULL). */
 int64_t gwi_debug_plan_read(const gwi_plan* p, int32_t what, void* dst, int64_t cap_items);
 /* The same reader on a live model (what = 0, 2, 3, 4, 5 as above; what = 1 copies the plan's stream columns back
