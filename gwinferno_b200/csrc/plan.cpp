@@ -920,7 +920,12 @@ int plan_geometry(const gwi_model_desc& desc, int sm_count, const PlanInputs& in
   // (measured optimum 64-128 on a 1.3e7-sample shard; on 1e8 samples 256 -> 2.40 ms, 512 -> 2.34,
   // 768 -> 2.33, 1024 -> 2.32 with the guided shrink below taking care of the tail).
   const int64_t per_warp = (total_steps + W - 1) / W;
-  int64_t L = roundQ(std::max<int64_t>(per_warp < 64 ? 32 : 64, std::min<int64_t>(768, per_warp / 4)));
+  // slices per warp the one-role kernel aims for: 4 on long catalogs, 2 where a warp only has a few hundred steps (an 8-way cfg3
+  // shard, 330 steps per warp: 4308 instead of 5764 chunks, step 0.304 -> 0.296 ms; cfg3 itself 1.600 vs 1.624 ms the other way:
+  // profiles/r02_call29_slices.txt).  GWI_TUNE_SLICES_PER_WARP overrides (tuning experiments).
+  int64_t spw = per_warp < 512 ? 2 : 4;
+  if (const char* e = std::getenv("GWI_TUNE_SLICES_PER_WARP")) spw = std::max(1, std::atoi(e));
+  int64_t L = roundQ(std::max<int64_t>(per_warp < 64 ? 32 : 64, std::min<int64_t>(768, per_warp / spw)));
   L = std::max<int64_t>(L, 8 * Q);
   bool fixed_L = false;  // one slice per CTA: no guided shrink
   if (plan.cta_mode) {
