@@ -30,7 +30,7 @@ unsigned stream_cta_smem_bytes(int nw, int ncol, int rows_total, int deep_entrie
 void launch_prologue_tables(const ModelDev* Md, const double* lam, int n_groups, int n_seg, bool two_pass, int nc, cudaStream_t st, int use_learned_shift);
 void launch_segmax_learn(const ModelDev* Md, int n_seg, int nc, cudaStream_t st);
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux);
-void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st);
+void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, int fan, cudaStream_t st);
 void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st);
 void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaStream_t st);
 void launch_export(const ModelDev* Md, const gwi_outputs& out, cudaStream_t st);
@@ -802,7 +802,7 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   }
   phase_mark(m, 2, st);
   const int n_levels = (int)m->level_tasks.size();
-  for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, st);
+  for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, l < (int)p.level_fan.size() ? p.level_fan[l] : 64, st);
   phase_mark(m, 3, st);
   cudaStreamWaitEvent(st, m->ev_join, 0);  // join
   // the last reduction level (one task per segment) is fused into finish_kernel

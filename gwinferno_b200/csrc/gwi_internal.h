@@ -145,6 +145,7 @@ struct Plan {
   // tasks of the segments that still have more than one fan-in of inputs (a 10 000-sample event goes straight from its
   // few records to the last level instead of being copied through every level)
   std::vector<std::vector<ReduceTask>> levels;
+  std::vector<int> level_fan;  // fan-in (64 / 128 / 256) of every level but the last
   // launch geometry (fixed at plan time: the chunk -> warp assignment depends on it)
   int grid_blocks = 0, warps_per_block = 0;
   int chunk_steps = 0;

@@ -467,10 +467,11 @@ __device__ __forceinline__ double reduce_element(const ModelDev& M, const Reduce
   return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
-// One block = one task x 32 record elements; the 8 warps split the task's <= 64 inputs (warp g takes inputs g, g+8, ...:
-// at most 8 independent loads per thread, ONE memory round trip) and the partial sums are combined through shared memory in
+// One block = one task x 32 record elements; the 8 warps split the task's <= 64 / 128 / 256 inputs (warp g takes inputs g, g+8, ...:
+// at most K = 8 / 16 / 32 independent loads per thread, ONE memory round trip) and the partial sums are combined through shared memory in
 // the same fixed order as reduce_element's.  (A thread per element walking all 64 inputs needed 8 dependent rounds: ~20 us per
 // level whatever the number of tasks.)
+template <int K>  // K = fan-in / 8 loads per thread
 __global__ void __launch_bounds__(256) reduce_kernel(const ModelDev* __restrict__ Mp, int level) {
   GWI_PDL_TRIGGER();
   const ModelDev& M = Mp[blockIdx.z];  // blockIdx.z = chain
@@ -488,16 +489,16 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ModelDev* __restrict_
     const bool sparse = T.src < 0 && NW > 0;
     const int RPC = NW + 1;
     const bool want_deep = sparse && i >= M.cta_lead_doubles;
-    double v[8];
+    double v[K];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < K; ++k) {
       const int r = g + 8 * k;
       bool use = r < T.in_count;
       if (use && sparse) use = (((T.in_first + r) % RPC) == NW) == want_deep;
       v[k] = use ? p[(size_t)r * rec] : 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += v[k];
+    for (int k = 0; k < K; ++k) acc += v[k];
   }
   part[g][j] = acc;
   __syncthreads();
@@ -965,9 +966,11 @@ void launch_segmax_learn(const ModelDev* Md, int n_seg, int nc, cudaStream_t st)
 void launch_prologue_groups(const ModelDev* Md, const double* lam, int n_groups, int max_grid, int nc, cudaStream_t aux) {
   if (n_groups > 0) GWI_LAUNCH(prologue_kernel, dim3(n_groups, nc), 256, (size_t)max_grid * sizeof(double), aux)(Md, lam, 0, 0);
 }
-void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, cudaStream_t st) {
+void launch_reduce(const ModelDev* Md, int level, int n_tasks, int rec, int nc, int fan, cudaStream_t st) {
   dim3 grid(n_tasks, (rec + 31) / 32, nc);
-  GWI_LAUNCH_PDL(reduce_kernel, grid, 256, 0, st)(Md, level);
+  if (fan <= 64) GWI_LAUNCH_PDL(reduce_kernel<8>, grid, 256, 0, st)(Md, level);
+  else if (fan <= 128) GWI_LAUNCH_PDL(reduce_kernel<16>, grid, 256, 0, st)(Md, level);
+  else GWI_LAUNCH_PDL(reduce_kernel<32>, grid, 256, 0, st)(Md, level);
 }
 void launch_segmax(const ModelDev* Md, int n_seg, int nc, cudaStream_t st) { GWI_LAUNCH(segmax_kernel, dim3(n_seg, nc), 256, 0, st)(Md); }
 void launch_finish(const ModelDev* Md, int n_seg, int rec_doubles, int nc, cudaStream_t st) {

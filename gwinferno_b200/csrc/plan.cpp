@@ -1204,18 +1204,29 @@ void plan_tree(Plan& plan) {
       cnt[plan.chunks[c].segment] += RPC;
     }
     for (int s = 0; s < n_seg; ++s) first[s] = plan.segments[s].first_chunk * RPC;  // chunks (hence records) of a segment are consecutive
-    // reduction tree, fan-in 64: per segment, levels are added only while it has more than one fan-in of inputs
-    constexpr int FAN = 64;
+    // reduction tree: per segment, levels are added only while it has more than LAST = 64 inputs (what finish_kernel sums
+    // itself).  The fan-in of a level is the smallest of 64 / 128 / 256 that brings every segment down to <= 64 inputs in ONE
+    // level (cfg3: 8477 records -> 34 tasks of 256 instead of 133 tasks of 64 + a second level of 3: one dependent launch
+    // less per evaluation; an 8-way shard: 4308 -> 34 tasks of 128); each task's inputs are split over the 8 warps of its block,
+    // fan/8 independent loads per thread, one memory round trip whatever the fan-in (kernels.cu: reduce_kernel).
+    constexpr int LAST = 64;
+    plan.level_fan.clear();
     std::vector<int> src(n_seg, -1);  // where the segment's current inputs are (-1 = level-0 records)
     for (;;) {
-      bool any = false;
-      for (int s = 0; s < n_seg; ++s)
-        if (cnt[s] > FAN) any = true;
-      if (!any) break;
+      int max_cnt = 0;
+      for (int s = 0; s < n_seg; ++s) max_cnt = std::max(max_cnt, cnt[s]);
+      if (max_cnt <= LAST) break;
+      int FAN = 64;
+      while (FAN < 256 && (max_cnt + FAN - 1) / FAN > LAST) FAN *= 2;
+      if (const char* e = std::getenv("GWI_TUNE_REDUCE_FAN")) {  // tuning experiments: force 64 / 128 / 256
+        const int v = std::atoi(e);
+        if (v == 64 || v == 128 || v == 256) FAN = v;
+      }
+      plan.level_fan.push_back(FAN);
       const int lvl = (int)plan.levels.size();
       std::vector<ReduceTask> tasks;
       for (int s = 0; s < n_seg; ++s) {
-        if (cnt[s] <= FAN) continue;
+        if (cnt[s] <= LAST) continue;
         const int nt = (cnt[s] + FAN - 1) / FAN;
         const int out0 = (int)tasks.size();
         for (int t = 0; t < nt; ++t) {
