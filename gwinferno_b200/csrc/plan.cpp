@@ -1204,11 +1204,12 @@ void plan_tree(Plan& plan) {
       cnt[plan.chunks[c].segment] += RPC;
     }
     for (int s = 0; s < n_seg; ++s) first[s] = plan.segments[s].first_chunk * RPC;  // chunks (hence records) of a segment are consecutive
-    // reduction tree: per segment, levels are added only while it has more than LAST = 64 inputs (what finish_kernel sums
-    // itself).  The fan-in of a level is the smallest of 64 / 128 / 256 that brings every segment down to <= 64 inputs in ONE
-    // level (cfg3: 8477 records -> 34 tasks of 256 instead of 133 tasks of 64 + a second level of 3: one dependent launch
-    // less per evaluation; an 8-way shard: 4308 -> 34 tasks of 128); each task's inputs are split over the 8 warps of its block,
-    // fan/8 independent loads per thread, one memory round trip whatever the fan-in (kernels.cu: reduce_kernel).
+    // reduction tree, fan-in 64: per segment, levels are added only while it has more than LAST = 64 inputs (what
+    // finish_kernel sums itself).  A larger fan-in (128 / 256: GWI_TUNE_REDUCE_FAN, reduce_kernel<16 / 32>) would bring cfg3's
+    // 8477 records down in ONE level instead of two, i.e. one dependent launch less -- measured SLOWER on B200
+    // (profiles/r02_call31_reduce_fan.txt: everything-but-the-stream-kernel per evaluation 76.7 us with two levels of 64 against
+    // 99-108 us with one level of 128 / 256 on cfg3, 69.6 against 78-83 us on an 8-way shard, 76 against 89-96 us on cfg5:
+    // finish_kernel's injection block then sums 34-67 inputs itself, which costs more than the extra launch).  64 it stays.
     constexpr int LAST = 64;
     plan.level_fan.clear();
     std::vector<int> src(n_seg, -1);  // where the segment's current inputs are (-1 = level-0 records)
@@ -1217,7 +1218,6 @@ void plan_tree(Plan& plan) {
       for (int s = 0; s < n_seg; ++s) max_cnt = std::max(max_cnt, cnt[s]);
       if (max_cnt <= LAST) break;
       int FAN = 64;
-      while (FAN < 256 && (max_cnt + FAN - 1) / FAN > LAST) FAN *= 2;
       if (const char* e = std::getenv("GWI_TUNE_REDUCE_FAN")) {  // tuning experiments: force 64 / 128 / 256
         const int v = std::atoi(e);
         if (v == 64 || v == 128 || v == 256) FAN = v;
