@@ -125,8 +125,6 @@ struct gwi_model {
   cudaStream_t aux_stream = nullptr;  // grid normalisers run here, concurrently with the stream kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t bytes_per_eval = 0;
-  int32_t* fuse_parent_dev = nullptr;  // second reduction level fused into the first (static task -> parent map), null = off
-  int fuse_counters = 0;
   bool plan_on_device = false;  // built by plan_device.cu
   double plan_seconds[5] = {0, 0, 0, 0, 0};
   // GWI_PHASE_TIMING=1 (diagnostic): CUDA events between the kernels of every single-chain evaluation; the mean device
@@ -404,11 +402,6 @@ static int alloc_chain_scratch(gwi_model* m, ModelDev& H) {
   UPS(upload<double>(m, nullptr, (size_t)nseg, &H.shift_next));
   UPS(upload<double>(m, nullptr, (size_t)nseg, &H.spec_bad));
   UPS(upload<int32_t>(m, nullptr, (size_t)1, &H.tail_counter));
-  H.fuse01 = m->fuse_parent_dev ? 1 : 0;
-  H.pad_fuse_ = 0;
-  H.fuse_parent = m->fuse_parent_dev;
-  H.fuse_counter = nullptr;
-  if (H.fuse01) UPS(upload<int32_t>(m, nullptr, (size_t)m->fuse_counters, &H.fuse_counter));
   H.n_levels = (int)p.levels.size();
   for (int l = 0; l < 6; ++l) {
     H.level_buf[l] = nullptr;
@@ -688,22 +681,6 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     UP(upload(m, p.levels[l].data(), p.levels[l].size(), &d_t));
     m->level_tasks.push_back({d_t, (int)p.levels[l].size()});
   }
-  {
-    // exactly two reduction levels before finish_kernel (long catalogs: cfg3 8477 -> 133 -> 3 records): the second is executed
-    // inside the first kernel by the last-arriving blocks (GWI_FUSE_REDUCE=0: two launches, bitwise the same results)
-    const char* e = std::getenv("GWI_FUSE_REDUCE");
-    if (p.levels.size() == 3 && !(e && e[0] == '0')) {
-      std::vector<int32_t> parent(p.levels[0].size(), -1);
-      for (size_t t1 = 0; t1 < p.levels[1].size(); ++t1) {
-        const ReduceTask& T1 = p.levels[1][t1];
-        if (T1.src != 0) continue;
-        for (int o = T1.in_first; o < T1.in_first + T1.in_count; ++o)
-          if (o >= 0 && o < (int)parent.size()) parent[o] = (int32_t)t1;
-      }
-      UP(upload(m, parent.data(), parent.size(), &m->fuse_parent_dev));
-      m->fuse_counters = (int)p.levels[1].size() * ((p.rec_doubles + 31) / 32);
-    }
-  }
   UP(alloc_chain_scratch(m, H));
   UP(upload(m, &H, 1, &m->dev));
   UP(upload<double>(m, nullptr, (size_t)P, &m->lam_dev));
@@ -786,7 +763,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     m->stream_grid_x = std::max(1, std::min(p.grid_blocks, (int)p.slice_begin.size() - 1));
     m->max_grid_x = std::max(1, std::min(4 * p.grid_blocks, (int)p.chunks.size()));
   }
-  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 1 - (m->fuse_parent_dev ? 1 : 0);
+  m->launches_per_eval = 2 + (H.two_pass ? 2 : 0) + 1 + ((int)p.levels.size() - 1) + 1 + 1;
   CUDA_TRY(cudaDeviceSynchronize());
   m->plan_seconds[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_plan0).count();
   *out = m;
@@ -825,10 +802,7 @@ static int run_eval(gwi_model* m, const double* lam_dev, int nc, cudaStream_t st
   }
   phase_mark(m, 2, st);
   const int n_levels = (int)m->level_tasks.size();
-  for (int l = 0; l + 1 < n_levels; ++l) {
-    if (l == 1 && H.fuse01) continue;  // executed inside the level-0 kernel
-    launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, l < (int)p.level_fan.size() ? p.level_fan[l] : 64, st);
-  }
+  for (int l = 0; l + 1 < n_levels; ++l) launch_reduce(m->dev, l, m->level_tasks[l].second, H.rec_doubles, nc, l < (int)p.level_fan.size() ? p.level_fan[l] : 64, st);
   phase_mark(m, 3, st);
   cudaStreamWaitEvent(st, m->ev_join, 0);  // join
   // the last reduction level (one task per segment) is fused into finish_kernel

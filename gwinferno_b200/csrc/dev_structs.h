@@ -151,11 +151,6 @@ struct ModelDev {
   // CTA-cooperative stream kernel (stream_cta.cuh): main warps per CTA (0 = the one-role kernel's geometry)
   int32_t cta_main_warps, cta_lead_doubles;  // cta_lead_doubles: header + linear slots + leading rows of a record (what a main warp writes)
   int32_t* tail_counter;  // arrival counter of partial_tail_kernel (zero between evaluations)
-  // second reduction level fused into the first (reduce_kernel): the block that completes the LAST input of a level-1 task
-  // (for its 32 record elements) sums that task right away -- same inputs, same order, one dependent launch less
-  const int32_t* fuse_parent;  // [tasks of level 0] -> task of level 1 that reads its output, -1 none (static)
-  int32_t* fuse_counter;       // [tasks of level 1][element blocks] arrivals (zero between evaluations)
-  int32_t fuse01, pad_fuse_;
 };
 
 // multi-GPU exchange (exchange_kernel): the exchange buffers of every rank as seen from this rank (peer

@@ -504,40 +504,6 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ModelDev* __restrict_
   __syncthreads();
   if (g == 0 && i < rec)
     M.level_buf[level][(size_t)T.out_slot * rec + i] = ((part[0][j] + part[1][j]) + (part[2][j] + part[3][j])) + ((part[4][j] + part[5][j]) + (part[6][j] + part[7][j]));
-  if (!(M.fuse01 && level == 0)) return;
-  // ---- the next level, fused: whoever completes the last input of a level-1 task (for these 32 elements) sums it now.
-  // Same inputs in the same order as a separate launch of that level would use: bitwise the same result.
-  const int parent = M.fuse_parent[blockIdx.x];
-  if (parent < 0) return;  // this segment goes straight to finish_kernel
-  const ReduceTask T1 = M.level_tasks[1][parent];
-  __shared__ int last_s;
-  __threadfence();  // the writers' stores are visible device-wide before the arrival is counted
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int* c = M.fuse_counter + (size_t)parent * gridDim.y + blockIdx.y;
-    const int k = atomicAdd(c, 1);
-    last_s = k == T1.in_count - 1;
-    if (last_s) *c = 0;  // nobody else touches it in this evaluation
-  }
-  __syncthreads();
-  if (!last_s) return;
-  __threadfence();
-  double acc1 = 0.0;
-  if (i < rec) {
-    const double* p1 = M.level_buf[0] + (size_t)T1.in_first * rec + i;
-    double v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int r = g + 8 * k;
-      v[k] = r < T1.in_count ? __ldcg(p1 + (size_t)r * rec) : 0.0;  // written by other blocks of this grid: L2, not L1
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc1 += v[k];
-  }
-  part[g][j] = acc1;
-  __syncthreads();
-  if (g == 0 && i < rec)
-    M.level_buf[1][(size_t)T1.out_slot * rec + i] = ((part[0][j] + part[1][j]) + (part[2][j] + part[3][j])) + ((part[4][j] + part[5][j]) + (part[6][j] + part[7][j]));
 }
 
 __global__ void __launch_bounds__(256) segmax_kernel(const ModelDev* __restrict__ Mp) {
