@@ -223,3 +223,61 @@ def test_plan_reproduces_oracle_on_random_small_models(seed):
             assert abs(m + np.log(S1) - np.log(denom) - sumZ - want) < 1e-11
             if s > 0:
                 assert abs(2 * np.log(S1) - np.log(S2) - ev["logNeff"][s - 1]) < 1e-11
+
+
+def test_explicit_knot_vectors_are_validated_by_the_library():
+    """gwi_term.knots / order (interpolation.py:72-106): order 1..4, n_knots == n_splines + order, non-decreasing knots,
+    at most 61 polynomial pieces inside the range; the piece tables are derived inside the library."""
+    import copy
+
+    from gwinferno_b200 import models as M
+    from gwinferno_b200 import lowering, synthetic
+
+    pe, inj, _ = synthetic.make_catalog(3, 40, 500, cfg=402)
+    cat = None
+
+    def plan(**kw):
+        nonlocal cat
+        a = M.BSplineSpinMagnitude(kw.pop("n", 8), pe["a_1"], inj["a_1"], normalize=True, **kw)
+        c = np.zeros(a.n_splines)
+        low = lowering.lower(a(c, pe_samples=True), a(c, pe_samples=False))
+        cat = capi.Catalog(low.pe_cols, low.inj_cols, 2000.0)
+        return low, cat
+
+    low, cat = plan(degree=2)
+    p = capi.HostPlan(cat, low.spec)
+    dims = p.read(4).reshape(-1, 4)
+    # quadratic, 8 bases on default knots: 6 spans inside [0, 1], the span that STARTS at 1 (half-open spans: x == 1 falls into
+    # it, interpolation.py:143-146), and the dummy row
+    assert dims[0, 1] == 6 + 1 + 1
+    p.close()
+    # a knot vector the library must refuse: decreasing
+    bad = copy.deepcopy(low.spec)
+    bad.terms[0].knots = bad.terms[0].knots[::-1].copy()
+    with pytest.raises(capi.GwiError, match="non-decreasing"):
+        capi.HostPlan(cat, bad)
+    # wrong length / order
+    bad = copy.deepcopy(low.spec)
+    bad.terms[0].order = 5
+    with pytest.raises(capi.GwiError, match="order 1..4"):
+        capi.HostPlan(cat, bad)
+    # too many pieces for the 6-bit piece index
+    low, cat = plan(n=80, knots=np.linspace(-0.05, 1.05, 84))
+    with pytest.raises(capi.GwiError, match="61 polynomial pieces"):
+        capi.HostPlan(cat, low.spec)
+    # the reference's default knots passed EXPLICITLY give the default plan's pieces (same words up to rounding of u)
+    a_def = M.BSplineSpinTilt(9, pe["cos_tilt_1"], inj["cos_tilt_1"], normalize=True)
+    dx = 2.0 / (9 - 2 - 1)
+    a_exp = M.BSplineSpinTilt(9, pe["cos_tilt_1"], inj["cos_tilt_1"], normalize=True, knots=np.linspace(-1 - 3 * dx, 1 + 3 * dx, 13))
+    c = np.linspace(-1, 1, 9)
+    words = []
+    for a in (a_def, a_exp):
+        low = lowering.lower(a(c, pe_samples=True), a(c, pe_samples=False))
+        cat = capi.Catalog(low.pe_cols, low.inj_cols, 2000.0)
+        hp = capi.HostPlan(cat, low.spec)
+        d = hp.read(0)
+        w = hp.read(1, dtype=np.uint64).reshape(int(d[1]) // 64, int(d[0]), 64)[:, 0, :].ravel()
+        words.append(w)
+        hp.close()
+    assert np.array_equal(words[0] & JMASK, words[1] & JMASK)
+    assert np.max(np.abs(words[0].view(np.float64) - words[1].view(np.float64))) < 1e-12
