@@ -49,11 +49,12 @@ grep "gwi plan" "$OUT/${TAG}_plan_on_device_catalog_err.txt" | tail -1 | tee -a 
 # launch list of the default command (short run: ncu serialises and replays)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --log-file "$OUT/${TAG}_cfg3_launches.csv" \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2> "$OUT/${TAG}_ncu_launches_err.txt"
-# full captures: the headline kernel (one-role, cfg3) and the CTA-cooperative kernel on an 8-way shard
+# full captures: the headline kernel (one-role, cfg3) and the CTA-cooperative kernel on cfg2
 ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 3 -c 1 -f -o "$OUT/${TAG}_cfg3_stream_kernel" \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2> "$OUT/${TAG}_ncu_full_err.txt"
-ncu --set full --clock-control none --import-source on -k regex:stream_cta_kernel -s 3 -c 1 -f -o "$OUT/${TAG}_shard8_stream_cta_kernel" \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --emulate-world 8 > /dev/null 2>> "$OUT/${TAG}_ncu_full_err.txt"
+# (the CTA-cooperative kernel runs the small catalogs: below 2.4e6 samples and chain batches; shards of cfg3 use the one-role kernel)
+ncu --set full --clock-control none --import-source on -k regex:stream_cta_kernel -s 3 -c 1 -f -o "$OUT/${TAG}_cfg2_stream_cta_kernel" \
+    python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>> "$OUT/${TAG}_ncu_full_err.txt"
 for w in "cfg3" "cfg3 --emulate-world 8" "cfg2 --steps 300 --warmup 20" "cfg5"; do
   echo "== $w" >> "$OUT/${TAG}_phases.txt"
   GWI_PHASE_TIMING=1 python bench.py --no-cpu-baseline --workload $w 2>&1 >/dev/null | grep "gwi phases" >> "$OUT/${TAG}_phases.txt"
