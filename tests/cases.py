@@ -32,6 +32,8 @@ GOLDEN_CASES = [
     "bspline_knots",
     "bspline_knots_margsel",
     "bspline_knots_density",
+    "inference_test_bspline_gwtc3",
+    "inference_test_parametric_gwtc3",
 ]
 # Cases whose model carries host-side glue (a parameter map / a host normaliser, lowering.pull_back and
 # lowering.host_log_norm): the DEVICE model is an ordinary one, so they are checked on the CPU with the
@@ -59,6 +61,8 @@ LIKE_KW = {
     "bspline_knots": dict(min_neff_cut=False),
     "bspline_knots_margsel": dict(marginalize_selection=True, min_neff_cut=False),
     "bspline_knots_density": dict(min_neff_cut=False),
+    "inference_test_bspline_gwtc3": dict(marginalize_selection=False, min_neff_cut=False),
+    "inference_test_parametric_gwtc3": dict(marginalize_selection=False, min_neff_cut=False),
 }
 
 

@@ -511,6 +511,46 @@ def case_bspline_knots_density():
     _save("bspline_knots_density", pe, inj, const, params, names, base, jac, dict(model="bspline_knots_density", mmin=mmin, mmax=mmax, **{f"n_{k}": v for k, v in ns.items()}))
 
 
+def case_inference_test_gwtc3():
+    """The reference's OWN test scenario on its OWN data (tests/inference_test.py:74-117,140-172,227-263): the vendored GWTC-3
+    posterior-sample file (69 events x 1000 samples, read here with gwinferno_b200/catalog_io.py -- xarray is not installed),
+    100 samples per event drawn without replacement (:78-82; seeded here), the B-spline and the power-law models of that
+    test at its parameter points.  The found injections of the reference test (tests/data/injections.h5) are not vendored:
+    synthetic ones stand in."""
+    from gwinferno_b200 import catalog_io
+
+    path = os.path.join(jax_shim.REFERENCE_ROOT, "tests", "data", "xarray_GWTC3_BBH_69evs_downsampled_1000samps_nospin.h5")
+    pe, events, _ = catalog_io.load_pe_dataset(path, n_samples=100, rng=np.random.default_rng(2021))
+    inj = synthetic.make_injections(6000, 150001)
+    const = {"total_inj": float(4 * 6000), "obs_time": 1.0, "nObs": len(events)}
+    mmin, mmax = 5.0, 100.0
+    # B-spline model (:98-117, 227-263)
+    rm = SEP.BSplinePrimaryBSplineRatio(10, 5, pe["mass_1"], inj["mass_1"], pe["mass_ratio"], inj["mass_ratio"], m1min=mmin, m2min=mmin, mmax=mmax)
+    rz = SPL.PowerlawSplineRedshiftModel(5, pe["redshift"], inj["redshift"])
+    params = dict(m1_coefs=np.random.default_rng(0).standard_normal(10), q_coefs=np.random.default_rng(1).standard_normal(5), lamb=np.float64(2.9), z_coefs=np.ones(5))
+    names = ["m1_coefs", "q_coefs", "lamb", "z_coefs"]
+
+    def weights(d, pe_samples, p):
+        w = rm(p["m1_coefs"], p["q_coefs"], pe_samples=pe_samples) * rz(d["redshift"], p["lamb"], p["z_coefs"]) / d["prior"]
+        return np.where(np.isnan(w) | np.isinf(w), 0, w)
+
+    vt = lambda p: rz.normalization(lamb=p["lamb"], cs=p["z_coefs"])  # noqa: E731
+    base, jac = _complex_step(weights, pe, inj, const, params, names, vt, dict(marginalize_selection=False, min_neff_cut=False))
+    _save("inference_test_bspline_gwtc3", pe, inj, const, params, names, base, jac, dict(model="inference_test_bspline", mmin=mmin, mmax=mmax))
+    # power-law model (:140-172)
+    rz2 = PAR.PowerlawRedshiftModel(z_pe=pe["redshift"], z_inj=inj["redshift"])
+    params = dict(alpha=np.float64(3.5), beta=np.float64(1.1), lamb=np.float64(2.9))
+    names = ["alpha", "beta", "lamb"]
+
+    def weights2(d, pe_samples, p):
+        w = PAR.powerlaw_primary_ratio_pdf(d["mass_1"], d["mass_ratio"], alpha=p["alpha"], beta=p["beta"], mmin=mmin, mmax=mmax) * rz2(d["redshift"], p["lamb"]) / d["prior"]
+        return np.where(np.isnan(w) | np.isinf(w), 0, w)
+
+    vt2 = lambda p: rz2.normalization(lamb=p["lamb"])  # noqa: E731
+    base, jac = _complex_step(weights2, pe, inj, const, params, names, vt2, dict(marginalize_selection=False, min_neff_cut=False))
+    _save("inference_test_parametric_gwtc3", pe, inj, const, params, names, base, jac, dict(model="inference_test_parametric", mmin=mmin, mmax=mmax))
+
+
 CASES = dict(
     bspline_full=case_bspline_full,
     bspline_full_maxvar=lambda: case_bspline_full(maxvar_only=True),
@@ -527,6 +567,7 @@ CASES = dict(
     bspline_redshift_default=case_bspline_redshift_default,
     bspline_knots=case_bspline_knots,
     bspline_knots_density=case_bspline_knots_density,
+    inference_test_gwtc3=case_inference_test_gwtc3,
 )
 
 if __name__ == "__main__":
