@@ -100,7 +100,7 @@ struct gwi_model {
   int max_grid_x = 1, max_block = 0;  // launch geometry of the max-only pass
   stream_fn k_full = nullptr, k_max = nullptr;
   size_t smem_full = 0, smem_max = 0;
-  // GWI_SPECULATIVE_SHIFT=1 on a -DGWI_EXP_TRACK_MAX=1 build (host call only, one chain): models that need
+  // speculative shift (GWI_SPECULATIVE_SHIFT=0 turns it off; host call only, one chain): models that need
   // the exact per-segment maximum take it from the previous evaluation's full pass instead of a max-only pass
   bool spec_shift = false;      // switch
   bool spec_learned = false;    // shift_next holds maxima of an earlier evaluation
@@ -753,7 +753,7 @@ int gwi_model_create(gwi_catalog* cat, const gwi_model_desc* desc, gwi_model** o
     m->use_graph = !(g && g[0] == '0') && !m->phase_timing;  // on by default (r02: +9 % e2e evals/s at config-2 size, bitwise-equal results)
 #if GWI_EXP_TRACK_MAX
     const char* sp = std::getenv("GWI_SPECULATIVE_SHIFT");
-    m->spec_shift = sp && sp[0] == '1' && H.two_pass;
+    m->spec_shift = H.two_pass && !(sp && sp[0] == '0');  // on by default (r02 call 37: cfg1 host call 308 -> 211 us, equal results)
     if (m->spec_shift) m->use_graph = false;  // the launch sequence differs from call to call
 #endif
   }

@@ -59,13 +59,15 @@ PdlLauncher<KArgs...> make_pdl_launcher(void (*k)(KArgs...), dim3 g, dim3 b, siz
 #define GWI_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #endif
 
-// GWI_EXP_TRACK_MAX (experiment switch, default 0; run-time side: GWI_SPECULATIVE_SHIFT=1): the full pass of
-// the stream kernel also records every chunk's max x, so that models without an a-priori bound (parametric
-// terms, spline densities) can take the NEXT evaluation's log-sum-exp shift from THIS evaluation's exact
-// maxima instead of running a max-only pass first; an evaluation whose maxima moved by more than
-// SPEC_SHIFT_TOL from the shift it used is flagged and repeated with the exact maximum by the host call.
+// Speculative shift (GWI_EXP_TRACK_MAX, default 1; run-time switch GWI_SPECULATIVE_SHIFT=0 turns it off): models without an
+// a-priori bound of their log-weights (parametric terms, spline densities) need the exact per-segment maximum as the
+// log-sum-exp shift -- a max-only pass before the full pass.  Instead the full pass of the generic-term stream kernel also
+// records every chunk's max x, and the NEXT evaluation of gwi_loglike_host takes its shift from THIS evaluation's exact maxima;
+// an evaluation whose maxima moved by more than SPEC_SHIFT_TOL from the shift it used is flagged and repeated with the exact
+// maximum by the host call.  Measured on B200 (cfg1, profiles/r02_call37_speculative_shift.txt): host call 308 -> 211 us per
+// evaluation, results equal; the recording costs the spline-only kernels nothing (compiled into the PARAM variants only).
 #ifndef GWI_EXP_TRACK_MAX
-#define GWI_EXP_TRACK_MAX 0
+#define GWI_EXP_TRACK_MAX 1
 #endif
 
 namespace gwi {
