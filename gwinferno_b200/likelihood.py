@@ -96,6 +96,9 @@ class LikelihoodResult:
     def grad(self, param):
         """Gradient of log_l with respect to a parameter OBJECT that was passed to the model calls
         (the total derivative: summed over every argument position the object was passed to)."""
+        if self._lowered is None:  # cached engine: the object -> Lambda slots map of THIS call's parameter objects
+            e = self._engine_lowered
+            self._lowered = lowering.Lowered(e.spec, e.pe_cols, e.inj_cols, e.param_layout, lowering.object_slot_map(self._pe_weights))
         sl = self._lowered.all_slots_for(param)
         g = self.grad_flat[sl[0]]
         for extra in sl[1:]:
@@ -167,8 +170,8 @@ def hierarchical_likelihood(
         lowered = eng.lowered
     else:
         _ENGINES.move_to_end(cache_key)
-        # same static structure, new hyper-parameter objects: rebuild only the slot map
-        lowered = lowering.Lowered(eng.spec, eng.lowered.pe_cols, eng.lowered.inj_cols, eng.lowered.param_layout, lowering.object_slot_map(pe_weights))
+        # same static structure, new hyper-parameter objects: the slot map is rebuilt on demand (LikelihoodResult.grad)
+        lowered = None
     lam = lowering.flatten_params(pe_weights, eng.n_params)
     log_l, grad, head = eng.loglike(lam, Nobs=Nobs, marginalize_selection=marginalize_selection, min_neff_cut=min_neff_cut, max_variance_cut=max_variance_cut)
     head = dict(head)
@@ -177,6 +180,7 @@ def hierarchical_likelihood(
     grad = lowering.pull_back(pe_weights, grad)
     log_l, grad, head = apply_host_norm(log_l, grad, head, *lowering.host_log_norm(pe_weights, eng.n_params), n_events=eng.n_events, Nobs=Nobs)
     res = LikelihoodResult(log_l, grad, head, lowered, pe_weights, surveyed_hypervolume, Tobs, Nobs)
+    res._engine_lowered = eng.lowered
     if reconstruct_rate and surveyed_hypervolume is not None:
         # analysis.py:265-268
         total_vt = float(surveyed_hypervolume) / 1.0e9 * Tobs

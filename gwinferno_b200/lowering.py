@@ -71,19 +71,48 @@ class Lowered:
         return sl[0]
 
 
+_ZEROS = {}  # n_params -> a shared all-zero vector (read-only use: "no host-side normaliser")
+
+
+def _walk(pe_w):
+    """ONE pass over the PE-side lazy terms, cached on the weight object: the parameter-sharing pattern, the distinct
+    parameter blocks ``(offset, value, ParamMap or None)`` in Lambda order, and whether any term carries a parameter map or
+    a host-side normaliser (hierarchical_likelihood runs on every sampler step: ~60 us of repeated walks otherwise)."""
+    w = getattr(pe_w, "_walk_cache", None)
+    if w is not None:
+        return w
+    seen, pattern, blocks, off = {}, [], [], 0
+    has_map = has_norm = False
+    for t in pe_w.terms:
+        maps = getattr(t, "maps", None) or {}
+        if getattr(t, "host_norm", None) is not None:
+            has_norm = True
+        for i, (p, k) in enumerate(zip(t.params, t.param_keys)):
+            m = maps.get(i)
+            j = seen.get(k)
+            if j is None:
+                j = seen[k] = len(blocks)
+                blocks.append((off, p, m))
+                off += p.size
+                if m is not None:
+                    has_map = True
+            elif blocks[j][2] is not m:
+                raise ValueError("a parameter object shared between terms must use the same parameter map in all of them")
+            pattern.append((j, p.size))
+    w = (tuple(pattern), blocks, off, has_map, has_norm)
+    try:
+        pe_w._walk_cache = w
+    except AttributeError:
+        pass
+    return w
+
+
 def _structure(pe_w, inj_w):
     """Hashable description of the static structure + the parameter-sharing pattern."""
     if len(pe_w.terms) != len(inj_w.terms):
         raise ValueError("PE and injection weights must be built from the same sequence of model terms")
-    seen = {}
-    pattern = []
-    for t in pe_w.terms:
-        for p, k in zip(t.params, t.param_keys):
-            if k not in seen:
-                seen[k] = len(seen)
-            pattern.append((seen[k], p.size))
     keys = tuple(t.key for t in pe_w.terms) + tuple(t.key for t in inj_w.terms)
-    return keys, tuple(pattern)
+    return keys, _walk(pe_w)[0]
 
 
 def object_slot_map(pe_w):
@@ -103,18 +132,8 @@ def object_slot_map(pe_w):
 
 def _param_blocks(pe_w):
     """``[(offset, value, ParamMap or None)]`` per distinct parameter object, in Lambda order."""
-    blocks, seen, off = [], {}, 0
-    for t in pe_w.terms:
-        for i, (p, k) in enumerate(zip(t.params, t.param_keys)):
-            m = getattr(t, "maps", {}).get(i)
-            if k in seen:
-                if blocks[seen[k]][2] is not m:
-                    raise ValueError("a parameter object shared between terms must use the same parameter map in all of them")
-                continue
-            seen[k] = len(blocks)
-            blocks.append((off, p, m))
-            off += p.size
-    return blocks, off
+    w = _walk(pe_w)
+    return w[1], w[2]
 
 
 def flatten_params(pe_w, n_params, param_layout=None):
@@ -132,8 +151,9 @@ def flatten_params(pe_w, n_params, param_layout=None):
 def pull_back(pe_w, grad):
     """Gradient (or Jacobian rows, last axis = Lambda) with respect to the kernel's Lambda -> with
     respect to the parameter values the caller passed (chain rule through the parameter maps)."""
-    blocks, _ = _param_blocks(pe_w)
-    if all(m is None for _, _, m in blocks):
+    w = _walk(pe_w)
+    blocks = w[1]
+    if not w[3]:
         return grad
     out = np.array(grad, dtype=np.float64, copy=True)
     flat = out.reshape(-1, out.shape[-1])
@@ -148,6 +168,8 @@ def host_log_norm(pe_w, n_params):
     """``(log Z, dlog Z/dLambda[P])`` of the host-side normalisers: every sample's log-weight is
     lower by ``log Z`` than what the device model evaluates (the derivative is with respect to the
     parameter values the caller passed)."""
+    if not _walk(pe_w)[4]:
+        return 0.0, _ZEROS.get(n_params) if n_params in _ZEROS else _ZEROS.setdefault(n_params, np.zeros(n_params))
     slot, off = {}, 0
     for t in pe_w.terms:
         for p, k in zip(t.params, t.param_keys):

@@ -166,6 +166,9 @@ class _Column:
         self.inj = None if inj is None else _as_samples(inj)
 
 
+_NO_MAPS = {}  # shared, never mutated
+
+
 class _LazyTerm:
     """One additive log-density term; ``params`` are the hyper-parameter VALUES of this call,
     ``build(slots, group_base)`` produces the static spec entries (terms, groups, cuts)."""
@@ -173,7 +176,7 @@ class _LazyTerm:
     def __init__(self, key, columns, params, build, maps=None, host_norm=None, param_keys=None):
         # ``maps``: {index in params: ParamMap} -- an O(P) host-side change of variables applied when
         # Lambda is assembled; gradients are pulled back through it (lowering.pull_back)
-        self.maps = dict(maps or {})
+        self.maps = dict(maps) if maps else _NO_MAPS
         # ``host_norm(params) -> (log Z, [dlog Z/dparam_i])``: a per-sample CONSTANT -log Z that is
         # not part of the device model (it cancels in log L when Nobs = number of events); the
         # front-end applies it to the reported sites (lowering.host_log_norm)
@@ -190,9 +193,11 @@ class _LazyTerm:
         # objects stay alive in ``_orig`` for that long.
         self._orig = list(params)
         if param_keys is None:
-            param_keys = [None] * len(self._orig)
-        self.param_keys = [k if k is not None else (("arr", id(p)) if np.ndim(p) >= 1 else ("pos", next(_UID))) for p, k in zip(self._orig, param_keys)]
-        self.params = [np.atleast_1d(np.asarray(p, dtype=np.float64)) for p in params]
+            self.param_keys = [("arr", id(p)) if (p.ndim if type(p) is np.ndarray else np.ndim(p)) >= 1 else ("pos", next(_UID)) for p in self._orig]
+        else:
+            self.param_keys = [k if k is not None else (("arr", id(p)) if np.ndim(p) >= 1 else ("pos", next(_UID))) for p, k in zip(self._orig, param_keys)]
+        # (fast path: coefficient vectors arrive as float64 arrays on every sampler step)
+        self.params = [p if (type(p) is np.ndarray and p.dtype == np.float64 and p.ndim >= 1) else np.atleast_1d(np.asarray(p, dtype=np.float64)) for p in self._orig]
         self.build = build
 
 
@@ -341,6 +346,14 @@ class Base1DBSplineModel:
         self.grid_xi = np.clip(grid_xi, *self.xi_range)
 
     def _lazy(self, coefs, pe_samples, tag=""):
+        if (coefs.shape if type(coefs) is np.ndarray else np.shape(coefs)) != (self.n_splines,):
+            raise ValueError(f"expected {self.n_splines} coefficients, got shape {np.shape(coefs)}")
+        static = self.__dict__.setdefault("_lazy_static", {}).get(tag)
+        if static is None:  # the static part of the term (identity key, column, spec builder): once per model and tag
+            static = self._lazy_static[tag] = ((_uid_of(self), tag), [self.column], self._make_build())
+        return LazyWeight([_LazyTerm(static[0], static[1], [coefs], static[2])], pe_samples)
+
+    def _make_build(self):
         model = self
 
         def build(slots, group_base, cols):
@@ -366,9 +379,7 @@ class Base1DBSplineModel:
             term.knots, term.order = model.knots, model.order
             return [term], groups, []
 
-        if np.shape(coefs) != (self.n_splines,):
-            raise ValueError(f"expected {self.n_splines} coefficients, got shape {np.shape(coefs)}")
-        return LazyWeight([_LazyTerm((_uid_of(self), tag), [self.column], [coefs], build)], pe_samples)
+        return build
 
     def __call__(self, coefs, pe_samples=True):
         return self._lazy(coefs, pe_samples)
