@@ -76,6 +76,7 @@ def test_random_configurations_against_the_oracle(monkeypatch):
         nd = int(rng.choice([-1, 0, 1, 2, 3, 4]))
         cs = int(rng.choice([0, 2, 4, 8, 32, 128]))
         monkeypatch.setenv("GWI_CTA_KERNEL", str(int(rng.integers(0, 2))))  # both stream kernels (spline models qualify for the CTA-cooperative one)
+        monkeypatch.setenv("GWI_PLAN_DEVICE", str(case % 2))  # both plan builders (host: plan.cpp, device kernels: plan_device.cu)
         try:
             eng = PopulationLikelihood(low, const["total_inj"], need_neff_grad=g2, chunk_steps=cs, n_deep=nd)
         except capi.GwiError as e:
@@ -108,6 +109,7 @@ def test_random_model_families_against_the_oracle(monkeypatch):
         low, lam, _ = workloads.lower_workload(weights, params_fn, pe, inj, seed=int(rng.integers(0, 1000)))
         g2, cs, nd = bool(rng.integers(0, 2)), int(rng.choice([0, 2, 8, 64])), int(rng.choice([-1, 0, 2, 4]))
         monkeypatch.setenv("GWI_CTA_KERNEL", str(int(rng.integers(0, 2))))  # both stream kernels (spline models qualify for the CTA-cooperative one)
+        monkeypatch.setenv("GWI_PLAN_DEVICE", str(case % 2))  # both plan builders
         eng = PopulationLikelihood(low, const["total_inj"], need_neff_grad=g2, chunk_steps=cs, n_deep=nd)
         r = eng.evaluate(lam)
         eng.model.close()
